@@ -1,0 +1,157 @@
+"""TEST INFRASTRUCTURE ONLY - torch-fp32 model of the *restructured* arithmetic the CUDA kernels use.
+
+The CUDA path never materialises the (E,340)/(E3,437) MLP inputs.  It relies on three exact
+re-associations of the reference arithmetic:
+
+1. first-Linear decomposition  W1 [e | h_i | h_j] = W1e e + W1i h_i + W1j h_j  (per-node / per-edge
+   projections computed once by GEMMs),
+2. key contraction   <q_i, W2k a + b2k>_head = <U_i[head], a> + const(i, head)   with
+   U_i[head] = sum_{c in head} q_i[c] W2k[c, :]   (the constant cancels in the softmax),
+3. value contraction sum_e w_e (W2v a_e + b2v) = W2v (sum_e w_e a_e) + b2v sum_e w_e.
+
+This file evaluates the network that way on the CPU so that `tests/test_fused_algebra.py` can show
+the re-association stays inside the stated tolerance (rtol 1e-4 / atol 1e-5) against
+`oracle/restate.py`, and so kernel unit tests have per-stage intermediates to compare with.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import restate as R
+from .ref_shims import scatter_softmax, scatter_sum
+
+
+def _ln_relu(z, sd, prefix):
+    z = F.layer_norm(z, (z.size(-1),), sd[f'{prefix}.net.1.weight'], sd[f'{prefix}.net.1.bias'], 1e-5)
+    return F.relu(z)
+
+
+def _key_logits(sd, prefix, q, a, group, n_heads=16):
+    """logits[e, h] = <U_{group(e)}[h], a_e> / sqrt(d_head) (bias term dropped: softmax-invariant)."""
+    W2 = sd[f'{prefix}.net.3.weight']  # (128 out, 128 in)
+    dh = 128 // n_heads
+    U = torch.einsum('nhc,hcm->nhm', q.view(-1, n_heads, dh), W2.view(n_heads, dh, 128))
+    return torch.einsum('ehm,em->eh', U[group], a) / np.sqrt(dh)
+
+
+def _value_out(sd, prefix, w, a, group, n_groups, n_heads=16):
+    """out[g] = W2v (sum_e w_e a_e) + b2v sum_e w_e, head-blocked."""
+    W2, b2 = sd[f'{prefix}.net.3.weight'], sd[f'{prefix}.net.3.bias']
+    dh = 128 // n_heads
+    S = scatter_sum(w.unsqueeze(-1) * a.unsqueeze(1), group, dim=0, dim_size=n_groups)  # (G, H, 128)
+    wsum = scatter_sum(w, group, dim=0, dim_size=n_groups)  # (G, H)
+    out = torch.einsum('ghm,hcm->ghc', S, W2.view(n_heads, dh, 128)) + wsum.unsqueeze(-1) * b2.view(n_heads, dh)
+    return out.reshape(n_groups, 128)
+
+
+def edge_first_layer(sd, prefix, etype, g):
+    """W1e [type (x) g | type] for the kNN-edge MLPs: 20 MACs per channel."""
+    W1 = sd[f'{prefix}.net.0.weight']
+    Wg = W1[:, :80].view(128, 4, 20)            # [c, type, gauss]
+    Wt = W1[:, 80:84]                           # [c, type]
+    return torch.einsum('ecg,eg->ec', Wg.permute(1, 0, 2)[etype], g) + Wt.t()[etype]
+
+
+def layer_fused(sd, p, h, x, etype, src, dst, h_bond, bsrc, bdst, mask_upd, e_w, trip):
+    N, Eb = h.size(0), h_bond.size(0)
+    rel_x = x[dst] - x[src]
+    g = R.gaussian_smearing(torch.norm(rel_x, p=2, dim=-1))
+
+    def knn_mlp_hidden(name, hh):
+        pf = f'{p}.{name}'
+        W1, b1 = sd[f'{pf}.net.0.weight'], sd[f'{pf}.net.0.bias']
+        Hi = hh @ W1[:, 84:212].t() + b1
+        Hj = hh @ W1[:, 212:340].t()
+        return _ln_relu(Hi[dst] + Hj[src] + edge_first_layer(sd, pf, etype, g), sd, pf)
+
+    def bond_mlp_hidden(name, hh, hb):
+        pf = f'{p}.{name}'
+        W1, b1 = sd[f'{pf}.net.0.weight'], sd[f'{pf}.net.0.bias']
+        return _ln_relu(hb @ W1[:, :128].t() + (hh @ W1[:, 128:256].t() + b1)[bdst] + (hh @ W1[:, 256:384].t())[bsrc],
+                        sd, pf)
+
+    # node update, kNN edges
+    pn = f'{p}.node_layer_with_edge'
+    q = R.mlp(sd, f'{pn}.hq_func', h)
+    alpha = scatter_softmax(_key_logits(sd, f'{pn}.hk_func', q, knn_mlp_hidden('node_layer_with_edge.hk_func', h), dst), dst, dim=0)
+    h1 = _value_out(sd, f'{pn}.hv_func', alpha * e_w.view(-1, 1), knn_mlp_hidden('node_layer_with_edge.hv_func', h), dst, N)
+    # node update, bond edges
+    pb = f'{p}.node_layer_with_bond'
+    q = R.mlp(sd, f'{pb}.hq_func', h)
+    alpha = scatter_softmax(_key_logits(sd, f'{pb}.hk_func', q, bond_mlp_hidden('node_layer_with_bond.hk_func', h, h_bond), bdst), bdst, dim=0)
+    h2 = _value_out(sd, f'{pb}.hv_func', alpha, bond_mlp_hidden('node_layer_with_bond.hv_func', h, h_bond), bdst, N)
+    # bond update (triplets)
+    pl = f'{p}.bond_layer'
+    idx_i, idx_j, idx_k, idx_kj, idx_ji = trip
+    dist = (x[bdst] - x[bsrc]).pow(2).sum(-1).sqrt()
+    r_feat = R.gaussian_smearing(dist)
+    pos_i = x[idx_i]
+    pji, pki = x[idx_j] - pos_i, x[idx_k] - pos_i
+    ang = R.angular_encoding(torch.atan2(torch.linalg.cross(pji, pki, dim=-1).norm(dim=-1), (pji * pki).sum(-1)))
+
+    def trip_hidden(name):
+        pf = f'{pl}.{name}'
+        W1, b1 = sd[f'{pf}.net.0.weight'], sd[f'{pf}.net.0.bias']
+        # everything that depends only on the edge k->j (k = src, j = dst of that edge)
+        P = h_bond @ W1[:, :128].t() + r_feat @ W1[:, 128:148].t() + (h @ W1[:, 181:309].t())[bsrc] \
+            + (h @ W1[:, 309:437].t() + b1)[bdst]
+        Q = r_feat @ W1[:, 148:168].t()          # depends only on the edge j->i
+        return _ln_relu(P[idx_kj] + Q[idx_ji] + ang @ W1[:, 168:181].t(), sd, pf)
+
+    W1q, b1q = sd[f'{pl}.hq_func.net.0.weight'], sd[f'{pl}.hq_func.net.0.bias']
+    qe = _ln_relu(h_bond @ W1q[:, :128].t() + (h @ W1q[:, 128:256].t() + b1q)[bdst], sd, f'{pl}.hq_func')
+    qe = qe @ sd[f'{pl}.hq_func.net.3.weight'].t() + sd[f'{pl}.hq_func.net.3.bias']   # per EDGE, not per triplet
+    alpha = scatter_softmax(_key_logits(sd, f'{pl}.hk_func', qe, trip_hidden('hk_func'), idx_ji), idx_ji, dim=0, dim_size=Eb)
+    new_h_bond = h_bond + _value_out(sd, f'{pl}.hv_func', alpha, trip_hidden('hv_func'), idx_ji, Eb)
+    # h update
+    new_h = h + F.linear(h1 + h2, sd[f'{p}.lin_node.weight'], sd[f'{p}.lin_node.bias'])
+
+    # pos updates (new h, old geometry)
+    def pos_out(prefix, a_k, a_v, q, grp, rel, ew):
+        alpha = scatter_softmax(_key_logits(sd, f'{prefix}.xk_func', q, a_k, grp), grp, dim=0)
+        v = a_v @ sd[f'{prefix}.xv_func.net.3.weight'].t() + sd[f'{prefix}.xv_func.net.3.bias']
+        if ew is not None:
+            v = v * ew.view(-1, 1)
+        return scatter_sum((alpha * v).unsqueeze(-1) * rel.unsqueeze(1), grp, dim=0, dim_size=N).mean(1)
+
+    pe = f'{p}.pos_layer_with_edge'
+    dx1 = pos_out(pe, knn_mlp_hidden('pos_layer_with_edge.xk_func', new_h), knn_mlp_hidden('pos_layer_with_edge.xv_func', new_h),
+                  R.mlp(sd, f'{pe}.xq_func', new_h), dst, rel_x, e_w)
+    pbx = f'{p}.pos_layer_with_bond'
+    dx2 = pos_out(pbx, bond_mlp_hidden('pos_layer_with_bond.xk_func', new_h, new_h_bond),
+                  bond_mlp_hidden('pos_layer_with_bond.xv_func', new_h, new_h_bond),
+                  R.mlp(sd, f'{pbx}.xq_func', new_h), bdst, x[bdst] - x[bsrc], None)
+    x = x + (dx1 + dx2) * mask_upd[:, None]
+    return new_h, new_h_bond, x
+
+
+def forward_fused(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v,
+                  init_ligand_v_aux, batch_ligand, ligand_fc_bond_index, init_ligand_fc_bond_type,
+                  ligand_atom_mask=None, **_unused):
+    nc, nb = cfg['num_classes'], cfg['num_bond_classes']
+    lig_feat = torch.cat([F.one_hot(init_ligand_v, nc).float(), init_ligand_v_aux], -1)
+    h_p = F.linear(protein_v, sd['protein_atom_emb.weight'], sd['protein_atom_emb.bias'])
+    h_l = F.linear(lig_feat, sd['ligand_atom_emb.weight'], sd['ligand_atom_emb.bias'])
+    h_p = torch.cat([h_p, torch.zeros(h_p.size(0), 1)], -1)
+    h_l = torch.cat([h_l, torch.ones(h_l.size(0), 1)], -1)
+    h, x, batch, mask_l, mask_la, l_idx = R.compose_context(
+        h_p, h_l, protein_pos, init_ligand_pos, batch_protein, batch_ligand, ligand_atom_mask)
+    bsrc, bdst = l_idx[ligand_fc_bond_index]
+    h_bond = F.linear(F.one_hot(init_ligand_fc_bond_type, nb).float(), sd['ligand_bond_emb.weight'],
+                      sd['ligand_bond_emb.bias'])
+    src, dst = R.knn_graph(x, k=cfg['knn'], batch=batch)
+    etype = R.edge_types(src, dst, mask_l)
+    e_w = torch.sigmoid(R.mlp(sd, 'refine_net.edge_pred_layer',
+                              R.gaussian_smearing(torch.norm(x[dst] - x[src], p=2, dim=-1))))
+    trip = R.bond_triplets(bsrc, bdst, h.size(0))
+    for l in range(cfg['num_layers']):
+        h, h_bond, x = layer_fused(sd, f'refine_net.base_block.{l}', h, x, etype, src, dst, h_bond, bsrc, bdst,
+                                   mask_la.to(x.dtype), e_w, trip)
+    fh = h[mask_la]
+    v_logits = F.linear(R.shifted_softplus(F.linear(fh, sd['v_inference.0.weight'], sd['v_inference.0.bias'])),
+                        sd['v_inference.2.weight'], sd['v_inference.2.bias'])
+    b_logits = F.linear(R.shifted_softplus(F.linear(h_bond, sd['bond_inference.0.weight'], sd['bond_inference.0.bias'])),
+                        sd['bond_inference.2.weight'], sd['bond_inference.2.bias'])
+    return {'pred_ligand_pos': x[mask_la], 'pred_ligand_v': v_logits, 'pred_bond': b_logits}
