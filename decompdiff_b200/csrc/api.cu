@@ -1,0 +1,820 @@
+// C ABI of decompdiff_b200 (include/decompdiff_b200.h): weight re-packing, static batch topology,
+// the per-forward kernel schedule and the reverse step.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/decompdiff_b200.h"
+#include "kernels.cuh"
+
+using namespace ddb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define DDB_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(DDB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+  } while (0)
+
+// ---- a growing host blob that becomes one device allocation; offsets are 32-float aligned -------
+struct Blob {
+  std::vector<float> data;
+  size_t alloc(size_t n) {
+    size_t off = (data.size() + 31) / 32 * 32;
+    data.resize(off + n, 0.f);
+    return off;
+  }
+};
+
+struct Mlp2 { size_t gamma, beta, W2, b2; };     // offsets: LayerNorm affine + second Linear (natural layout)
+struct KnnMlpOff { size_t Wg, Wt; Mlp2 m; };
+struct TripOff { size_t Wd, Wc, Wa; Mlp2 m; };
+struct GemmW { size_t Wt, bias; int N; };          // K-major weight (128 x N) + bias (N)
+
+struct LayerOff {
+  GemmW n1, n2, l1, l2, b1, b2, lin;              // node / ligand / bond-edge projection GEMMs, lin_node
+  GemmW q_ne, q_nb, q_bl, q_pe, q_pb;             // second Linear of the five query MLPs
+  Mlp2 ln_q_ne, ln_q_nb, ln_q_bl, ln_q_pe, ln_q_pb;
+  KnnMlpOff ne_k, ne_v, pe_k, pe_v;
+  Mlp2 nb_k, nb_v, pb_k, pb_v;
+  TripOff bl_k, bl_v;
+};
+
+}  // namespace
+
+struct ddb_model {
+  ddb_config cfg{};
+  std::map<std::string, std::vector<float>> host;
+  bool finalized = false;
+  Blob blob;
+  float* dev = nullptr;
+  std::vector<LayerOff> layers;
+  size_t ew_W1t = 0, ew_b1 = 0, ew_gamma = 0, ew_beta = 0, ew_w2 = 0; float ew_b2 = 0.f;
+  size_t lig_Wv = 0, bond_table = 0;
+  GemmW v_head0{}, b_head0{};
+  size_t v_W2 = 0, v_b2 = 0, b_W2 = 0, b_b2 = 0;
+  size_t tab_c0 = 0, tab_ct = 0, tab_logvar = 0;
+  size_t tab_a[5] = {0, 0, 0, 0, 0}, tab_b[5] = {0, 0, 0, 0, 0};   // log_alpha, log_1m_alpha, log_cumprod, log_1m_cumprod, prior
+  const float* p(size_t off) const { return dev + off; }
+};
+
+namespace {
+
+struct Packer {
+  ddb_model& m;
+  std::string missing;
+  explicit Packer(ddb_model& mm) : m(mm) {}
+  const std::vector<float>* get(const std::string& name, size_t numel) {
+    auto it = m.host.find(name);
+    if (it == m.host.end() || it->second.size() != numel) {
+      if (missing.empty()) missing = name + (it == m.host.end() ? " (absent)" : " (wrong size)");
+      return nullptr;
+    }
+    return &it->second;
+  }
+  size_t vec(const std::string& name, size_t numel) {
+    size_t off = m.blob.alloc(numel);
+    if (auto* v = get(name, numel)) std::copy(v->begin(), v->end(), m.blob.data.begin() + off);
+    return off;
+  }
+  struct Block { std::string w; int in_dim; int col0; std::string bias; };   // 128 columns [col0, col0+128) of a (128,in_dim) weight
+  GemmW gemm(const std::vector<Block>& blocks) {
+    GemmW g;
+    g.N = (int)blocks.size() * H;
+    g.Wt = m.blob.alloc((size_t)H * g.N);
+    g.bias = m.blob.alloc(g.N);
+    for (size_t b = 0; b < blocks.size(); ++b) {
+      auto* w = get(blocks[b].w, (size_t)H * blocks[b].in_dim);
+      if (w)
+        for (int k = 0; k < H; ++k)
+          for (int c = 0; c < H; ++c)
+            m.blob.data[g.Wt + (size_t)k * g.N + b * H + c] = (*w)[(size_t)c * blocks[b].in_dim + blocks[b].col0 + k];
+      if (!blocks[b].bias.empty())
+        if (auto* bv = get(blocks[b].bias, H)) std::copy(bv->begin(), bv->end(), m.blob.data.begin() + g.bias + b * H);
+    }
+    return g;
+  }
+  Mlp2 mlp2(const std::string& pre, int out_dim, float scale) {
+    Mlp2 r;
+    r.gamma = vec(pre + ".net.1.weight", H);
+    r.beta = vec(pre + ".net.1.bias", H);
+    r.W2 = m.blob.alloc((size_t)out_dim * H);
+    if (auto* w = get(pre + ".net.3.weight", (size_t)out_dim * H))
+      for (size_t i = 0; i < w->size(); ++i) m.blob.data[r.W2 + i] = (*w)[i] * scale;
+    r.b2 = vec(pre + ".net.3.bias", out_dim);
+    return r;
+  }
+  // columns [col0, col0+n) of W1 (128,in_dim) transposed to [n][128]
+  size_t cols_t(const std::string& wname, int in_dim, int col0, int n) {
+    size_t off = m.blob.alloc((size_t)n * H);
+    if (auto* w = get(wname, (size_t)H * in_dim))
+      for (int j = 0; j < n; ++j)
+        for (int c = 0; c < H; ++c) m.blob.data[off + (size_t)j * H + c] = (*w)[(size_t)c * in_dim + col0 + j];
+    return off;
+  }
+  KnnMlpOff knn_mlp(const std::string& pre, int out_dim, float scale) {
+    KnnMlpOff r;
+    r.Wg = cols_t(pre + ".net.0.weight", 340, 0, 80);     // [type*20+g][128]
+    r.Wt = cols_t(pre + ".net.0.weight", 340, 80, 4);
+    r.m = mlp2(pre, out_dim, scale);
+    return r;
+  }
+  TripOff trip(const std::string& pre, float scale) {
+    TripOff r;
+    r.Wd = cols_t(pre + ".net.0.weight", 437, 128, NG);
+    r.Wc = cols_t(pre + ".net.0.weight", 437, 148, NG);
+    r.Wa = cols_t(pre + ".net.0.weight", 437, 168, NANG);
+    r.m = mlp2(pre, H, scale);
+    return r;
+  }
+  GemmW second(const std::string& pre) {   // second Linear of a query MLP as a GEMM weight
+    return gemm({{pre + ".net.3.weight", H, 0, pre + ".net.3.bias"}});
+  }
+  Mlp2 ln_only(const std::string& pre) {
+    Mlp2 r{};
+    r.gamma = vec(pre + ".net.1.weight", H);
+    r.beta = vec(pre + ".net.1.bias", H);
+    return r;
+  }
+};
+
+const float kInvSqrtDh = 0.35355339059327373f;   // 1/sqrt(8): folded into the key second Linear
+
+}  // namespace
+
+extern "C" const char* ddb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* ddb_version(void) { return "decompdiff_b200 0.1 (sm_100a)"; }
+
+extern "C" int ddb_model_create(ddb_model** out, const ddb_config* cfg) {
+  if (!out || !cfg) return fail(DDB_ERR_INVALID, "null argument");
+  if (cfg->hidden_dim != H || cfg->n_heads != NH)
+    return fail(DDB_ERR_INVALID, "kernels are specialised for hidden_dim=128, n_heads=16");
+  if (cfg->knn < 1 || cfg->knn > KNN) return fail(DDB_ERR_INVALID, "knn must be in [1,32]");
+  if (cfg->num_blocks != 1) return fail(DDB_ERR_INVALID, "num_blocks must be 1");
+  if (cfg->num_classes < 1 || cfg->num_classes > 16 || cfg->num_bond_classes < 1 || cfg->num_bond_classes > 8)
+    return fail(DDB_ERR_INVALID, "num_classes <= 16 and num_bond_classes <= 8 supported");
+  if (cfg->num_layers < 1) return fail(DDB_ERR_INVALID, "num_layers must be >= 1");
+  auto* m = new ddb_model();
+  m->cfg = *cfg;
+  *out = m;
+  return DDB_OK;
+}
+
+extern "C" int ddb_model_set_tensor(ddb_model* m, const char* name, const float* host_data, int64_t numel) {
+  if (!m || !name || (!host_data && numel > 0) || numel < 0) return fail(DDB_ERR_INVALID, "bad tensor argument");
+  m->host[name] = std::vector<float>(host_data, host_data + numel);
+  m->finalized = false;
+  return DDB_OK;
+}
+
+extern "C" void ddb_model_destroy(ddb_model* m) {
+  if (!m) return;
+  if (m->dev) cudaFree(m->dev);
+  delete m;
+}
+
+extern "C" int ddb_model_finalize(ddb_model* m) {
+  if (!m) return fail(DDB_ERR_INVALID, "null model");
+  m->blob = Blob();
+  m->layers.clear();
+  Packer P(*m);
+  const ddb_config& c = m->cfg;
+  const int T = c.num_timesteps, C = c.num_classes, Cb = c.num_bond_classes;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const std::string b = "refine_net.base_block." + std::to_string(l) + ".";
+    const std::string ne = b + "node_layer_with_edge.", nb = b + "node_layer_with_bond.", bl = b + "bond_layer.",
+                      pe = b + "pos_layer_with_edge.", pb = b + "pos_layer_with_bond.";
+    auto w0 = [](const std::string& f) { return f + ".net.0.weight"; };
+    auto b0 = [](const std::string& f) { return f + ".net.0.bias"; };
+    LayerOff L;
+    // node projections of the layer input h: [hk_i | hk_j | hv_i | hv_j | hq hidden]
+    L.n1 = P.gemm({{w0(ne + "hk_func"), 340, 84, b0(ne + "hk_func")}, {w0(ne + "hk_func"), 340, 212, ""},
+                   {w0(ne + "hv_func"), 340, 84, b0(ne + "hv_func")}, {w0(ne + "hv_func"), 340, 212, ""},
+                   {w0(ne + "hq_func"), 128, 0, b0(ne + "hq_func")}});
+    // ligand-atom projections of h: bond-node k/v (i,j), bond-node q, triplet k (h_k,h_j) v (h_k,h_j), triplet q (h_i)
+    L.l1 = P.gemm({{w0(nb + "hk_func"), 384, 128, b0(nb + "hk_func")}, {w0(nb + "hk_func"), 384, 256, ""},
+                   {w0(nb + "hv_func"), 384, 128, b0(nb + "hv_func")}, {w0(nb + "hv_func"), 384, 256, ""},
+                   {w0(nb + "hq_func"), 128, 0, b0(nb + "hq_func")},
+                   {w0(bl + "hk_func"), 437, 181, ""}, {w0(bl + "hk_func"), 437, 309, b0(bl + "hk_func")},
+                   {w0(bl + "hv_func"), 437, 181, ""}, {w0(bl + "hv_func"), 437, 309, b0(bl + "hv_func")},
+                   {w0(bl + "hq_func"), 256, 128, b0(bl + "hq_func")}});
+    // bond-edge projections of h_bond: bond-node k,v | triplet k,v | triplet q
+    L.b1 = P.gemm({{w0(nb + "hk_func"), 384, 0, ""}, {w0(nb + "hv_func"), 384, 0, ""},
+                   {w0(bl + "hk_func"), 437, 0, ""}, {w0(bl + "hv_func"), 437, 0, ""},
+                   {w0(bl + "hq_func"), 256, 0, ""}});
+    L.lin = P.gemm({{b + "lin_node.weight", 128, 0, b + "lin_node.bias"}});
+    // pos phase (new h): source-side xk_j, xv_j for every node
+    L.n2 = P.gemm({{w0(pe + "xk_func"), 340, 212, ""}, {w0(pe + "xv_func"), 340, 212, ""}});
+    L.l2 = P.gemm({{w0(pe + "xk_func"), 340, 84, b0(pe + "xk_func")}, {w0(pe + "xv_func"), 340, 84, b0(pe + "xv_func")},
+                   {w0(pe + "xq_func"), 128, 0, b0(pe + "xq_func")},
+                   {w0(pb + "xk_func"), 384, 128, b0(pb + "xk_func")}, {w0(pb + "xk_func"), 384, 256, ""},
+                   {w0(pb + "xv_func"), 384, 128, b0(pb + "xv_func")}, {w0(pb + "xv_func"), 384, 256, ""},
+                   {w0(pb + "xq_func"), 128, 0, b0(pb + "xq_func")}});
+    L.b2 = P.gemm({{w0(pb + "xk_func"), 384, 0, ""}, {w0(pb + "xv_func"), 384, 0, ""}});
+    L.q_ne = P.second(ne + "hq_func"); L.ln_q_ne = P.ln_only(ne + "hq_func");
+    L.q_nb = P.second(nb + "hq_func"); L.ln_q_nb = P.ln_only(nb + "hq_func");
+    L.q_bl = P.second(bl + "hq_func"); L.ln_q_bl = P.ln_only(bl + "hq_func");
+    L.q_pe = P.second(pe + "xq_func"); L.ln_q_pe = P.ln_only(pe + "xq_func");
+    L.q_pb = P.second(pb + "xq_func"); L.ln_q_pb = P.ln_only(pb + "xq_func");
+    L.ne_k = P.knn_mlp(ne + "hk_func", H, kInvSqrtDh);
+    L.ne_v = P.knn_mlp(ne + "hv_func", H, 1.f);
+    L.pe_k = P.knn_mlp(pe + "xk_func", H, kInvSqrtDh);
+    L.pe_v = P.knn_mlp(pe + "xv_func", NH, 1.f);
+    L.nb_k = P.mlp2(nb + "hk_func", H, kInvSqrtDh);
+    L.nb_v = P.mlp2(nb + "hv_func", H, 1.f);
+    L.pb_k = P.mlp2(pb + "xk_func", H, kInvSqrtDh);
+    L.pb_v = P.mlp2(pb + "xv_func", NH, 1.f);
+    L.bl_k = P.trip(bl + "hk_func", kInvSqrtDh);
+    L.bl_v = P.trip(bl + "hv_func", 1.f);
+    m->layers.push_back(L);
+  }
+  // global edge weight MLP (20 -> 128 -> 1)
+  m->ew_W1t = P.cols_t("refine_net.edge_pred_layer.net.0.weight", NG, 0, NG);
+  m->ew_b1 = P.vec("refine_net.edge_pred_layer.net.0.bias", H);
+  m->ew_gamma = P.vec("refine_net.edge_pred_layer.net.1.weight", H);
+  m->ew_beta = P.vec("refine_net.edge_pred_layer.net.1.bias", H);
+  m->ew_w2 = P.vec("refine_net.edge_pred_layer.net.3.weight", H);
+  if (auto* b = P.get("refine_net.edge_pred_layer.net.3.bias", 1)) m->ew_b2 = (*b)[0];
+  // ligand atom embedding: one-hot part as a table [C][128] (column 127 = node indicator, filled per batch)
+  m->lig_Wv = m->blob.alloc((size_t)C * H);
+  if (auto* w = P.get("ligand_atom_emb.weight", (size_t)(H - 1) * c.ligand_feature_dim))
+    for (int v = 0; v < C; ++v)
+      for (int ch = 0; ch < H - 1; ++ch) m->blob.data[m->lig_Wv + (size_t)v * H + ch] = (*w)[(size_t)ch * c.ligand_feature_dim + v];
+  P.get("ligand_atom_emb.bias", H - 1);
+  P.get("protein_atom_emb.weight", (size_t)(H - 1) * c.protein_feature_dim);
+  P.get("protein_atom_emb.bias", H - 1);
+  // bond embedding table [Cb][128] = W[:,t] + b
+  m->bond_table = m->blob.alloc((size_t)Cb * H);
+  {
+    auto* w = P.get("ligand_bond_emb.weight", (size_t)H * Cb);
+    auto* b = P.get("ligand_bond_emb.bias", H);
+    if (w && b)
+      for (int t = 0; t < Cb; ++t)
+        for (int ch = 0; ch < H; ++ch) m->blob.data[m->bond_table + (size_t)t * H + ch] = (*w)[(size_t)ch * Cb + t] + (*b)[ch];
+  }
+  m->v_head0 = P.gemm({{"v_inference.0.weight", 128, 0, "v_inference.0.bias"}});
+  m->v_W2 = P.vec("v_inference.2.weight", (size_t)C * H);
+  m->v_b2 = P.vec("v_inference.2.bias", C);
+  m->b_head0 = P.gemm({{"bond_inference.0.weight", 128, 0, "bond_inference.0.bias"}});
+  m->b_W2 = P.vec("bond_inference.2.weight", (size_t)Cb * H);
+  m->b_b2 = P.vec("bond_inference.2.bias", Cb);
+  m->tab_c0 = P.vec("posterior_mean_c0_coef", T);
+  m->tab_ct = P.vec("posterior_mean_ct_coef", T);
+  m->tab_logvar = P.vec("posterior_logvar", T);
+  const char* tn[4] = {"log_alphas_v", "log_one_minus_alphas_v", "log_alphas_cumprod_v", "log_one_minus_alphas_cumprod_v"};
+  for (int i = 0; i < 4; ++i) {
+    m->tab_a[i] = P.vec(std::string("atom_type_trans.") + tn[i], T);
+    m->tab_b[i] = P.vec(std::string("bond_type_trans.") + tn[i], T);
+  }
+  m->tab_a[4] = P.vec("atom_type_trans.prior_probs", C);
+  m->tab_b[4] = P.vec("bond_type_trans.prior_probs", Cb);
+  if (!P.missing.empty()) return fail(DDB_ERR_MISSING, "state_dict tensor missing: " + P.missing);
+  if (m->dev) { cudaFree(m->dev); m->dev = nullptr; }
+  DDB_CUDA(cudaMalloc(&m->dev, m->blob.data.size() * sizeof(float)));
+  DDB_CUDA(cudaMemcpy(m->dev, m->blob.data.data(), m->blob.data.size() * sizeof(float), cudaMemcpyHostToDevice));
+  m->finalized = true;
+  return DDB_OK;
+}
+
+// =================================================================================================== batch
+struct ddb_batch {
+  const ddb_model* m = nullptr;
+  int B = 0, N = 0, NL = 0, NP = 0, Eb = 0, max_graph_nodes = 0, num_sms = 148;
+  long long trip_slots = 0;
+  std::vector<void*> allocs;
+  std::vector<float> offset_host;
+  // static topology
+  int *node_ptr = nullptr, *graph_of = nullptr, *lig_idx = nullptr, *lig_ptr = nullptr;
+  uint8_t *is_lig = nullptr, *upd_mask = nullptr;
+  int *bsrc = nullptr, *bdst = nullptr, *in_ptr = nullptr, *in_eid = nullptr, *in_src = nullptr, *trip_base = nullptr;
+  float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
+  // evolving state
+  float* x_lig = nullptr; int64_t* v = nullptr; int64_t* bond = nullptr; bool has_state = false;
+  int *t_dev = nullptr, *t_start_dev = nullptr;
+  // workspace
+  float *hA = nullptr, *hB = nullptr, *h1 = nullptr, *PN = nullptr, *qN = nullptr, *PNx = nullptr;
+  float *PL = nullptr, *qNB = nullptr, *PLx = nullptr, *qXe = nullptr, *qXb = nullptr;
+  float *hbA = nullptr, *hbB = nullptr, *PB = nullptr, *qE = nullptr, *Pk = nullptr, *Pv = nullptr, *PBx = nullptr;
+  float *wb_knn = nullptr, *wb_bond = nullptr, *wb_trip = nullptr, *e_w = nullptr, *dx_edge = nullptr;
+  int *nbr = nullptr, *deg = nullptr, *nlig = nullptr;
+  float *hid_v = nullptr, *v_logits = nullptr, *b_logits = nullptr, *x0 = nullptr, *grad = nullptr;
+  // results of the last forward
+  float *h_fin = nullptr, *x_fin = nullptr, *hb_fin = nullptr;
+  // guidance
+  int enable_armsca = 0, enable_clash = 0; float min_d = 0, max_d = 0, sigma = 0, gamma = 0;
+  int* decomp_index = nullptr; float* full_pos4 = nullptr; int* full_ptr = nullptr;
+  long long launches = 0;
+
+  template <typename T>
+  int dalloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return DDB_OK;
+  }
+  template <typename T>
+  int upload(T** p, const std::vector<T>& v) {
+    int r = dalloc(p, v.size());
+    if (r) return r;
+    if (!v.empty()) {
+      cudaError_t e = cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+    }
+    return DDB_OK;
+  }
+};
+
+extern "C" void ddb_batch_destroy(ddb_batch* b) {
+  if (!b) return;
+  for (void* p : b->allocs) cudaFree(p);
+  delete b;
+}
+
+#define DDB_TRY(expr) do { int _r = (expr); if (_r) { ddb_batch_destroy(b); return _r; } } while (0)
+
+extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num_graphs, int64_t n_protein,
+                                const float* protein_pos, const float* protein_v, const int64_t* batch_protein,
+                                int64_t n_ligand, const int64_t* batch_ligand, const float* ligand_v_aux,
+                                int64_t n_bonds, const int64_t* bond_index, const uint8_t* ligand_atom_mask,
+                                int32_t center_mode) {
+  if (!out || !m) return fail(DDB_ERR_INVALID, "null argument");
+  if (!m->finalized) return fail(DDB_ERR_STATE, "model not finalized");
+  if (num_graphs < 1 || n_protein < 0 || n_ligand < 0 || n_bonds < 0) return fail(DDB_ERR_INVALID, "negative size");
+  if (center_mode != 0 && center_mode != 1) return fail(DDB_ERR_INVALID, "center_pos_mode must be 'none' or 'protein'");
+  const ddb_config& c = m->cfg;
+  const int B = num_graphs, NP = (int)n_protein, NL = (int)n_ligand, N = NP + NL, Eb = (int)n_bonds;
+  for (int64_t i = 0; i < n_protein; ++i) {
+    if (batch_protein[i] < 0 || batch_protein[i] >= B) return fail(DDB_ERR_INVALID, "batch_protein out of range");
+    if (i && batch_protein[i] < batch_protein[i - 1]) return fail(DDB_ERR_INVALID, "batch_protein must be ascending");
+  }
+  for (int64_t i = 0; i < n_ligand; ++i) {
+    if (batch_ligand[i] < 0 || batch_ligand[i] >= B) return fail(DDB_ERR_INVALID, "batch_ligand out of range");
+    if (i && batch_ligand[i] < batch_ligand[i - 1]) return fail(DDB_ERR_INVALID, "batch_ligand must be ascending");
+  }
+  for (int64_t e = 0; e < 2 * n_bonds; ++e)
+    if (bond_index[e] < 0 || bond_index[e] >= n_ligand) return fail(DDB_ERR_INVALID, "ligand_fc_bond_index out of range");
+
+  auto* b = new ddb_batch();
+  b->m = m; b->B = B; b->N = N; b->NL = NL; b->NP = NP; b->Eb = Eb;
+  {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // ---- merged node order: stable sort of [protein; ligand] by graph id (common.py:172-191)
+  std::vector<int> cnt_p(B, 0), cnt_l(B, 0);
+  for (int i = 0; i < NP; ++i) cnt_p[batch_protein[i]]++;
+  for (int i = 0; i < NL; ++i) cnt_l[batch_ligand[i]]++;
+  std::vector<int> node_ptr(B + 1, 0), lig_ptr(B + 1, 0), prot_ptr(B + 1, 0);
+  for (int g = 0; g < B; ++g) {
+    node_ptr[g + 1] = node_ptr[g] + cnt_p[g] + cnt_l[g];
+    lig_ptr[g + 1] = lig_ptr[g] + cnt_l[g];
+    prot_ptr[g + 1] = prot_ptr[g] + cnt_p[g];
+    b->max_graph_nodes = std::max(b->max_graph_nodes, cnt_p[g] + cnt_l[g]);
+  }
+  std::vector<int> graph_of(N), lig_idx(NL), prot_idx(NP);
+  std::vector<uint8_t> is_lig(N, 0);
+  for (int g = 0; g < B; ++g) {
+    int base = node_ptr[g];
+    for (int i = 0; i < cnt_p[g]; ++i) { prot_idx[prot_ptr[g] + i] = base + i; graph_of[base + i] = g; }
+    for (int i = 0; i < cnt_l[g]; ++i) {
+      int nid = base + cnt_p[g] + i;
+      lig_idx[lig_ptr[g] + i] = nid; graph_of[nid] = g; is_lig[nid] = 1;
+    }
+  }
+  // ---- centring offset = per-graph mean of protein positions (scatter_mean, decompdiff.py:25)
+  b->offset_host.assign((size_t)B * 3, 0.f);
+  if (center_mode == 1) {
+    for (int g = 0; g < B; ++g) {
+      float s[3] = {0.f, 0.f, 0.f};
+      for (int i = prot_ptr[g]; i < prot_ptr[g + 1]; ++i)
+        for (int d = 0; d < 3; ++d) s[d] += protein_pos[(size_t)i * 3 + d];
+      float cntf = (float)std::max(cnt_p[g], 1);
+      for (int d = 0; d < 3; ++d) b->offset_host[(size_t)g * 3 + d] = s[d] / cntf;
+    }
+  }
+  std::vector<float> x4((size_t)N * 4, 0.f), offset_lig((size_t)NL * 3, 0.f);
+  for (int i = 0; i < NP; ++i) {
+    int g = (int)batch_protein[i];
+    for (int d = 0; d < 3; ++d) x4[(size_t)prot_idx[i] * 4 + d] = protein_pos[(size_t)i * 3 + d] - b->offset_host[(size_t)g * 3 + d];
+  }
+  for (int i = 0; i < NL; ++i)
+    for (int d = 0; d < 3; ++d) offset_lig[(size_t)i * 3 + d] = b->offset_host[(size_t)batch_ligand[i] * 3 + d];
+  // ---- protein embedding (decompdiff.py:238,252-255): Linear(F_p -> 127) | indicator 0
+  std::vector<float> h0((size_t)N * H, 0.f);
+  {
+    const auto& W = m->host.at("protein_atom_emb.weight");
+    const auto& bias = m->host.at("protein_atom_emb.bias");
+    const int F = c.protein_feature_dim;
+    for (int i = 0; i < NP; ++i) {
+      float* row = &h0[(size_t)prot_idx[i] * H];
+      const float* f = protein_v + (size_t)i * F;
+      for (int ch = 0; ch < H - 1; ++ch) {
+        float s = 0.f;
+        for (int k = 0; k < F; ++k) s += f[k] * W[(size_t)ch * F + k];
+        row[ch] = s + bias[ch];
+      }
+      row[H - 1] = 0.f;
+    }
+  }
+  // ---- ligand embedding base: b + W[:, C:C+2] aux | indicator 1 (decompdiff.py:219-222,239,253-256)
+  std::vector<float> lig_base((size_t)NL * H, 0.f);
+  {
+    const auto& W = m->host.at("ligand_atom_emb.weight");
+    const auto& bias = m->host.at("ligand_atom_emb.bias");
+    const int F = c.ligand_feature_dim, C = c.num_classes, A = F - C;
+    for (int i = 0; i < NL; ++i) {
+      float* row = &lig_base[(size_t)i * H];
+      for (int ch = 0; ch < H - 1; ++ch) {
+        float s = 0.f;
+        for (int k = 0; k < A; ++k) s += ligand_v_aux[(size_t)i * A + k] * W[(size_t)ch * F + C + k];
+        row[ch] = s + bias[ch];
+      }
+      row[H - 1] = 1.f;
+    }
+  }
+  // ---- bond graph CSR by destination atom; triplet slot bases (uni_transformer_edge.py:103-123)
+  std::vector<int> bsrc(Eb), bdst(Eb), in_ptr(NL + 1, 0), in_eid(Eb), in_src(Eb), trip_base(Eb);
+  for (int e = 0; e < Eb; ++e) { bsrc[e] = (int)bond_index[e]; bdst[e] = (int)bond_index[(size_t)Eb + e]; in_ptr[bdst[e] + 1]++; }
+  for (int a = 0; a < NL; ++a) in_ptr[a + 1] += in_ptr[a];
+  {
+    std::vector<int> order(Eb);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      return bdst[x] != bdst[y] ? bdst[x] < bdst[y] : bsrc[x] < bsrc[y];
+    });
+    for (int s = 0; s < Eb; ++s) { in_eid[s] = order[s]; in_src[s] = bsrc[order[s]]; }
+  }
+  long long slots = 0;
+  for (int e = 0; e < Eb; ++e) {
+    if (slots > 2000000000LL) { ddb_batch_destroy(b); return fail(DDB_ERR_INVALID, "too many bond triplets"); }
+    trip_base[e] = (int)slots;
+    slots += in_ptr[bsrc[e] + 1] - in_ptr[bsrc[e]];
+  }
+  b->trip_slots = slots;
+  std::vector<uint8_t> upd(NL, 1);
+  if (ligand_atom_mask) for (int i = 0; i < NL; ++i) upd[i] = ligand_atom_mask[i] ? 1 : 0;
+
+  DDB_TRY(b->upload(&b->node_ptr, node_ptr)); DDB_TRY(b->upload(&b->graph_of, graph_of));
+  DDB_TRY(b->upload(&b->lig_idx, lig_idx)); DDB_TRY(b->upload(&b->lig_ptr, lig_ptr));
+  DDB_TRY(b->upload(&b->is_lig, is_lig)); DDB_TRY(b->upload(&b->upd_mask, upd));
+  DDB_TRY(b->upload(&b->bsrc, bsrc)); DDB_TRY(b->upload(&b->bdst, bdst));
+  DDB_TRY(b->upload(&b->in_ptr, in_ptr)); DDB_TRY(b->upload(&b->in_eid, in_eid)); DDB_TRY(b->upload(&b->in_src, in_src));
+  DDB_TRY(b->upload(&b->trip_base, trip_base));
+  DDB_TRY(b->upload(&b->x4_0, x4)); DDB_TRY(b->upload(&b->x4_a, x4)); DDB_TRY(b->upload(&b->x4_b, x4));
+  DDB_TRY(b->upload(&b->h0, h0)); DDB_TRY(b->upload(&b->lig_base, lig_base)); DDB_TRY(b->upload(&b->offset_lig, offset_lig));
+  const size_t n = (size_t)N, nl = (size_t)NL, eb = (size_t)Eb;
+  DDB_TRY(b->dalloc(&b->x_lig, nl * 3)); DDB_TRY(b->dalloc(&b->v, nl)); DDB_TRY(b->dalloc(&b->bond, eb));
+  DDB_TRY(b->dalloc(&b->t_dev, 1)); DDB_TRY(b->dalloc(&b->t_start_dev, 1));
+  DDB_TRY(b->dalloc(&b->hA, n * H)); DDB_TRY(b->dalloc(&b->hB, n * H)); DDB_TRY(b->dalloc(&b->h1, n * H));
+  DDB_TRY(b->dalloc(&b->PN, n * 5 * H)); DDB_TRY(b->dalloc(&b->qN, n * H)); DDB_TRY(b->dalloc(&b->PNx, n * 2 * H));
+  DDB_TRY(b->dalloc(&b->PL, nl * 10 * H)); DDB_TRY(b->dalloc(&b->qNB, nl * H)); DDB_TRY(b->dalloc(&b->PLx, nl * 8 * H));
+  DDB_TRY(b->dalloc(&b->qXe, nl * H)); DDB_TRY(b->dalloc(&b->qXb, nl * H));
+  DDB_TRY(b->dalloc(&b->hbA, eb * H)); DDB_TRY(b->dalloc(&b->hbB, eb * H)); DDB_TRY(b->dalloc(&b->PB, eb * 5 * H));
+  DDB_TRY(b->dalloc(&b->qE, eb * H)); DDB_TRY(b->dalloc(&b->Pk, eb * H)); DDB_TRY(b->dalloc(&b->Pv, eb * H));
+  DDB_TRY(b->dalloc(&b->PBx, eb * 2 * H));
+  DDB_TRY(b->dalloc(&b->wb_knn, n * KNN * NH)); DDB_TRY(b->dalloc(&b->wb_bond, eb * NH));
+  DDB_TRY(b->dalloc(&b->wb_trip, (size_t)slots * NH));
+  DDB_TRY(b->dalloc(&b->e_w, n * KNN)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4));
+  DDB_TRY(b->dalloc(&b->nbr, n * KNN)); DDB_TRY(b->dalloc(&b->deg, n)); DDB_TRY(b->dalloc(&b->nlig, n));
+  DDB_TRY(b->dalloc(&b->hid_v, nl * H)); DDB_TRY(b->dalloc(&b->v_logits, nl * c.num_classes));
+  DDB_TRY(b->dalloc(&b->b_logits, eb * c.num_bond_classes)); DDB_TRY(b->dalloc(&b->x0, nl * 3));
+  DDB_TRY(b->dalloc(&b->grad, nl * 3));
+  cudaMemset(b->nbr, 0, n * KNN * sizeof(int));
+  *out = b;
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_get_offset(const ddb_batch* b, float* offset_out) {
+  if (!b || !offset_out) return fail(DDB_ERR_INVALID, "null argument");
+  std::copy(b->offset_host.begin(), b->offset_host.end(), offset_out);
+  return DDB_OK;
+}
+
+namespace {
+// x_centred = x - offset  /  x = x_centred + offset   (decompdiff.py:28, :687, :691)
+__global__ void shift_kernel(const float* __restrict__ in, const float* __restrict__ off, float sign, int n3, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n3) out[i] = in[i] + sign * off[i];
+}
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+}  // namespace
+
+extern "C" int ddb_batch_set_state(ddb_batch* b, const float* ligand_pos, const int64_t* ligand_v, const int64_t* bond_type,
+                                   void* stream) {
+  if (!b || !ligand_pos || !ligand_v || (b->Eb > 0 && !bond_type)) return fail(DDB_ERR_INVALID, "null state pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int n3 = b->NL * 3;
+  if (n3 > 0) shift_kernel<<<(n3 + 255) / 256, 256, 0, s>>>(ligand_pos, b->offset_lig, -1.f, n3, b->x_lig);
+  DDB_CUDA(cudaMemcpyAsync(b->v, ligand_v, (size_t)b->NL * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (b->Eb > 0) DDB_CUDA(cudaMemcpyAsync(b->bond, bond_type, (size_t)b->Eb * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  DDB_CUDA(cudaGetLastError());
+  b->has_state = true;
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_get_state(const ddb_batch* b, float* ligand_pos, int64_t* ligand_v, int64_t* bond_type, void* stream) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  if (!b->has_state) return fail(DDB_ERR_STATE, "no state set");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int n3 = b->NL * 3;
+  if (ligand_pos && n3 > 0) shift_kernel<<<(n3 + 255) / 256, 256, 0, s>>>(b->x_lig, b->offset_lig, 1.f, n3, ligand_pos);
+  if (ligand_v) DDB_CUDA(cudaMemcpyAsync(ligand_v, b->v, (size_t)b->NL * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (bond_type && b->Eb > 0) DDB_CUDA(cudaMemcpyAsync(bond_type, b->bond, (size_t)b->Eb * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  DDB_CUDA(cudaGetLastError());
+  return DDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+namespace {
+
+void gemm(ddb_batch* b, cudaStream_t s, const float* A, int lda, const int* a_rows, int M, const GemmW& w, float* C, int ldc,
+          const Mlp2* ln = nullptr, const float* A2 = nullptr, int lda2 = 0, const int* a2_rows = nullptr,
+          const float* R = nullptr, int ldr = 0, const int* c_rows = nullptr, int act = 0) {
+  const ddb_model* m = b->m;
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.a_rows = a_rows; g.A2 = A2; g.lda2 = lda2; g.a2_rows = a2_rows;
+  if (ln) { g.ln_gamma = m->p(ln->gamma); g.ln_beta = m->p(ln->beta); }
+  g.Wt = m->p(w.Wt); g.ldw = w.N; g.bias = m->p(w.bias);
+  g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.c_rows = c_rows; g.M = M; g.N = w.N; g.act = act;
+  launch_gemm128(g, s);
+  b->launches++;
+}
+
+KnnMlpW knn_w(const ddb_model* m, const KnnMlpOff& o) {
+  return KnnMlpW{m->p(o.Wg), m->p(o.Wt), m->p(o.m.gamma), m->p(o.m.beta), m->p(o.m.W2), m->p(o.m.b2)};
+}
+BondMlpW bond_w(const ddb_model* m, const Mlp2& o) { return BondMlpW{m->p(o.gamma), m->p(o.beta), m->p(o.W2), m->p(o.b2)}; }
+
+int run_forward(ddb_batch* b, cudaStream_t s) {
+  const ddb_model* m = b->m;
+  const ddb_config& c = m->cfg;
+  const int N = b->N, NL = b->NL, Eb = b->Eb, sms = b->num_sms;
+  b->launches = 0;
+  launch_set_ligand_x(b->x_lig, NL, b->lig_idx, b->x4_0, s);
+  launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s);
+  launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s);
+  launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s);
+  launch_edge_weight(b->x4_0, b->nbr, b->deg, N, m->p(m->ew_W1t), m->p(m->ew_b1), m->p(m->ew_gamma), m->p(m->ew_beta),
+                     m->p(m->ew_w2), m->ew_b2, b->e_w, s);
+  b->launches += 5;
+  float *h_in = b->h0, *x_in = b->x4_0, *hb_in = b->hbA;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const LayerOff& L = m->layers[l];
+    float* h_out = (l % 2 == 0) ? b->hA : b->hB;
+    float* x_out = (l % 2 == 0) ? b->x4_a : b->x4_b;
+    float* hb_out = (l % 2 == 0) ? b->hbB : b->hbA;
+    // --- projections of the layer input
+    gemm(b, s, h_in, H, nullptr, N, L.n1, b->PN, 5 * H);
+    gemm(b, s, b->PN + 4 * H, 5 * H, nullptr, N, L.q_ne, b->qN, H, &L.ln_q_ne);
+    gemm(b, s, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
+    gemm(b, s, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
+    gemm(b, s, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
+    gemm(b, s, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
+    // --- node update over kNN edges  -> h1
+    KnnAttnArgs ka;
+    ka.n_dst = N; ka.Hi = b->PN; ka.ldhi = 5 * H; ka.Hj = b->PN + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
+    ka.x4 = x_in; ka.nbr = b->nbr; ka.deg = b->deg; ka.nlig = b->nlig; ka.is_lig = b->is_lig; ka.e_w = b->e_w;
+    ka.wbuf = b->wb_knn; ka.w = knn_w(m, L.ne_k);
+    launch_knn_attn_k(ka, sms, s);
+    ka.Hi = b->PN + 2 * H; ka.Hj = b->PN + 3 * H; ka.w = knn_w(m, L.ne_v); ka.out_h = b->h1; ka.ldo = H;
+    launch_knn_attn_v_node(ka, sms, s);
+    // --- node update over bond edges -> h1[ligand rows] +=
+    BondAttnArgs ba;
+    ba.n_lig = NL; ba.lig_idx = b->lig_idx; ba.in_ptr = b->in_ptr; ba.in_eid = b->in_eid; ba.in_src = b->in_src;
+    ba.ldh = 10 * H; ba.ldpe = 5 * H;
+    ba.k.Hi = b->PL; ba.k.Hj = b->PL + H; ba.k.Pe = b->PB; ba.k.w = bond_w(m, L.nb_k);
+    ba.v.Hi = b->PL + 2 * H; ba.v.Hj = b->PL + 3 * H; ba.v.Pe = b->PB + H; ba.v.w = bond_w(m, L.nb_v);
+    ba.q = b->qNB; ba.ldq = H; ba.x4 = x_in; ba.wbuf = b->wb_bond; ba.out_h = b->h1; ba.ldo = H;
+    launch_bond_attn_node(ba, sms, s);
+    // --- bond update over triplets -> hb_out
+    TripArgs ta;
+    ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
+    ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
+    ta.k.Pe = b->PB + 2 * H; ta.k.Hk = b->PL + 5 * H; ta.k.Hj = b->PL + 6 * H; ta.k.Wd = m->p(L.bl_k.Wd);
+    ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m);
+    ta.v.Pe = b->PB + 3 * H; ta.v.Hk = b->PL + 7 * H; ta.v.Hj = b->PL + 8 * H; ta.v.Wd = m->p(L.bl_v.Wd);
+    ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m);
+    ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
+    launch_trip_prep(ta, s);
+    launch_trip_k(ta, sms, s);
+    launch_trip_v(ta, sms, s);
+    b->launches += 6;
+    // --- h_out = h_in + lin_node(h1)    (:277)
+    gemm(b, s, b->h1, H, nullptr, N, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H);
+    // --- projections of the new h / new h_bond for the position update
+    gemm(b, s, h_out, H, nullptr, N, L.n2, b->PNx, 2 * H);
+    gemm(b, s, h_out, H, b->lig_idx, NL, L.l2, b->PLx, 8 * H);
+    gemm(b, s, b->PLx + 2 * H, 8 * H, nullptr, NL, L.q_pe, b->qXe, H, &L.ln_q_pe);
+    gemm(b, s, b->PLx + 7 * H, 8 * H, nullptr, NL, L.q_pb, b->qXb, H, &L.ln_q_pb);
+    gemm(b, s, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);
+    // --- position update over kNN edges (ligand destinations only) -> dx_edge
+    KnnAttnArgs kp;
+    kp.n_dst = NL; kp.dst_list = b->lig_idx; kp.Hi = b->PLx; kp.ldhi = 8 * H; kp.hi_by_slot = 1;
+    kp.Hj = b->PNx; kp.ldhj = 2 * H; kp.q = b->qXe; kp.ldq = H; kp.q_by_slot = 1;
+    kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
+    kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k);
+    launch_knn_attn_k(kp, sms, s);
+    kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
+    launch_knn_attn_v_pos(kp, sms, s);
+    // --- position update over bond edges + x_out = x_in + (dx_edge + dx_bond) * mask   (:280-285)
+    BondAttnArgs bp;
+    bp.n_lig = NL; bp.lig_idx = b->lig_idx; bp.in_ptr = b->in_ptr; bp.in_eid = b->in_eid; bp.in_src = b->in_src;
+    bp.ldh = 8 * H; bp.ldpe = 2 * H;
+    bp.k.Hi = b->PLx + 3 * H; bp.k.Hj = b->PLx + 4 * H; bp.k.Pe = b->PBx; bp.k.w = bond_w(m, L.pb_k);
+    bp.v.Hi = b->PLx + 5 * H; bp.v.Hj = b->PLx + 6 * H; bp.v.Pe = b->PBx + H; bp.v.w = bond_w(m, L.pb_v);
+    bp.q = b->qXb; bp.ldq = H; bp.x4 = x_in; bp.wbuf = b->wb_bond; bp.dx_edge = b->dx_edge; bp.upd_mask = b->upd_mask;
+    bp.x4_out = x_out;
+    launch_bond_attn_pos(bp, sms, s);
+    b->launches += 3;
+    h_in = h_out; x_in = x_out; hb_in = hb_out;
+  }
+  b->h_fin = h_in; b->x_fin = x_in; b->hb_fin = hb_in;
+  // --- heads (decompdiff.py:315-338)
+  gemm(b, s, b->h_fin, H, b->lig_idx, NL, m->v_head0, b->hid_v, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
+  launch_head_logits(b->hid_v, H, NL, m->p(m->v_W2), m->p(m->v_b2), c.num_classes, b->v_logits, s);
+  gemm(b, s, b->hb_fin, H, nullptr, Eb, m->b_head0, b->qE, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
+  launch_head_logits(b->qE, H, Eb, m->p(m->b_W2), m->p(m->b_b2), c.num_bond_classes, b->b_logits, s);
+  launch_get_ligand_x(b->x_fin, NL, b->lig_idx, b->x0, s);
+  b->launches += 3;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("forward launch: ") + cudaGetErrorString(e));
+  return DDB_OK;
+}
+
+}  // namespace
+
+extern "C" int ddb_forward(ddb_batch* b, float* out_pos, float* out_v_logits, float* out_bond_logits, void* stream) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  if (!b->has_state) return fail(DDB_ERR_STATE, "ddb_batch_set_state must precede ddb_forward");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int r = run_forward(b, s);
+  if (r) return r;
+  const ddb_config& c = b->m->cfg;
+  if (out_pos) DDB_CUDA(cudaMemcpyAsync(out_pos, b->x0, (size_t)b->NL * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (out_v_logits)
+    DDB_CUDA(cudaMemcpyAsync(out_v_logits, b->v_logits, (size_t)b->NL * c.num_classes * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (out_bond_logits && b->Eb > 0)
+    DDB_CUDA(cudaMemcpyAsync(out_bond_logits, b->b_logits, (size_t)b->Eb * c.num_bond_classes * sizeof(float),
+                             cudaMemcpyDeviceToDevice, s));
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_set_time(ddb_batch* b, int32_t t_start, void* stream) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  if (t_start < 0 || t_start >= b->m->cfg.num_timesteps) return fail(DDB_ERR_INVALID, "t_start out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  set_int_kernel<<<1, 1, 0, s>>>(b->t_dev, t_start);
+  set_int_kernel<<<1, 1, 0, s>>>(b->t_start_dev, t_start);
+  DDB_CUDA(cudaGetLastError());
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_set_guidance(ddb_batch* b, int32_t enable_armsca, const int64_t* ligand_decomp_index, float min_d,
+                                      float max_d, int32_t enable_clash, int64_t n_full, const float* full_protein_pos,
+                                      const int64_t* full_batch_protein, float sigma, float gamma) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  b->enable_armsca = 0; b->enable_clash = 0;
+  if (enable_armsca) {
+    if (!ligand_decomp_index) return fail(DDB_ERR_INVALID, "armsca_prox needs ligand_decomp_index");
+    std::vector<int> di(b->NL);
+    for (int i = 0; i < b->NL; ++i) di[i] = (int)ligand_decomp_index[i];
+    int r = b->upload(&b->decomp_index, di);
+    if (r) return r;
+    b->min_d = min_d; b->max_d = max_d; b->enable_armsca = 1;
+  }
+  if (enable_clash) {
+    if (!full_protein_pos || !full_batch_protein || n_full < 0) return fail(DDB_ERR_INVALID, "clash needs the full protein");
+    // group by graph (stable), as the reference selects full_batch_protein == i
+    std::vector<int> cnt(b->B, 0);
+    for (int64_t i = 0; i < n_full; ++i) {
+      if (full_batch_protein[i] < 0 || full_batch_protein[i] >= b->B) return fail(DDB_ERR_INVALID, "full_batch_protein out of range");
+      cnt[full_batch_protein[i]]++;
+    }
+    std::vector<int> ptr(b->B + 1, 0);
+    for (int g = 0; g < b->B; ++g) ptr[g + 1] = ptr[g] + cnt[g];
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    std::vector<float> p4((size_t)n_full * 4, 0.f);
+    for (int64_t i = 0; i < n_full; ++i) {
+      int dst = fill[full_batch_protein[i]]++;
+      for (int d = 0; d < 3; ++d) p4[(size_t)dst * 4 + d] = full_protein_pos[(size_t)i * 3 + d];
+    }
+    int r = b->upload(&b->full_pos4, p4);
+    if (r) return r;
+    r = b->upload(&b->full_ptr, ptr);
+    if (r) return r;
+    b->sigma = sigma; b->gamma = gamma; b->enable_clash = 1;
+  }
+  return DDB_OK;
+}
+
+extern "C" int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* stream) {
+  if (!b || !io) return fail(DDB_ERR_INVALID, "null argument");
+  if (!b->has_state) return fail(DDB_ERR_STATE, "ddb_batch_set_state must precede ddb_reverse_step");
+  if (!io->prior_std_atom || !io->u_atom || !io->eps_pos || (b->Eb > 0 && !io->u_bond))
+    return fail(DDB_ERR_INVALID, "noise / prior_std pointers are required");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int r = run_forward(b, s);
+  if (r) return r;
+  const ddb_model* m = b->m;
+  const ddb_config& c = m->cfg;
+  const bool guided = b->enable_armsca || b->enable_clash;
+  if (guided) {
+    GuidanceArgs g;
+    g.num_graphs = b->B; g.n_lig = b->NL; g.lig_ptr = b->lig_ptr; g.x = b->x_lig; g.offset_lig = b->offset_lig; g.grad = b->grad;
+    g.enable_armsca = b->enable_armsca; g.decomp_index = b->decomp_index; g.min_d = b->min_d; g.max_d = b->max_d;
+    g.enable_clash = b->enable_clash; g.full_pos4 = b->full_pos4; g.full_ptr = b->full_ptr; g.sigma = b->sigma; g.gamma = b->gamma;
+    launch_guidance(g, s);
+    b->launches++;
+  }
+  StepArgs a;
+  a.n_lig = b->NL; a.n_bonds = b->Eb; a.C = c.num_classes; a.Cb = c.num_bond_classes; a.num_timesteps = c.num_timesteps;
+  a.t_dev = b->t_dev; a.t_start_dev = b->t_start_dev;
+  a.c0 = m->p(m->tab_c0); a.ct = m->p(m->tab_ct); a.logvar = m->p(m->tab_logvar);
+  a.a_log_alpha = m->p(m->tab_a[0]); a.a_log_1m_alpha = m->p(m->tab_a[1]); a.a_log_cumprod = m->p(m->tab_a[2]);
+  a.a_log_1m_cumprod = m->p(m->tab_a[3]); a.a_prior = m->p(m->tab_a[4]);
+  a.b_log_alpha = m->p(m->tab_b[0]); a.b_log_1m_alpha = m->p(m->tab_b[1]); a.b_log_cumprod = m->p(m->tab_b[2]);
+  a.b_log_1m_cumprod = m->p(m->tab_b[3]); a.b_prior = m->p(m->tab_b[4]);
+  a.x0 = b->x0; a.v_logits = b->v_logits; a.b_logits = b->b_logits;
+  a.x = b->x_lig; a.v = b->v; a.bond = b->bond; a.upd_mask = b->upd_mask; a.offset_lig = b->offset_lig;
+  a.grad = guided ? b->grad : nullptr;
+  a.prior_std = io->prior_std_atom; a.u_atom = io->u_atom; a.u_bond = io->u_bond; a.eps = io->eps_pos;
+  a.pos_traj = io->pos_traj; a.v_traj = io->v_traj; a.v0_traj = io->v0_traj; a.vt_traj = io->vt_traj;
+  a.bond_traj = io->bond_traj; a.bt_traj = io->bt_traj;
+  launch_reverse_step(a, s);
+  launch_advance_time(b->t_dev, s);
+  b->launches += 2;
+  DDB_CUDA(cudaGetLastError());
+  return DDB_OK;
+}
+
+// ----------------------------------------------------------------------------------- building blocks
+extern "C" int ddb_knn_graph(const float* x4, const int32_t* node_ptr, const uint8_t* is_ligand, int32_t num_graphs, int32_t n,
+                             int32_t k, int32_t* nbr, int32_t* deg, int32_t* nlig, void* stream) {
+  if (!x4 || !node_ptr || !is_ligand || !nbr || !deg || !nlig) return fail(DDB_ERR_INVALID, "null argument");
+  if (k < 1 || k > KNN) return fail(DDB_ERR_INVALID, "k must be in [1,32]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // graph id per node from the CSR (tiny; built on the host from a copy of node_ptr)
+  std::vector<int> ptr(num_graphs + 1);
+  DDB_CUDA(cudaMemcpyAsync(ptr.data(), node_ptr, ptr.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  DDB_CUDA(cudaStreamSynchronize(s));
+  std::vector<int> graph_of(n);
+  int mx = 0;
+  for (int g = 0; g < num_graphs; ++g) {
+    mx = std::max(mx, ptr[g + 1] - ptr[g]);
+    for (int i = ptr[g]; i < ptr[g + 1]; ++i) graph_of[i] = g;
+  }
+  int* d_graph_of = nullptr;
+  DDB_CUDA(cudaMalloc(&d_graph_of, std::max(n, 1) * sizeof(int)));
+  DDB_CUDA(cudaMemcpyAsync(d_graph_of, graph_of.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+  launch_knn(x4, node_ptr, d_graph_of, is_ligand, n, k, mx, nbr, deg, nlig, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(d_graph_of);
+  if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("knn: ") + cudaGetErrorString(e));
+  return DDB_OK;
+}
+
+extern "C" int ddb_gemm128(const float* A, int32_t lda, const float* Wt, int32_t ldw, const float* bias, float* C, int32_t ldc,
+                           int32_t M, int32_t N, int32_t act, void* stream) {
+  if (!A || !Wt || !C) return fail(DDB_ERR_INVALID, "null argument");
+  if (N <= 0 || N % 128 != 0) return fail(DDB_ERR_INVALID, "N must be a positive multiple of 128");
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.Wt = Wt; g.ldw = ldw; g.bias = bias; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.act = act;
+  launch_gemm128(g, static_cast<cudaStream_t>(stream));
+  DDB_CUDA(cudaGetLastError());
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, const void** ptr, int64_t* rows, int64_t* cols) {
+  if (!b || !name || !ptr || !rows || !cols) return fail(DDB_ERR_INVALID, "null argument");
+  std::string n(name);
+  if (n == "h") { *ptr = b->h_fin; *rows = b->N; *cols = H; }
+  else if (n == "x") { *ptr = b->x_fin; *rows = b->N; *cols = 4; }
+  else if (n == "h_bond") { *ptr = b->hb_fin; *rows = b->Eb; *cols = H; }
+  else if (n == "nbr") { *ptr = b->nbr; *rows = b->N; *cols = KNN; }
+  else if (n == "deg") { *ptr = b->deg; *rows = b->N; *cols = 1; }
+  else if (n == "nlig") { *ptr = b->nlig; *rows = b->N; *cols = 1; }
+  else if (n == "e_w") { *ptr = b->e_w; *rows = b->N; *cols = KNN; }
+  else return fail(DDB_ERR_INVALID, "unknown buffer " + n);
+  if (*ptr == nullptr) return fail(DDB_ERR_STATE, "no forward has run yet");
+  return DDB_OK;
+}
+
+extern "C" int ddb_copy_device(void* dst, const void* src, int64_t bytes, void* stream) {
+  if (!dst || !src || bytes < 0) return fail(DDB_ERR_INVALID, "bad copy argument");
+  DDB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return DDB_OK;
+}
+
+extern "C" int64_t ddb_batch_last_launch_count(const ddb_batch* b) { return b ? b->launches : 0; }

@@ -1,0 +1,141 @@
+// K1: exact kNN graph per complex + the global edge weight.
+//
+// Replaces torch_geometric.nn.knn_graph (-> torch_cluster.knn) at
+// /root/reference/models/encoders/uni_transformer_edge.py:353 and the edge_pred_layer block at :422-427.
+//
+// A complex has a few hundred atoms, so its coordinates (16 B each) sit in L1/L2 and a brute-force
+// sweep per query is the right candidate generator at these sizes: one warp per query node, every lane
+// keeps its strided share of candidate keys in registers, 32 rounds of warp-arg-min pick the k nearest.
+// Keys are (fp32 bits of d^2) << 32 | index, with d^2 = ((dx*dx)+(dy*dy))+(dz*dz) evaluated without
+// FMA contraction, so membership and order are bit-identical to the oracle (ties -> lower index).
+#include "kernels.cuh"
+
+namespace ddb {
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    unsigned long long o = __shfl_xor_sync(FULL, v, m);
+    v = o < v ? o : v;
+  }
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long knn_key(float4 xi, const float* __restrict__ x4, int c, int self) {
+  float4 xj = ldg4(x4 + (size_t)c * 4);
+  float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+  float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)c;
+  return c == self ? ~0ull : key;
+}
+
+// MAXT > 0: candidate keys cached in registers (graphs up to 32*MAXT nodes); MAXT == 0: recompute per round.
+template <int MAXT>
+__global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, const int* __restrict__ node_ptr,
+                                                  const int* __restrict__ graph_of, const uint8_t* __restrict__ is_lig,
+                                                  int n, int k, int* __restrict__ nbr, int* __restrict__ deg_out,
+                                                  int* __restrict__ nlig_out) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int g = graph_of[i];
+  const int s = node_ptr[g], e = node_ptr[g + 1];
+  const float4 xi = ldg4(x4 + (size_t)i * 4);
+  const int deg = min(k, e - s - 1);
+
+  unsigned long long keys[MAXT > 0 ? MAXT : 1];
+  if (MAXT > 0) {
+#pragma unroll
+    for (int t = 0; t < MAXT; ++t) {
+      int c = s + lane + 32 * t;
+      keys[t] = c < e ? knn_key(xi, x4, c, i) : ~0ull;
+    }
+  }
+  unsigned long long last = 0ull;     // keys are unique, so "> last" walks them in order
+  bool first = true;
+  int mine = -1;                       // neighbour picked in round == lane
+  for (int r = 0; r < deg; ++r) {
+    unsigned long long best = ~0ull;
+    if (MAXT > 0) {
+#pragma unroll
+      for (int t = 0; t < MAXT; ++t) {
+        bool ok = first || keys[t] > last;
+        best = (ok && keys[t] < best) ? keys[t] : best;
+      }
+    } else {
+      for (int c = s + lane; c < e; c += 32) {
+        unsigned long long kk = knn_key(xi, x4, c, i);
+        bool ok = first || kk > last;
+        best = (ok && kk < best) ? kk : best;
+      }
+    }
+    best = warp_min_u64(best);
+    last = best;
+    first = false;
+    if (lane == r) mine = (int)(best & 0xffffffffu);
+  }
+  // stable partition: ligand sources first (so the attention kernels see type-uniform runs)
+  const bool has = lane < deg;
+  const bool lig = has && is_lig[mine];
+  const unsigned mlig = __ballot_sync(FULL, lig), mhas = __ballot_sync(FULL, has);
+  const int nlig = __popc(mlig);
+  const unsigned below = (1u << lane) - 1u;
+  if (has) {
+    int pos = lig ? __popc(mlig & below) : nlig + __popc(mhas & ~mlig & below);
+    nbr[(size_t)i * KNN + pos] = mine;
+  }
+  if (lane == 0) { deg_out[i] = deg; nlig_out[i] = nlig; }
+}
+
+void launch_knn(const float* x4, const int* node_ptr, const int* graph_of, const uint8_t* is_lig, int n, int k,
+                int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream) {
+  if (n <= 0) return;
+  const int wpb = 8;
+  dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
+  if (max_graph_nodes <= 32 * 16) knn_kernel<16><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
+  else if (max_graph_nodes <= 32 * 32) knn_kernel<32><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
+  else if (max_graph_nodes <= 32 * 64) knn_kernel<64><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
+  else knn_kernel<0><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
+}
+
+// e_w = sigmoid(MLP_{20->128->1}(gauss(d)))  (uni_transformer_edge.py:422-427), one warp per destination node,
+// lane = 4 hidden channels, first-layer weights (20 x 128) held in registers.
+__global__ void __launch_bounds__(256) edge_weight_kernel(const float* __restrict__ x4, const int* __restrict__ nbr,
+                                                          const int* __restrict__ deg, int n,
+                                                          const float* __restrict__ W1t /*[20][128]*/,
+                                                          const float* __restrict__ b1, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ w2,
+                                                          float b2, float* __restrict__ e_w) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  float4 w[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) w[g] = ldg4(W1t + g * H + lane * 4);
+  const float4 bb = ldg4(b1 + lane * 4), gm = ldg4(gamma + lane * 4), bt = ldg4(beta + lane * 4), w2v = ldg4(w2 + lane * 4);
+  const float4 xi = ldg4(x4 + (size_t)i * 4);
+  const int d_i = deg[i];
+  for (int e = 0; e < d_i; ++e) {
+    int j = nbr[(size_t)i * KNN + e];
+    float4 xj = ldg4(x4 + (size_t)j * 4);
+    float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
+    float4 z[1] = {bb};
+#pragma unroll
+    for (int g = 0; g < NG; ++g) z[0] = fma4(__shfl_sync(FULL, gl, g), w[g], z[0]);
+    ln_relu_rows<1>(z, gm, bt, lane);
+    float logit = warp_sum(dot4(z[0], w2v)) + b2;
+    if (lane == 0) e_w[(size_t)i * KNN + e] = 1.0f / (1.0f + expf(-logit));
+  }
+}
+
+void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, const float* W1t, const float* b1,
+                        const float* gamma, const float* beta, const float* w2, float b2, float* e_w,
+                        cudaStream_t stream) {
+  if (n <= 0) return;
+  const int wpb = 8;
+  edge_weight_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, stream>>>(x4, nbr, deg, n, W1t, b1, gamma, beta, w2, b2, e_w);
+}
+
+}  // namespace ddb

@@ -1,0 +1,162 @@
+/*
+ * decompdiff_b200 - C ABI of the B200-native DecompDiff sampling hot path.
+ *
+ * The reference (bytedance/DecompDiff) is pure Python and has no FFI of its own
+ * (SURVEY.md section 8b): the seam it offers is three Python-level contracts -
+ *   (1) the model API      models/decompdiff.py:77,213,553  (DecompScorePosNet3D)
+ *   (2) the refine-net API models/encoders/uni_transformer_edge.py:394
+ *   (3) the collated-batch attribute contract scripts/sample_diffusion_decomp.py:317-352
+ * This header is the plain-C boundary underneath them.  Every entry point takes
+ * raw pointers and sizes only (no torch types), returns an int status
+ * (0 = ok, see ddb_status) and never throws.  `ddb_last_error()` returns the text
+ * of the last failure on the calling thread.
+ *
+ * Conventions
+ *   - "host"   pointers are ordinary CPU memory, read during the call only.
+ *   - "device" pointers are CUDA device memory on the current device; kernels are
+ *     launched on the `stream` argument (a cudaStream_t passed as void*), nothing
+ *     synchronises unless stated, so every per-step call is CUDA-graph capturable.
+ *   - fp32 everywhere the reference is fp32; indices are int64 at the boundary
+ *     exactly as the reference passes them (torch.long).
+ */
+#ifndef DECOMPDIFF_B200_H
+#define DECOMPDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ddb_status {
+  DDB_OK = 0,
+  DDB_ERR_INVALID = 1,      /* bad argument / unsupported configuration (reference: ValueError) */
+  DDB_ERR_MISSING = 2,      /* a required state_dict tensor was never set                        */
+  DDB_ERR_CUDA = 3,         /* CUDA runtime failure; text in ddb_last_error()                    */
+  DDB_ERR_STATE = 4         /* call order violated (e.g. forward before set_state)              */
+} ddb_status;
+
+typedef struct ddb_model ddb_model;   /* weights of one DecompScorePosNet3D                     */
+typedef struct ddb_batch ddb_batch;   /* static topology + workspace + evolving state of a batch */
+
+/* `model:` section of configs/training.yml:16-57 (only the fields that shape the path). */
+typedef struct ddb_config {
+  int32_t hidden_dim;          /* 128 (kernels are specialised for it)                        */
+  int32_t n_heads;             /* 16                                                           */
+  int32_t knn;                 /* 32  (<= 32)                                                  */
+  int32_t num_layers;          /* 6                                                            */
+  int32_t num_blocks;          /* 1                                                            */
+  int32_t num_classes;         /* 8   ligand atom types ('basic')                              */
+  int32_t num_bond_classes;    /* 5                                                            */
+  int32_t protein_feature_dim; /* 29 = 27 + 2                                                  */
+  int32_t ligand_feature_dim;  /* 10 = 8 + 2                                                   */
+  int32_t num_timesteps;       /* 1000                                                         */
+} ddb_config;
+
+const char* ddb_last_error(void);
+const char* ddb_version(void);
+
+/* ---------------------------------------------------------------- model ------------------
+ * Replaces: DecompScorePosNet3D.__init__ + load_state_dict(ckpt['model'], strict=True)
+ * (scripts/sample_diffusion_decomp.py:537-544).  Tensors are handed over under their
+ * reference state_dict names (616 keys, e.g.
+ * "refine_net.base_block.0.bond_layer.hk_func.net.0.weight"), row-major fp32, host memory. */
+int ddb_model_create(ddb_model** out, const ddb_config* cfg);
+int ddb_model_set_tensor(ddb_model* m, const char* name, const float* host_data, int64_t numel);
+/* Re-packs the weights into the kernels' layouts and uploads them.  Fails with
+ * DDB_ERR_MISSING naming the first absent key (strict=True behaviour). */
+int ddb_model_finalize(ddb_model* m);
+void ddb_model_destroy(ddb_model* m);
+
+/* ---------------------------------------------------------------- batch ------------------
+ * Replaces the per-call set-up of sample_diffusion / forward that does not depend on t:
+ * center_pos (decompdiff.py:20-32,567), protein_atom_emb (:238), compose_context ordering
+ * (common.py:167-194), bond index remap (:291), BondUpdateLayer.triplets
+ * (uni_transformer_edge.py:103-123).  All pointers are HOST memory.
+ *   batch_protein / batch_ligand : graph id per atom, ascending (PyG collate order)
+ *   bond_index  : (2, n_bonds) row-major, [0]=src [1]=dst, ligand-atom numbering
+ *   ligand_atom_mask : optional (NULL = all ones): 0 freezes an atom's position (decompdiff.py:285)
+ *   center_mode : 0 = 'none', 1 = 'protein'                                                    */
+int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num_graphs,
+                     int64_t n_protein, const float* protein_pos, const float* protein_v,
+                     const int64_t* batch_protein,
+                     int64_t n_ligand, const int64_t* batch_ligand, const float* ligand_v_aux,
+                     int64_t n_bonds, const int64_t* bond_index,
+                     const uint8_t* ligand_atom_mask, int32_t center_mode);
+void ddb_batch_destroy(ddb_batch* b);
+/* per-graph offset subtracted by center_pos, (num_graphs,3) host out */
+int ddb_batch_get_offset(const ddb_batch* b, float* offset_out);
+
+/* Evolving state (x_t, v_t, b_t).  DEVICE pointers; positions are in the caller's
+ * (un-centred) frame - the batch applies / removes the centring offset itself. */
+int ddb_batch_set_state(ddb_batch* b, const float* ligand_pos, const int64_t* ligand_v,
+                        const int64_t* bond_type, void* stream);
+int ddb_batch_get_state(const ddb_batch* b, float* ligand_pos, int64_t* ligand_v,
+                        int64_t* bond_type, void* stream);
+
+/* ---------------------------------------------------------------- forward ----------------
+ * Replaces DecompScorePosNet3D.forward (decompdiff.py:213-351) on the batch's current state:
+ * out_pos (n_ligand,3) centred frame as in the reference, out_v_logits (n_ligand,num_classes),
+ * out_bond_logits (n_bonds,num_bond_classes).  DEVICE pointers, any may be NULL.              */
+int ddb_forward(ddb_batch* b, float* out_pos, float* out_v_logits, float* out_bond_logits,
+                void* stream);
+
+/* ---------------------------------------------------------------- reverse step -----------
+ * Replaces one iteration of the loop in sample_diffusion (decompdiff.py:576-689): forward,
+ * Gaussian posterior, categorical posteriors + Gumbel-argmax, optional drift, x_{t-1}.
+ *   prior_std_atom : (n_ligand,3) device, prior_stds[ligand_decomp_batch]
+ *   u_atom (n_ligand,num_classes), u_bond (n_bonds,num_bond_classes) : U[0,1) draws,
+ *   eps_pos (n_ligand,3) : N(0,1) draws - the three draws the reference makes per step, in
+ *   its order (transitions.py:79 via decompdiff.py:620, :633, :680).
+ * The time index lives on the device (ddb_batch_set_time) so one captured CUDA graph can be
+ * replayed for every step; each call uses t and then decrements it.
+ * Trajectory outputs (device, any may be NULL), all written at row `step slot` =
+ * (t_start - t): pos_traj (S,n,3) un-centred, v_traj (S,n) i64, v0_traj / vt_traj (S,n,C),
+ * bond_traj (S,Eb) i64, bt_traj (S,Eb,Cb).                                                     */
+typedef struct ddb_step_io {
+  const float* prior_std_atom;
+  const float* u_atom;
+  const float* u_bond;
+  const float* eps_pos;
+  float* pos_traj; int64_t* v_traj; float* v0_traj; float* vt_traj;
+  int64_t* bond_traj; float* bt_traj;
+} ddb_step_io;
+int ddb_batch_set_time(ddb_batch* b, int32_t t_start, void* stream);
+int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* stream);
+
+/* Drift guidance (decompdiff.py:638-677, utils/guidance_funcs.py:24-78); host pointers, copied.
+ *   armsca_prox: ligand_decomp_index (n_ligand) arm id or -1, min_d/max_d
+ *   clash      : full protein cloud in the un-centred frame, sigma / gamma (surface_ct)
+ * Pass enable_* = 0 to switch a term off.                                                      */
+int ddb_batch_set_guidance(ddb_batch* b,
+                           int32_t enable_armsca, const int64_t* ligand_decomp_index,
+                           float min_d, float max_d,
+                           int32_t enable_clash, int64_t n_full, const float* full_protein_pos,
+                           const int64_t* full_batch_protein, float sigma, float gamma);
+
+/* ---------------------------------------------------------------- building blocks --------
+ * Stand-alone entry points for the kernels (unit-testable seams; DEVICE pointers).            */
+/* kNN graph, replaces torch_geometric.nn.knn_graph at uni_transformer_edge.py:353.
+ * x4: (n,4) fp32 (xyz + pad); node_ptr: (num_graphs+1) int32 CSR of nodes per graph;
+ * is_ligand: (n) uint8.  Outputs: nbr (n,K) int32 source node ids (ligand sources first,
+ * then by ascending distance, ties by index), deg (n) int32, nlig (n) int32.                  */
+int ddb_knn_graph(const float* x4, const int32_t* node_ptr, const uint8_t* is_ligand,
+                  int32_t num_graphs, int32_t n, int32_t k,
+                  int32_t* nbr, int32_t* deg, int32_t* nlig, void* stream);
+/* C[M,N] = act(A[M,128] @ Wt[128,N] + bias) fp32 GEMM used for all node / edge projections.   */
+int ddb_gemm128(const float* A, int32_t lda, const float* Wt, int32_t ldw, const float* bias,
+                float* C, int32_t ldc, int32_t M, int32_t N, int32_t act, void* stream);
+
+/* Introspection for tests / profiling: device pointers to internal buffers of the last forward.
+ * name in {"h","x","h_bond","nbr","deg","nlig","e_w"}; rows/cols describe the layout.          */
+int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, const void** ptr,
+                           int64_t* rows, int64_t* cols);
+/* stream-ordered device-to-device copy (lets a host language read a debug buffer without its own CUDA binding) */
+int ddb_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
+/* number of kernel launches issued by the last ddb_forward / ddb_reverse_step on this batch    */
+int64_t ddb_batch_last_launch_count(const ddb_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECOMPDIFF_B200_H */
