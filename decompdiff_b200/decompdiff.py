@@ -1,0 +1,351 @@
+"""`DecompScorePosNet3D` - the reference model API on top of the sm_100a kernels.
+
+Mirrors /root/reference/models/decompdiff.py:75-703 for the sampling path:
+  * constructor signature and the 616 `state_dict` keys (so `load_state_dict(ckpt['model'], strict=True)`
+    works on a reference checkpoint; the sub-module tree below only carries parameters / buffers),
+  * `forward(...)`            -> {'pred_ligand_pos', 'pred_ligand_v', 'pred_bond'}         (:213-351)
+  * `sample_diffusion(...)`   -> {'pos','v','bond', '*_traj'}                             (:552-703)
+All arithmetic runs in the CUDA library (`decompdiff_b200/csrc`); there is no torch / CPU fallback.
+
+Out of scope (raises NotImplementedError): training loss, `add_prior_node`, time embedding,
+`model_mean_type='noise'`, other refine nets / cutoff modes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, schedules
+from .engine import EngineBatch, EngineModel, require_cuda
+
+GAUSS_OFFSETS = [0, 1, 1.25, 1.5, 1.75, 2, 2.25, 2.5, 2.75, 3, 3.5, 4, 4.5, 5, 5.5, 6, 7, 8, 9, 10]
+
+
+def _const(x: np.ndarray) -> nn.Parameter:
+    """Non-trainable Parameter (part of the state_dict, like models/common.py:280-283)."""
+    return nn.Parameter(torch.from_numpy(np.asarray(x)).float(), requires_grad=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module names (no compute here)
+# ---------------------------------------------------------------------------------------------------
+class GaussianSmearing(nn.Module):
+    def __init__(self, start=0.0, stop=5.0, num_gaussians=50, fix_offset=True):
+        super().__init__()
+        offset = torch.tensor(GAUSS_OFFSETS, dtype=torch.float32) if fix_offset else torch.linspace(start, stop, num_gaussians)
+        self.register_buffer('offset', offset)
+
+
+class AngularEncoding(nn.Module):
+    def __init__(self, num_funcs=3):
+        super().__init__()
+        self.register_buffer('freq_bands', torch.FloatTensor(
+            [i + 1 for i in range(num_funcs)] + [1. / (i + 1) for i in range(num_funcs)]))
+
+
+class ShiftedSoftplus(nn.Module):
+    pass
+
+
+class MLP(nn.Module):
+    """Linear -> LayerNorm -> ReLU -> Linear; keys net.0 / net.1 / net.3 (models/common.py:85-105)."""
+
+    def __init__(self, in_dim, out_dim, hidden_dim):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(in_dim, hidden_dim), nn.LayerNorm(hidden_dim), nn.ReLU(),
+                                 nn.Linear(hidden_dim, out_dim))
+
+
+class NodeUpdateLayer(nn.Module):
+    def __init__(self, hidden, n_heads, edge_feat_dim):
+        super().__init__()
+        kv = hidden * 2 + edge_feat_dim
+        self.hk_func, self.hv_func, self.hq_func = MLP(kv, hidden, hidden), MLP(kv, hidden, hidden), MLP(hidden, hidden, hidden)
+
+
+class BondUpdateLayer(nn.Module):
+    def __init__(self, hidden, n_heads, include_h_node):
+        super().__init__()
+        self.distance_expansion = GaussianSmearing()
+        self.angle_expansion = AngularEncoding()
+        kv = hidden + 20 * 2 + 13 + (2 * hidden if include_h_node else 0)
+        q = hidden + (hidden if include_h_node else 0)
+        self.hk_func, self.hv_func, self.hq_func = MLP(kv, hidden, hidden), MLP(kv, hidden, hidden), MLP(q, hidden, hidden)
+
+
+class PosUpdateLayer(nn.Module):
+    def __init__(self, hidden, n_heads, edge_feat_dim):
+        super().__init__()
+        kv = hidden * 2 + edge_feat_dim
+        self.xk_func, self.xv_func, self.xq_func = MLP(kv, hidden, hidden), MLP(kv, n_heads, hidden), MLP(hidden, hidden, hidden)
+
+
+class AttentionLayerO2TwoUpdateNodeGeneral(nn.Module):
+    def __init__(self, hidden, n_heads, num_r_gaussian, edge_feat_dim, include_h_node):
+        super().__init__()
+        self.distance_expansion = GaussianSmearing(0., 10., num_gaussians=num_r_gaussian)
+        self.lin_node = nn.Linear(hidden, hidden)
+        e = num_r_gaussian * edge_feat_dim + edge_feat_dim
+        self.node_layer_with_edge = NodeUpdateLayer(hidden, n_heads, e)
+        self.node_layer_with_bond = NodeUpdateLayer(hidden, n_heads, hidden)
+        self.bond_layer = BondUpdateLayer(hidden, n_heads, include_h_node)
+        self.pos_layer_with_edge = PosUpdateLayer(hidden, n_heads, e)
+        self.pos_layer_with_bond = PosUpdateLayer(hidden, n_heads, hidden)
+
+
+class UniTransformerO2TwoUpdateGeneralBond(nn.Module):
+    """Parameter tree of the bond-aware refine net (uni_transformer_edge.py:290-347)."""
+
+    def __init__(self, num_blocks, num_layers, hidden_dim, n_heads=1, k=32, num_r_gaussian=50, edge_feat_dim=0,
+                 act_fn='relu', norm=True, cutoff_mode='radius', r_max=10., x2h_out_fc=True, sync_twoup=False,
+                 h_node_in_bond_net=False):
+        super().__init__()
+        if cutoff_mode != 'knn':
+            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')   # radius is broken upstream (:351), hybrid: N3
+        if act_fn != 'relu' or not norm or x2h_out_fc or not h_node_in_bond_net or num_blocks != 1:
+            raise NotImplementedError('only the shipped uni_o2_bond configuration (configs/training.yml) is implemented')
+        self.num_blocks, self.num_layers, self.hidden_dim, self.n_heads, self.k = num_blocks, num_layers, hidden_dim, n_heads, k
+        self.distance_expansion = GaussianSmearing(0., r_max, num_gaussians=num_r_gaussian)
+        self.edge_pred_layer = MLP(num_r_gaussian, 1, hidden_dim)
+        self.base_block = nn.ModuleList([
+            AttentionLayerO2TwoUpdateNodeGeneral(hidden_dim, n_heads, num_r_gaussian, edge_feat_dim, h_node_in_bond_net)
+            for _ in range(num_layers)])
+
+
+def get_refine_net(refine_net_type, config):
+    """models/encoders/__init__.py:5-43 ('uni_o2' cannot be driven by DecompScorePosNet3D upstream either)."""
+    if refine_net_type != 'uni_o2_bond':
+        raise ValueError(refine_net_type)
+    return UniTransformerO2TwoUpdateGeneralBond(
+        num_blocks=config.num_blocks, num_layers=config.num_layers, hidden_dim=config.hidden_dim,
+        n_heads=config.n_heads, k=config.knn, edge_feat_dim=config.edge_feat_dim,
+        num_r_gaussian=config.num_r_gaussian, act_fn=config.act_fn, norm=config.norm,
+        cutoff_mode=config.cutoff_mode, r_max=config.r_max, x2h_out_fc=config.x2h_out_fc,
+        sync_twoup=config.sync_twoup, h_node_in_bond_net=config.h_node_in_bond_net)
+
+
+class DiscreteTransition(nn.Module):
+    def __init__(self, noise_schedule, num_timesteps, s, num_classes, prior_probs=None):
+        super().__init__()
+        if noise_schedule != 'cosine':
+            raise NotImplementedError
+        self.num_timesteps, self.num_classes = num_timesteps, num_classes
+        for k, v in schedules.categorical_tables(num_timesteps, s, num_classes, prior_probs).items():
+            setattr(self, k, _const(v))
+
+
+class AttrDict(dict):
+    """5-line stand-in for easydict (absent from the image)."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def as_config(cfg):
+    return cfg if hasattr(cfg, 'hidden_dim') and not isinstance(cfg, dict) else AttrDict(cfg)
+
+
+# ---------------------------------------------------------------------------------------------------
+class DecompScorePosNet3D(nn.Module):
+
+    def __init__(self, config, protein_atom_feature_dim, ligand_atom_feature_dim, num_classes,
+                 prior_atom_types=None, prior_bond_types=None):
+        super().__init__()
+        config = as_config(config)
+        self.config = config
+        self.model_mean_type = config.model_mean_type
+        self.add_prior_node = getattr(config, 'add_prior_node', False)
+        self.bond_diffusion = getattr(config, 'bond_diffusion', False)
+        self.bond_net_type = getattr(config, 'bond_net_type', 'mlp')
+        if self.add_prior_node or not self.bond_diffusion or self.bond_net_type != 'lin' \
+                or config.time_emb_dim != 0 or not config.node_indicator or config.model_type != 'uni_o2_bond':
+            raise NotImplementedError('only the shipped configuration (configs/training.yml:16-57) is implemented')
+        for k, v in schedules.position_tables(config).items():
+            setattr(self, k, _const(v))
+        self.num_timesteps = self.betas.size(0)
+        self.num_classes = num_classes
+        self.num_bond_classes = getattr(config, 'num_bond_classes', 1)
+        self.atom_type_trans = DiscreteTransition(config.v_beta_schedule, self.num_timesteps, s=config.v_beta_s,
+                                                  num_classes=self.num_classes, prior_probs=prior_atom_types)
+        self.bond_type_trans = DiscreteTransition(config.v_beta_schedule, self.num_timesteps, s=config.v_beta_s,
+                                                  num_classes=self.num_bond_classes, prior_probs=prior_bond_types)
+        self.register_buffer('Lt_history', torch.zeros(self.num_timesteps))
+        self.register_buffer('Lt_count', torch.zeros(self.num_timesteps))
+        self.hidden_dim = config.hidden_dim
+        emb_dim = self.hidden_dim - 1
+        self.protein_atom_feature_dim, self.ligand_atom_feature_dim = protein_atom_feature_dim, ligand_atom_feature_dim
+        self.protein_atom_emb = nn.Linear(protein_atom_feature_dim, emb_dim)
+        self.center_pos_mode = config.center_pos_mode
+        self.time_emb_dim = config.time_emb_dim
+        self.ligand_atom_emb = nn.Linear(ligand_atom_feature_dim, emb_dim)
+        self.refine_net_type = config.model_type
+        self.refine_net = get_refine_net(self.refine_net_type, config)
+        self.ligand_bond_emb = nn.Linear(self.num_bond_classes, self.hidden_dim)
+        self.v_inference = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), ShiftedSoftplus(),
+                                         nn.Linear(self.hidden_dim, self.num_classes))
+        self.distance_expansion = GaussianSmearing(0., 5., num_gaussians=config.num_r_gaussian, fix_offset=False)
+        self.bond_inference = nn.Sequential(nn.Linear(self.hidden_dim, self.hidden_dim), ShiftedSoftplus(),
+                                            nn.Linear(self.hidden_dim, self.num_bond_classes))
+        self._engine: Optional[EngineModel] = None
+        self.use_cuda_graph = True
+
+    # -- engine handling ---------------------------------------------------------------------------
+    def engine_config(self) -> Dict[str, int]:
+        c = self.config
+        return dict(hidden_dim=c.hidden_dim, n_heads=c.n_heads, knn=c.knn, num_layers=c.num_layers,
+                    num_blocks=c.num_blocks, num_classes=self.num_classes, num_bond_classes=self.num_bond_classes,
+                    protein_feature_dim=self.protein_atom_feature_dim, ligand_feature_dim=self.ligand_atom_feature_dim,
+                    num_timesteps=self.num_timesteps)
+
+    def engine(self) -> EngineModel:
+        """Hand the current parameters to the CUDA library (once; call `refresh_engine` after editing them)."""
+        if self._engine is None:
+            self._engine = EngineModel(self.engine_config(), self.state_dict())
+        return self._engine
+
+    def refresh_engine(self):
+        self._engine = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._engine = None
+        return out
+
+    def _new_batch(self, protein_pos, protein_v, batch_protein, batch_ligand, ligand_v_aux, bond_index,
+                   ligand_atom_mask, center_mode) -> EngineBatch:
+        num_graphs = int(batch_protein.max().item()) + 1
+        return EngineBatch(self.engine(), num_graphs, protein_pos, protein_v, batch_protein, batch_ligand,
+                           ligand_v_aux, bond_index, ligand_atom_mask, center_mode)
+
+    # -- forward -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, protein_pos, protein_v, batch_protein, protein_group_idx,
+                init_ligand_pos, init_ligand_v, init_ligand_v_aux, batch_ligand, ligand_group_idx,
+                prior_centers, prior_stds, batch_prior, prior_group_idx,
+                ligand_fc_bond_index, init_ligand_fc_bond_type,
+                ligand_atom_mask=None, time_step=None, return_all=False):
+        if return_all:
+            raise NotImplementedError('return_all (per-layer predictions) is a training-time diagnostic')
+        if ligand_fc_bond_index is None:
+            raise NotImplementedError('uni_o2_bond needs ligand_fc_bond_index')
+        require_cuda()
+        out_dev = init_ligand_pos.device
+        eb = self._new_batch(protein_pos, protein_v, batch_protein, batch_ligand, init_ligand_v_aux,
+                             ligand_fc_bond_index, ligand_atom_mask, center_mode=0)
+        eb.set_state(init_ligand_pos, init_ligand_v, init_ligand_fc_bond_type)
+        pos, v_logits, b_logits = eb.forward()
+        if ligand_atom_mask is not None:      # final_pos[mask_ligand_atom] (:316)
+            keep = ligand_atom_mask.to(pos.device).bool()
+            pos, v_logits = pos[keep], v_logits[keep]
+        return {'pred_ligand_pos': pos.to(out_dev), 'pred_ligand_v': v_logits.to(out_dev), 'pred_bond': b_logits.to(out_dev)}
+
+    def get_diffusion_loss(self, *a, **k):
+        raise NotImplementedError('training is out of scope of the sampling hot path (SURVEY.md section 8f, N4)')
+
+    # -- sampling ----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample_diffusion(self, protein_pos, protein_v, batch_protein, protein_group_idx,
+                         init_ligand_pos, init_ligand_v, ligand_v_aux, batch_ligand, ligand_group_idx,
+                         prior_centers, prior_stds, prior_num_atoms, batch_prior, prior_group_idx,
+                         ligand_decomp_batch, ligand_decomp_index,
+                         ligand_atom_mask=None,
+                         ligand_fc_bond_index=None, init_ligand_fc_bond_type=None, batch_ligand_bond=None,
+                         num_steps=None, center_pos_mode=None,
+                         energy_drift_opt=None,
+                         full_protein_pos=None, full_batch_protein=None,
+                         noise: Optional[List[Dict[str, torch.Tensor]]] = None, keep_traj: bool = True,
+                         traj_on_device: bool = False):
+        """Reverse diffusion (decompdiff.py:552-703).  Extra keyword arguments beyond the reference:
+        `noise` injects the per-step draws ({'u_atom','u_bond','eps_pos'}, first step first) instead of the
+        torch generator; `keep_traj=False` skips the six per-step trajectories; `traj_on_device=True`
+        returns them as stacked device tensors instead of lists of CPU tensors."""
+        require_cuda()
+        if self.model_mean_type != 'C0':
+            raise NotImplementedError("model_mean_type 'noise' (N4)") if self.model_mean_type == 'noise' else ValueError
+        if ligand_fc_bond_index is None or init_ligand_fc_bond_type is None:
+            raise NotImplementedError('uni_o2_bond needs the ligand bond graph')
+        if center_pos_mode == 'protein':
+            center_mode = 1
+        elif center_pos_mode == 'none':
+            center_mode = 0
+        else:
+            raise NotImplementedError          # center_pos (:20-32)
+        T = self.num_timesteps
+        num_steps = T if num_steps is None else int(num_steps)
+        out_dev = init_ligand_pos.device
+        eb = self._new_batch(protein_pos, protein_v, batch_protein, batch_ligand, ligand_v_aux,
+                             ligand_fc_bond_index, ligand_atom_mask, center_mode)
+        dev = eb.device
+        armsca = clash = None
+        for drift in (energy_drift_opt or []):
+            if drift['type'] == 'armsca_prox':
+                armsca = (ligand_decomp_index, drift['min_d'], drift['max_d'])
+            elif drift['type'] == 'clash':
+                clash = (full_protein_pos, full_batch_protein, drift['sigma'], drift['gamma'])
+            elif drift['type'] in ('center_prox', 'mmff_min'):
+                raise NotImplementedError(f"drift {drift['type']} is not part of the shipped sampling config")
+            else:
+                raise ValueError(drift['type'])
+            if drift.get('scale', False):
+                raise NotImplementedError('drift scale=True is not part of the shipped sampling config')
+        if armsca or clash:
+            eb.set_guidance(armsca, clash)
+        eb.set_state(init_ligand_pos, init_ligand_v, init_ligand_fc_bond_type)
+        eb.set_time(T - 1)
+        n, Eb, Cn, Cb = eb.n_ligand, eb.n_bonds, self.num_classes, self.num_bond_classes
+        prior_std_atom = prior_stds.to(dev, torch.float32)[ligand_decomp_batch.to(dev)].contiguous()
+        u_atom = torch.empty(n, Cn, device=dev)
+        u_bond = torch.empty(Eb, Cb, device=dev)
+        eps = torch.empty(n, 3, device=dev)
+        S = num_steps
+        traj = {}
+        if keep_traj:
+            traj = dict(pos_traj=torch.empty(S, n, 3, device=dev), v_traj=torch.empty(S, n, dtype=torch.int64, device=dev),
+                        v0_traj=torch.empty(S, n, Cn, device=dev), vt_traj=torch.empty(S, n, Cn, device=dev),
+                        bond_traj=torch.empty(S, Eb, dtype=torch.int64, device=dev), bt_traj=torch.empty(S, Eb, Cb, device=dev))
+        io = _lib.StepIO(prior_std_atom=prior_std_atom.data_ptr(), u_atom=u_atom.data_ptr(), u_bond=u_bond.data_ptr(),
+                         eps_pos=eps.data_ptr(),
+                         **{k: (traj[k].data_ptr() if keep_traj else None) for k in
+                            ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj', 'bond_traj', 'bt_traj')})
+
+        def draw():
+            # the three draws of the reference, same order / shapes / generator
+            # (transitions.py:79 via decompdiff.py:620 and :633, then :680)
+            u_atom.uniform_()
+            u_bond.uniform_()
+            eps.normal_()
+
+        if noise is not None:
+            if len(noise) < S:
+                raise ValueError('noise list shorter than num_steps')
+            for s in range(S):
+                u_atom.copy_(noise[s]['u_atom']); u_bond.copy_(noise[s]['u_bond']); eps.copy_(noise[s]['eps_pos'])
+                eb.reverse_step(io)
+        elif self.use_cuda_graph and S >= 4:
+            # one step = 3 RNG kernels + ~135 launches of the library; captured once, replayed S-1 times
+            draw(); eb.reverse_step(io)                    # warm-up step outside capture (lazy inits)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                draw(); eb.reverse_step(io)
+            for _ in range(S - 1):
+                graph.replay()
+        else:
+            for _ in range(S):
+                draw(); eb.reverse_step(io)
+        self.last_launches_per_step = eb.launch_count() + 3
+        pos, v, bond = eb.get_state()
+        result = {'pos': pos.to(out_dev), 'v': v.to(out_dev), 'bond': bond.to(out_dev)}
+        names = {'pos_traj': 'pos_traj', 'v_traj': 'v_traj', 'v0_traj': 'v0_traj', 'vt_traj': 'vt_traj',
+                 'bond_traj': 'bond_traj', 'bt_traj': 'bt_traj'}
+        for key in names:
+            if not keep_traj:
+                result[key] = []
+            elif traj_on_device:
+                result[key] = traj[key]
+            else:   # reference: python lists of per-step CPU tensors (:624-636, :688-689); one D2H per array here
+                result[key] = list(traj[key].cpu().unbind(0))
+        return result

@@ -1,0 +1,162 @@
+"""Thin object wrappers over the C ABI (include/decompdiff_b200.h).
+
+`EngineModel`  <-> ddb_model : weights handed over under their reference state_dict names.
+`EngineBatch`  <-> ddb_batch : static topology + workspace + evolving (x_t, v_t, b_t) state.
+
+torch is used here for device memory and streams only; every computation is a kernel of the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _host(t: torch.Tensor, dtype) -> torch.Tensor:
+    return t.detach().to(device='cpu', dtype=dtype).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('decompdiff_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+
+
+class EngineModel:
+    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor]):
+        require_cuda()
+        L = _lib.lib()
+        c = _lib.Config(**cfg)
+        self._h = C.c_void_p()
+        _lib.check(L.ddb_model_create(C.byref(self._h), C.byref(c)))
+        self.cfg = dict(cfg)
+        for name, t in state_dict.items():
+            if not torch.is_floating_point(t):
+                continue
+            ht = _host(t, torch.float32)
+            _lib.check(L.ddb_model_set_tensor(self._h, name.encode(), C.c_void_p(ht.data_ptr()), ht.numel()))
+        _lib.check(L.ddb_model_finalize(self._h))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            try:
+                _lib.lib().ddb_model_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class EngineBatch:
+    """One collated batch on the device.  See ddb_batch_create for the meaning of the arguments."""
+
+    def __init__(self, model: EngineModel, num_graphs: int, protein_pos, protein_v, batch_protein,
+                 batch_ligand, ligand_v_aux, bond_index, ligand_atom_mask=None, center_mode: int = 0):
+        require_cuda()
+        L = _lib.lib()
+        self.model = model
+        pp, pv = _host(protein_pos, torch.float32), _host(protein_v, torch.float32)
+        bp, bl = _host(batch_protein, torch.int64), _host(batch_ligand, torch.int64)
+        aux = _host(ligand_v_aux, torch.float32)
+        if bond_index is None:
+            bond_index = torch.zeros(2, 0, dtype=torch.int64)
+        bi = _host(bond_index, torch.int64)
+        mask = None if ligand_atom_mask is None else _host(ligand_atom_mask, torch.uint8)
+        if pv.dim() != 2 or pv.size(1) != model.cfg['protein_feature_dim']:
+            raise ValueError(f'protein_v must be (n, {model.cfg["protein_feature_dim"]})')
+        if aux.numel() != bl.numel() * (model.cfg['ligand_feature_dim'] - model.cfg['num_classes']):
+            raise ValueError('ligand_v_aux has the wrong width')
+        self.n_protein, self.n_ligand, self.n_bonds = pp.size(0), bl.numel(), bi.size(1)
+        self.num_graphs = num_graphs
+        self.C, self.Cb = model.cfg['num_classes'], model.cfg['num_bond_classes']
+        self._h = C.c_void_p()
+        _lib.check(L.ddb_batch_create(
+            C.byref(self._h), model._h, num_graphs, self.n_protein, _ptr(pp), _ptr(pv), _ptr(bp),
+            self.n_ligand, _ptr(bl), _ptr(aux), self.n_bonds, _ptr(bi), _ptr(mask), center_mode))
+        self.device = torch.device('cuda', torch.cuda.current_device())
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            try:
+                _lib.lib().ddb_batch_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- state ---------------------------------------------------------------------------------
+    def offset(self) -> torch.Tensor:
+        out = torch.empty(self.num_graphs, 3, dtype=torch.float32)
+        _lib.check(_lib.lib().ddb_batch_get_offset(self._h, _ptr(out)))
+        return out
+
+    def set_state(self, ligand_pos, ligand_v, bond_type):
+        dev = self.device
+        if bond_type is None:
+            bond_type = torch.zeros(0, dtype=torch.int64)
+        self._pos = ligand_pos.detach().to(dev, torch.float32).contiguous()
+        self._v = ligand_v.detach().to(dev, torch.int64).contiguous()
+        self._b = bond_type.detach().to(dev, torch.int64).contiguous()
+        if self._pos.shape != (self.n_ligand, 3) or self._v.numel() != self.n_ligand or self._b.numel() != self.n_bonds:
+            raise ValueError('state tensors do not match the batch')
+        if self._v.numel() and (int(self._v.max()) >= self.C or int(self._v.min()) < 0):
+            raise AssertionError(f'Error: {int(self._v.max())} >= {self.C}')      # transitions.py:66
+        if self._b.numel() and (int(self._b.max()) >= self.Cb or int(self._b.min()) < 0):
+            raise AssertionError(f'Error: {int(self._b.max())} >= {self.Cb}')
+        _lib.check(_lib.lib().ddb_batch_set_state(self._h, _ptr(self._pos), _ptr(self._v), _ptr(self._b), _stream_ptr()))
+
+    def get_state(self):
+        dev = self.device
+        pos = torch.empty(self.n_ligand, 3, device=dev, dtype=torch.float32)
+        v = torch.empty(self.n_ligand, device=dev, dtype=torch.int64)
+        b = torch.empty(self.n_bonds, device=dev, dtype=torch.int64)
+        _lib.check(_lib.lib().ddb_batch_get_state(self._h, _ptr(pos), _ptr(v), _ptr(b), _stream_ptr()))
+        return pos, v, b
+
+    # -- compute -------------------------------------------------------------------------------
+    def forward(self):
+        dev = self.device
+        pos = torch.empty(self.n_ligand, 3, device=dev, dtype=torch.float32)
+        vl = torch.empty(self.n_ligand, self.C, device=dev, dtype=torch.float32)
+        bl = torch.empty(self.n_bonds, self.Cb, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().ddb_forward(self._h, _ptr(pos), _ptr(vl), _ptr(bl), _stream_ptr()))
+        return pos, vl, bl
+
+    def set_time(self, t_start: int):
+        _lib.check(_lib.lib().ddb_batch_set_time(self._h, int(t_start), _stream_ptr()))
+
+    def set_guidance(self, armsca=None, clash=None):
+        """armsca = (ligand_decomp_index, min_d, max_d) | None;  clash = (full_pos, full_batch, sigma, gamma) | None"""
+        L = _lib.lib()
+        di = _host(armsca[0], torch.int64) if armsca else None
+        fp = _host(clash[0], torch.float32) if clash else None
+        fb = _host(clash[1], torch.int64) if clash else None
+        _lib.check(L.ddb_batch_set_guidance(
+            self._h, 1 if armsca else 0, _ptr(di), float(armsca[1]) if armsca else 0.0, float(armsca[2]) if armsca else 0.0,
+            1 if clash else 0, fp.size(0) if clash else 0, _ptr(fp), _ptr(fb),
+            float(clash[2]) if clash else 0.0, float(clash[3]) if clash else 0.0))
+
+    def reverse_step(self, io):
+        _lib.check(_lib.lib().ddb_reverse_step(self._h, C.byref(io), _stream_ptr()))
+
+    def launch_count(self) -> int:
+        return int(_lib.lib().ddb_batch_last_launch_count(self._h))
+
+    def debug_buffer(self, name: str) -> torch.Tensor:
+        """Copy of an internal buffer of the last forward (tests / profiling)."""
+        p, r, c = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().ddb_batch_debug_buffer(self._h, name.encode(), C.byref(p), C.byref(r), C.byref(c)))
+        dtype = torch.int32 if name in ('nbr', 'deg', 'nlig') else torch.float32
+        out = torch.empty(r.value, c.value, device=self.device, dtype=dtype)
+        _lib.check(_lib.lib().ddb_copy_device(_ptr(out), p, out.numel() * out.element_size(), _stream_ptr()))
+        return out

@@ -55,12 +55,12 @@ def position_tables(cfg) -> Dict[str, np.ndarray]:
         'posterior_mean_c0_coef': betas * np.sqrt(ac_prev) / (1. - ac),
         'posterior_mean_ct_coef': (1. - ac_prev) * np.sqrt(alphas) / (1. - ac),
         'posterior_var': post_var,
-        'pos_score_coef': betas / np.sqrt(alphas),
     }
     out = {k: v.astype(np.float32) for k, v in out.items()}
     # decompdiff.py:130 takes the log of the already-fp32 variance, entry 0 := entry 1
     pv = out['posterior_var']
     out['posterior_logvar'] = np.log(np.append(pv[1], pv[1:])).astype(np.float32)
+    out['pos_score_coef'] = (betas / np.sqrt(alphas)).astype(np.float32)
     return out
 
 

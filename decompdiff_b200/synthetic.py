@@ -186,3 +186,42 @@ DEFAULT_MODEL_CONFIG = dict(  # `model:` of /root/reference/configs/training.yml
 PROTEIN_FEATURE_DIM = 29   # 27 (FeaturizeProteinAtom) + 2 (AddDecompIndicator)
 LIGAND_FEATURE_DIM = 10    # 8 ('basic' atom types) + 2 (arm/scaffold indicator)
 NUM_CLASSES = 8
+
+
+def synthetic_state_dict(model, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic random weights keyed by parameter name (no checkpoint offline).
+
+    Linear weights ~ U(+-1/sqrt(fan_in)) as torch's default init, Linear biases ~ 0.05 N(0,1),
+    LayerNorm affine = (1 + 0.1 N(0,1), 0.1 N(0,1)) so that every term of the arithmetic is exercised.
+    Schedule tables and buffers keep their values.  Independent of module construction order, so the
+    reference model, the oracle and the CUDA path can all be given the very same tensors.
+    """
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    gen = torch.Generator().manual_seed(seed)
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    for name in sorted(sd):
+        if name not in trainable:
+            continue
+        t = sd[name]
+        if '.net.1.' in name:                      # LayerNorm
+            r = 0.1 * torch.randn(t.shape, generator=gen)
+            sd[name] = (1.0 + r) if name.endswith('weight') else r
+        elif t.dim() >= 2:
+            bound = 1.0 / (t.size(1) ** 0.5)
+            sd[name] = (torch.rand(t.shape, generator=gen) * 2 - 1) * bound
+        else:
+            sd[name] = 0.05 * torch.randn(t.shape, generator=gen)
+    return sd
+
+
+def step_noise(n_ligand: int, n_bonds: int, num_steps: int, seed: int, num_classes: int = NUM_CLASSES,
+               num_bond_classes: int = 5):
+    """The draws a CPU run of the reference makes after `torch.manual_seed(seed)`: per step
+    rand(n,C) -> rand(Eb,Cb) -> randn(n,3) (transitions.py:79 via decompdiff.py:620,633; :680)."""
+    gen = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(num_steps):
+        out.append({'u_atom': torch.rand(n_ligand, num_classes, generator=gen),
+                    'u_bond': torch.rand(n_bonds, num_bond_classes, generator=gen),
+                    'eps_pos': torch.randn(n_ligand, 3, generator=gen)})
+    return out
