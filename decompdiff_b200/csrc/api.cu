@@ -806,6 +806,7 @@ extern "C" int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, cons
   else if (n == "deg") { *ptr = b->deg; *rows = b->N; *cols = 1; }
   else if (n == "nlig") { *ptr = b->nlig; *rows = b->N; *cols = 1; }
   else if (n == "e_w") { *ptr = b->e_w; *rows = b->N; *cols = KNN; }
+  else if (n == "grad") { *ptr = b->grad; *rows = b->NL; *cols = 3; }
   else return fail(DDB_ERR_INVALID, "unknown buffer " + n);
   if (*ptr == nullptr) return fail(DDB_ERR_STATE, "no forward has run yet");
   return DDB_OK;

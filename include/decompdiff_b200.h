@@ -148,7 +148,7 @@ int ddb_gemm128(const float* A, int32_t lda, const float* Wt, int32_t ldw, const
                 float* C, int32_t ldc, int32_t M, int32_t N, int32_t act, void* stream);
 
 /* Introspection for tests / profiling: device pointers to internal buffers of the last forward.
- * name in {"h","x","h_bond","nbr","deg","nlig","e_w"}; rows/cols describe the layout.          */
+ * name in {"h","x","h_bond","nbr","deg","nlig","e_w","grad"}; rows/cols describe the layout.          */
 int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, const void** ptr,
                            int64_t* rows, int64_t* cols);
 /* stream-ordered device-to-device copy (lets a host language read a debug buffer without its own CUDA binding) */
