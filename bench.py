@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the DecompDiff sampling hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+Metric (BASELINE.json): molecules/sec at T=1000.  A "step" is ONE reverse-diffusion step (score-network forward +
+Gaussian / categorical posterior) over the whole 64-pocket batch (cfg 2: 64 x (370 protein + 30 ligand) atoms,
+ref_prior, no drift).  The network is not conditioned on t (time_emb_dim 0) and all shapes are static, so
+    value = pockets_per_rank * n_gpus / (1000 * seconds_per_step)
+and `e2e` is measured by actually running a T-step `sample_diffusion` call from pinned host tensors through the
+public API (H2D of the batch, all steps, D2H of the molecules and the six trajectories inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+T_FULL = 1000
+WORKLOADS = {   # BASELINE.json configs; cfg2 is the headline (64 pockets fit one GPU)
+    'cfg2': dict(n_pockets=64, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, guided=False),
+    'cfg3': dict(n_pockets=64, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, guided=True),
+    'cfg1': dict(n_pockets=1, n_protein=300, arm_sizes=(8, 8), n_scaffold=14, guided=False),
+}
+DRIFT = [{'type': 'armsca_prox', 'min_d': 1.2, 'max_d': 1.9}, {'type': 'clash', 'sigma': 2, 'gamma': 4}]
+
+
+def measured_peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            p = [x.strip() for x in r.split(',')]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+                for n, v in zip(names, p[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+        return {'sm_mhz': busy[len(busy) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def shape_counts(kw):
+    n_nodes = kw['protein_pos'].size(0) + kw['init_ligand_pos'].size(0)
+    B = int(kw['batch_protein'].max()) + 1
+    n_lig = kw['init_ligand_pos'].size(0)
+    Eb = kw['init_ligand_fc_bond_type'].numel()
+    per = torch.bincount(kw['batch_ligand'], minlength=B)
+    E3 = int((per * (per - 1) * (per - 2)).sum())
+    return dict(B=B, N=n_nodes, NL=n_lig, Eb=Eb, E=n_nodes * 32, E3=E3)
+
+
+def kernel_report(prof, cnt, layers, peak_gbs, steps):
+    """Per-kernel-group device time of one step + achieved rates on the ALGORITHMIC work of SURVEY.md section 8(d)."""
+    E, N, Eb, E3, NL = cnt['E'], cnt['N'], cnt['Eb'], cnt['E3'], cnt['NL']
+    mlp = lambda R, i, o: 2.0 * R * (128 * i + 128 * o)
+    groups = {
+        # the EGNN kNN-edge kernels: node update (k,v) + position update (k,v)
+        'knn_edge_attention': dict(cats=['knn_attn_k', 'knn_attn_v_node', 'knn_pos_k', 'knn_pos_v'],
+                                   bytes=layers * (E * 528.0 + 2 * N * 528.0 + 8.0 * E),
+                                   flops=layers * (3 * mlp(E, 340, 128) + mlp(E, 340, 16))),
+        'bond_triplet_attention': dict(cats=['trip_prep', 'trip_k', 'trip_v'],
+                                       bytes=layers * (E3 * (512.0 + 2 * 528.0) + 2 * Eb * 512.0),
+                                       flops=layers * (2 * mlp(E3, 437, 128) + mlp(E3, 256, 128))),
+        'bond_edge_attention': dict(cats=['bond_attn_node', 'bond_attn_pos'],
+                                    bytes=layers * 2 * (Eb * (512.0 + 528.0) + 2 * NL * 528.0),
+                                    flops=layers * (3 * mlp(Eb, 384, 128) + mlp(Eb, 384, 16))),
+        'projection_gemms': dict(cats=['gemm_node', 'gemm_ligand', 'gemm_bond'],
+                                 bytes=layers * ((N * (128 + 640 + 128 + 128 + 256) + Eb * (128 + 640 + 128 + 256)) * 4.0),
+                                 flops=layers * 2.0 * 128 * (N * (640 + 128 + 128 + 256) + NL * (1280 + 128 + 1024 + 256)
+                                                              + Eb * (640 + 128 + 256))),
+        'knn_graph_build': dict(cats=['knn_graph', 'edge_weight'], bytes=N * 16.0 + E * 4.0 + E * 4.0, flops=0.0),
+        'reverse_step_and_heads': dict(cats=['heads', 'reverse_step', 'setup_embed', 'guidance'],
+                                       bytes=(NL * (3 * 4 * 4 + 8 * 4 * 4) + Eb * (128 * 4 * 2 + 5 * 4 * 4)) * 1.0, flops=0.0),
+    }
+    total_ms = sum(v['ms'] for v in prof.values()) / steps
+    out = []
+    for name, g in groups.items():
+        ms = sum(prof.get(c, {'ms': 0.0})['ms'] for c in g['cats']) / steps
+        launches = sum(prof.get(c, {'count': 0})['count'] for c in g['cats']) / steps
+        if ms <= 0:
+            continue
+        gbs = g['bytes'] / (ms * 1e-3) / 1e9
+        out.append({'kernel': name, 'ms_per_step': round(ms, 4), 'share': round(ms / total_ms, 4),
+                    'launches_per_step': launches, 'alg_bytes_per_step': g['bytes'], 'achieved_gbs': round(gbs, 1),
+                    'hbm_frac': round(gbs / peak_gbs, 4), 'ref_formulation_tflops': round(g['flops'] / (ms * 1e-3) / 1e12, 2)})
+    out.sort(key=lambda r: -r['ms_per_step'])
+    return out, total_ms
+
+
+def cpu_reference_step_time(n_pockets, wl, steps, warmup, guided):
+    """Seconds per reverse step of the reference algorithm (oracle port, torch CPU, all host threads) on
+    `n_pockets` pockets of the workload's shape."""
+    from decompdiff_b200 import synthetic as syn
+    import decompdiff_b200 as ddb
+    from oracle import restate
+    kw = syn.make_batch(n_pockets, wl['n_protein'], wl['arm_sizes'], wl['n_scaffold'], seed=4242,
+                        n_full_extra=2000 if guided else 0)
+    shell = ddb.DecompScorePosNet3D(syn.DEFAULT_MODEL_CONFIG, syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
+    sd = syn.synthetic_state_dict(shell, seed=0)
+    cfg = dict(syn.DEFAULT_MODEL_CONFIG, num_classes=syn.NUM_CLASSES)
+    gen = torch.Generator().manual_seed(1)
+    call = lambda s: restate.sample_diffusion(sd, cfg, **kw, num_steps=s, center_pos_mode='protein', generator=gen,
+                                              energy_drift_opt=DRIFT if guided else None, keep_traj=True)
+    if warmup > 0:
+        call(warmup)
+    t0 = time.perf_counter()
+    call(steps)
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's own algorithm on the host cores.  The reference is pure Python + PyG wheels
+    that are absent here, so the timed code is the oracle port (bit-identical to the reference on CPU, see
+    tests/test_oracle_golden.py); rank 0 only."""
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    # bounded sample: a few pockets of the workload's shape so that (steps + warmup) stay within minutes
+    budget_s = 150.0
+    est_per_pocket = 1.0 * (8.0 / max(cores, 1)) ** 0.7
+    n_s = int(max(1, min(wl['n_pockets'], 8, budget_s / ((args.steps + args.warmup) * est_per_pocket))))
+    sec = cpu_reference_step_time(n_s, wl, args.steps, args.warmup, wl['guided'])
+    value = n_s / (T_FULL * sec)
+    sample = (f'{n_s} of {wl["n_pockets"]} pockets ({wl["n_protein"]}+{sum(wl["arm_sizes"]) + wl["n_scaffold"]} atoms each), '
+              f'{args.warmup} warm-up + {args.steps} timed reverse steps, extrapolated x{T_FULL} steps (network is '
+              f't-independent); per-pocket cost is batch-size independent on CPU')
+    line = {
+        'impl': 'reference', 'metric': 'molecules/sec (T=1000)', 'value': value, 'unit': 'molecules/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: {wl["n_pockets"]} synthetic pockets x ({wl["n_protein"]} protein + 30 ligand '
+                               f'atoms), T=1000, ref_prior' + (', drift guidance' if wl['guided'] else ''),
+                   'step': 'one reverse-diffusion step over the bounded sample'},
+        'cpu_baseline': {'value': value, 'unit': 'molecules/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'molecules/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=list(WORKLOADS))
+    ap.add_argument('--e2e-steps', type=int, default=-1, help='-1: full T=1000 when it fits ~60 s, else 200')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-profile', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import decompdiff_b200 as ddb
+    from decompdiff_b200 import synthetic as syn
+    from decompdiff_b200.dist import gather_molecules
+
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device; there is no CPU fallback for the product path')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    wl = WORKLOADS[args.workload]
+    warmup = max(args.warmup, 3)
+    if warmup + args.steps + 8 > T_FULL:
+        raise SystemExit('warmup + steps must stay below T=1000')
+
+    model = ddb.DecompScorePosNet3D(syn.DEFAULT_MODEL_CONFIG, syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
+    model.load_state_dict(syn.synthetic_state_dict(model, seed=0))
+    model.eval()
+    kw = syn.make_batch(wl['n_pockets'], wl['n_protein'], wl['arm_sizes'], wl['n_scaffold'], seed=1000 + rank,
+                        n_full_extra=2000 if wl['guided'] else 0)
+    drift = DRIFT if wl['guided'] else None
+    cnt = shape_counts(kw)
+    atoms_per_mol = torch.bincount(kw['batch_ligand']).tolist()
+    bonds_per_mol = torch.bincount(kw['batch_ligand_bond']).tolist()
+    torch.manual_seed(2021 + rank)
+
+    # ---------------------------------------------------------------- device-resident steps (value)
+    run = model.begin_sampling(**kw, num_steps=T_FULL, center_pos_mode='protein', energy_drift_opt=drift)
+    run.advance(warmup)
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    run.advance(args.steps)
+    if world > 1:   # the one exchange of the path: gather the sampled molecules (here after K steps)
+        pos, v, bond = run.eb.get_state()
+        gather_molecules({'pos': pos, 'v': v, 'bond': bond}, atoms_per_mol, bonds_per_mol)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    launches_per_step = run.launches_per_step
+    value = wl['n_pockets'] * world / (T_FULL * ms_per_step * 1e-3)
+
+    # ---------------------------------------------------------------- per-kernel device time (roofline)
+    peak_gbs, peak_src = measured_peaks()
+    kernels, roof = [], None
+    if not args.no_profile and rank == 0:
+        prof_steps = 3
+        run.eb.profile(True, reset=True)
+        for _ in range(prof_steps):
+            run.step_eager()
+        run.eb.profile(False)
+        kernels, prof_total = kernel_report(run.eb.profile_read(), cnt, model.config.num_layers, peak_gbs, prof_steps)
+        egnn = next(k for k in kernels if k['kernel'] == 'knn_edge_attention')
+        roof = {'kernel': 'knn_edge_attention (EGNN message+aggregate+coordinate update over kNN edges; 4 launches/layer)',
+                'bound': 'hbm', 'achieved': egnn['achieved_gbs'], 'peak': peak_gbs, 'unit': 'GB/s', 'frac': egnn['hbm_frac'],
+                'traffic': None, 'peak_source': peak_src, 'time_share_of_step': egnn['share'],
+                'alg_bytes_per_step': egnn['alg_bytes_per_step'],
+                'note': 'algorithmic bytes = gather-counted (E*528 + 2N*528 + 8E) B per layer (SURVEY.md 8d); the kernel is '
+                        'fp32-FMA / issue bound (working set is L2 resident), see DESIGN.md section 5',
+                'profiled_step_ms': round(prof_total, 3)}
+    del run
+
+    # ---------------------------------------------------------------- end to end through the public API (e2e)
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = args.e2e_steps if args.e2e_steps > 0 else (T_FULL if ms_per_step * T_FULL < 60e3 else 200)
+        host_kw = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in kw.items()}
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r = model.sample_diffusion(**host_kw, num_steps=e2e_steps, center_pos_mode='protein', energy_drift_opt=drift)
+        if world > 1:
+            gather_molecules({k: r[k].to(dev) for k in ('pos', 'v', 'bond')}, atoms_per_mol, bonds_per_mol)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        d2h = sum(r[k].numel() * r[k].element_size() for k in ('pos', 'v', 'bond'))
+        d2h += sum(sum(x.numel() * x.element_size() for x in r[k]) for k in ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj', 'bond_traj', 'bt_traj'))
+        eb_probe = model._new_batch(kw['protein_pos'], kw['protein_v'], kw['batch_protein'], kw['batch_ligand'],
+                                    kw['ligand_v_aux'], kw['ligand_fc_bond_index'], None, 1)
+        h2d = eb_probe.h2d_bytes() + sum(kw[k].numel() * kw[k].element_size() for k in
+                                         ('init_ligand_pos', 'init_ligand_v', 'init_ligand_fc_bond_type', 'prior_stds', 'ligand_decomp_batch'))
+        del eb_probe
+        e2e = {'value': wl['n_pockets'] * world / (el * T_FULL / e2e_steps), 'unit': 'molecules/s',
+               'h2d_bytes_per_step': h2d / e2e_steps, 'd2h_bytes_per_step': d2h / e2e_steps,
+               'h2d_bytes_per_call': h2d, 'd2h_bytes_per_call': d2h, 'steps_run': e2e_steps, 'seconds': el,
+               'call': 'DecompScorePosNet3D.sample_diffusion(pinned host tensors) -> molecules + 6 trajectories on the host'}
+    clocks = sampler.stop()
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_s = 4 if wl['n_pockets'] >= 4 else wl['n_pockets']
+        sec = cpu_reference_step_time(n_s, wl, steps=2, warmup=1, guided=wl['guided'])
+        cpu = {'value': n_s / (T_FULL * sec), 'unit': 'molecules/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': f'{n_s} of {wl["n_pockets"]} pockets, 1 warm-up + 2 timed reverse steps of the oracle port '
+                         f'({sec:.2f} s/step), extrapolated x{T_FULL} steps'}
+
+    if rank == 0:
+        line = {
+            'metric': 'molecules/sec (T=1000)', 'value': value, 'unit': 'molecules/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: {wl["n_pockets"]} synthetic pockets per GPU x ({wl["n_protein"]} protein + 30 '
+                                   f'ligand atoms), T=1000, ref_prior' + (', beta-prior style drift guidance' if wl['guided'] else ''),
+                       'step': 'one reverse-diffusion step (network forward + posterior) over the batch; value = pockets / (1000 steps)',
+                       'nodes': cnt['N'], 'knn_edges': cnt['E'], 'bond_edges': cnt['Eb'], 'triplets': cnt['E3'],
+                       'l2': 'per-step working set ~1.4 GB of activations > 126 MB L2, no explicit flush (steady-state of the loop)',
+                       'cuda_graph': True, 'trajectories': 'kept on device, one D2H at the end'},
+            'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps), 'launches_per_step': launches_per_step,
+            'clocks': clocks, 'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

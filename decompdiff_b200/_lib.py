@@ -17,7 +17,8 @@ SYMBOLS = [
     'ddb_model_create', 'ddb_model_set_tensor', 'ddb_model_finalize', 'ddb_model_destroy',
     'ddb_batch_create', 'ddb_batch_destroy', 'ddb_batch_get_offset', 'ddb_batch_set_state', 'ddb_batch_get_state',
     'ddb_forward', 'ddb_batch_set_time', 'ddb_reverse_step', 'ddb_batch_set_guidance',
-    'ddb_knn_graph', 'ddb_gemm128', 'ddb_batch_debug_buffer', 'ddb_copy_device', 'ddb_batch_last_launch_count',
+    'ddb_knn_graph', 'ddb_gemm128', 'ddb_batch_debug_buffer', 'ddb_copy_device', 'ddb_batch_last_launch_count', 'ddb_batch_h2d_bytes',
+    'ddb_batch_profile', 'ddb_profile_num_categories', 'ddb_profile_category_name', 'ddb_batch_profile_read',
 ]
 
 
@@ -68,11 +69,19 @@ def lib():
     L.ddb_gemm128.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp]
     L.ddb_batch_debug_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.ddb_copy_device.argtypes = [vp, vp, i64, vp]
+    L.ddb_batch_profile.argtypes = [vp, i32, i32]
+    L.ddb_profile_num_categories.restype = i32
+    L.ddb_profile_category_name.argtypes = [i32]
+    L.ddb_profile_category_name.restype = C.c_char_p
+    L.ddb_batch_profile_read.argtypes = [vp, vp, vp]
     L.ddb_batch_last_launch_count.argtypes = [vp]
     L.ddb_batch_last_launch_count.restype = i64
+    L.ddb_batch_h2d_bytes.argtypes = [vp]
+    L.ddb_batch_h2d_bytes.restype = i64
     for s in SYMBOLS:
         if s not in ('ddb_last_error', 'ddb_version', 'ddb_model_destroy', 'ddb_batch_destroy',
-                     'ddb_batch_last_launch_count'):
+                     'ddb_batch_last_launch_count', 'ddb_batch_h2d_bytes', 'ddb_profile_num_categories',
+                     'ddb_profile_category_name'):
             getattr(L, s).restype = C.c_int
     _lib = L
     return L

@@ -314,6 +314,12 @@ struct ddb_batch {
   int enable_armsca = 0, enable_clash = 0; float min_d = 0, max_d = 0, sigma = 0, gamma = 0;
   int* decomp_index = nullptr; float* full_pos4 = nullptr; int* full_ptr = nullptr;
   long long launches = 0;
+  long long h2d_bytes = 0;
+  // optional per-kernel timing (CUDA events on the launch stream; eager passes only, never under graph capture)
+  bool profiling = false;
+  struct ProfEv { int cat; cudaEvent_t a, b; };
+  std::vector<ProfEv> prof_events;
+  double prof_ms[32] = {0}; long long prof_cnt[32] = {0};
 
   template <typename T>
   int dalloc(T** p, size_t n) {
@@ -329,6 +335,7 @@ struct ddb_batch {
     int r = dalloc(p, v.size());
     if (r) return r;
     if (!v.empty()) {
+      h2d_bytes += (long long)(v.size() * sizeof(T));
       cudaError_t e = cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
       if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
     }
@@ -539,7 +546,37 @@ extern "C" int ddb_batch_get_state(const ddb_batch* b, float* ligand_pos, int64_
 // ------------------------------------------------------------------------------------------ forward
 namespace {
 
-void gemm(ddb_batch* b, cudaStream_t s, const float* A, int lda, const int* a_rows, int M, const GemmW& w, float* C, int ldc,
+enum ProfCat { PC_SETUP = 0, PC_KNN_GRAPH, PC_EDGE_WEIGHT, PC_GEMM_NODE, PC_GEMM_LIG, PC_GEMM_BOND, PC_KNN_ATTN_K, PC_KNN_ATTN_V,
+               PC_KNN_POS_K, PC_KNN_POS_V, PC_BOND_NODE, PC_BOND_POS, PC_TRIP_PREP, PC_TRIP_K, PC_TRIP_V, PC_HEADS,
+               PC_GUIDANCE, PC_REVERSE_STEP, PC_COUNT };
+const char* kProfNames[PC_COUNT] = {"setup_embed", "knn_graph", "edge_weight", "gemm_node", "gemm_ligand", "gemm_bond",
+                                    "knn_attn_k", "knn_attn_v_node", "knn_pos_k", "knn_pos_v", "bond_attn_node",
+                                    "bond_attn_pos", "trip_prep", "trip_k", "trip_v", "heads", "guidance", "reverse_step"};
+
+struct ProfScope {
+  ddb_batch* b; cudaStream_t s; int idx = -1;
+  ProfScope(ddb_batch* bb, cudaStream_t ss, int cat) : b(bb), s(ss) {
+    if (!b->profiling) return;
+    ddb_batch::ProfEv e; e.cat = cat;
+    cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+    cudaEventRecord(e.a, s);
+    b->prof_events.push_back(e); idx = (int)b->prof_events.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(b->prof_events[idx].b, s); }
+};
+
+void prof_collect(ddb_batch* b, cudaStream_t s) {
+  if (!b->profiling || b->prof_events.empty()) return;
+  cudaStreamSynchronize(s);
+  for (auto& e : b->prof_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { b->prof_ms[e.cat] += ms; b->prof_cnt[e.cat]++; }
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  b->prof_events.clear();
+}
+
+void gemm(ddb_batch* b, cudaStream_t s, int cat, const float* A, int lda, const int* a_rows, int M, const GemmW& w, float* C, int ldc,
           const Mlp2* ln = nullptr, const float* A2 = nullptr, int lda2 = 0, const int* a2_rows = nullptr,
           const float* R = nullptr, int ldr = 0, const int* c_rows = nullptr, int act = 0) {
   const ddb_model* m = b->m;
@@ -548,6 +585,7 @@ void gemm(ddb_batch* b, cudaStream_t s, const float* A, int lda, const int* a_ro
   if (ln) { g.ln_gamma = m->p(ln->gamma); g.ln_beta = m->p(ln->beta); }
   g.Wt = m->p(w.Wt); g.ldw = w.N; g.bias = m->p(w.bias);
   g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.c_rows = c_rows; g.M = M; g.N = w.N; g.act = act;
+  ProfScope ps(b, s, cat);
   launch_gemm128(g, s);
   b->launches++;
 }
@@ -562,12 +600,12 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   const ddb_config& c = m->cfg;
   const int N = b->N, NL = b->NL, Eb = b->Eb, sms = b->num_sms;
   b->launches = 0;
-  launch_set_ligand_x(b->x_lig, NL, b->lig_idx, b->x4_0, s);
-  launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s);
-  launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s);
-  launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s);
-  launch_edge_weight(b->x4_0, b->nbr, b->deg, N, m->p(m->ew_W1t), m->p(m->ew_b1), m->p(m->ew_gamma), m->p(m->ew_beta),
-                     m->p(m->ew_w2), m->ew_b2, b->e_w, s);
+  { ProfScope ps(b, s, PC_SETUP); launch_set_ligand_x(b->x_lig, NL, b->lig_idx, b->x4_0, s); }
+  { ProfScope ps(b, s, PC_SETUP); launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s); }
+  { ProfScope ps(b, s, PC_SETUP); launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s); }
+  { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s); }
+  { ProfScope ps(b, s, PC_EDGE_WEIGHT); launch_edge_weight(b->x4_0, b->nbr, b->deg, N, m->p(m->ew_W1t), m->p(m->ew_b1), m->p(m->ew_gamma), m->p(m->ew_beta),
+                     m->p(m->ew_w2), m->ew_b2, b->e_w, s); }
   b->launches += 5;
   float *h_in = b->h0, *x_in = b->x4_0, *hb_in = b->hbA;
   for (int l = 0; l < c.num_layers; ++l) {
@@ -576,20 +614,20 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     float* x_out = (l % 2 == 0) ? b->x4_a : b->x4_b;
     float* hb_out = (l % 2 == 0) ? b->hbB : b->hbA;
     // --- projections of the layer input
-    gemm(b, s, h_in, H, nullptr, N, L.n1, b->PN, 5 * H);
-    gemm(b, s, b->PN + 4 * H, 5 * H, nullptr, N, L.q_ne, b->qN, H, &L.ln_q_ne);
-    gemm(b, s, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
-    gemm(b, s, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
-    gemm(b, s, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
-    gemm(b, s, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
+    gemm(b, s, PC_GEMM_NODE, h_in, H, nullptr, N, L.n1, b->PN, 5 * H);
+    gemm(b, s, PC_GEMM_NODE, b->PN + 4 * H, 5 * H, nullptr, N, L.q_ne, b->qN, H, &L.ln_q_ne);
+    gemm(b, s, PC_GEMM_LIG, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
+    gemm(b, s, PC_GEMM_LIG, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
+    gemm(b, s, PC_GEMM_BOND, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
+    gemm(b, s, PC_GEMM_BOND, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
     // --- node update over kNN edges  -> h1
     KnnAttnArgs ka;
     ka.n_dst = N; ka.Hi = b->PN; ka.ldhi = 5 * H; ka.Hj = b->PN + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
     ka.x4 = x_in; ka.nbr = b->nbr; ka.deg = b->deg; ka.nlig = b->nlig; ka.is_lig = b->is_lig; ka.e_w = b->e_w;
     ka.wbuf = b->wb_knn; ka.w = knn_w(m, L.ne_k);
-    launch_knn_attn_k(ka, sms, s);
+    { ProfScope ps(b, s, PC_KNN_ATTN_K); launch_knn_attn_k(ka, sms, s); }
     ka.Hi = b->PN + 2 * H; ka.Hj = b->PN + 3 * H; ka.w = knn_w(m, L.ne_v); ka.out_h = b->h1; ka.ldo = H;
-    launch_knn_attn_v_node(ka, sms, s);
+    { ProfScope ps(b, s, PC_KNN_ATTN_V); launch_knn_attn_v_node(ka, sms, s); }
     // --- node update over bond edges -> h1[ligand rows] +=
     BondAttnArgs ba;
     ba.n_lig = NL; ba.lig_idx = b->lig_idx; ba.in_ptr = b->in_ptr; ba.in_eid = b->in_eid; ba.in_src = b->in_src;
@@ -597,7 +635,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ba.k.Hi = b->PL; ba.k.Hj = b->PL + H; ba.k.Pe = b->PB; ba.k.w = bond_w(m, L.nb_k);
     ba.v.Hi = b->PL + 2 * H; ba.v.Hj = b->PL + 3 * H; ba.v.Pe = b->PB + H; ba.v.w = bond_w(m, L.nb_v);
     ba.q = b->qNB; ba.ldq = H; ba.x4 = x_in; ba.wbuf = b->wb_bond; ba.out_h = b->h1; ba.ldo = H;
-    launch_bond_attn_node(ba, sms, s);
+    { ProfScope ps(b, s, PC_BOND_NODE); launch_bond_attn_node(ba, sms, s); }
     // --- bond update over triplets -> hb_out
     TripArgs ta;
     ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
@@ -607,27 +645,27 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ta.v.Pe = b->PB + 3 * H; ta.v.Hk = b->PL + 7 * H; ta.v.Hj = b->PL + 8 * H; ta.v.Wd = m->p(L.bl_v.Wd);
     ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m);
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
-    launch_trip_prep(ta, s);
-    launch_trip_k(ta, sms, s);
-    launch_trip_v(ta, sms, s);
+    { ProfScope ps(b, s, PC_TRIP_PREP); launch_trip_prep(ta, s); }
+    { ProfScope ps(b, s, PC_TRIP_K); launch_trip_k(ta, sms, s); }
+    { ProfScope ps(b, s, PC_TRIP_V); launch_trip_v(ta, sms, s); }
     b->launches += 6;
     // --- h_out = h_in + lin_node(h1)    (:277)
-    gemm(b, s, b->h1, H, nullptr, N, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H);
+    gemm(b, s, PC_GEMM_NODE, b->h1, H, nullptr, N, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H);
     // --- projections of the new h / new h_bond for the position update
-    gemm(b, s, h_out, H, nullptr, N, L.n2, b->PNx, 2 * H);
-    gemm(b, s, h_out, H, b->lig_idx, NL, L.l2, b->PLx, 8 * H);
-    gemm(b, s, b->PLx + 2 * H, 8 * H, nullptr, NL, L.q_pe, b->qXe, H, &L.ln_q_pe);
-    gemm(b, s, b->PLx + 7 * H, 8 * H, nullptr, NL, L.q_pb, b->qXb, H, &L.ln_q_pb);
-    gemm(b, s, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);
+    gemm(b, s, PC_GEMM_NODE, h_out, H, nullptr, N, L.n2, b->PNx, 2 * H);
+    gemm(b, s, PC_GEMM_LIG, h_out, H, b->lig_idx, NL, L.l2, b->PLx, 8 * H);
+    gemm(b, s, PC_GEMM_LIG, b->PLx + 2 * H, 8 * H, nullptr, NL, L.q_pe, b->qXe, H, &L.ln_q_pe);
+    gemm(b, s, PC_GEMM_LIG, b->PLx + 7 * H, 8 * H, nullptr, NL, L.q_pb, b->qXb, H, &L.ln_q_pb);
+    gemm(b, s, PC_GEMM_BOND, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);
     // --- position update over kNN edges (ligand destinations only) -> dx_edge
     KnnAttnArgs kp;
     kp.n_dst = NL; kp.dst_list = b->lig_idx; kp.Hi = b->PLx; kp.ldhi = 8 * H; kp.hi_by_slot = 1;
     kp.Hj = b->PNx; kp.ldhj = 2 * H; kp.q = b->qXe; kp.ldq = H; kp.q_by_slot = 1;
     kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
     kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k);
-    launch_knn_attn_k(kp, sms, s);
+    { ProfScope ps(b, s, PC_KNN_POS_K); launch_knn_attn_k(kp, sms, s); }
     kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
-    launch_knn_attn_v_pos(kp, sms, s);
+    { ProfScope ps(b, s, PC_KNN_POS_V); launch_knn_attn_v_pos(kp, sms, s); }
     // --- position update over bond edges + x_out = x_in + (dx_edge + dx_bond) * mask   (:280-285)
     BondAttnArgs bp;
     bp.n_lig = NL; bp.lig_idx = b->lig_idx; bp.in_ptr = b->in_ptr; bp.in_eid = b->in_eid; bp.in_src = b->in_src;
@@ -636,20 +674,21 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     bp.v.Hi = b->PLx + 5 * H; bp.v.Hj = b->PLx + 6 * H; bp.v.Pe = b->PBx + H; bp.v.w = bond_w(m, L.pb_v);
     bp.q = b->qXb; bp.ldq = H; bp.x4 = x_in; bp.wbuf = b->wb_bond; bp.dx_edge = b->dx_edge; bp.upd_mask = b->upd_mask;
     bp.x4_out = x_out;
-    launch_bond_attn_pos(bp, sms, s);
+    { ProfScope ps(b, s, PC_BOND_POS); launch_bond_attn_pos(bp, sms, s); }
     b->launches += 3;
     h_in = h_out; x_in = x_out; hb_in = hb_out;
   }
   b->h_fin = h_in; b->x_fin = x_in; b->hb_fin = hb_in;
   // --- heads (decompdiff.py:315-338)
-  gemm(b, s, b->h_fin, H, b->lig_idx, NL, m->v_head0, b->hid_v, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
-  launch_head_logits(b->hid_v, H, NL, m->p(m->v_W2), m->p(m->v_b2), c.num_classes, b->v_logits, s);
-  gemm(b, s, b->hb_fin, H, nullptr, Eb, m->b_head0, b->qE, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
-  launch_head_logits(b->qE, H, Eb, m->p(m->b_W2), m->p(m->b_b2), c.num_bond_classes, b->b_logits, s);
-  launch_get_ligand_x(b->x_fin, NL, b->lig_idx, b->x0, s);
+  gemm(b, s, PC_HEADS, b->h_fin, H, b->lig_idx, NL, m->v_head0, b->hid_v, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
+  { ProfScope ps(b, s, PC_HEADS); launch_head_logits(b->hid_v, H, NL, m->p(m->v_W2), m->p(m->v_b2), c.num_classes, b->v_logits, s); }
+  gemm(b, s, PC_HEADS, b->hb_fin, H, nullptr, Eb, m->b_head0, b->qE, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
+  { ProfScope ps(b, s, PC_HEADS); launch_head_logits(b->qE, H, Eb, m->p(m->b_W2), m->p(m->b_b2), c.num_bond_classes, b->b_logits, s); }
+  { ProfScope ps(b, s, PC_HEADS); launch_get_ligand_x(b->x_fin, NL, b->lig_idx, b->x0, s); }
   b->launches += 3;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("forward launch: ") + cudaGetErrorString(e));
+  prof_collect(b, s);
   return DDB_OK;
 }
 
@@ -735,7 +774,7 @@ extern "C" int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* strea
     g.num_graphs = b->B; g.n_lig = b->NL; g.lig_ptr = b->lig_ptr; g.x = b->x_lig; g.offset_lig = b->offset_lig; g.grad = b->grad;
     g.enable_armsca = b->enable_armsca; g.decomp_index = b->decomp_index; g.min_d = b->min_d; g.max_d = b->max_d;
     g.enable_clash = b->enable_clash; g.full_pos4 = b->full_pos4; g.full_ptr = b->full_ptr; g.sigma = b->sigma; g.gamma = b->gamma;
-    launch_guidance(g, s);
+    { ProfScope ps(b, s, PC_GUIDANCE); launch_guidance(g, s); }
     b->launches++;
   }
   StepArgs a;
@@ -752,10 +791,11 @@ extern "C" int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* strea
   a.prior_std = io->prior_std_atom; a.u_atom = io->u_atom; a.u_bond = io->u_bond; a.eps = io->eps_pos;
   a.pos_traj = io->pos_traj; a.v_traj = io->v_traj; a.v0_traj = io->v0_traj; a.vt_traj = io->vt_traj;
   a.bond_traj = io->bond_traj; a.bt_traj = io->bt_traj;
-  launch_reverse_step(a, s);
-  launch_advance_time(b->t_dev, s);
+  { ProfScope ps(b, s, PC_REVERSE_STEP); launch_reverse_step(a, s); }
+  { ProfScope ps(b, s, PC_REVERSE_STEP); launch_advance_time(b->t_dev, s); }
   b->launches += 2;
   DDB_CUDA(cudaGetLastError());
+  prof_collect(b, s);
   return DDB_OK;
 }
 
@@ -812,6 +852,20 @@ extern "C" int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, cons
   return DDB_OK;
 }
 
+extern "C" int ddb_batch_profile(ddb_batch* b, int32_t enable, int32_t reset) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  b->profiling = enable != 0;
+  if (reset) for (int i = 0; i < 32; ++i) { b->prof_ms[i] = 0; b->prof_cnt[i] = 0; }
+  return DDB_OK;
+}
+extern "C" int32_t ddb_profile_num_categories(void) { return PC_COUNT; }
+extern "C" const char* ddb_profile_category_name(int32_t i) { return (i >= 0 && i < PC_COUNT) ? kProfNames[i] : ""; }
+extern "C" int ddb_batch_profile_read(const ddb_batch* b, double* ms_out, int64_t* count_out) {
+  if (!b || !ms_out || !count_out) return fail(DDB_ERR_INVALID, "null argument");
+  for (int i = 0; i < PC_COUNT; ++i) { ms_out[i] = b->prof_ms[i]; count_out[i] = b->prof_cnt[i]; }
+  return DDB_OK;
+}
+
 extern "C" int ddb_copy_device(void* dst, const void* src, int64_t bytes, void* stream) {
   if (!dst || !src || bytes < 0) return fail(DDB_ERR_INVALID, "bad copy argument");
   DDB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
@@ -819,3 +873,4 @@ extern "C" int ddb_copy_device(void* dst, const void* src, int64_t bytes, void* 
 }
 
 extern "C" int64_t ddb_batch_last_launch_count(const ddb_batch* b) { return b ? b->launches : 0; }
+extern "C" int64_t ddb_batch_h2d_bytes(const ddb_batch* b) { return b ? b->h2d_bytes : 0; }

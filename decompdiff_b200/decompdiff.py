@@ -247,21 +247,18 @@ class DecompScorePosNet3D(nn.Module):
 
     # -- sampling ----------------------------------------------------------------------------------
     @torch.no_grad()
-    def sample_diffusion(self, protein_pos, protein_v, batch_protein, protein_group_idx,
-                         init_ligand_pos, init_ligand_v, ligand_v_aux, batch_ligand, ligand_group_idx,
-                         prior_centers, prior_stds, prior_num_atoms, batch_prior, prior_group_idx,
-                         ligand_decomp_batch, ligand_decomp_index,
-                         ligand_atom_mask=None,
-                         ligand_fc_bond_index=None, init_ligand_fc_bond_type=None, batch_ligand_bond=None,
-                         num_steps=None, center_pos_mode=None,
-                         energy_drift_opt=None,
-                         full_protein_pos=None, full_batch_protein=None,
-                         noise: Optional[List[Dict[str, torch.Tensor]]] = None, keep_traj: bool = True,
-                         traj_on_device: bool = False):
-        """Reverse diffusion (decompdiff.py:552-703).  Extra keyword arguments beyond the reference:
-        `noise` injects the per-step draws ({'u_atom','u_bond','eps_pos'}, first step first) instead of the
-        torch generator; `keep_traj=False` skips the six per-step trajectories; `traj_on_device=True`
-        returns them as stacked device tensors instead of lists of CPU tensors."""
+    def begin_sampling(self, protein_pos, protein_v, batch_protein, protein_group_idx,
+                       init_ligand_pos, init_ligand_v, ligand_v_aux, batch_ligand, ligand_group_idx,
+                       prior_centers, prior_stds, prior_num_atoms, batch_prior, prior_group_idx,
+                       ligand_decomp_batch, ligand_decomp_index,
+                       ligand_atom_mask=None,
+                       ligand_fc_bond_index=None, init_ligand_fc_bond_type=None, batch_ligand_bond=None,
+                       num_steps=None, center_pos_mode=None,
+                       energy_drift_opt=None,
+                       full_protein_pos=None, full_batch_protein=None,
+                       keep_traj: bool = True) -> 'SamplingRun':
+        """Set a reverse-diffusion run up (everything of `sample_diffusion` before its loop) and return the
+        handle that advances it; `sample_diffusion` = `begin_sampling(...).advance(num_steps)` + `.finish()`."""
         require_cuda()
         if self.model_mean_type != 'C0':
             raise NotImplementedError("model_mean_type 'noise' (N4)") if self.model_mean_type == 'noise' else ValueError
@@ -275,10 +272,10 @@ class DecompScorePosNet3D(nn.Module):
             raise NotImplementedError          # center_pos (:20-32)
         T = self.num_timesteps
         num_steps = T if num_steps is None else int(num_steps)
-        out_dev = init_ligand_pos.device
+        if not 0 <= num_steps <= T:
+            raise ValueError('num_steps must be in [0, num_diffusion_timesteps]')
         eb = self._new_batch(protein_pos, protein_v, batch_protein, batch_ligand, ligand_v_aux,
                              ligand_fc_bond_index, ligand_atom_mask, center_mode)
-        dev = eb.device
         armsca = clash = None
         for drift in (energy_drift_opt or []):
             if drift['type'] == 'armsca_prox':
@@ -295,57 +292,121 @@ class DecompScorePosNet3D(nn.Module):
             eb.set_guidance(armsca, clash)
         eb.set_state(init_ligand_pos, init_ligand_v, init_ligand_fc_bond_type)
         eb.set_time(T - 1)
-        n, Eb, Cn, Cb = eb.n_ligand, eb.n_bonds, self.num_classes, self.num_bond_classes
-        prior_std_atom = prior_stds.to(dev, torch.float32)[ligand_decomp_batch.to(dev)].contiguous()
-        u_atom = torch.empty(n, Cn, device=dev)
-        u_bond = torch.empty(Eb, Cb, device=dev)
-        eps = torch.empty(n, 3, device=dev)
+        prior_std_atom = prior_stds.to(eb.device, torch.float32)[ligand_decomp_batch.to(eb.device)].contiguous()
+        return SamplingRun(self, eb, prior_std_atom, num_steps, keep_traj, init_ligand_pos.device)
+
+    @torch.no_grad()
+    def sample_diffusion(self, protein_pos, protein_v, batch_protein, protein_group_idx,
+                         init_ligand_pos, init_ligand_v, ligand_v_aux, batch_ligand, ligand_group_idx,
+                         prior_centers, prior_stds, prior_num_atoms, batch_prior, prior_group_idx,
+                         ligand_decomp_batch, ligand_decomp_index,
+                         ligand_atom_mask=None,
+                         ligand_fc_bond_index=None, init_ligand_fc_bond_type=None, batch_ligand_bond=None,
+                         num_steps=None, center_pos_mode=None,
+                         energy_drift_opt=None,
+                         full_protein_pos=None, full_batch_protein=None,
+                         noise: Optional[List[Dict[str, torch.Tensor]]] = None, keep_traj: bool = True,
+                         traj_on_device: bool = False):
+        """Reverse diffusion (decompdiff.py:552-703).  Extra keyword arguments beyond the reference:
+        `noise` injects the per-step draws ({'u_atom','u_bond','eps_pos'}, first step first) instead of the
+        torch generator; `keep_traj=False` skips the six per-step trajectories; `traj_on_device=True`
+        returns them as stacked device tensors instead of lists of CPU tensors."""
+        run = self.begin_sampling(
+            protein_pos, protein_v, batch_protein, protein_group_idx, init_ligand_pos, init_ligand_v, ligand_v_aux,
+            batch_ligand, ligand_group_idx, prior_centers, prior_stds, prior_num_atoms, batch_prior, prior_group_idx,
+            ligand_decomp_batch, ligand_decomp_index, ligand_atom_mask, ligand_fc_bond_index, init_ligand_fc_bond_type,
+            batch_ligand_bond, num_steps, center_pos_mode, energy_drift_opt, full_protein_pos, full_batch_protein,
+            keep_traj)
+        run.advance(run.num_steps, noise=noise)
+        return run.finish(traj_on_device=traj_on_device)
+
+
+class SamplingRun:
+    """The loop of `sample_diffusion` (decompdiff.py:576-689) as a resumable object.
+
+    One step = the three noise draws of the reference (torch generator, its order) + one `ddb_reverse_step`
+    (~140 kernels of the library).  After one eager step the step is captured into a CUDA graph and replayed;
+    the time index and the trajectory slot live on the device, so the same graph serves every step."""
+
+    def __init__(self, model: DecompScorePosNet3D, eb: EngineBatch, prior_std_atom, num_steps, keep_traj, out_device):
+        self.model, self.eb, self.num_steps, self.keep_traj, self.out_device = model, eb, num_steps, keep_traj, out_device
+        dev = eb.device
+        n, Eb, Cn, Cb = eb.n_ligand, eb.n_bonds, model.num_classes, model.num_bond_classes
+        self.prior_std_atom = prior_std_atom
+        self.u_atom = torch.empty(n, Cn, device=dev)
+        self.u_bond = torch.empty(Eb, Cb, device=dev)
+        self.eps = torch.empty(n, 3, device=dev)
         S = num_steps
-        traj = {}
+        self.traj = {}
         if keep_traj:
-            traj = dict(pos_traj=torch.empty(S, n, 3, device=dev), v_traj=torch.empty(S, n, dtype=torch.int64, device=dev),
-                        v0_traj=torch.empty(S, n, Cn, device=dev), vt_traj=torch.empty(S, n, Cn, device=dev),
-                        bond_traj=torch.empty(S, Eb, dtype=torch.int64, device=dev), bt_traj=torch.empty(S, Eb, Cb, device=dev))
-        io = _lib.StepIO(prior_std_atom=prior_std_atom.data_ptr(), u_atom=u_atom.data_ptr(), u_bond=u_bond.data_ptr(),
-                         eps_pos=eps.data_ptr(),
-                         **{k: (traj[k].data_ptr() if keep_traj else None) for k in
-                            ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj', 'bond_traj', 'bt_traj')})
+            self.traj = dict(
+                pos_traj=torch.empty(S, n, 3, device=dev), v_traj=torch.empty(S, n, dtype=torch.int64, device=dev),
+                v0_traj=torch.empty(S, n, Cn, device=dev), vt_traj=torch.empty(S, n, Cn, device=dev),
+                bond_traj=torch.empty(S, Eb, dtype=torch.int64, device=dev), bt_traj=torch.empty(S, Eb, Cb, device=dev))
+        self.io = _lib.StepIO(
+            prior_std_atom=prior_std_atom.data_ptr(), u_atom=self.u_atom.data_ptr(), u_bond=self.u_bond.data_ptr(),
+            eps_pos=self.eps.data_ptr(),
+            **{k: (self.traj[k].data_ptr() if keep_traj else None) for k in
+               ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj', 'bond_traj', 'bt_traj')})
+        self.done = 0
+        self.graph = None
 
-        def draw():
-            # the three draws of the reference, same order / shapes / generator
-            # (transitions.py:79 via decompdiff.py:620 and :633, then :680)
-            u_atom.uniform_()
-            u_bond.uniform_()
-            eps.normal_()
+    def _draw(self):
+        # the three draws of the reference: same order, shapes and generator
+        # (transitions.py:79 via decompdiff.py:620 and :633, then :680)
+        self.u_atom.uniform_()
+        self.u_bond.uniform_()
+        self.eps.normal_()
 
-        if noise is not None:
-            if len(noise) < S:
-                raise ValueError('noise list shorter than num_steps')
-            for s in range(S):
-                u_atom.copy_(noise[s]['u_atom']); u_bond.copy_(noise[s]['u_bond']); eps.copy_(noise[s]['eps_pos'])
-                eb.reverse_step(io)
-        elif self.use_cuda_graph and S >= 4:
-            # one step = 3 RNG kernels + ~135 launches of the library; captured once, replayed S-1 times
-            draw(); eb.reverse_step(io)                    # warm-up step outside capture (lazy inits)
-            torch.cuda.current_stream().synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                draw(); eb.reverse_step(io)
-            for _ in range(S - 1):
-                graph.replay()
+    def step_eager(self, noise=None):
+        if noise is None:
+            self._draw()
         else:
-            for _ in range(S):
-                draw(); eb.reverse_step(io)
-        self.last_launches_per_step = eb.launch_count() + 3
-        pos, v, bond = eb.get_state()
-        result = {'pos': pos.to(out_dev), 'v': v.to(out_dev), 'bond': bond.to(out_dev)}
-        names = {'pos_traj': 'pos_traj', 'v_traj': 'v_traj', 'v0_traj': 'v0_traj', 'vt_traj': 'vt_traj',
-                 'bond_traj': 'bond_traj', 'bt_traj': 'bt_traj'}
-        for key in names:
-            if not keep_traj:
+            self.u_atom.copy_(noise['u_atom']); self.u_bond.copy_(noise['u_bond']); self.eps.copy_(noise['eps_pos'])
+        self.eb.reverse_step(self.io)
+        self.done += 1
+
+    def advance(self, k: int, noise=None):
+        """Run `k` more reverse steps."""
+        if self.done + k > self.num_steps:
+            raise ValueError('advancing past num_steps')
+        if noise is not None:
+            if len(noise) < self.done + k:
+                raise ValueError('noise list shorter than the requested steps')
+            for _ in range(k):
+                self.step_eager(noise[self.done])
+            return self
+        if not self.model.use_cuda_graph or (self.graph is None and k < 4):
+            for _ in range(k):
+                self.step_eager()
+            return self
+        if self.graph is None:
+            self.step_eager()                                # lazy initialisation outside the capture
+            k -= 1
+            torch.cuda.current_stream().synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._draw()
+                self.eb.reverse_step(self.io)
+        for _ in range(k):
+            self.graph.replay()
+        self.done += k
+        return self
+
+    @property
+    def launches_per_step(self) -> int:
+        """library kernels + the three torch RNG kernels of one step"""
+        return self.eb.launch_count() + 3
+
+    def finish(self, traj_on_device: bool = False):
+        pos, v, bond = self.eb.get_state()
+        dev = self.out_device
+        result = {'pos': pos.to(dev), 'v': v.to(dev), 'bond': bond.to(dev)}
+        for key in ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj', 'bond_traj', 'bt_traj'):
+            if not self.keep_traj:
                 result[key] = []
             elif traj_on_device:
-                result[key] = traj[key]
+                result[key] = self.traj[key][:self.done]
             else:   # reference: python lists of per-step CPU tensors (:624-636, :688-689); one D2H per array here
-                result[key] = list(traj[key].cpu().unbind(0))
+                result[key] = list(self.traj[key][:self.done].cpu().unbind(0))
         return result

@@ -152,6 +152,20 @@ class EngineBatch:
     def launch_count(self) -> int:
         return int(_lib.lib().ddb_batch_last_launch_count(self._h))
 
+    def h2d_bytes(self) -> int:
+        return int(_lib.lib().ddb_batch_h2d_bytes(self._h))
+
+    def profile(self, enable: bool, reset: bool = False):
+        _lib.check(_lib.lib().ddb_batch_profile(self._h, int(enable), int(reset)))
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        """{category: {'ms': total device ms, 'count': launches}} accumulated while profiling was enabled."""
+        L = _lib.lib()
+        n = L.ddb_profile_num_categories()
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(L.ddb_batch_profile_read(self._h, ms, cnt))
+        return {L.ddb_profile_category_name(i).decode(): {'ms': ms[i], 'count': int(cnt[i])} for i in range(n) if cnt[i]}
+
     def debug_buffer(self, name: str) -> torch.Tensor:
         """Copy of an internal buffer of the last forward (tests / profiling)."""
         p, r, c = C.c_void_p(), C.c_int64(), C.c_int64()

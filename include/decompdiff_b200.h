@@ -151,10 +151,18 @@ int ddb_gemm128(const float* A, int32_t lda, const float* Wt, int32_t ldw, const
  * name in {"h","x","h_bond","nbr","deg","nlig","e_w","grad"}; rows/cols describe the layout.          */
 int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, const void** ptr,
                            int64_t* rows, int64_t* cols);
+/* Per-kernel device timing of eager (non-captured) forward / reverse-step calls: CUDA events recorded on the launch
+ * stream around every kernel, accumulated per category.  enable=1 makes each call end with a stream synchronise. */
+int ddb_batch_profile(ddb_batch* b, int32_t enable, int32_t reset);
+int32_t ddb_profile_num_categories(void);
+const char* ddb_profile_category_name(int32_t i);
+int ddb_batch_profile_read(const ddb_batch* b, double* ms_out, int64_t* count_out);
 /* stream-ordered device-to-device copy (lets a host language read a debug buffer without its own CUDA binding) */
 int ddb_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
 /* number of kernel launches issued by the last ddb_forward / ddb_reverse_step on this batch    */
 int64_t ddb_batch_last_launch_count(const ddb_batch* b);
+/* bytes copied host->device by ddb_batch_create / ddb_batch_set_guidance for this batch */
+int64_t ddb_batch_h2d_bytes(const ddb_batch* b);
 
 #ifdef __cplusplus
 }

@@ -415,8 +415,7 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
     """DecompScorePosNet3D.sample_diffusion.  `noise` = optional list (one per step, first step
     first) of dicts {'u_atom','u_bond','eps_pos'}; otherwise drawn with torch in the reference's
     order rand(n,8) -> rand(Eb,5) -> randn(n,3) from `generator` (or the global CPU generator)."""
-    tab = {k: v for k, v in sd.items() if v.dim() <= 2 and ('alphas' in k or 'posterior' in k or
-                                                            'prior_probs' in k or 'betas' in k)}
+    tab = sd        # the schedule tables are part of the state_dict (models/common.py:280-283)
     T = cfg['num_diffusion_timesteps']
     num_steps = T if num_steps is None else num_steps
     B = int(batch_protein.max()) + 1
