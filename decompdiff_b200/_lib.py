@@ -66,7 +66,7 @@ def lib():
     L.ddb_reverse_step.argtypes = [vp, C.POINTER(StepIO), vp]
     L.ddb_batch_set_guidance.argtypes = [vp, i32, vp, f32, f32, i32, i64, vp, vp, f32, f32]
     L.ddb_knn_graph.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
-    L.ddb_gemm128.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp]
+    L.ddb_gemm128.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]
     L.ddb_batch_debug_buffer.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]
     L.ddb_copy_device.argtypes = [vp, vp, i64, vp]
     L.ddb_batch_profile.argtypes = [vp, i32, i32]

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -39,7 +40,7 @@ struct Blob {
 struct Mlp2 { size_t gamma, beta, W2, b2; };     // offsets: LayerNorm affine + second Linear (natural layout)
 struct KnnMlpOff { size_t Wg, Wt; Mlp2 m; };
 struct TripOff { size_t Wd, Wc, Wa; Mlp2 m; };
-struct GemmW { size_t Wt, bias; int N; };          // K-major weight (128 x N) + bias (N)
+struct GemmW { size_t Wt, bias, Wtc; int N; };     // K-major weight (128 x N) + bias (N) + tensor-core image (2*128*N)
 
 struct LayerOff {
   GemmW n1, n2, l1, l2, b1, b2, lin;              // node / ligand / bond-edge projection GEMMs, lin_node
@@ -101,6 +102,11 @@ struct Packer {
             m.blob.data[g.Wt + (size_t)k * g.N + b * H + c] = (*w)[(size_t)c * blocks[b].in_dim + blocks[b].col0 + k];
       if (!blocks[b].bias.empty())
         if (auto* bv = get(blocks[b].bias, H)) std::copy(bv->begin(), bv->end(), m.blob.data.begin() + g.bias + b * H);
+    }
+    g.Wtc = m.blob.alloc((size_t)2 * H * g.N);
+    {
+      std::vector<float> wt(m.blob.data.begin() + g.Wt, m.blob.data.begin() + g.Wt + (size_t)H * g.N);
+      pack_gemm_tc(wt.data(), g.N, m.blob.data.data() + g.Wtc);
     }
     return g;
   }
@@ -315,6 +321,7 @@ struct ddb_batch {
   int* decomp_index = nullptr; float* full_pos4 = nullptr; int* full_ptr = nullptr;
   long long launches = 0;
   long long h2d_bytes = 0;
+  bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
   // optional per-kernel timing (CUDA events on the launch stream; eager passes only, never under graph capture)
   bool profiling = false;
   struct ProfEv { int cat; cudaEvent_t a, b; };
@@ -375,6 +382,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
 
   auto* b = new ddb_batch();
   b->m = m; b->B = B; b->N = N; b->NL = NL; b->NP = NP; b->Eb = Eb;
+  if (const char* e = getenv("DDB_GEMM")) b->use_tc = std::string(e) != "simt";
   {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -586,7 +594,7 @@ void gemm(ddb_batch* b, cudaStream_t s, int cat, const float* A, int lda, const 
   g.Wt = m->p(w.Wt); g.ldw = w.N; g.bias = m->p(w.bias);
   g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.c_rows = c_rows; g.M = M; g.N = w.N; g.act = act;
   ProfScope ps(b, s, cat);
-  launch_gemm128(g, s);
+  if (b->use_tc) launch_gemm128_tc(g, m->p(w.Wtc), b->num_sms, s); else launch_gemm128(g, s);
   b->launches++;
 }
 
@@ -826,13 +834,31 @@ extern "C" int ddb_knn_graph(const float* x4, const int32_t* node_ptr, const uin
 }
 
 extern "C" int ddb_gemm128(const float* A, int32_t lda, const float* Wt, int32_t ldw, const float* bias, float* C, int32_t ldc,
-                           int32_t M, int32_t N, int32_t act, void* stream) {
+                           int32_t M, int32_t N, int32_t act, int32_t impl, void* stream) {
   if (!A || !Wt || !C) return fail(DDB_ERR_INVALID, "null argument");
   if (N <= 0 || N % 128 != 0) return fail(DDB_ERR_INVALID, "N must be a positive multiple of 128");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   GemmArgs g;
   g.A = A; g.lda = lda; g.Wt = Wt; g.ldw = ldw; g.bias = bias; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.act = act;
-  launch_gemm128(g, static_cast<cudaStream_t>(stream));
-  DDB_CUDA(cudaGetLastError());
+  if (impl == 0) {
+    launch_gemm128(g, s);
+    DDB_CUDA(cudaGetLastError());
+    return DDB_OK;
+  }
+  // tensor-core path: pack the weight into the kernel's image (host round trip - this entry point is a test seam)
+  std::vector<float> wt((size_t)H * N), packed((size_t)2 * H * N);
+  DDB_CUDA(cudaMemcpy2DAsync(wt.data(), (size_t)N * 4, Wt, (size_t)ldw * 4, (size_t)N * 4, H, cudaMemcpyDeviceToHost, s));
+  DDB_CUDA(cudaStreamSynchronize(s));
+  pack_gemm_tc(wt.data(), N, packed.data());
+  float* d = nullptr;
+  DDB_CUDA(cudaMalloc(&d, packed.size() * 4));
+  DDB_CUDA(cudaMemcpyAsync(d, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, s));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  launch_gemm128_tc(g, d, sms, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("gemm128_tc: ") + cudaGetErrorString(e));
   return DDB_OK;
 }
 

@@ -29,5 +29,8 @@ constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 32, GEMM_THREADS = 256;
 constexpr int GEMM_SMEM = (H * GEMM_BM + 2 * GEMM_BK * GEMM_BN) * 4;   // 64 KB A + 32 KB W stages
 
 void launch_gemm128(const GemmArgs& a, cudaStream_t stream);
+// tcgen05 / TMEM 3xTF32 version (gemm_tc.cu); Wtc = weight packed by pack_gemm_tc (2*128*N floats)
+void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream);
+void pack_gemm_tc(const float* Wt, int N, float* out);
 
 }  // namespace ddb

@@ -143,9 +143,10 @@ int ddb_batch_set_guidance(ddb_batch* b,
 int ddb_knn_graph(const float* x4, const int32_t* node_ptr, const uint8_t* is_ligand,
                   int32_t num_graphs, int32_t n, int32_t k,
                   int32_t* nbr, int32_t* deg, int32_t* nlig, void* stream);
-/* C[M,N] = act(A[M,128] @ Wt[128,N] + bias) fp32 GEMM used for all node / edge projections.   */
+/* C[M,N] = act(A[M,128] @ Wt[128,N] + bias): the GEMM used for all node / edge projections.
+ * impl 0 = fp32 FMA kernel, 1 = tcgen05 / TMEM 3xTF32 kernel (synchronises; test seam).      */
 int ddb_gemm128(const float* A, int32_t lda, const float* Wt, int32_t ldw, const float* bias,
-                float* C, int32_t ldc, int32_t M, int32_t N, int32_t act, void* stream);
+                float* C, int32_t ldc, int32_t M, int32_t N, int32_t act, int32_t impl, void* stream);
 
 /* Introspection for tests / profiling: device pointers to internal buffers of the last forward.
  * name in {"h","x","h_bond","nbr","deg","nlig","e_w","grad"}; rows/cols describe the layout.          */
