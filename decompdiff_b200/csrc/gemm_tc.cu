@@ -28,11 +28,14 @@ constexpr int TC_A_PART = TC_NKB * TC_A_KB;             // 64 KB (hi or lo)
 constexpr int TC_B_KB = TC_BN * TC_KB_BYTES;            // 4 KB per K-block of a B chunk
 constexpr int TC_B_PART = TC_NKB * TC_B_KB;             // 16 KB (hi or lo)
 constexpr int TC_B_CHUNK = 2 * TC_B_PART;               // 32 KB per chunk (hi | lo)
-constexpr int TC_THREADS = 128;
-constexpr int TC_SMEM = 2 * TC_A_PART + 2 * TC_B_CHUNK + 1024 /*alignment slack*/ + 64 /*barriers*/;
+constexpr int TC_THREADS = 256;          // 8 warps stage A; warps 0-3 / 4-7 drain the even / odd accumulator
+constexpr int TC_EPI_LD = 36;            // padded row of the per-warp 32x32 transpose tile (floats)
+constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;   // only one warp group drains at a time
+constexpr int TC_SMEM = 2 * TC_A_PART + 2 * TC_B_CHUNK + TC_EPI_BYTES + 1024 /*alignment slack*/ + 64 /*barriers*/;
 constexpr int TC_TMEM_COLS = 64;        // two 32-column fp32 accumulators
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   uint8_t* sA_hi = smem;
   uint8_t* sA_lo = smem + TC_A_PART;
   uint8_t* sB = smem + 2 * TC_A_PART;                       // 2 buffers x (hi | lo)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * TC_B_CHUNK);
+  float* sEpi = reinterpret_cast<float*>(sB + 2 * TC_B_CHUNK);      // per-warp 32 x 36 transpose tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * TC_B_CHUNK + TC_EPI_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const uint32_t bar_b0 = smem_u32(&bars[0]), bar_b1 = smem_u32(&bars[1]);        // B chunk landed
   const uint32_t bar_m0 = smem_u32(&bars[2]), bar_m1 = smem_u32(&bars[3]);        // MMAs of a chunk retired
@@ -113,23 +117,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
     const bool do_ln = a.ln_gamma != nullptr;
     if (do_ln) { gam = ldg4(a.ln_gamma + lane * 4); bet = ldg4(a.ln_beta + lane * 4); }
     const int kb = lane >> 3, ch = lane & 7;
-    for (int r = warp; r < TC_BM; r += TC_THREADS / 32) {
-      int m = row0 + r;
-      float4 z[1] = {make_float4(0, 0, 0, 0)};
-      if (m < a.M) {
-        int ar = a.a_rows ? a.a_rows[m] : m;
-        z[0] = ld4(a.A + (size_t)ar * a.lda + lane * 4);
-        if (a.A2) {
-          int r2 = a.a2_rows[m];
-          if (r2 >= 0) z[0] = add4(z[0], ld4(a.A2 + (size_t)r2 * a.lda2 + lane * 4));
+    constexpr int ROWS_PER_WARP = TC_BM / (TC_THREADS / 32);
+    for (int rb = 0; rb < ROWS_PER_WARP; rb += 4) {
+      float4 z[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {         // all loads first: 4 rows in flight per warp
+        const int m = row0 + warp * ROWS_PER_WARP + rb + i;
+        z[i] = make_float4(0, 0, 0, 0);
+        if (m < a.M) {
+          int ar = a.a_rows ? a.a_rows[m] : m;
+          z[i] = ld4(a.A + (size_t)ar * a.lda + lane * 4);
+          if (a.A2) {
+            int r2 = a.a2_rows[m];
+            if (r2 >= 0) z[i] = add4(z[i], ld4(a.A2 + (size_t)r2 * a.lda2 + lane * 4));
+          }
         }
-        if (do_ln) ln_relu_rows<1>(z, gam, bet, lane);
       }
-      float4 hi = make_float4(tf32_rna(z[0].x), tf32_rna(z[0].y), tf32_rna(z[0].z), tf32_rna(z[0].w));
-      float4 lo = make_float4(tf32_rna(z[0].x - hi.x), tf32_rna(z[0].y - hi.y), tf32_rna(z[0].z - hi.z), tf32_rna(z[0].w - hi.w));
-      int off = kb * TC_A_KB + r * TC_KB_BYTES + ((ch ^ (r & 7)) << 4);
-      *reinterpret_cast<float4*>(sA_hi + off) = hi;
-      *reinterpret_cast<float4*>(sA_lo + off) = lo;
+      if (do_ln) ln_relu_rows<4>(z, gam, bet, lane);    // rows past M are zeros: LN of zeros is finite, never stored
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = warp * ROWS_PER_WARP + rb + i;
+        float4 hi = make_float4(tf32_rna(z[i].x), tf32_rna(z[i].y), tf32_rna(z[i].z), tf32_rna(z[i].w));
+        float4 lo = make_float4(tf32_rna(z[i].x - hi.x), tf32_rna(z[i].y - hi.y), tf32_rna(z[i].z - hi.z), tf32_rna(z[i].w - hi.w));
+        int off = kb * TC_A_KB + r * TC_KB_BYTES + ((ch ^ (r & 7)) << 4);
+        *reinterpret_cast<float4*>(sA_hi + off) = hi;
+        *reinterpret_cast<float4*>(sA_lo + off) = lo;
+      }
     }
   }
   // generic-proxy writes -> visible to the async proxy (tensor core reads smem through it)
@@ -143,8 +156,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
   const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
 
-  auto epilogue = [&](int c) {          // chunk c -> 32 output columns of this thread's row
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((c & 1) * TC_BN);
+  auto epilogue = [&](int c) {          // chunk c (32 columns) is drained by warps 0-3 (even c) or 4-7 (odd c)
+    if ((warp >> 2) != (c & 1)) return;
+    const int q = warp & 3;             // TMEM lane quadrant this warp may read: lanes 32q .. 32q+31
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c & 1) * TC_BN);
     uint32_t v[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -154,17 +169,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
                    "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const int m = row0 + tid;
-    if (m < a.M) {
-      const int cr = a.c_rows ? a.c_rows[m] : m;
-      const int n0 = (chunk0 + c) * TC_BN;
+    // thread = row -> transpose through a padded smem tile so that 8 lanes write one 128-byte row segment
+    float* tile = sEpi + q * 32 * TC_EPI_LD;
+    __syncwarp();
 #pragma unroll
-      for (int j = 0; j < TC_BN; j += 4) {
-        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        if (a.bias) o = add4(o, ldg4(a.bias + n0 + j));
-        if (a.R) o = add4(o, ld4(a.R + (size_t)cr * a.ldr + n0 + j));
+    for (int j = 0; j < TC_BN; j += 4)
+      st4(tile + lane * TC_EPI_LD + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+    __syncwarp();
+    const int n0 = (chunk0 + c) * TC_BN + (lane & 7) * 4;
+    float4 bias4 = a.bias ? ldg4(a.bias + n0) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rl = it * 4 + (lane >> 3);
+      const int m = row0 + q * 32 + rl;
+      if (m < a.M) {
+        const int cr = a.c_rows ? a.c_rows[m] : m;
+        float4 o = add4(ld4(tile + rl * TC_EPI_LD + (lane & 7) * 4), bias4);
+        if (a.R) o = add4(o, ld4(a.R + (size_t)cr * a.ldr + n0));
         if (a.act == 1) { o.x = ssp(o.x); o.y = ssp(o.y); o.z = ssp(o.z); o.w = ssp(o.w); }
-        st4(a.C + (size_t)cr * a.ldc + n0 + j, o);
+        st4(a.C + (size_t)cr * a.ldc + n0, o);
       }
     }
   };
@@ -222,14 +245,17 @@ void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStr
     attr_set = true;
   }
   const int row_tiles = (a.M + TC_BM - 1) / TC_BM, chunks = a.N / TC_BN;
-  // split the columns over CTAs until the grid has a few waves (A is re-staged per CTA, which is cheap)
-  int nsplit = 1;
-  while (row_tiles * nsplit < 4 * num_sms && nsplit < chunks) {
-    int next = nsplit + 1;
-    while (next < chunks && chunks % next) ++next;
-    nsplit = next;
+  // Split the N chunks over `nsplit` CTAs per row tile.  Cost model in units of one chunk of MMA work: every CTA pays ~4
+  // units to stage its A tile, then chunks/nsplit units; CTAs run in waves of num_sms (1 CTA per SM).
+  int best = 1; double best_cost = 1e30;
+  for (int ns = 1; ns <= chunks; ++ns) {
+    if (chunks % ns) continue;
+    long ctas = (long)row_tiles * ns;
+    double waves = (double)((ctas + num_sms - 1) / num_sms);
+    double cost = waves * (4.0 + (double)chunks / ns);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
-  const int per = (chunks + nsplit - 1) / nsplit;
+  const int per = chunks / best;
   dim3 grid(row_tiles, (chunks + per - 1) / per);
   gemm128_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(a, Wtc, per);
 }
