@@ -264,14 +264,16 @@ def main():
 
     # ---------------------------------------------------------------- per-kernel device time (roofline)
     peak_gbs, peak_src = measured_peaks()
-    kernels, roof = [], None
+    kernels, roof, prof_raw = [], None, None
     if not args.no_profile and rank == 0:
         prof_steps = 3
         run.eb.profile(True, reset=True)
         for _ in range(prof_steps):
             run.step_eager()
         run.eb.profile(False)
-        kernels, prof_total = kernel_report(run.eb.profile_read(), cnt, model.config.num_layers, peak_gbs, prof_steps)
+        prof_raw = run.eb.profile_read()
+        kernels, prof_total = kernel_report(prof_raw, cnt, model.config.num_layers, peak_gbs, prof_steps)
+        prof_raw = {k: {'ms_per_step': round(v['ms'] / prof_steps, 4), 'launches_per_step': v['count'] / prof_steps} for k, v in prof_raw.items()}
         egnn = next(k for k in kernels if k['kernel'] == 'knn_edge_attention')
         roof = {'kernel': 'knn_edge_attention (EGNN message+aggregate+coordinate update over kNN edges; 4 launches/layer)',
                 'bound': 'hbm', 'achieved': egnn['achieved_gbs'], 'peak': peak_gbs, 'unit': 'GB/s', 'frac': egnn['hbm_frac'],
@@ -335,7 +337,7 @@ def main():
                        'l2': 'per-step working set ~1.4 GB of activations > 126 MB L2, no explicit flush (steady-state of the loop)',
                        'cuda_graph': True, 'trajectories': 'kept on device, one D2H at the end'},
             'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps), 'launches_per_step': launches_per_step,
-            'clocks': clocks, 'roofline': roof, 'kernels': kernels, 'cpu_baseline': cpu,
+            'clocks': clocks, 'roofline': roof, 'kernels': kernels, 'kernel_categories': prof_raw, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

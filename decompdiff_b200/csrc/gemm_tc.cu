@@ -1,183 +1,160 @@
 // Tensor-core projection GEMM for sm_100a:  C = act(prologue(A)[M,128] @ W[128,N] + bias) (+ R)
-// tcgen05.mma (kind::tf32) with the accumulator in TMEM, operands in 128B-swizzled shared memory.
+// tcgen05.mma (kind::tf32), A operand AND accumulators in TMEM, B (weights) streamed through shared memory.
 //
 // fp32 parity: plain TF32 inputs break the rtol 1e-4 contract, so every product is evaluated as
 // the 3xTF32 split  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi)), three
 // MMAs into the same fp32 accumulator; the dropped a_lo*b_lo term is O(2^-22).
 //
-// Structure (one CTA per 128-row tile x a slice of the N columns):
-//   * all threads stage the A tile once: full rows (gather / add / LayerNorm+ReLU prologue), split hi/lo, written
-//     K-major into 4 K-blocks of [128 rows x 128 B] with the 128B swizzle the UMMA descriptor expects
-//   * B (weights) is pre-split and pre-swizzled on the host into 32-column chunks of 32 KB (hi | lo); a chunk is ONE
-//     cp.async.bulk (TMA engine, mbarrier complete_tx), double buffered
-//   * one elected thread issues 48 tcgen05.mma (M128 N32 K8) per chunk and commits to an mbarrier; two 32-column TMEM
-//     accumulators ping-pong so the epilogue of chunk c-1 (tcgen05.ld -> bias/residual/activation -> global) and the
-//     load of chunk c+1 overlap the MMAs of chunk c
+// Structure (one CTA of 16 warps per 128-row tile x a slice of the N columns):
+//   * thread (row r = 32q + lane, channel slice s) of warp w = 4s + q stages 32 channels of one row: gather / add /
+//     LayerNorm+ReLU prologue (row statistics exchanged through smem between the 4 warps of a quadrant), hi/lo split,
+//     tcgen05.st into TMEM (A_hi columns 0..127, A_lo columns 128..255; row -> lane, k -> column)
+//   * B is pre-split and pre-swizzled on the host into 32-column chunks of 32 KB (hi | lo, K-major, 128B swizzle); a chunk
+//     is ONE cp.async.bulk (TMA engine, mbarrier complete_tx) into a 4-stage ring
+//   * one elected thread issues 48 tcgen05.mma (M128 N32 K8, A from TMEM) per chunk and commits to an mbarrier; four
+//     32-column TMEM accumulators rotate, the epilogue of chunk c (tcgen05.ld -> smem transpose -> bias / residual /
+//     activation -> coalesced global stores) is done by the 4 warps of slice c%4 while later chunks are in flight
 #include <cstring>
 
 #include "gemm.cuh"
+#include "tc_common.cuh"
 
 namespace ddb {
 
 constexpr int TC_BM = 128;              // rows per CTA (UMMA M)
 constexpr int TC_BN = 32;               // columns per chunk (UMMA N)
-constexpr int TC_KB_BYTES = 128;        // one swizzle atom row: 32 tf32 along K
-constexpr int TC_NKB = 4;               // K = 128 = 4 K-blocks of 32
-constexpr int TC_A_KB = TC_BM * TC_KB_BYTES;            // 16 KB per K-block of A
-constexpr int TC_A_PART = TC_NKB * TC_A_KB;             // 64 KB (hi or lo)
-constexpr int TC_B_KB = TC_BN * TC_KB_BYTES;            // 4 KB per K-block of a B chunk
-constexpr int TC_B_PART = TC_NKB * TC_B_KB;             // 16 KB (hi or lo)
+constexpr int TC_STAGES = 4;            // B ring depth == accumulator ring depth
+constexpr int TC_B_KB = TC_BN * 128;                    // 4 KB per K-block (32 tf32 along K) of a B chunk
+constexpr int TC_B_PART = 4 * TC_B_KB;                  // 16 KB (hi or lo)
 constexpr int TC_B_CHUNK = 2 * TC_B_PART;               // 32 KB per chunk (hi | lo)
-constexpr int TC_THREADS = 256;          // 8 warps stage A; warps 0-3 / 4-7 drain the even / odd accumulator
-constexpr int TC_EPI_LD = 36;            // padded row of the per-warp 32x32 transpose tile (floats)
-constexpr int TC_EPI_BYTES = 4 * 32 * TC_EPI_LD * 4;   // only one warp group drains at a time
-constexpr int TC_SMEM = 2 * TC_A_PART + 2 * TC_B_CHUNK + TC_EPI_BYTES + 1024 /*alignment slack*/ + 64 /*barriers*/;
-constexpr int TC_TMEM_COLS = 64;        // two 32-column fp32 accumulators
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+constexpr int TC_THREADS = 512;
+constexpr int TC_EPI_LD = 36;                           // padded row of a per-warp 32x32 transpose tile (floats)
+constexpr int TC_EPI_BYTES = 16 * 32 * TC_EPI_LD * 4;   // 72 KB
+constexpr int TC_STAT_BYTES = 128 * 4 * 4;              // LayerNorm partial sums [row][slice]
+constexpr int TC_SMEM = TC_STAGES * TC_B_CHUNK + TC_EPI_BYTES + TC_STAT_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int TC_COL_AHI = 0, TC_COL_ALO = 128, TC_COL_D = 256;   // TMEM column map (512 allocated)
 static_assert(TC_SMEM <= 232448, "shared memory budget");
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  unsigned long long spins = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && ++spins > (1ull << 28)) __trap();     // turn a protocol bug into an error instead of a hang
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO<<16 | SBO<<32 |
-// version 1 <<46 | layout SWIZZLE_128B (2) << 61.  SBO = 1024 B between 8-row groups; LBO is 1 for swizzled K-major.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 __device__ __forceinline__ float ssp(float x) { return (x > 20.f ? x : log1pf(expf(x))) - 0.69314718055994530942f; }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArgs a, const float* __restrict__ Wtc,
                                                                    int chunks_per_cta) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA_hi = smem;
-  uint8_t* sA_lo = smem + TC_A_PART;
-  uint8_t* sB = smem + 2 * TC_A_PART;                       // 2 buffers x (hi | lo)
-  float* sEpi = reinterpret_cast<float*>(sB + 2 * TC_B_CHUNK);      // per-warp 32 x 36 transpose tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 2 * TC_B_CHUNK + TC_EPI_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  const uint32_t bar_b0 = smem_u32(&bars[0]), bar_b1 = smem_u32(&bars[1]);        // B chunk landed
-  const uint32_t bar_m0 = smem_u32(&bars[2]), bar_m1 = smem_u32(&bars[3]);        // MMAs of a chunk retired
+  uint8_t* sB = smem;                                                   // TC_STAGES x (hi | lo)
+  float* sEpi = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_CHUNK);  // per-warp 32 x 36 transpose tiles
+  float* sStat = sEpi + 16 * 32 * TC_EPI_LD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 128 * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, s = warp >> 2;                  // TMEM lane quadrant, channel slice
   const int row0 = blockIdx.x * TC_BM;
   const int chunk0 = blockIdx.y * chunks_per_cta;
   const int n_chunks = min(chunks_per_cta, a.N / TC_BN - chunk0);
+  auto bar_b = [&](int i) { return smem_u32(&bars[i]); };                 // B chunk landed in stage i
+  auto bar_m = [&](int i) { return smem_u32(&bars[TC_STAGES + i]); };     // MMAs into accumulator i retired
 
   if (tid == 0) {
-    mbar_init(bar_b0, 1); mbar_init(bar_b1, 1); mbar_init(bar_m0, 1); mbar_init(bar_m1, 1);
+    for (int i = 0; i < 2 * TC_STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 512); }
+  tc_fence_before();
   __syncthreads();
-  // kick off the first two weight chunks while the A tile is being staged
-  if (tid == 0) {
-    for (int c = 0; c < min(2, n_chunks); ++c) {
-      uint32_t bar = c ? bar_b1 : bar_b0;
-      mbar_expect_tx(bar, TC_B_CHUNK);
-      bulk_g2s(smem_u32(sB + c * TC_B_CHUNK), Wtc + (size_t)(chunk0 + c) * (TC_B_CHUNK / 4), TC_B_CHUNK, bar);
+  tc_fence_after();
+  if (tid == 0) {     // fill the weight ring while the A tile is being staged
+    for (int c = 0; c < min(TC_STAGES, n_chunks); ++c) {
+      mbar_expect_tx(bar_b(c), TC_B_CHUNK);
+      bulk_g2s(smem_u32(sB + c * TC_B_CHUNK), Wtc + (size_t)(chunk0 + c) * (TC_B_CHUNK / 4), TC_B_CHUNK, bar_b(c));
     }
   }
+  const uint32_t tmem_base = *tmem_slot;
 
-  // ---- stage A: one warp per row; lane l owns channels 4l..4l+3 = K-block l>>3, 16-byte chunk l&7 of that block
+  // ---- stage A into TMEM: this thread owns channels [32s, 32s+32) of row 32q + lane
   {
-    float4 gam = make_float4(1, 1, 1, 1), bet = make_float4(0, 0, 0, 0);
-    const bool do_ln = a.ln_gamma != nullptr;
-    if (do_ln) { gam = ldg4(a.ln_gamma + lane * 4); bet = ldg4(a.ln_beta + lane * 4); }
-    const int kb = lane >> 3, ch = lane & 7;
-    constexpr int ROWS_PER_WARP = TC_BM / (TC_THREADS / 32);
-    for (int rb = 0; rb < ROWS_PER_WARP; rb += 4) {
-      float4 z[4];
+    const int r = q * 32 + lane, m = row0 + r;
+    float z[32];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {         // all loads first: 4 rows in flight per warp
-        const int m = row0 + warp * ROWS_PER_WARP + rb + i;
-        z[i] = make_float4(0, 0, 0, 0);
-        if (m < a.M) {
-          int ar = a.a_rows ? a.a_rows[m] : m;
-          z[i] = ld4(a.A + (size_t)ar * a.lda + lane * 4);
-          if (a.A2) {
-            int r2 = a.a2_rows[m];
-            if (r2 >= 0) z[i] = add4(z[i], ld4(a.A2 + (size_t)r2 * a.lda2 + lane * 4));
-          }
+    for (int i = 0; i < 32; ++i) z[i] = 0.f;
+    if (m < a.M) {
+      const float* src = a.A + (size_t)(a.a_rows ? a.a_rows[m] : m) * a.lda + s * 32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { float4 v = ld4(src + i * 4); z[4 * i] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w; }
+      if (a.A2) {
+        int r2 = a.a2_rows[m];
+        if (r2 >= 0) {
+          const float* s2 = a.A2 + (size_t)r2 * a.lda2 + s * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { float4 v = ld4(s2 + i * 4); z[4 * i] += v.x; z[4 * i + 1] += v.y; z[4 * i + 2] += v.z; z[4 * i + 3] += v.w; }
         }
       }
-      if (do_ln) ln_relu_rows<4>(z, gam, bet, lane);    // rows past M are zeros: LN of zeros is finite, never stored
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = warp * ROWS_PER_WARP + rb + i;
-        float4 hi = make_float4(tf32_rna(z[i].x), tf32_rna(z[i].y), tf32_rna(z[i].z), tf32_rna(z[i].w));
-        float4 lo = make_float4(tf32_rna(z[i].x - hi.x), tf32_rna(z[i].y - hi.y), tf32_rna(z[i].z - hi.z), tf32_rna(z[i].w - hi.w));
-        int off = kb * TC_A_KB + r * TC_KB_BYTES + ((ch ^ (r & 7)) << 4);
-        *reinterpret_cast<float4*>(sA_hi + off) = hi;
-        *reinterpret_cast<float4*>(sA_lo + off) = lo;
-      }
     }
+    if (a.ln_gamma != nullptr) {       // LayerNorm + ReLU over the full row: two-pass statistics via smem
+      float p = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) p += z[i];
+      sStat[r * 4 + s] = p;
+      __syncthreads();
+      float4 t = ld4(sStat + r * 4);
+      const float mu = ((t.x + t.y) + (t.z + t.w)) * (1.0f / H);
+      __syncthreads();
+      p = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { z[i] -= mu; p = fmaf(z[i], z[i], p); }
+      sStat[r * 4 + s] = p;
+      __syncthreads();
+      t = ld4(sStat + r * 4);
+      const float rstd = 1.0f / sqrtf(((t.x + t.y) + (t.z + t.w)) * (1.0f / H) + LN_EPS);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        z[i] = fmaxf(fmaf(z[i] * rstd, __ldg(a.ln_gamma + s * 32 + i), __ldg(a.ln_beta + s * 32 + i)), 0.f);
+    }
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { float h = tf32_rna(z[i]); hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(tf32_rna(z[i] - h)); }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    tmem_st32(lane_addr + TC_COL_AHI + s * 32, hi);
+    tmem_st32(lane_addr + TC_COL_ALO + s * 32, lo);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
-  // generic-proxy writes -> visible to the async proxy (tensor core reads smem through it)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  tc_fence_after();
 
   // instruction descriptor: D=F32, A=B=TF32, both K-major, N=32, M=128 (cute::UMMA::InstrDescriptor)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-  const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo);
 
-  auto epilogue = [&](int c) {          // chunk c (32 columns) is drained by warps 0-3 (even c) or 4-7 (odd c)
-    if ((warp >> 2) != (c & 1)) return;
-    const int q = warp & 3;             // TMEM lane quadrant this warp may read: lanes 32q .. 32q+31
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((c & 1) * TC_BN);
+  auto issue_mma = [&](int c) {         // tid 0 only
+    const int st = c % TC_STAGES;
+    mbar_wait(bar_b(st), (c / TC_STAGES) & 1);
+    tc_fence_after();
+    const uint32_t b_hi = smem_u32(sB + st * TC_B_CHUNK), b_lo = b_hi + TC_B_PART;
+    const uint32_t d = tmem_base + TC_COL_D + st * TC_BN;
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {   // UMMA K = 8 tf32: 8 TMEM columns of A, 32 bytes inside the 128-byte swizzle atom of B
+      const uint32_t bo = (kk >> 2) * TC_B_KB + (kk & 3) * 32;
+      umma_tf32_ts(d, tmem_base + TC_COL_AHI + kk * 8, umma_desc_sw128(b_hi + bo), idesc, kk ? 1u : 0u);
+      umma_tf32_ts(d, tmem_base + TC_COL_ALO + kk * 8, umma_desc_sw128(b_hi + bo), idesc, 1u);
+      umma_tf32_ts(d, tmem_base + TC_COL_AHI + kk * 8, umma_desc_sw128(b_lo + bo), idesc, 1u);
+    }
+    umma_commit(bar_m(st));             // implies tcgen05.fence::before_thread_sync
+  };
+
+  auto epilogue = [&](int c) {          // warps with s == c % 4 drain accumulator c % TC_STAGES (32 columns)
+    const int st = c % TC_STAGES;
+    mbar_wait(bar_m(st), (c / TC_STAGES) & 1);
+    tc_fence_after();
     uint32_t v[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                 : "r"(taddr));
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TC_COL_D + st * TC_BN, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    // thread = row -> transpose through a padded smem tile so that 8 lanes write one 128-byte row segment
-    float* tile = sEpi + q * 32 * TC_EPI_LD;
+    float* tile = sEpi + warp * 32 * TC_EPI_LD;      // thread = row -> transpose so that 8 lanes write one 128-byte segment
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < TC_BN; j += 4)
       st4(tile + lane * TC_EPI_LD + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
     __syncwarp();
     const int n0 = (chunk0 + c) * TC_BN + (lane & 7) * 4;
-    float4 bias4 = a.bias ? ldg4(a.bias + n0) : make_float4(0, 0, 0, 0);
+    const float4 bias4 = a.bias ? ldg4(a.bias + n0) : make_float4(0, 0, 0, 0);
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int rl = it * 4 + (lane >> 3);
@@ -192,49 +169,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
     }
   };
 
-  for (int c = 0; c < n_chunks; ++c) {
-    const int buf = c & 1;
-    if (tid == 0) {
-      mbar_wait(buf ? bar_b1 : bar_b0, (c >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t b_hi = smem_u32(sB + buf * TC_B_CHUNK), b_lo = b_hi + TC_B_PART;
-      const uint32_t d = tmem_base + (uint32_t)(buf * TC_BN);
-#pragma unroll
-      for (int kb = 0; kb < TC_NKB; ++kb) {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {       // UMMA K = 8 tf32 = 32 bytes inside the 128-byte swizzle atom
-          const uint32_t ao = kb * TC_A_KB + ks * 32, bo = kb * TC_B_KB + ks * 32;
-          umma_tf32(d, umma_desc(a_hi + ao), umma_desc(b_hi + bo), idesc, (kb | ks) ? 1u : 0u);
-          umma_tf32(d, umma_desc(a_lo + ao), umma_desc(b_hi + bo), idesc, 1u);
-          umma_tf32(d, umma_desc(a_hi + ao), umma_desc(b_lo + bo), idesc, 1u);
-        }
-      }
-      umma_commit(buf ? bar_m1 : bar_m0);      // implies tcgen05.fence::before_thread_sync
-    }
+  // Software pipeline over chunks.  Iteration c: (tid 0) issue the MMAs of chunk c; slice (c-1)%4's warps drain chunk
+  // c-1; then everybody meets, and stage / accumulator (c-1) % 4 is refilled with chunk c-1+TC_STAGES.
+  for (int c = 0; c <= n_chunks; ++c) {
+    if (tid == 0 && c < n_chunks) issue_mma(c);
     if (c > 0) {
-      const int pb = (c - 1) & 1;
-      mbar_wait(pb ? bar_m1 : bar_m0, ((c - 1) >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      epilogue(c - 1);
-      // accumulator + weight buffer pb are free again: fetch chunk c+1 into it
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (s == ((c - 1) & 3)) epilogue(c - 1);
+      tc_fence_before();
       __syncthreads();
-      if (tid == 0 && c + 1 < n_chunks) {
-        uint32_t bar = pb ? bar_b1 : bar_b0;
-        mbar_expect_tx(bar, TC_B_CHUNK);
-        bulk_g2s(smem_u32(sB + pb * TC_B_CHUNK), Wtc + (size_t)(chunk0 + c + 1) * (TC_B_CHUNK / 4), TC_B_CHUNK, bar);
+      const int nxt = c - 1 + TC_STAGES;
+      if (tid == 0 && nxt < n_chunks) {
+        const int st = (c - 1) % TC_STAGES;
+        mbar_expect_tx(bar_b(st), TC_B_CHUNK);
+        bulk_g2s(smem_u32(sB + st * TC_B_CHUNK), Wtc + (size_t)(chunk0 + nxt) * (TC_B_CHUNK / 4), TC_B_CHUNK, bar_b(st));
       }
     }
   }
-  if (n_chunks > 0) {
-    const int c = n_chunks - 1;
-    mbar_wait((c & 1) ? bar_m1 : bar_m0, (c >> 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    epilogue(c);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS));
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream) {
@@ -245,14 +198,14 @@ void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStr
     attr_set = true;
   }
   const int row_tiles = (a.M + TC_BM - 1) / TC_BM, chunks = a.N / TC_BN;
-  // Split the N chunks over `nsplit` CTAs per row tile.  Cost model in units of one chunk of MMA work: every CTA pays ~4
+  // Split the N chunks over `nsplit` CTAs per row tile.  Cost model in units of one chunk of MMA work: every CTA pays ~3
   // units to stage its A tile, then chunks/nsplit units; CTAs run in waves of num_sms (1 CTA per SM).
   int best = 1; double best_cost = 1e30;
   for (int ns = 1; ns <= chunks; ++ns) {
     if (chunks % ns) continue;
     long ctas = (long)row_tiles * ns;
     double waves = (double)((ctas + num_sms - 1) / num_sms);
-    double cost = waves * (4.0 + (double)chunks / ns);
+    double cost = waves * (3.0 + (double)chunks / ns);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
   const int per = chunks / best;
@@ -262,13 +215,6 @@ void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStr
 
 // host-side packing of a K-major weight Wt[128][N] into the chunked, hi/lo-split, 128B-swizzled image the kernel copies
 void pack_gemm_tc(const float* Wt, int N, float* out /* N*128*2 floats */) {
-  auto rna = [](float x) {
-    uint32_t u; memcpy(&u, &x, 4);
-    if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;
-    u &= 0xffffe000u;
-    float r; memcpy(&r, &u, 4);
-    return r;
-  };
   const int chunks = N / TC_BN;
   for (int c = 0; c < chunks; ++c) {
     float* hi = out + (size_t)c * (TC_B_CHUNK / 4);
@@ -276,11 +222,10 @@ void pack_gemm_tc(const float* Wt, int N, float* out /* N*128*2 floats */) {
     for (int nl = 0; nl < TC_BN; ++nl) {
       for (int k = 0; k < H; ++k) {
         float w = Wt[(size_t)k * N + c * TC_BN + nl];
-        float h = rna(w), l = rna(w - h);
-        int kb = k >> 5, kk = k & 31;
-        int off_bytes = kb * TC_B_KB + nl * TC_KB_BYTES + ((((kk >> 2) ^ (nl & 7))) << 4) + (kk & 3) * 4;
-        hi[off_bytes / 4] = h;
-        lo[off_bytes / 4] = l;
+        float h = host_tf32_rna(w), l = host_tf32_rna(w - h);
+        int off = sw128_offset_bytes(nl, k, TC_BN) / 4;
+        hi[off] = h;
+        lo[off] = l;
       }
     }
   }

@@ -64,7 +64,8 @@ def test_knn_graph_bit_exact(sizes, k):
     nbr = torch.full((n, 32), -1, dtype=torch.int32, device='cuda')
     deg = torch.empty(n, dtype=torch.int32, device='cuda')
     nlig = torch.empty(n, dtype=torch.int32, device='cuda')
-    _lib.check(_lib.lib().ddb_knn_graph(P(x4), P(ptr.cuda()), P(is_lig.to(torch.uint8).cuda()), len(sizes), n, k, P(nbr), P(deg), P(nlig),
+    ptr_d, lig_d = ptr.cuda(), is_lig.to(torch.uint8).cuda()      # keep the device tensors alive across the call
+    _lib.check(_lib.lib().ddb_knn_graph(P(x4), P(ptr_d), P(lig_d), len(sizes), n, k, P(nbr), P(deg), P(nlig),
                                         torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     src, dst = ref_shims.knn_graph(x, k=k, batch=batch)      # oracle: nearest first, ties -> lower index
