@@ -37,7 +37,7 @@ struct Blob {
   }
 };
 
-struct Mlp2 { size_t gamma, beta, W2, b2; };     // offsets: LayerNorm affine + second Linear (natural layout)
+struct Mlp2 { size_t gamma, beta, W2, b2, W2tc; };   // offsets: LayerNorm affine + second Linear (natural layout) + tensor-core image
 struct KnnMlpOff { size_t Wg, Wt; Mlp2 m; };
 struct TripOff { size_t Wd, Wc, Wa; Mlp2 m; };
 struct GemmW { size_t Wt, bias, Wtc; int N; };     // K-major weight (128 x N) + bias (N) + tensor-core image (2*128*N)
@@ -118,6 +118,12 @@ struct Packer {
     if (auto* w = get(pre + ".net.3.weight", (size_t)out_dim * H))
       for (size_t i = 0; i < w->size(); ++i) m.blob.data[r.W2 + i] = (*w)[i] * scale;
     r.b2 = vec(pre + ".net.3.bias", out_dim);
+    r.W2tc = 0;
+    if (out_dim == H) {
+      r.W2tc = m.blob.alloc((size_t)2 * H * H);
+      std::vector<float> w2(m.blob.data.begin() + r.W2, m.blob.data.begin() + r.W2 + (size_t)H * H);
+      pack_w2_tc(w2.data(), m.blob.data.data() + r.W2tc);
+    }
     return r;
   }
   // columns [col0, col0+n) of W1 (128,in_dim) transposed to [n][128]
@@ -322,6 +328,8 @@ struct ddb_batch {
   long long launches = 0;
   long long h2d_bytes = 0;
   bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
+  int tc_attn = 15;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v: tensor-core attention kernels (DDB_TC_ATTN=<mask>)
+  int max_indeg = 0;
   // optional per-kernel timing (CUDA events on the launch stream; eager passes only, never under graph capture)
   bool profiling = false;
   struct ProfEv { int cat; cudaEvent_t a, b; };
@@ -383,6 +391,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   auto* b = new ddb_batch();
   b->m = m; b->B = B; b->N = N; b->NL = NL; b->NP = NP; b->Eb = Eb;
   if (const char* e = getenv("DDB_GEMM")) b->use_tc = std::string(e) != "simt";
+  if (const char* e = getenv("DDB_TC_ATTN")) b->tc_attn = atoi(e);
   {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -471,11 +480,14 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     });
     for (int s = 0; s < Eb; ++s) { in_eid[s] = order[s]; in_src[s] = bsrc[order[s]]; }
   }
+  for (int a = 0; a < NL; ++a) b->max_indeg = std::max(b->max_indeg, in_ptr[a + 1] - in_ptr[a]);
+  if (b->max_indeg > 32) b->tc_attn &= ~3;     // triplet groups of more than 32 rows: fp32 FMA kernels
   long long slots = 0;
   for (int e = 0; e < Eb; ++e) {
     if (slots > 2000000000LL) { ddb_batch_destroy(b); return fail(DDB_ERR_INVALID, "too many bond triplets"); }
     trip_base[e] = (int)slots;
-    slots += in_ptr[bsrc[e] + 1] - in_ptr[bsrc[e]];
+    // rows of a softmax group are 32 apart when the tensor-core kernels may run (they write whole 32-row groups)
+    slots += (b->max_indeg <= 32) ? 32 : (in_ptr[bsrc[e] + 1] - in_ptr[bsrc[e]]);
   }
   b->trip_slots = slots;
   std::vector<uint8_t> upd(NL, 1);
@@ -632,10 +644,10 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     KnnAttnArgs ka;
     ka.n_dst = N; ka.Hi = b->PN; ka.ldhi = 5 * H; ka.Hj = b->PN + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
     ka.x4 = x_in; ka.nbr = b->nbr; ka.deg = b->deg; ka.nlig = b->nlig; ka.is_lig = b->is_lig; ka.e_w = b->e_w;
-    ka.wbuf = b->wb_knn; ka.w = knn_w(m, L.ne_k);
-    { ProfScope ps(b, s, PC_KNN_ATTN_K); launch_knn_attn_k(ka, sms, s); }
-    ka.Hi = b->PN + 2 * H; ka.Hj = b->PN + 3 * H; ka.w = knn_w(m, L.ne_v); ka.out_h = b->h1; ka.ldo = H;
-    { ProfScope ps(b, s, PC_KNN_ATTN_V); launch_knn_attn_v_node(ka, sms, s); }
+    ka.wbuf = b->wb_knn; ka.w = knn_w(m, L.ne_k); ka.W2tc = m->p(L.ne_k.m.W2tc);
+    { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, false, sms, s); else launch_knn_attn_k(ka, sms, s); }
+    ka.Hi = b->PN + 2 * H; ka.Hj = b->PN + 3 * H; ka.w = knn_w(m, L.ne_v); ka.W2tc = m->p(L.ne_v.m.W2tc); ka.out_h = b->h1; ka.ldo = H;
+    { ProfScope ps(b, s, PC_KNN_ATTN_V); if (b->tc_attn & 8) launch_knn_tc(ka, true, sms, s); else launch_knn_attn_v_node(ka, sms, s); }
     // --- node update over bond edges -> h1[ligand rows] +=
     BondAttnArgs ba;
     ba.n_lig = NL; ba.lig_idx = b->lig_idx; ba.in_ptr = b->in_ptr; ba.in_eid = b->in_eid; ba.in_src = b->in_src;
@@ -649,13 +661,13 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
     ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
     ta.k.Pe = b->PB + 2 * H; ta.k.Hk = b->PL + 5 * H; ta.k.Hj = b->PL + 6 * H; ta.k.Wd = m->p(L.bl_k.Wd);
-    ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m);
+    ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m); ta.k.W2tc = m->p(L.bl_k.m.W2tc);
     ta.v.Pe = b->PB + 3 * H; ta.v.Hk = b->PL + 7 * H; ta.v.Hj = b->PL + 8 * H; ta.v.Wd = m->p(L.bl_v.Wd);
-    ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m);
+    ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc);
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
     { ProfScope ps(b, s, PC_TRIP_PREP); launch_trip_prep(ta, s); }
-    { ProfScope ps(b, s, PC_TRIP_K); launch_trip_k(ta, sms, s); }
-    { ProfScope ps(b, s, PC_TRIP_V); launch_trip_v(ta, sms, s); }
+    { ProfScope ps(b, s, PC_TRIP_K); if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, s); else launch_trip_k(ta, sms, s); }
+    { ProfScope ps(b, s, PC_TRIP_V); if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, s); else launch_trip_v(ta, sms, s); }
     b->launches += 6;
     // --- h_out = h_in + lin_node(h1)    (:277)
     gemm(b, s, PC_GEMM_NODE, b->h1, H, nullptr, N, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H);
@@ -670,8 +682,8 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     kp.n_dst = NL; kp.dst_list = b->lig_idx; kp.Hi = b->PLx; kp.ldhi = 8 * H; kp.hi_by_slot = 1;
     kp.Hj = b->PNx; kp.ldhj = 2 * H; kp.q = b->qXe; kp.ldq = H; kp.q_by_slot = 1;
     kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
-    kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k);
-    { ProfScope ps(b, s, PC_KNN_POS_K); launch_knn_attn_k(kp, sms, s); }
+    kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k); kp.W2tc = m->p(L.pe_k.m.W2tc);
+    { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, false, sms, s); else launch_knn_attn_k(kp, sms, s); }
     kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
     { ProfScope ps(b, s, PC_KNN_POS_V); launch_knn_attn_v_pos(kp, sms, s); }
     // --- position update over bond edges + x_out = x_in + (dx_edge + dx_bond) * mask   (:280-285)

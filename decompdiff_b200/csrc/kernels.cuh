@@ -22,6 +22,7 @@ struct KnnMlpW {
   const float* W2;      // second Linear, natural [out][128] layout (k: pre-scaled by 1/sqrt(8))
   const float* b2;      // second Linear bias (unused for k: softmax-invariant)
 };
+struct KnnAttnArgs;
 
 // ---- K2: attention over kNN edges --------------------------------------------------------------
 struct KnnAttnArgs {
@@ -36,6 +37,7 @@ struct KnnAttnArgs {
   const float* e_w = nullptr;         // (N,32) global edge weight
   float* wbuf = nullptr;              // (N*32,16) logits -> alpha * e_w
   KnnMlpW w;
+  const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 for the tensor-core kernels (attn_tc.cu)
   // v pass outputs
   float* out_h = nullptr; int ldo = 0;          // node variant: (N,128) rows by node id
   float* out_dx = nullptr;                      // pos variant: (n_dst,4) by slot
@@ -89,6 +91,7 @@ struct TripSide {
   const float* Wa = nullptr;          // [13][128]  W1[:,168:181]^T  (angular encoding)
   float* P = nullptr;                 // (Eb,128) written by prep, read by the k / v pass
   BondMlpW w;
+  const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 (tensor-core kernels)
 };
 struct TripArgs {
   int n_bonds = 0;
@@ -106,6 +109,11 @@ struct TripArgs {
 void launch_trip_prep(const TripArgs& a, cudaStream_t stream);
 void launch_trip_k(const TripArgs& a, int num_sms, cudaStream_t stream);
 void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
+
+// ---- tensor-core variants (attn_tc.cu): same arguments, wbuf rows of a group are 32 apart; groups of <= 32 rows only
+void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t stream);
+void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
+void pack_w2_tc(const float* W2, float* out);
 
 // ---- embeddings, heads, reverse step, guidance (step.cu) -----------------------------------------
 void launch_embed_ligand(const float* base /*(n,128) W[:,8:10] aux + b, col 127 = 1*/, const float* Wv /*[8][128]*/,
