@@ -21,6 +21,7 @@ namespace ddb {
 
 constexpr int ATC_THREADS = 512;
 constexpr int ATC_W2_BYTES = 2 * 128 * 128 * 4;                       // hi | lo image of W2
+constexpr int ANG_LD = 20;              // padded row of the per-tile angular features (bank-conflict-free float4 reads)
 constexpr int ATC_COL_AHI = 0, ATC_COL_ALO = 128, ATC_COL_D = 256;    // TMEM column map (512 allocated)
 
 __device__ __forceinline__ void quad_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory"); }
@@ -134,6 +135,7 @@ __device__ __forceinline__ float sel4(float4 v, int i) { return i == 0 ? v.x : i
 // common prologue: barrier, TMEM, W2 image -> smem (one bulk copy), returns the TMEM base
 __device__ __forceinline__ uint32_t atc_setup(uint8_t* sW2, const float* W2tc, uint64_t* bars, uint32_t* tmem_slot) {
   const int tid = threadIdx.x, warp = tid >> 5;
+  if ((smem_u32(sW2) & 1023u) != 0u) __trap();      // SWIZZLE_128B operands need a 1024-byte aligned base
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);     // W2 landed
     mbar_init(smem_u32(&bars[1]), 1);     // MMAs of a tile retired
@@ -155,14 +157,15 @@ __device__ __forceinline__ uint32_t atc_setup(uint8_t* sW2, const float* W2tc, u
 struct TripTcSmem {
   uint8_t* W2; float *Wa, *Wc, *gamma, *beta, *b2, *ang, *Q, *qry, *statA, *statB; uint64_t* bars; uint32_t* tmem_slot;
   __device__ explicit TripTcSmem(uint8_t* raw) {
-    uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* p = raw;      // dynamic smem is declared __align__(1024); keeping the pointer arithmetic purely additive
+                           // lets the compiler keep these in the shared address space (LDS/STS instead of generic LD/ST)
     W2 = p; p += ATC_W2_BYTES;
     Wa = reinterpret_cast<float*>(p); p += 16 * H * 4;
     Wc = reinterpret_cast<float*>(p); p += NG * H * 4;
     gamma = reinterpret_cast<float*>(p); p += H * 4;
     beta = reinterpret_cast<float*>(p); p += H * 4;
     b2 = reinterpret_cast<float*>(p); p += H * 4;
-    ang = reinterpret_cast<float*>(p); p += 128 * 16 * 4;
+    ang = reinterpret_cast<float*>(p); p += 128 * ANG_LD * 4;
     Q = reinterpret_cast<float*>(p); p += 4 * H * 4;
     qry = reinterpret_cast<float*>(p); p += 2 * 4 * H * 4;
     statA = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
@@ -171,13 +174,13 @@ struct TripTcSmem {
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
   static constexpr int bytes() {
-    return 1024 + ATC_W2_BYTES + (16 * H + NG * H + 3 * H + 128 * 16 + 4 * H + 8 * H + 2 * 128 * 4) * 4 + 64;
+    return ATC_W2_BYTES + (16 * H + NG * H + 3 * H + 128 * ANG_LD + 4 * H + 8 * H + 2 * 128 * 4) * 4 + 64;
   }
 };
 
 template <bool VPASS>
 __global__ void __launch_bounds__(ATC_THREADS, 1) trip_tc_kernel(const TripArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   TripTcSmem sm(smem_raw);
   const TripSide& side = VPASS ? a.v : a.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = warp >> 2, r = q * 32 + lane;
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) trip_tc_kernel(const TripArgs 
         float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
         th = atan2f(sqrtf(cx * cx + cy * cy + cz * cz), ax * bx + ay * by + az * bz);
       }
-      float* o = sm.ang + r * 16;
+      float* o = sm.ang + r * ANG_LD;
       float sv, cv;
       if (s == 0) { sincosf(th, &sv, &cv); o[0] = th; o[1] = sv; o[4] = sv; o[7] = cv; o[10] = cv; }
       else if (s == 1) { sincosf(th * 2.f, &sv, &cv); o[2] = sv; o[8] = cv; }
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) trip_tc_kernel(const TripArgs 
       }
       float an[16];
 #pragma unroll
-      for (int i4 = 0; i4 < 4; ++i4) { float4 t = ld4(sm.ang + r * 16 + i4 * 4); an[i4 * 4] = t.x; an[i4 * 4 + 1] = t.y; an[i4 * 4 + 2] = t.z; an[i4 * 4 + 3] = t.w; }
+      for (int i4 = 0; i4 < 4; ++i4) { float4 t = ld4(sm.ang + r * ANG_LD + i4 * 4); an[i4 * 4] = t.x; an[i4 * 4 + 1] = t.y; an[i4 * 4 + 2] = t.z; an[i4 * 4 + 3] = t.w; }
 #pragma unroll
       for (int aa = 0; aa < NANG; ++aa) {
 #pragma unroll
@@ -323,7 +326,7 @@ void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t str
 struct KnnTcSmem {
   uint8_t* W2; float *Wg, *Wt, *gamma, *beta, *b2, *G, *Hi, *qry, *statA, *statB; uint64_t* bars; uint32_t* tmem_slot;
   __device__ explicit KnnTcSmem(uint8_t* raw) {
-    uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* p = raw;
     W2 = p; p += ATC_W2_BYTES;
     Wg = reinterpret_cast<float*>(p); p += 4 * NG * H * 4;
     Wt = reinterpret_cast<float*>(p); p += 4 * H * 4;
@@ -339,14 +342,14 @@ struct KnnTcSmem {
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
   static constexpr int bytes() {
-    return 1024 + ATC_W2_BYTES + (4 * NG * H + 4 * H + 3 * H + 128 * NG + 4 * H + 8 * H + 2 * 128 * 4) * 4 + 64;
+    return ATC_W2_BYTES + (4 * NG * H + 4 * H + 3 * H + 128 * NG + 4 * H + 8 * H + 2 * 128 * 4) * 4 + 64;
   }
 };
 static_assert(KnnTcSmem::bytes() <= 232448 && TripTcSmem::bytes() <= 232448, "shared memory budget");
 
 template <bool VPASS>
 __global__ void __launch_bounds__(ATC_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   KnnTcSmem sm(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = warp >> 2, r = q * 32 + lane;
   const uint32_t tmem_base = atc_setup(sm.W2, a.W2tc, sm.bars, sm.tmem_slot);

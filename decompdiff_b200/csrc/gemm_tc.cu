@@ -39,9 +39,8 @@ __device__ __forceinline__ float ssp(float x) { return (x > 20.f ? x : log1pf(ex
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArgs a, const float* __restrict__ Wtc,
                                                                    int chunks_per_cta) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;                                                   // TC_STAGES x (hi | lo)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* sB = smem_raw;                                                  // TC_STAGES x (hi | lo)
   float* sEpi = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_CHUNK);  // per-warp 32 x 36 transpose tiles
   float* sStat = sEpi + 16 * 32 * TC_EPI_LD;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + 128 * 4);
@@ -54,6 +53,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   auto bar_b = [&](int i) { return smem_u32(&bars[i]); };                 // B chunk landed in stage i
   auto bar_m = [&](int i) { return smem_u32(&bars[TC_STAGES + i]); };     // MMAs into accumulator i retired
 
+  if ((smem_u32(sB) & 1023u) != 0u) __trap();      // SWIZZLE_128B operands need a 1024-byte aligned base
   if (tid == 0) {
     for (int i = 0; i < 2 * TC_STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
