@@ -39,7 +39,7 @@ struct Blob {
 
 struct Mlp2 { size_t gamma, beta, W2, b2, W2tc; };   // offsets: LayerNorm affine + second Linear (natural layout) + tensor-core image
 struct KnnMlpOff { size_t Wg, Wt; Mlp2 m; };
-struct TripOff { size_t Wd, Wc, Wa; Mlp2 m; };
+struct TripOff { size_t Wd, Wc, Wa, Watc; Mlp2 m; };
 struct GemmW { size_t Wt, bias, Wtc; int N; };     // K-major weight (128 x N) + bias (N) + tensor-core image (2*128*N)
 
 struct LayerOff {
@@ -146,6 +146,11 @@ struct Packer {
     r.Wd = cols_t(pre + ".net.0.weight", 437, 128, NG);
     r.Wc = cols_t(pre + ".net.0.weight", 437, 148, NG);
     r.Wa = cols_t(pre + ".net.0.weight", 437, 168, NANG);
+    r.Watc = m.blob.alloc((size_t)2 * 128 * 32);
+    {
+      std::vector<float> wa(m.blob.data.begin() + r.Wa, m.blob.data.begin() + r.Wa + (size_t)NANG * H);
+      pack_wa_tc(wa.data(), m.blob.data.data() + r.Watc);
+    }
     r.m = mlp2(pre, H, scale);
     return r;
   }
@@ -309,6 +314,7 @@ struct ddb_batch {
   int *node_ptr = nullptr, *graph_of = nullptr, *lig_idx = nullptr, *lig_ptr = nullptr;
   uint8_t *is_lig = nullptr, *upd_mask = nullptr;
   int *bsrc = nullptr, *bdst = nullptr, *in_ptr = nullptr, *in_eid = nullptr, *in_src = nullptr, *trip_base = nullptr;
+  int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr;
   float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
   // evolving state
   float* x_lig = nullptr; int64_t* v = nullptr; int64_t* bond = nullptr; bool has_state = false;
@@ -490,6 +496,18 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     slots += (b->max_indeg <= 32) ? 32 : (in_ptr[bsrc[e] + 1] - in_ptr[bsrc[e]]);
   }
   b->trip_slots = slots;
+  if (b->max_indeg <= 32) {      // static per-row metadata of the tensor-core triplet kernels
+    std::vector<int2> row_meta((size_t)Eb * 32, make_int2(-1, -1)), grp_meta(Eb);
+    for (int e = 0; e < Eb; ++e) {
+      const int j = bsrc[e], i = bdst[e];
+      grp_meta[e] = make_int2(lig_idx[i], lig_idx[j]);
+      for (int p = in_ptr[j]; p < in_ptr[j + 1]; ++p) {
+        const int k = in_src[p];
+        row_meta[(size_t)e * 32 + (p - in_ptr[j])] = make_int2(in_eid[p], k == i ? -1 : lig_idx[k]);
+      }
+    }
+    DDB_TRY(b->upload(&b->trip_row_meta, row_meta)); DDB_TRY(b->upload(&b->trip_grp_meta, grp_meta));
+  }
   std::vector<uint8_t> upd(NL, 1);
   if (ligand_atom_mask) for (int i = 0; i < NL; ++i) upd[i] = ligand_atom_mask[i] ? 1 : 0;
 
@@ -659,11 +677,11 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     // --- bond update over triplets -> hb_out
     TripArgs ta;
     ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
-    ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
+    ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.row_meta = b->trip_row_meta; ta.grp_meta = b->trip_grp_meta; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
     ta.k.Pe = b->PB + 2 * H; ta.k.Hk = b->PL + 5 * H; ta.k.Hj = b->PL + 6 * H; ta.k.Wd = m->p(L.bl_k.Wd);
-    ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m); ta.k.W2tc = m->p(L.bl_k.m.W2tc);
+    ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m); ta.k.W2tc = m->p(L.bl_k.m.W2tc); ta.k.Watc = m->p(L.bl_k.Watc);
     ta.v.Pe = b->PB + 3 * H; ta.v.Hk = b->PL + 7 * H; ta.v.Hj = b->PL + 8 * H; ta.v.Wd = m->p(L.bl_v.Wd);
-    ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc);
+    ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc); ta.v.Watc = m->p(L.bl_v.Watc);
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
     { ProfScope ps(b, s, PC_TRIP_PREP); launch_trip_prep(ta, s); }
     { ProfScope ps(b, s, PC_TRIP_K); if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, s); else launch_trip_k(ta, sms, s); }

@@ -1,0 +1,218 @@
+// Tensor-core bond update over triplets k->j->i (BondUpdateLayer, uni_transformer_edge.py:125-167); structure in attn_tc.cuh.
+// Two GEMMs per 128-row tile run on tcgen05:
+//   D2 = Ang[128 x 16] * Wa^T      the angular-feature term of the first Linear (A2 / B2 in 128B-swizzled smem, SS form)
+//   D  = a[128 x 128]  * W2^T      the second Linear on the hidden activations (A in TMEM, TS form)
+// so the SIMT side of a row is: gather P[kj] + Q[ji] + D2, LayerNorm, ReLU, TF32 split, and the thread-local epilogue.
+#include "attn_tc.cuh"
+
+namespace ddb {
+
+constexpr int TT_A2_BYTES = 2 * 128 * 128;        // hi | lo, [128 rows][128 B] each (16 tf32 used per row)
+constexpr int TT_COL_D2 = 384;
+
+struct TripTcSmem {
+  uint8_t *W2, *B2, *A2; float *Wc, *gamma, *beta, *b2, *Q, *qry, *statA, *statB; uint64_t* bars; uint32_t* tmem_slot;
+  __device__ explicit TripTcSmem(uint8_t* raw) {
+    uint8_t* p = raw;      // purely additive carving keeps everything in the shared address space (LDS / STS)
+    W2 = p; p += ATC_W2_BYTES;
+    B2 = p; p += TT_A2_BYTES;
+    A2 = p; p += TT_A2_BYTES;
+    Wc = reinterpret_cast<float*>(p); p += NG * H * 4;
+    gamma = reinterpret_cast<float*>(p); p += H * 4;
+    beta = reinterpret_cast<float*>(p); p += H * 4;
+    b2 = reinterpret_cast<float*>(p); p += H * 4;
+    Q = reinterpret_cast<float*>(p); p += 4 * H * 4;
+    qry = reinterpret_cast<float*>(p); p += 2 * 4 * H * 4;
+    statA = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
+    statB = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
+    bars = reinterpret_cast<uint64_t*>(p); p += 32;
+    tmem_slot = reinterpret_cast<uint32_t*>(p);
+  }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (NG * H + 3 * H + 4 * H + 8 * H + 2 * 128 * 4) * 4 + 64; }
+};
+static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
+
+// byte offset of feature k (< 32) of row r inside a [128 rows][128 B] K-major SWIZZLE_128B tile
+__device__ __forceinline__ int a2_off(int r, int k) { return r * 128 + ((((k >> 2) ^ (r & 7))) << 4) + (k & 3) * 4; }
+
+__device__ __forceinline__ void a2_put(uint8_t* A2, int r, int k, float v) {
+  uint32_t hi, lo;
+  tf32_split(v, hi, lo);
+  *reinterpret_cast<uint32_t*>(A2 + a2_off(r, k)) = hi;
+  *reinterpret_cast<uint32_t*>(A2 + TT_A2_BYTES / 2 + a2_off(r, k)) = lo;
+}
+
+template <bool VPASS>
+__device__ __forceinline__ void trip_epilogue(const TripArgs& a, const TripTcSmem& sm, uint32_t tmem_base, int q, int s, int lane,
+                                              int buf, int prev_e, bool prev_ok, int prev_nvalid) {
+  if (!VPASS) {
+    float4 w4 = atc_logits_softmax(tmem_base, q, s, sm.qry + (buf * 4 + q) * H, prev_ok);
+    if (prev_e >= 0) st4(a.wbuf + ((size_t)a.trip_base[prev_e] + lane) * NH + s * 4, w4);
+  } else {
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (prev_ok) w4 = ld4(a.wbuf + ((size_t)a.trip_base[prev_e] + lane) * NH + s * 4);
+    float tot = atc_weighted_colsum(tmem_base, q, s, lane, w4);
+    if (prev_e >= 0) {
+      const int c = s * 32 + lane;
+      float upd = prev_nvalid > 0 ? tot + sm.b2[c] : 0.f;
+      a.h_bond_out[(size_t)prev_e * H + c] = a.h_bond_in[(size_t)prev_e * H + c] + upd;      // :274
+    }
+  }
+}
+
+template <bool VPASS>
+__global__ void __launch_bounds__(ATC_THREADS, 1) trip_tc_kernel(const TripArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TripTcSmem sm(smem_raw);
+  const TripSide& side = VPASS ? a.v : a.k;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = warp >> 2, r = q * 32 + lane;
+  // barriers: [0] weights landed, [1] main MMA retired, [2] angular MMA retired
+  if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
+  if (tid == 0) {
+    mbar_init(smem_u32(&sm.bars[0]), 1); mbar_init(smem_u32(&sm.bars[1]), 1); mbar_init(smem_u32(&sm.bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t bar = smem_u32(&sm.bars[0]);
+    mbar_expect_tx(bar, ATC_W2_BYTES + TT_A2_BYTES);
+    bulk_g2s(smem_u32(sm.W2), side.W2tc, ATC_W2_BYTES / 2, bar);
+    bulk_g2s(smem_u32(sm.W2) + ATC_W2_BYTES / 2, side.W2tc + ATC_W2_BYTES / 8, ATC_W2_BYTES / 2, bar);
+    bulk_g2s(smem_u32(sm.B2), side.Watc, TT_A2_BYTES, bar);
+  }
+  const uint32_t tmem_base = *sm.tmem_slot;
+  cta_copy_f4(sm.Wc, side.Wc, NG * H);
+  cta_copy_f4(sm.gamma, side.w.gamma, H);
+  cta_copy_f4(sm.beta, side.w.beta, H);
+  cta_copy_f4(sm.b2, side.w.b2, H);
+  // rows of A2 are 128 bytes but only 16 features are used: clear both images once (features 13..31 stay zero)
+  for (int i = tid * 16; i < TT_A2_BYTES; i += ATC_THREADS * 16) *reinterpret_cast<float4*>(sm.A2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  mbar_wait(smem_u32(&sm.bars[0]), 0);
+  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]);
+  const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  const int n_tiles = (a.n_bonds + 3) / 4;
+  int it = 0;
+  int prev_e = -1; bool prev_ok = false; int prev_nvalid = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    // ---- P0: geometry of this row (static metadata: one load each), angular features -> A2, per-group Q and query
+    const int e = tile * 4 + q;
+    const bool gvalid = e < a.n_bonds;
+    int2 gm = make_int2(0, 0), rm = make_int2(-1, -1);
+    if (gvalid) { gm = __ldg(a.grp_meta + e); rm = __ldg(a.row_meta + (size_t)e * 32 + lane); }
+    const bool rvalid = rm.x >= 0, rowok = rm.y >= 0;          // rowok: valid and k != i (:117-118)
+    const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
+    {
+      float th = 0.f;
+      if (rowok) {
+        const float4 xk = ldg4(a.x4 + (size_t)rm.y * 4);
+        float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
+        float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+        th = atan2f(sqrtf(cx * cx + cy * cy + cz * cz), ax * bx + ay * by + az * bz);      // :133-137
+      }
+      // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3]; the 5 distinct sin/cos pairs are split
+      // over the 4 slice-warps of the row
+      float sv, cv;
+      if (s == 0) { sincosf(th, &sv, &cv); a2_put(sm.A2, r, 0, th); a2_put(sm.A2, r, 1, sv); a2_put(sm.A2, r, 4, sv); a2_put(sm.A2, r, 7, cv); a2_put(sm.A2, r, 10, cv); }
+      else if (s == 1) { sincosf(th * 2.f, &sv, &cv); a2_put(sm.A2, r, 2, sv); a2_put(sm.A2, r, 8, cv); }
+      else if (s == 2) { sincosf(th * 3.f, &sv, &cv); a2_put(sm.A2, r, 3, sv); a2_put(sm.A2, r, 9, cv); }
+      else {
+        sincosf(th * 0.5f, &sv, &cv); a2_put(sm.A2, r, 5, sv); a2_put(sm.A2, r, 11, cv);
+        sincosf(th * (float)(1.0 / 3.0), &sv, &cv); a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
+      }
+      float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      float d = sqrtf(dx * dx + dy * dy + dz * dz);
+      float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
+      float qv = 0.f;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) qv = fmaf(__shfl_sync(FULL, gl, g), sm.Wc[g * H + s * 32 + lane], qv);
+      sm.Q[q * H + s * 32 + lane] = qv;
+      if (!VPASS) sm.qry[((it & 1) * 4 + q) * H + s * 32 + lane] = gvalid ? __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane) : 0.f;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {        // K = 16 features: two k-steps of 8 inside the first 64 bytes of the rows
+        umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, ks ? 1u : 0u);
+        umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + TT_A2_BYTES / 2 + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, 1u);
+        umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + TT_A2_BYTES / 2 + ks * 32), idesc, 1u);
+      }
+      umma_commit(bar_ang);
+    }
+    // ---- P1: z = P[kj] + Q[ji] + D2, LayerNorm, ReLU
+    float z[32];
+    {
+      const float* prow = side.P + (size_t)(rvalid ? rm.x : 0) * H + s * 32;
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        float4 p = rvalid ? ldg4(prow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 qq = ld4(sm.Q + q * H + s * 32 + i4 * 4);
+        z[i4 * 4] = p.x + qq.x; z[i4 * 4 + 1] = p.y + qq.y; z[i4 * 4 + 2] = p.z + qq.z; z[i4 * 4 + 3] = p.w + qq.w;
+      }
+      mbar_wait(bar_ang, it & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TT_COL_D2 + s * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) z[i] += __uint_as_float(v[i]);
+    }
+    atc_ln_relu(z, sm.statA, sm.statB, r, s, q, sm.gamma, sm.beta);
+    // ---- epilogue of the previous tile (its main MMA has had this tile's P0/P1 to finish)
+    if (it > 0) {
+      mbar_wait(bar_mma, (it - 1) & 1);
+      tc_fence_after();
+      trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 1, prev_e, prev_ok, prev_nvalid);
+    }
+    // ---- P2: hidden activations -> TMEM, main MMA
+    atc_store_and_mma(z, rowok, tmem_base, q, s, w2_smem, bar_mma);
+    prev_e = gvalid ? e : -1; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok));
+  }
+  if (it > 0) {
+    mbar_wait(bar_mma, (it - 1) & 1);
+    tc_fence_after();
+    trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 1, prev_e, prev_ok, prev_nvalid);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream) {
+  if (a.n_bonds <= 0) return;
+  static bool once = false;
+  const int bytes = TripTcSmem::bytes();
+  if (!once) {
+    cudaFuncSetAttribute(trip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(trip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    once = true;
+  }
+  const int grid = atc_grid((a.n_bonds + 3) / 4, num_sms);
+  if (vpass) trip_tc_kernel<true><<<grid, ATC_THREADS, bytes, stream>>>(a);
+  else trip_tc_kernel<false><<<grid, ATC_THREADS, bytes, stream>>>(a);
+}
+
+// host-side packing of Wa[13][128] (first-Linear columns of the angular encoding, transposed) into the B operand of the
+// angular MMA: rows n = output channel, K = 16 features (13 used), hi | lo, 128-byte rows with the 128B swizzle
+void pack_wa_tc(const float* Wa, float* out /* 2*128*32 floats */) {
+  for (int i = 0; i < 2 * 128 * 32; ++i) out[i] = 0.f;
+  float* hi = out;
+  float* lo = out + 128 * 32;
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < NANG; ++k) {
+      float w = Wa[k * H + n];
+      float h = host_tf32_rna(w), l = host_tf32_rna(w - h);
+      int off = (n * 128 + ((((k >> 2) ^ (n & 7))) << 4) + (k & 3) * 4) / 4;
+      hi[off] = h; lo[off] = l;
+    }
+}
+
+}  // namespace ddb

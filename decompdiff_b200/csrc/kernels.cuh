@@ -92,6 +92,7 @@ struct TripSide {
   float* P = nullptr;                 // (Eb,128) written by prep, read by the k / v pass
   BondMlpW w;
   const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 (tensor-core kernels)
+  const float* Watc = nullptr;        // hi | lo swizzled image of Wa^T: B operand of the angular-feature MMA
 };
 struct TripArgs {
   int n_bonds = 0;
@@ -99,6 +100,9 @@ struct TripArgs {
   const int* lig_idx = nullptr;
   const int* in_ptr = nullptr; const int* in_eid = nullptr; const int* in_src = nullptr;
   const int* trip_base = nullptr;     // (Eb) offset of edge e's triplet slots in wbuf (one per edge entering src(e))
+  // static row metadata for the tensor-core kernels (groups of <= 32 rows): row_meta[e*32+p] = {edge id k->j or -1,
+  // merged node id of k or -1 when k == i}; grp_meta[e] = {merged node id of i, of j}
+  const int2* row_meta = nullptr; const int2* grp_meta = nullptr;
   const float* x4 = nullptr;
   int ldh = 0, ldpe = 0;
   TripSide k, v;
@@ -114,6 +118,7 @@ void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
 void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t stream);
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
 void pack_w2_tc(const float* W2, float* out);
+void pack_wa_tc(const float* Wa, float* out);
 
 // ---- embeddings, heads, reverse step, guidance (step.cu) -----------------------------------------
 void launch_embed_ligand(const float* base /*(n,128) W[:,8:10] aux + b, col 127 = 1*/, const float* Wv /*[8][128]*/,
