@@ -21,14 +21,14 @@ struct TripTcSmem {
     gamma = reinterpret_cast<float*>(p); p += H * 4;
     beta = reinterpret_cast<float*>(p); p += H * 4;
     b2 = reinterpret_cast<float*>(p); p += H * 4;
-    Q = reinterpret_cast<float*>(p); p += 4 * H * 4;
-    qry = reinterpret_cast<float*>(p); p += 2 * 4 * H * 4;
+    Q = reinterpret_cast<float*>(p); p += 2 * 4 * H * 4;
+    qry = reinterpret_cast<float*>(p); p += 4 * 4 * H * 4;
     statA = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
     statB = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
     bars = reinterpret_cast<uint64_t*>(p); p += 32;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (NG * H + 3 * H + 4 * H + 8 * H + 2 * 128 * 4) * 4 + 64; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (NG * H + 3 * H + 8 * H + 16 * H + 2 * 128 * 4) * 4 + 64; }
 };
 static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -60,12 +60,17 @@ __device__ __forceinline__ void trip_epilogue(const TripArgs& a, const TripTcSme
   }
 }
 
+constexpr int TT_THREADS = ATC_THREADS + 32;     // 16 worker warps + 1 MMA-issuing warp
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+constexpr int BAR_A2_READY = 5, BAR_A_READY = 6;  // named barriers: workers arrive, the issuer warp syncs
+
 template <bool VPASS>
-__global__ void __launch_bounds__(ATC_THREADS, 1) trip_tc_kernel(const TripArgs a) {
+__global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TripTcSmem sm(smem_raw);
   const TripSide& side = VPASS ? a.v : a.k;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = warp >> 2, r = q * 32 + lane;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
   // barriers: [0] weights landed, [1] main MMA retired, [2] angular MMA retired
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
@@ -89,25 +94,58 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) trip_tc_kernel(const TripArgs 
   cta_copy_f4(sm.beta, side.w.beta, H);
   cta_copy_f4(sm.b2, side.w.b2, H);
   // rows of A2 are 128 bytes but only 16 features are used: clear both images once (features 13..31 stay zero)
-  for (int i = tid * 16; i < TT_A2_BYTES; i += ATC_THREADS * 16) *reinterpret_cast<float4*>(sm.A2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid * 16; i < TT_A2_BYTES; i += TT_THREADS * 16) *reinterpret_cast<float4*>(sm.A2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]);
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
   const int n_tiles = (a.n_bonds + 3) / 4;
-  int it = 0;
-  int prev_e = -1; bool prev_ok = false; int prev_nvalid = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    // ---- P0: geometry of this row (static metadata: one load each), angular features -> A2, per-group Q and query
-    const int e = tile * 4 + q;
-    const bool gvalid = e < a.n_bonds;
+
+  if (warp == 16) {
+    // ---------------------------------------------------------------- MMA issuer warp (one elected lane issues)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      named_sync(BAR_A2_READY, TT_THREADS);          // every worker has written its A2 features (and is done with D2)
+      if (lane == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {             // K = 16 features: two k-steps of 8 inside the first 64 bytes of the rows
+          umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, ks ? 1u : 0u);
+          umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + TT_A2_BYTES / 2 + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, 1u);
+          umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + TT_A2_BYTES / 2 + ks * 32), idesc, 1u);
+        }
+        umma_commit(bar_ang);
+      }
+      __syncwarp();
+      named_sync(BAR_A_READY, TT_THREADS);           // hidden activations are in TMEM, D of the previous tile is drained
+      if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- 16 worker warps: thread = (row r, channel slice s)
+    int it = 0;
+    int prev_e = -1; bool prev_ok = false; int prev_nvalid = 0;
     int2 gm = make_int2(0, 0), rm = make_int2(-1, -1);
-    if (gvalid) { gm = __ldg(a.grp_meta + e); rm = __ldg(a.row_meta + (size_t)e * 32 + lane); }
-    const bool rvalid = rm.x >= 0, rowok = rm.y >= 0;          // rowok: valid and k != i (:117-118)
-    const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
     {
+      const int e0 = blockIdx.x * 4 + q;
+      if (blockIdx.x < n_tiles && e0 < a.n_bonds) { gm = __ldg(a.grp_meta + e0); rm = __ldg(a.row_meta + (size_t)e0 * 32 + lane); }
+    }
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int e = tile * 4 + q;
+      const bool gvalid = e < a.n_bonds;
+      const bool rvalid = rm.x >= 0, rowok = rm.y >= 0;          // rowok: valid and k != i (:117-118)
+      // the P row of this thread is requested first so that its latency hides behind the geometry below
+      float z[32];
+      {
+        const float* prow = side.P + (size_t)(rvalid ? rm.x : 0) * H + s * 32;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          float4 p = rvalid ? ldg4(prow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          z[i4 * 4] = p.x; z[i4 * 4 + 1] = p.y; z[i4 * 4 + 2] = p.z; z[i4 * 4 + 3] = p.w;
+        }
+      }
+      // ---- P0: geometry of this row, angular features -> A2, per-group Q and query
+      const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
       float th = 0.f;
       if (rowok) {
         const float4 xk = ldg4(a.x4 + (size_t)rm.y * 4);
@@ -115,71 +153,78 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) trip_tc_kernel(const TripArgs 
         float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
         th = atan2f(sqrtf(cx * cx + cy * cy + cz * cz), ax * bx + ay * by + az * bz);      // :133-137
       }
-      // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3]; the 5 distinct sin/cos pairs are split
-      // over the 4 slice-warps of the row
-      float sv, cv;
-      if (s == 0) { sincosf(th, &sv, &cv); a2_put(sm.A2, r, 0, th); a2_put(sm.A2, r, 1, sv); a2_put(sm.A2, r, 4, sv); a2_put(sm.A2, r, 7, cv); a2_put(sm.A2, r, 10, cv); }
-      else if (s == 1) { sincosf(th * 2.f, &sv, &cv); a2_put(sm.A2, r, 2, sv); a2_put(sm.A2, r, 8, cv); }
-      else if (s == 2) { sincosf(th * 3.f, &sv, &cv); a2_put(sm.A2, r, 3, sv); a2_put(sm.A2, r, 9, cv); }
-      else {
-        sincosf(th * 0.5f, &sv, &cv); a2_put(sm.A2, r, 5, sv); a2_put(sm.A2, r, 11, cv);
-        sincosf(th * (float)(1.0 / 3.0), &sv, &cv); a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
+      // static metadata of the next tile (hides its latency behind this tile)
+      int2 gm_n = make_int2(0, 0), rm_n = make_int2(-1, -1);
+      {
+        const int en = (tile + gridDim.x) * 4 + q;
+        if (tile + gridDim.x < n_tiles && en < a.n_bonds) { gm_n = __ldg(a.grp_meta + en); rm_n = __ldg(a.row_meta + (size_t)en * 32 + lane); }
       }
-      float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-      float d = sqrtf(dx * dx + dy * dy + dz * dz);
-      float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
-      float qv = 0.f;
+      {
+        // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3]; the 5 distinct sin/cos pairs are split
+        // over the 4 slice-warps of the row
+        float sv, cv;
+        if (s == 0) { sincosf(th, &sv, &cv); a2_put(sm.A2, r, 0, th); a2_put(sm.A2, r, 1, sv); a2_put(sm.A2, r, 4, sv); a2_put(sm.A2, r, 7, cv); a2_put(sm.A2, r, 10, cv); }
+        else if (s == 1) { sincosf(th * 2.f, &sv, &cv); a2_put(sm.A2, r, 2, sv); a2_put(sm.A2, r, 8, cv); }
+        else if (s == 2) { sincosf(th * 3.f, &sv, &cv); a2_put(sm.A2, r, 3, sv); a2_put(sm.A2, r, 9, cv); }
+        else {
+          sincosf(th * 0.5f, &sv, &cv); a2_put(sm.A2, r, 5, sv); a2_put(sm.A2, r, 11, cv);
+          sincosf(th * (float)(1.0 / 3.0), &sv, &cv); a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
+        tc_fence_before();
+        named_arrive(BAR_A2_READY, TT_THREADS);
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float d = sqrtf(dx * dx + dy * dy + dz * dz);
+        float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
+        float qv = 0.f;
 #pragma unroll
-      for (int g = 0; g < NG; ++g) qv = fmaf(__shfl_sync(FULL, gl, g), sm.Wc[g * H + s * 32 + lane], qv);
-      sm.Q[q * H + s * 32 + lane] = qv;
-      if (!VPASS) sm.qry[((it & 1) * 4 + q) * H + s * 32 + lane] = gvalid ? __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane) : 0.f;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {        // K = 16 features: two k-steps of 8 inside the first 64 bytes of the rows
-        umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, ks ? 1u : 0u);
-        umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + TT_A2_BYTES / 2 + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, 1u);
-        umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + TT_A2_BYTES / 2 + ks * 32), idesc, 1u);
+        for (int g = 0; g < NG; ++g) qv = fmaf(__shfl_sync(FULL, gl, g), sm.Wc[g * H + s * 32 + lane], qv);
+        sm.Q[((it & 1) * 4 + q) * H + s * 32 + lane] = qv;
+        if (!VPASS) sm.qry[((it & 3) * 4 + q) * H + s * 32 + lane] = gvalid ? __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane) : 0.f;
       }
-      umma_commit(bar_ang);
-    }
-    // ---- P1: z = P[kj] + Q[ji] + D2, LayerNorm, ReLU
-    float z[32];
-    {
-      const float* prow = side.P + (size_t)(rvalid ? rm.x : 0) * H + s * 32;
+      quad_barrier(q);
+      // ---- P1: z = P[kj] + Q[ji] + D2, LayerNorm, ReLU
+      {
 #pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
-        float4 p = rvalid ? ldg4(prow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 qq = ld4(sm.Q + q * H + s * 32 + i4 * 4);
-        z[i4 * 4] = p.x + qq.x; z[i4 * 4 + 1] = p.y + qq.y; z[i4 * 4 + 2] = p.z + qq.z; z[i4 * 4 + 3] = p.w + qq.w;
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 qq = ld4(sm.Q + ((it & 1) * 4 + q) * H + s * 32 + i4 * 4);
+          z[i4 * 4] += qq.x; z[i4 * 4 + 1] += qq.y; z[i4 * 4 + 2] += qq.z; z[i4 * 4 + 3] += qq.w;
+        }
+        mbar_wait(bar_ang, it & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TT_COL_D2 + s * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] += __uint_as_float(v[i]);
       }
-      mbar_wait(bar_ang, it & 1);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TT_COL_D2 + s * 32, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      atc_ln_relu(z, sm.statA, sm.statB, r, s, q, sm.gamma, sm.beta);
+      // ---- epilogue of the previous tile (its main MMA has had this tile's P0/P1 to finish)
+      if (it > 0) {
+        mbar_wait(bar_mma, (it - 1) & 1);
+        tc_fence_after();
+        trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 3, prev_e, prev_ok, prev_nvalid);
+      }
+      // ---- P2: hidden activations -> TMEM; the issuer warp starts the main MMA once every worker has arrived
+      {
+        uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) z[i] += __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) tf32_split(rowok ? z[i] : 0.f, hi[i], lo[i]);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        tmem_st32(lane_addr + ATC_COL_AHI + s * 32, hi);
+        tmem_st32(lane_addr + ATC_COL_ALO + s * 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        named_arrive(BAR_A_READY, TT_THREADS);
+      }
+      prev_e = gvalid ? e : -1; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok));
+      gm = gm_n; rm = rm_n;
     }
-    atc_ln_relu(z, sm.statA, sm.statB, r, s, q, sm.gamma, sm.beta);
-    // ---- epilogue of the previous tile (its main MMA has had this tile's P0/P1 to finish)
     if (it > 0) {
       mbar_wait(bar_mma, (it - 1) & 1);
       tc_fence_after();
-      trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 1, prev_e, prev_ok, prev_nvalid);
+      trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 3, prev_e, prev_ok, prev_nvalid);
     }
-    // ---- P2: hidden activations -> TMEM, main MMA
-    atc_store_and_mma(z, rowok, tmem_base, q, s, w2_smem, bar_mma);
-    prev_e = gvalid ? e : -1; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok));
-  }
-  if (it > 0) {
-    mbar_wait(bar_mma, (it - 1) & 1);
-    tc_fence_after();
-    trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 1, prev_e, prev_ok, prev_nvalid);
   }
   tc_fence_before();
   __syncthreads();
@@ -196,8 +241,8 @@ void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t str
     once = true;
   }
   const int grid = atc_grid((a.n_bonds + 3) / 4, num_sms);
-  if (vpass) trip_tc_kernel<true><<<grid, ATC_THREADS, bytes, stream>>>(a);
-  else trip_tc_kernel<false><<<grid, ATC_THREADS, bytes, stream>>>(a);
+  if (vpass) trip_tc_kernel<true><<<grid, TT_THREADS, bytes, stream>>>(a);
+  else trip_tc_kernel<false><<<grid, TT_THREADS, bytes, stream>>>(a);
 }
 
 // host-side packing of Wa[13][128] (first-Linear columns of the angular encoding, transposed) into the B operand of the
