@@ -323,6 +323,7 @@ struct ddb_batch {
   float *hA = nullptr, *hB = nullptr, *h1 = nullptr, *PN = nullptr, *qN = nullptr, *PNx = nullptr;
   float *PL = nullptr, *qNB = nullptr, *PLx = nullptr, *qXe = nullptr, *qXb = nullptr;
   float *hbA = nullptr, *hbB = nullptr, *PB = nullptr, *qE = nullptr, *Pk = nullptr, *Pv = nullptr, *PBx = nullptr;
+  float *Qk = nullptr, *Qv = nullptr, *Pmk = nullptr, *Pmv = nullptr, *Qmk = nullptr, *Qmv = nullptr;
   float *wb_knn = nullptr, *wb_bond = nullptr, *wb_trip = nullptr, *e_w = nullptr, *dx_edge = nullptr;
   int *nbr = nullptr, *deg = nullptr, *nlig = nullptr;
   float *hid_v = nullptr, *v_logits = nullptr, *b_logits = nullptr, *x0 = nullptr, *grad = nullptr;
@@ -529,6 +530,8 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   DDB_TRY(b->dalloc(&b->hbA, eb * H)); DDB_TRY(b->dalloc(&b->hbB, eb * H)); DDB_TRY(b->dalloc(&b->PB, eb * 5 * H));
   DDB_TRY(b->dalloc(&b->qE, eb * H)); DDB_TRY(b->dalloc(&b->Pk, eb * H)); DDB_TRY(b->dalloc(&b->Pv, eb * H));
   DDB_TRY(b->dalloc(&b->PBx, eb * 2 * H));
+  DDB_TRY(b->dalloc(&b->Qk, eb * H)); DDB_TRY(b->dalloc(&b->Qv, eb * H));
+  DDB_TRY(b->dalloc(&b->Pmk, eb)); DDB_TRY(b->dalloc(&b->Pmv, eb)); DDB_TRY(b->dalloc(&b->Qmk, eb)); DDB_TRY(b->dalloc(&b->Qmv, eb));
   DDB_TRY(b->dalloc(&b->wb_knn, n * KNN * NH)); DDB_TRY(b->dalloc(&b->wb_bond, eb * NH));
   DDB_TRY(b->dalloc(&b->wb_trip, (size_t)slots * NH));
   DDB_TRY(b->dalloc(&b->e_w, n * KNN)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4));
@@ -680,8 +683,10 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.row_meta = b->trip_row_meta; ta.grp_meta = b->trip_grp_meta; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
     ta.k.Pe = b->PB + 2 * H; ta.k.Hk = b->PL + 5 * H; ta.k.Hj = b->PL + 6 * H; ta.k.Wd = m->p(L.bl_k.Wd);
     ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m); ta.k.W2tc = m->p(L.bl_k.m.W2tc); ta.k.Watc = m->p(L.bl_k.Watc);
+    if (b->tc_attn & 1) { ta.k.Q = b->Qk; ta.k.Pm = b->Pmk; ta.k.Qm = b->Qmk; }
     ta.v.Pe = b->PB + 3 * H; ta.v.Hk = b->PL + 7 * H; ta.v.Hj = b->PL + 8 * H; ta.v.Wd = m->p(L.bl_v.Wd);
     ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc); ta.v.Watc = m->p(L.bl_v.Watc);
+    if (b->tc_attn & 2) { ta.v.Q = b->Qv; ta.v.Pm = b->Pmv; ta.v.Qm = b->Qmv; }
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
     { ProfScope ps(b, s, PC_TRIP_PREP); launch_trip_prep(ta, s); }
     { ProfScope ps(b, s, PC_TRIP_K); if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, s); else launch_trip_k(ta, sms, s); }

@@ -254,9 +254,19 @@ __global__ void __launch_bounds__(256) trip_prep_kernel(const TripArgs a) {
     const TripSide& t = side ? a.v : a.k;
     float4 z = add4(add4(ldg4(t.Pe + (size_t)e * a.ldpe + lane * 4), ldg4(t.Hk + (size_t)k * a.ldh + lane * 4)),
                     ldg4(t.Hj + (size_t)j * a.ldh + lane * 4));
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int g = 0; g < NG; ++g) z = fma4(__shfl_sync(FULL, gl, g), ldg4(t.Wd + g * H + lane * 4), z);
+    for (int g = 0; g < NG; ++g) {
+      const float gg = __shfl_sync(FULL, gl, g);
+      z = fma4(gg, ldg4(t.Wd + g * H + lane * 4), z);
+      if (t.Q) qv = fma4(gg, ldg4(t.Wc + g * H + lane * 4), qv);
+    }
     st4(t.P + (size_t)e * H + lane * 4, z);
+    if (t.Q) {      // the same edge seen as j->i: Q = Wc . gauss(d), plus the row means used as LayerNorm shift
+      st4(t.Q + (size_t)e * H + lane * 4, qv);
+      float pm = warp_sum((z.x + z.y) + (z.z + z.w)) * (1.0f / H), qm = warp_sum((qv.x + qv.y) + (qv.z + qv.w)) * (1.0f / H);
+      if (lane == 0) { t.Pm[e] = pm; t.Qm[e] = qm; }
+    }
   }
 }
 

@@ -11,24 +11,21 @@ constexpr int TT_A2_BYTES = 2 * 128 * 128;        // hi | lo, [128 rows][128 B] 
 constexpr int TT_COL_D2 = 384;
 
 struct TripTcSmem {
-  uint8_t *W2, *B2, *A2; float *Wc, *gamma, *beta, *b2, *Q, *qry, *statA, *statB; uint64_t* bars; uint32_t* tmem_slot;
+  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *qry; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
   __device__ explicit TripTcSmem(uint8_t* raw) {
     uint8_t* p = raw;      // purely additive carving keeps everything in the shared address space (LDS / STS)
     W2 = p; p += ATC_W2_BYTES;
     B2 = p; p += TT_A2_BYTES;
     A2 = p; p += TT_A2_BYTES;
-    Wc = reinterpret_cast<float*>(p); p += NG * H * 4;
     gamma = reinterpret_cast<float*>(p); p += H * 4;
     beta = reinterpret_cast<float*>(p); p += H * 4;
     b2 = reinterpret_cast<float*>(p); p += H * 4;
-    Q = reinterpret_cast<float*>(p); p += 2 * 4 * H * 4;
     qry = reinterpret_cast<float*>(p); p += 4 * 4 * H * 4;
-    statA = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
-    statB = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
+    stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][row][slice] {sum, sum of squares}
     bars = reinterpret_cast<uint64_t*>(p); p += 32;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (NG * H + 3 * H + 8 * H + 16 * H + 2 * 128 * 4) * 4 + 64; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 2 * 2 * 128 * 4) * 4 + 64; }
 };
 static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -89,7 +86,6 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     bulk_g2s(smem_u32(sm.B2), side.Watc, TT_A2_BYTES, bar);
   }
   const uint32_t tmem_base = *sm.tmem_slot;
-  cta_copy_f4(sm.Wc, side.Wc, NG * H);
   cta_copy_f4(sm.gamma, side.w.gamma, H);
   cta_copy_f4(sm.beta, side.w.beta, H);
   cta_copy_f4(sm.b2, side.w.b2, H);
@@ -144,14 +140,56 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
           z[i4 * 4] = p.x; z[i4 * 4 + 1] = p.y; z[i4 * 4 + 2] = p.z; z[i4 * 4 + 3] = p.w;
         }
       }
-      // ---- P0: geometry of this row, angular features -> A2, per-group Q and query
-      const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
-      float th = 0.f;
-      if (rowok) {
-        const float4 xk = ldg4(a.x4 + (size_t)rm.y * 4);
-        float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
-        float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-        th = atan2f(sqrtf(cx * cx + cy * cy + cz * cz), ax * bx + ay * by + az * bz);      // :133-137
+      // the j->i term Q[e] of this group (one row, broadcast over the warp) and the LayerNorm shift of this row
+      float shift = 0.f;
+      if (gvalid) {
+        const float* qrow = side.Q + (size_t)e * H + s * 32;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 qq = ldg4(qrow + i4 * 4);
+          z[i4 * 4] += qq.x; z[i4 * 4 + 1] += qq.y; z[i4 * 4 + 2] += qq.z; z[i4 * 4 + 3] += qq.w;
+        }
+        shift = __ldg(side.Qm + e) + (rvalid ? __ldg(side.Pm + rm.x) : 0.f);
+      }
+      // ---- P0: geometry of this row -> angular features -> A2 (the 13 features are split over the 4 slice-warps)
+      {
+        const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
+        float dot = 1.f, cn = 0.f;          // invalid / excluded rows: theta = 0
+        if (rowok) {
+          const float4 xk = ldg4(a.x4 + (size_t)rm.y * 4);
+          float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
+          float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+          cn = sqrtf(cx * cx + cy * cy + cz * cz);           // |(j-i) x (k-i)|          (:134-137)
+          dot = ax * bx + ay * by + az * bz;
+        }
+        // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3] (common.py:46-54).  sin / cos of theta
+        // follow from (cn, dot) directly (cn^2 + dot^2 = |a|^2 |b|^2), multiples and the half angle from the usual identities;
+        // only theta itself and theta/3 need atan2f / sincosf
+        if (s == 0) {
+          a2_put(sm.A2, r, 0, atan2f(cn, dot));
+        } else if (s == 3) {
+          float sv, cv;
+          sincosf(atan2f(cn, dot) * (float)(1.0 / 3.0), &sv, &cv);
+          a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
+        } else {
+          const float n2 = cn * cn + dot * dot;
+          const float inv = n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f;
+          const float sn = cn * inv, cs = n2 > 0.f ? dot * inv : 1.f;
+          if (s == 1) {
+            a2_put(sm.A2, r, 1, sn); a2_put(sm.A2, r, 4, sn); a2_put(sm.A2, r, 7, cs); a2_put(sm.A2, r, 10, cs);
+            a2_put(sm.A2, r, 2, 2.f * sn * cs); a2_put(sm.A2, r, 8, cs * cs - sn * sn);
+            a2_put(sm.A2, r, 3, sn * (3.f - 4.f * sn * sn)); a2_put(sm.A2, r, 9, cs * (4.f * cs * cs - 3.f));
+          } else {    // half angle, theta/2 in [0, pi/2]: take the root that does not cancel, derive the other from sin(theta)
+            float sh, ch;
+            if (cs >= 0.f) { ch = sqrtf(0.5f * (1.f + cs)); sh = sn / (2.f * ch); }
+            else { sh = sqrtf(0.5f * (1.f - cs)); ch = sn / (2.f * sh); }
+            a2_put(sm.A2, r, 5, sh); a2_put(sm.A2, r, 11, ch);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
+        tc_fence_before();
+        named_arrive(BAR_A2_READY, TT_THREADS);
+        if (!VPASS) sm.qry[((it & 3) * 4 + q) * H + s * 32 + lane] = gvalid ? __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane) : 0.f;
       }
       // static metadata of the next tile (hides its latency behind this tile)
       int2 gm_n = make_int2(0, 0), rm_n = make_int2(-1, -1);
@@ -159,46 +197,33 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         const int en = (tile + gridDim.x) * 4 + q;
         if (tile + gridDim.x < n_tiles && en < a.n_bonds) { gm_n = __ldg(a.grp_meta + en); rm_n = __ldg(a.row_meta + (size_t)en * 32 + lane); }
       }
+      // ---- P1: z += D2 (angular term from the tensor core); LayerNorm with ONE exchange: the row statistics are taken
+      // about the shift Pm[kj] + Qm[ji] (known to every slice without communication), then ReLU
       {
-        // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3]; the 5 distinct sin/cos pairs are split
-        // over the 4 slice-warps of the row
-        float sv, cv;
-        if (s == 0) { sincosf(th, &sv, &cv); a2_put(sm.A2, r, 0, th); a2_put(sm.A2, r, 1, sv); a2_put(sm.A2, r, 4, sv); a2_put(sm.A2, r, 7, cv); a2_put(sm.A2, r, 10, cv); }
-        else if (s == 1) { sincosf(th * 2.f, &sv, &cv); a2_put(sm.A2, r, 2, sv); a2_put(sm.A2, r, 8, cv); }
-        else if (s == 2) { sincosf(th * 3.f, &sv, &cv); a2_put(sm.A2, r, 3, sv); a2_put(sm.A2, r, 9, cv); }
-        else {
-          sincosf(th * 0.5f, &sv, &cv); a2_put(sm.A2, r, 5, sv); a2_put(sm.A2, r, 11, cv);
-          sincosf(th * (float)(1.0 / 3.0), &sv, &cv); a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
-        tc_fence_before();
-        named_arrive(BAR_A2_READY, TT_THREADS);
-        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        float d = sqrtf(dx * dx + dy * dy + dz * dz);
-        float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
-        float qv = 0.f;
-#pragma unroll
-        for (int g = 0; g < NG; ++g) qv = fmaf(__shfl_sync(FULL, gl, g), sm.Wc[g * H + s * 32 + lane], qv);
-        sm.Q[((it & 1) * 4 + q) * H + s * 32 + lane] = qv;
-        if (!VPASS) sm.qry[((it & 3) * 4 + q) * H + s * 32 + lane] = gvalid ? __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane) : 0.f;
-      }
-      quad_barrier(q);
-      // ---- P1: z = P[kj] + Q[ji] + D2, LayerNorm, ReLU
-      {
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 qq = ld4(sm.Q + ((it & 1) * 4 + q) * H + s * 32 + i4 * 4);
-          z[i4 * 4] += qq.x; z[i4 * 4 + 1] += qq.y; z[i4 * 4 + 2] += qq.z; z[i4 * 4 + 3] += qq.w;
-        }
         mbar_wait(bar_ang, it & 1);
         tc_fence_after();
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TT_COL_D2 + s * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) z[i] += __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) { z[i] = (z[i] - shift) + __uint_as_float(v[i]); s1 += z[i]; s2 = fmaf(z[i], z[i], s2); }
+        float2* st = sm.stat + ((it & 1) * 128 + r) * 4;
+        st[s] = make_float2(s1, s2);
+        quad_barrier(q);
+        const float4 t01 = *reinterpret_cast<const float4*>(st), t23 = *reinterpret_cast<const float4*>(st + 2);
+        const float mu = ((t01.x + t01.z) + (t23.x + t23.z)) * (1.0f / H);
+        const float var = fmaxf(((t01.y + t01.w) + (t23.y + t23.w)) * (1.0f / H) - mu * mu, 0.f);
+        const float rstd = 1.0f / sqrtf(var + LN_EPS);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 g = ld4(sm.gamma + s * 32 + i4 * 4), b = ld4(sm.beta + s * 32 + i4 * 4);
+          z[i4 * 4 + 0] = fmaxf(fmaf((z[i4 * 4 + 0] - mu) * rstd, g.x, b.x), 0.f);
+          z[i4 * 4 + 1] = fmaxf(fmaf((z[i4 * 4 + 1] - mu) * rstd, g.y, b.y), 0.f);
+          z[i4 * 4 + 2] = fmaxf(fmaf((z[i4 * 4 + 2] - mu) * rstd, g.z, b.z), 0.f);
+          z[i4 * 4 + 3] = fmaxf(fmaf((z[i4 * 4 + 3] - mu) * rstd, g.w, b.w), 0.f);
+        }
       }
-      atc_ln_relu(z, sm.statA, sm.statB, r, s, q, sm.gamma, sm.beta);
       // ---- epilogue of the previous tile (its main MMA has had this tile's P0/P1 to finish)
       if (it > 0) {
         mbar_wait(bar_mma, (it - 1) & 1);

@@ -90,6 +90,8 @@ struct TripSide {
   const float* Wc = nullptr;          // [20][128]  W1[:,148:168]^T  (gauss(d_ji))
   const float* Wa = nullptr;          // [13][128]  W1[:,168:181]^T  (angular encoding)
   float* P = nullptr;                 // (Eb,128) written by prep, read by the k / v pass
+  float* Q = nullptr;                 // (Eb,128) Wc . gauss(d_e): the j->i term, written by prep (tensor-core kernels)
+  float* Pm = nullptr; float* Qm = nullptr;   // (Eb) channel means of P / Q rows (LayerNorm shift of the tensor-core kernels)
   BondMlpW w;
   const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 (tensor-core kernels)
   const float* Watc = nullptr;        // hi | lo swizzled image of Wa^T: B operand of the angular-feature MMA
