@@ -99,9 +99,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
 
   if (warp == 16) {
     // ---------------------------------------------------------------- MMA issuer warp (one elected lane issues)
+    // tensor-pipe order: ang(t0), [ang(t1), main(t0)], [ang(t2), main(t1)], ...  - the angular MMA runs one tile ahead
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      named_sync(BAR_A2_READY, TT_THREADS);          // every worker has written its A2 features (and is done with D2)
+    auto issue_ang = [&]() {
+      named_sync(BAR_A2_READY, TT_THREADS);          // every worker has written its A2 features and is done with D2
       if (lane == 0) {
         tc_fence_after();
 #pragma unroll
@@ -113,101 +114,112 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         umma_commit(bar_ang);
       }
       __syncwarp();
+    };
+    if (blockIdx.x < n_tiles) issue_ang();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      if (tile + gridDim.x < n_tiles) issue_ang();
       named_sync(BAR_A_READY, TT_THREADS);           // hidden activations are in TMEM, D of the previous tile is drained
       if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
       __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- 16 worker warps: thread = (row r, channel slice s)
+    // geometry of a row -> angular features -> A2 (the 13 features are split over the 4 slice-warps), then hand A2 over
+    auto features = [&](int2 gm, int2 rm) {
+      const bool rowok = rm.y >= 0;
+      const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
+      float dot = 1.f, cn = 0.f;          // invalid / excluded rows: theta = 0
+      if (rowok) {
+        const float4 xk = ldg4(a.x4 + (size_t)rm.y * 4);
+        float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
+        float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+        cn = sqrtf(cx * cx + cy * cy + cz * cz);           // |(j-i) x (k-i)|          (:134-137)
+        dot = ax * bx + ay * by + az * bz;
+      }
+      // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3] (common.py:46-54).  sin / cos of theta
+      // follow from (cn, dot) directly (cn^2 + dot^2 = |a|^2 |b|^2), multiples and the half angle from the usual identities;
+      // only theta itself and theta/3 need atan2f / sincosf
+      if (s == 0) {
+        a2_put(sm.A2, r, 0, atan2f(cn, dot));
+      } else if (s == 3) {
+        float sv, cv;
+        sincosf(atan2f(cn, dot) * (float)(1.0 / 3.0), &sv, &cv);
+        a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
+      } else {
+        const float n2 = cn * cn + dot * dot;
+        const float inv = n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f;
+        const float sn = cn * inv, cs = n2 > 0.f ? dot * inv : 1.f;
+        if (s == 1) {
+          a2_put(sm.A2, r, 1, sn); a2_put(sm.A2, r, 4, sn); a2_put(sm.A2, r, 7, cs); a2_put(sm.A2, r, 10, cs);
+          a2_put(sm.A2, r, 2, 2.f * sn * cs); a2_put(sm.A2, r, 8, cs * cs - sn * sn);
+          a2_put(sm.A2, r, 3, sn * (3.f - 4.f * sn * sn)); a2_put(sm.A2, r, 9, cs * (4.f * cs * cs - 3.f));
+        } else {    // half angle, theta/2 in [0, pi/2]: take the root that does not cancel, derive the other from sin(theta)
+          float sh, ch;
+          if (cs >= 0.f) { ch = sqrtf(0.5f * (1.f + cs)); sh = sn / (2.f * ch); }
+          else { sh = sqrtf(0.5f * (1.f - cs)); ch = sn / (2.f * sh); }
+          a2_put(sm.A2, r, 5, sh); a2_put(sm.A2, r, 11, ch);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
+      tc_fence_before();
+      named_arrive(BAR_A2_READY, TT_THREADS);
+    };
+    auto load_meta = [&](int tile, int2& gm, int2& rm) {
+      gm = make_int2(0, 0); rm = make_int2(-1, -1);
+      const int en = tile * 4 + q;
+      if (tile < n_tiles && en < a.n_bonds) { gm = __ldg(a.grp_meta + en); rm = __ldg(a.row_meta + (size_t)en * 32 + lane); }
+    };
+
     int it = 0;
     int prev_e = -1; bool prev_ok = false; int prev_nvalid = 0;
-    int2 gm = make_int2(0, 0), rm = make_int2(-1, -1);
-    {
-      const int e0 = blockIdx.x * 4 + q;
-      if (blockIdx.x < n_tiles && e0 < a.n_bonds) { gm = __ldg(a.grp_meta + e0); rm = __ldg(a.row_meta + (size_t)e0 * 32 + lane); }
-    }
+    int2 gm, rm, gm_n, rm_n;
+    load_meta(blockIdx.x, gm, rm);
+    load_meta(blockIdx.x + gridDim.x, gm_n, rm_n);
+    if (blockIdx.x < n_tiles) features(gm, rm);          // prologue: the angular MMA of the first tile
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int e = tile * 4 + q;
       const bool gvalid = e < a.n_bonds;
       const bool rvalid = rm.x >= 0, rowok = rm.y >= 0;          // rowok: valid and k != i (:117-118)
-      // the P row of this thread is requested first so that its latency hides behind the geometry below
+      // all global loads of this row are requested up front (P[kj] slice, Q[ji] slice, the LayerNorm shift, the query)
       float z[32];
       {
         const float* prow = side.P + (size_t)(rvalid ? rm.x : 0) * H + s * 32;
+        const float* qrow = side.Q + (size_t)(gvalid ? e : 0) * H + s * 32;
+        float4 pv[8], qv[8];
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          float4 p = rvalid ? ldg4(prow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          z[i4 * 4] = p.x; z[i4 * 4 + 1] = p.y; z[i4 * 4 + 2] = p.z; z[i4 * 4 + 3] = p.w;
-        }
-      }
-      // the j->i term Q[e] of this group (one row, broadcast over the warp) and the LayerNorm shift of this row
-      float shift = 0.f;
-      if (gvalid) {
-        const float* qrow = side.Q + (size_t)e * H + s * 32;
+        for (int i4 = 0; i4 < 8; ++i4) pv[i4] = rvalid ? ldg4(prow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 qq = ldg4(qrow + i4 * 4);
-          z[i4 * 4] += qq.x; z[i4 * 4 + 1] += qq.y; z[i4 * 4 + 2] += qq.z; z[i4 * 4 + 3] += qq.w;
-        }
-        shift = __ldg(side.Qm + e) + (rvalid ? __ldg(side.Pm + rm.x) : 0.f);
-      }
-      // ---- P0: geometry of this row -> angular features -> A2 (the 13 features are split over the 4 slice-warps)
-      {
-        const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
-        float dot = 1.f, cn = 0.f;          // invalid / excluded rows: theta = 0
-        if (rowok) {
-          const float4 xk = ldg4(a.x4 + (size_t)rm.y * 4);
-          float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
-          float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-          cn = sqrtf(cx * cx + cy * cy + cz * cz);           // |(j-i) x (k-i)|          (:134-137)
-          dot = ax * bx + ay * by + az * bz;
-        }
-        // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3] (common.py:46-54).  sin / cos of theta
-        // follow from (cn, dot) directly (cn^2 + dot^2 = |a|^2 |b|^2), multiples and the half angle from the usual identities;
-        // only theta itself and theta/3 need atan2f / sincosf
-        if (s == 0) {
-          a2_put(sm.A2, r, 0, atan2f(cn, dot));
-        } else if (s == 3) {
-          float sv, cv;
-          sincosf(atan2f(cn, dot) * (float)(1.0 / 3.0), &sv, &cv);
-          a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
-        } else {
-          const float n2 = cn * cn + dot * dot;
-          const float inv = n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f;
-          const float sn = cn * inv, cs = n2 > 0.f ? dot * inv : 1.f;
-          if (s == 1) {
-            a2_put(sm.A2, r, 1, sn); a2_put(sm.A2, r, 4, sn); a2_put(sm.A2, r, 7, cs); a2_put(sm.A2, r, 10, cs);
-            a2_put(sm.A2, r, 2, 2.f * sn * cs); a2_put(sm.A2, r, 8, cs * cs - sn * sn);
-            a2_put(sm.A2, r, 3, sn * (3.f - 4.f * sn * sn)); a2_put(sm.A2, r, 9, cs * (4.f * cs * cs - 3.f));
-          } else {    // half angle, theta/2 in [0, pi/2]: take the root that does not cancel, derive the other from sin(theta)
-            float sh, ch;
-            if (cs >= 0.f) { ch = sqrtf(0.5f * (1.f + cs)); sh = sn / (2.f * ch); }
-            else { sh = sqrtf(0.5f * (1.f - cs)); ch = sn / (2.f * sh); }
-            a2_put(sm.A2, r, 5, sh); a2_put(sm.A2, r, 11, ch);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
-        tc_fence_before();
-        named_arrive(BAR_A2_READY, TT_THREADS);
-        if (!VPASS) sm.qry[((it & 3) * 4 + q) * H + s * 32 + lane] = gvalid ? __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane) : 0.f;
-      }
-      // static metadata of the next tile (hides its latency behind this tile)
-      int2 gm_n = make_int2(0, 0), rm_n = make_int2(-1, -1);
-      {
-        const int en = (tile + gridDim.x) * 4 + q;
-        if (tile + gridDim.x < n_tiles && en < a.n_bonds) { gm_n = __ldg(a.grp_meta + en); rm_n = __ldg(a.row_meta + (size_t)en * 32 + lane); }
-      }
-      // ---- P1: z += D2 (angular term from the tensor core); LayerNorm with ONE exchange: the row statistics are taken
-      // about the shift Pm[kj] + Qm[ji] (known to every slice without communication), then ReLU
-      {
+        for (int i4 = 0; i4 < 8; ++i4) qv[i4] = gvalid ? ldg4(qrow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float shift = (gvalid ? __ldg(side.Qm + e) : 0.f) + (rvalid ? __ldg(side.Pm + rm.x) : 0.f);
+        float qry_v = 0.f;
+        if (!VPASS && gvalid) qry_v = __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane);
+        // metadata two tiles ahead
+        int2 gm_nn, rm_nn;
+        load_meta(tile + 2 * gridDim.x, gm_nn, rm_nn);
+        // ---- D2 of this tile was issued one iteration ago
         mbar_wait(bar_ang, it & 1);
         tc_fence_after();
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TT_COL_D2 + s * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!VPASS) sm.qry[((it & 3) * 4 + q) * H + s * 32 + lane] = qry_v;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          z[i4 * 4 + 0] = ((pv[i4].x + qv[i4].x) - shift) + __uint_as_float(v[i4 * 4 + 0]);
+          z[i4 * 4 + 1] = ((pv[i4].y + qv[i4].y) - shift) + __uint_as_float(v[i4 * 4 + 1]);
+          z[i4 * 4 + 2] = ((pv[i4].z + qv[i4].z) - shift) + __uint_as_float(v[i4 * 4 + 2]);
+          z[i4 * 4 + 3] = ((pv[i4].w + qv[i4].w) - shift) + __uint_as_float(v[i4 * 4 + 3]);
+        }
+        // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
+        if (tile + gridDim.x < n_tiles) features(gm_n, rm_n);
+        gm = gm_n; rm = rm_n; gm_n = gm_nn; rm_n = rm_nn;
+      }
+      // ---- LayerNorm with ONE exchange: the row statistics are taken about the shift Pm[kj] + Qm[ji] (known to every
+      // slice without communication), then ReLU
+      {
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { z[i] = (z[i] - shift) + __uint_as_float(v[i]); s1 += z[i]; s2 = fmaf(z[i], z[i], s2); }
+        for (int i = 0; i < 32; ++i) { s1 += z[i]; s2 = fmaf(z[i], z[i], s2); }
         float2* st = sm.stat + ((it & 1) * 128 + r) * 4;
         st[s] = make_float2(s1, s2);
         quad_barrier(q);
@@ -224,13 +236,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
           z[i4 * 4 + 3] = fmaxf(fmaf((z[i4 * 4 + 3] - mu) * rstd, g.w, b.w), 0.f);
         }
       }
-      // ---- epilogue of the previous tile (its main MMA has had this tile's P0/P1 to finish)
+      // ---- epilogue of the previous tile (its main MMA has had this tile's loads / features / LayerNorm to finish)
       if (it > 0) {
         mbar_wait(bar_mma, (it - 1) & 1);
         tc_fence_after();
         trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 3, prev_e, prev_ok, prev_nvalid);
       }
-      // ---- P2: hidden activations -> TMEM; the issuer warp starts the main MMA once every worker has arrived
+      // ---- hidden activations -> TMEM; the issuer warp starts the main MMA once every worker has arrived
       {
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -243,7 +255,6 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         named_arrive(BAR_A_READY, TT_THREADS);
       }
       prev_e = gvalid ? e : -1; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok));
-      gm = gm_n; rm = rm_n;
     }
     if (it > 0) {
       mbar_wait(bar_mma, (it - 1) & 1);
