@@ -14,6 +14,7 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -225,3 +226,45 @@ def step_noise(n_ligand: int, n_bonds: int, num_steps: int, seed: int, num_class
                     'u_bond': torch.rand(n_bonds, num_bond_classes, generator=gen),
                     'eps_pos': torch.randn(n_ligand, 3, generator=gen)})
     return out
+
+
+def make_raw_pocket(seed: int = 0, n_protein: int = 60, arm_sizes: Sequence[int] = (3, 4), n_scaffold: int = 5,
+                    arm_radius: float = 10.0) -> ProteinLigandData:
+    """A synthetic complex BEFORE the sampling-time transforms: the attributes a dataset item carries when the driver
+    receives it (scripts/sample_diffusion_decomp.py:556-590) - protein atoms with element / residue / backbone
+    fields, a reference ligand with its arm decomposition (`ligand_atom_mask`, -1 = scaffold) and the arm sub-pocket
+    masks.  Feed it to `transforms.FeaturizeProteinAtom`, `prior.compute_golden_prior_from_data` (ref_prior) or
+    `prior.substitute_golden_prior_with_given_prior` (beta_prior) and then to `sampling.sample_diffusion_ligand_decomp`."""
+    gen = torch.Generator().manual_seed(seed)
+    num_arms = len(arm_sizes)
+    d = ProteinLigandData()
+    d.protein_pos = torch.randn(n_protein, 3, generator=gen) * 8.0
+    d.protein_element = PROTEIN_ELEMENTS[torch.randint(0, 6, (n_protein,), generator=gen)]
+    d.protein_atom_to_aa_type = torch.randint(0, 20, (n_protein,), generator=gen)
+    d.protein_is_backbone = torch.randint(0, 2, (n_protein,), generator=gen).bool()
+    centers = torch.randn(num_arms + 1, 3, generator=gen) * 3.0
+    spread = 0.5 + torch.rand(num_arms + 1, 1, generator=gen)
+    mask: List[int] = []
+    for a, s in enumerate(arm_sizes):
+        mask += [a] * s
+    mask += [-1] * n_scaffold
+    d.ligand_atom_mask = torch.tensor(mask, dtype=torch.long)
+    part = torch.where(d.ligand_atom_mask < 0, torch.tensor(num_arms), d.ligand_atom_mask)
+    d.ligand_pos = centers[part] + torch.randn(len(mask), 3, generator=gen) * spread[part]
+    d.ligand_element = torch.full((len(mask),), 6, dtype=torch.long)
+    d.num_arms = num_arms
+    d.num_scaffold = 1 if n_scaffold > 0 else 0
+    d.pocket_atom_masks = torch.stack([(d.protein_pos - centers[a]).norm(dim=-1) < arm_radius for a in range(num_arms)])
+    return d
+
+
+def beta_prior_dict(seed: int, arm_sizes: Sequence[int] = (3, 4), n_scaffold: int = 5, scalar_scaffold_cov: bool = True) -> Dict:
+    """A synthetic 'beta prior' in the pickle format of utils/prior.py:48-68: tuples (num, iso_mu, iso_cov, aniso_mu, aniso_cov);
+    the scaffold variance may be a scalar (utils/transforms.py:229-236)."""
+    rng = np.random.RandomState(seed)
+    arms = [(int(n), rng.randn(3) * 3.0, np.eye(3) * float(rng.uniform(0.2, 2.0)), None, None) for n in arm_sizes]
+    sca = []
+    if n_scaffold > 0:
+        var = float(rng.uniform(0.2, 2.0))
+        sca.append((int(n_scaffold), rng.randn(3) * 3.0, var if scalar_scaffold_cov else np.eye(3) * var, None, None))
+    return {'arms_prior': arms, 'scaffold_prior': sca, 'num_arms': len(arms), 'num_scaffold': len(sca)}

@@ -5,3 +5,4 @@ mkdir -p gpurun_out
 ncu --set full --clock-control none --import-source on -k regex:"$RE" -s $SKIP -c $CNT -o gpurun_out/prof_${TAG} -f \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-profile > gpurun_out/prof_${TAG}.log 2>&1
 ncu -i gpurun_out/prof_${TAG}.ncu-rep --page raw --csv > gpurun_out/raw_${TAG}.csv 2>/dev/null
+ncu -i gpurun_out/prof_${TAG}.ncu-rep --page source --csv > gpurun_out/src_${TAG}.csv 2>/dev/null
