@@ -261,11 +261,13 @@ __global__ void __launch_bounds__(256) trip_prep_kernel(const TripArgs a) {
       z = fma4(gg, ldg4(t.Wd + g * H + lane * 4), z);
       if (t.Q) qv = fma4(gg, ldg4(t.Wc + g * H + lane * 4), qv);
     }
-    st4(t.P + (size_t)e * H + lane * 4, z);
-    if (t.Q) {      // the same edge seen as j->i: Q = Wc . gauss(d), plus the row means used as LayerNorm shift
-      st4(t.Q + (size_t)e * H + lane * 4, qv);
-      float pm = warp_sum((z.x + z.y) + (z.z + z.w)) * (1.0f / H), qm = warp_sum((qv.x + qv.y) + (qv.z + qv.w)) * (1.0f / H);
-      if (lane == 0) { t.Pm[e] = pm; t.Qm[e] = qm; }
+    if (t.Q) {      // tensor-core kernels: rows are stored CENTRED (LayerNorm is invariant to a per-row shift, and centred rows
+      // keep its single-pass statistics well conditioned); Q = Wc . gauss(d) is the same edge seen as j->i
+      const float pm = warp_sum((z.x + z.y) + (z.z + z.w)) * (1.0f / H), qm = warp_sum((qv.x + qv.y) + (qv.z + qv.w)) * (1.0f / H);
+      st4(t.P + (size_t)e * H + lane * 4, make_float4(z.x - pm, z.y - pm, z.z - pm, z.w - pm));
+      st4(t.Q + (size_t)e * H + lane * 4, make_float4(qv.x - qm, qv.y - qm, qv.z - qm, qv.w - qm));
+    } else {
+      st4(t.P + (size_t)e * H + lane * 4, z);
     }
   }
 }

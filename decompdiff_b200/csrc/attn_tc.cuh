@@ -34,17 +34,18 @@ __device__ __forceinline__ void tf32_split(float a, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(a - __uint_as_float(hi));
 }
 
-// D (+)= A[tmem hi/lo] * W2[smem hi/lo]  : 16 k-steps x 3 MMAs, N = 128
+// D (+)= A[tmem hi/lo] * W2[smem hi/lo]  : 16 k-steps x 3 MMAs, N = 128.  The k loop is NOT unrolled: the issuing thread is
+// paced by the tensor pipe (64 cycles per MMA) anyway, and 48 hoisted descriptors would only spill.
 __device__ __forceinline__ void atc_issue_mma(uint32_t tmem_base, uint32_t w2_smem, uint32_t bar) {
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t d = tmem_base + ATC_COL_D;
-  const uint32_t b_hi = w2_smem, b_lo = w2_smem + ATC_W2_BYTES / 2;
-#pragma unroll
+  const uint64_t b_hi0 = umma_desc_sw128(w2_smem), b_lo0 = umma_desc_sw128(w2_smem + ATC_W2_BYTES / 2);
+#pragma unroll 1
   for (int kk = 0; kk < 16; ++kk) {
-    const uint32_t bo = (kk >> 2) * (128 * 128) + (kk & 3) * 32;
-    umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, umma_desc_sw128(b_hi + bo), idesc, kk ? 1u : 0u);
-    umma_tf32_ts(d, tmem_base + ATC_COL_ALO + kk * 8, umma_desc_sw128(b_hi + bo), idesc, 1u);
-    umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, umma_desc_sw128(b_lo + bo), idesc, 1u);
+    const uint64_t bo = (uint64_t)(((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4);      // start-address field is in 16-byte units
+    umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, b_hi0 + bo, idesc, kk ? 1u : 0u);
+    umma_tf32_ts(d, tmem_base + ATC_COL_ALO + kk * 8, b_hi0 + bo, idesc, 1u);
+    umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, b_lo0 + bo, idesc, 1u);
   }
   umma_commit(bar);
 }

@@ -11,7 +11,7 @@ constexpr int TT_A2_BYTES = 2 * 128 * 128;        // hi | lo, [128 rows][128 B] 
 constexpr int TT_COL_D2 = 384;
 
 struct TripTcSmem {
-  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *qry; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
+  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *qry, *qrow; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
   __device__ explicit TripTcSmem(uint8_t* raw) {
     uint8_t* p = raw;      // purely additive carving keeps everything in the shared address space (LDS / STS)
     W2 = p; p += ATC_W2_BYTES;
@@ -20,12 +20,13 @@ struct TripTcSmem {
     gamma = reinterpret_cast<float*>(p); p += H * 4;
     beta = reinterpret_cast<float*>(p); p += H * 4;
     b2 = reinterpret_cast<float*>(p); p += H * 4;
-    qry = reinterpret_cast<float*>(p); p += 4 * 4 * H * 4;
+    qry = reinterpret_cast<float*>(p); p += 16 * 128 * 4;       // per warp: 4-deep ring of 32-float query slices
+    qrow = reinterpret_cast<float*>(p); p += 16 * 64 * 4;       // per warp: 2 x 32-float slices of the centred Q row
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][row][slice] {sum, sum of squares}
     bars = reinterpret_cast<uint64_t*>(p); p += 32;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 2 * 2 * 128 * 4) * 4 + 64; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 2 * 2 * 128 * 4) * 4 + 64; }
 };
 static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -39,28 +40,34 @@ __device__ __forceinline__ void a2_put(uint8_t* A2, int r, int k, float v) {
   *reinterpret_cast<uint32_t*>(A2 + TT_A2_BYTES / 2 + a2_off(r, k)) = lo;
 }
 
-template <bool VPASS>
-__device__ __forceinline__ void trip_epilogue(const TripArgs& a, const TripTcSmem& sm, uint32_t tmem_base, int q, int s, int lane,
-                                              int buf, int prev_e, bool prev_ok, int prev_nvalid) {
-  if (!VPASS) {
-    float4 w4 = atc_logits_softmax(tmem_base, q, s, sm.qry + (buf * 4 + q) * H, prev_ok);
-    if (prev_e >= 0) st4(a.wbuf + ((size_t)a.trip_base[prev_e] + lane) * NH + s * 4, w4);
-  } else {
-    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (prev_ok) w4 = ld4(a.wbuf + ((size_t)a.trip_base[prev_e] + lane) * NH + s * 4);
-    float tot = atc_weighted_colsum(tmem_base, q, s, lane, w4);
-    if (prev_e >= 0) {
-      const int c = s * 32 + lane;
-      float upd = prev_nvalid > 0 ? tot + sm.b2[c] : 0.f;
-      a.h_bond_out[(size_t)prev_e * H + c] = a.h_bond_in[(size_t)prev_e * H + c] + upd;      // :274
-    }
-  }
-}
+// ---- packed fp32 (FADD2 / FMUL2 / FFMA2 on sm_100): the element-wise phases work on channel pairs
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 u2f(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
-constexpr int TT_THREADS = ATC_THREADS + 32;     // 16 worker warps + 1 MMA-issuing warp
+// 16 worker warps + one warpgroup whose first warp issues the MMAs (tcgen05.mma blocks its issuing thread while the tensor
+// queue is full, so the issuer must not be a worker).  setmaxnreg moves the registers of the idle warps to the workers.
+constexpr int TT_THREADS = ATC_THREADS + 128;
+constexpr int TT_ISSUER = 16;
+#ifndef TT_EARLY_PREFETCH
+#define TT_EARLY_PREFETCH 0
+#endif
+constexpr int TT_SYNC = ATC_THREADS + 32;       // participants of the hand-over barriers: 512 workers + the issuing warp
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-constexpr int BAR_A2_READY = 5, BAR_A_READY = 6;  // named barriers: workers arrive, the issuer warp syncs
+constexpr int BAR_A2_READY = 5, BAR_A_READY = 6;  // named barriers: every warp arrives, the issuing warp waits on them
+
+// Optional in-kernel timeline (compile with -DDDB_TIMELINE): CTA 0, lane 0 of warps 0 and TT_ISSUER add the SM cycles spent in
+// each phase of the tile loop to g_trip_timeline[VPASS][warp slot][phase]; read with ddb_debug_trip_timeline().
+#ifdef DDB_TIMELINE
+__device__ unsigned long long g_trip_timeline[2][2][16];
+#define TL_DECL unsigned long long tl_t = clock64(), tl_acc[12] = {0}; const bool tl_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 13);
+#define TL_MARK(i) do { if (tl_on) { unsigned long long n_ = clock64(); tl_acc[i] += n_ - tl_t; tl_t = n_; } } while (0)
+#define TL_FLUSH(vp) do { if (tl_on) { for (int i_ = 0; i_ < 12; ++i_) g_trip_timeline[vp][warp == 0 ? 0 : 1][i_] = tl_acc[i_]; g_trip_timeline[vp][warp == 0 ? 0 : 1][12] = it; } } while (0)
+#else
+#define TL_DECL
+#define TL_MARK(i)
+#define TL_FLUSH(vp)
+#endif
 
 template <bool VPASS>
 __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a) {
@@ -97,45 +104,52 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
   const int n_tiles = (a.n_bonds + 3) / 4;
 
-  if (warp == 16) {
-    // ---------------------------------------------------------------- MMA issuer warp (one elected lane issues)
-    // tensor-pipe order: ang(t0), [ang(t1), main(t0)], [ang(t2), main(t1)], ...  - the angular MMA runs one tile ahead
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    auto issue_ang = [&]() {
-      named_sync(BAR_A2_READY, TT_THREADS);          // every worker has written its A2 features and is done with D2
-      if (lane == 0) {
-        tc_fence_after();
+  if (warp >= 16) {
+    // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == TT_ISSUER) {
+      // tensor-pipe order: ang(t0), [ang(t1), main(t0)], [ang(t2), main(t1)], ...  - the angular MMA runs one tile ahead
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      auto issue_ang = [&]() {
+        named_sync(BAR_A2_READY, TT_SYNC);          // every worker has written its A2 features and is done with D2
+        if (lane == 0) {
+          tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {             // K = 16 features: two k-steps of 8 inside the first 64 bytes of the rows
-          umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, ks ? 1u : 0u);
-          umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + TT_A2_BYTES / 2 + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, 1u);
-          umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + TT_A2_BYTES / 2 + ks * 32), idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {             // K = 16 features: two k-steps of 8 inside the first 64 bytes of the rows
+            umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, ks ? 1u : 0u);
+            umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + TT_A2_BYTES / 2 + ks * 32), umma_desc_sw128(b2_smem + ks * 32), idesc, 1u);
+            umma_tf32_ss(tmem_base + TT_COL_D2, umma_desc_sw128(a2_smem + ks * 32), umma_desc_sw128(b2_smem + TT_A2_BYTES / 2 + ks * 32), idesc, 1u);
+          }
+          umma_commit(bar_ang);
         }
-        umma_commit(bar_ang);
+        __syncwarp();
+      };
+      if (blockIdx.x < n_tiles) issue_ang();
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tile + gridDim.x < n_tiles) issue_ang();
+        named_sync(BAR_A_READY, TT_SYNC);           // hidden activations are in TMEM, D of the previous tile is in registers
+        if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
+        __syncwarp();
       }
-      __syncwarp();
-    };
-    if (blockIdx.x < n_tiles) issue_ang();
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      if (tile + gridDim.x < n_tiles) issue_ang();
-      named_sync(BAR_A_READY, TT_THREADS);           // hidden activations are in TMEM, D of the previous tile is drained
-      if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
-      __syncwarp();
     }
   } else {
-    // ---------------------------------------------------------------- 16 worker warps: thread = (row r, channel slice s)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    auto hand_over_a2 = [&]() { named_arrive(BAR_A2_READY, TT_SYNC); };
+    auto hand_over_a = [&]() { named_arrive(BAR_A_READY, TT_SYNC); };
+    // ---------------------------------------------------------------- 16 warps: thread = (row r, channel slice s)
     // geometry of a row -> angular features -> A2 (the 13 features are split over the 4 slice-warps), then hand A2 over
-    auto features = [&](int2 gm, int2 rm) {
+    // positions for the features of a tile: requested one phase early (gathers through L2), consumed in features()
+    auto load_xyz = [&](int2 gm, int2 rm, float4& xi, float4& xj, float4& xk) {
+      xi = ldg4(a.x4 + (size_t)gm.x * 4); xj = ldg4(a.x4 + (size_t)gm.y * 4);
+      xk = ldg4(a.x4 + (size_t)(rm.y >= 0 ? rm.y : gm.y) * 4);      // excluded rows: k := j, theta = 0
+    };
+    auto features = [&](int2 rm, float4 xi, float4 xj, float4 xk) {
       const bool rowok = rm.y >= 0;
-      const float4 xi = ldg4(a.x4 + (size_t)gm.x * 4), xj = ldg4(a.x4 + (size_t)gm.y * 4);
-      float dot = 1.f, cn = 0.f;          // invalid / excluded rows: theta = 0
-      if (rowok) {
-        const float4 xk = ldg4(a.x4 + (size_t)rm.y * 4);
-        float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
-        float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-        cn = sqrtf(cx * cx + cy * cy + cz * cz);           // |(j-i) x (k-i)|          (:134-137)
-        dot = ax * bx + ay * by + az * bz;
-      }
+      const float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
+      const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+      float cn = sqrtf(cx * cx + cy * cy + cz * cz);             // |(j-i) x (k-i)|          (:134-137)
+      float dot = ax * bx + ay * by + az * bz;
+      if (!rowok) { cn = 0.f; dot = 1.f; }
       // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3] (common.py:46-54).  sin / cos of theta
       // follow from (cn, dot) directly (cn^2 + dot^2 = |a|^2 |b|^2), multiples and the half angle from the usual identities;
       // only theta itself and theta/3 need atan2f / sincosf
@@ -162,104 +176,223 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
       tc_fence_before();
-      named_arrive(BAR_A2_READY, TT_THREADS);
+      hand_over_a2();
     };
+    // metadata of a tile: clamped so that every load below is unconditional (padding rows read edge 0 / node 0; their
+    // results are never stored and they get zero attention weight)
     auto load_meta = [&](int tile, int2& gm, int2& rm) {
-      gm = make_int2(0, 0); rm = make_int2(-1, -1);
+      gm = make_int2(0, 0); rm = make_int2(0, -1);
       const int en = tile * 4 + q;
       if (tile < n_tiles && en < a.n_bonds) { gm = __ldg(a.grp_meta + en); rm = __ldg(a.row_meta + (size_t)en * 32 + lane); }
     };
+    float* const wq = sm.qrow + warp * 64;          // this warp's private staging: [parity][32] slice of the Q row
+    float* const wqry = sm.qry + warp * 128;        // k pass: [4-deep ring][32] slice of the query row
+    const float* __restrict__ Pc = side.P;          // centred rows (trip_prep): LayerNorm is shift invariant
+    const float* __restrict__ Qc = side.Q;
 
     int it = 0;
-    int prev_e = -1; bool prev_ok = false; int prev_nvalid = 0;
+    int prev_e = -1, prev_tb = 0; bool prev_ok = false; int prev_nvalid = 0;
     int2 gm, rm, gm_n, rm_n;
     load_meta(blockIdx.x, gm, rm);
     load_meta(blockIdx.x + gridDim.x, gm_n, rm_n);
-    if (blockIdx.x < n_tiles) features(gm, rm);          // prologue: the angular MMA of the first tile
+    float4 pv[8];
+    if (blockIdx.x < n_tiles) {
+      float4 xi, xj, xk;
+      load_xyz(gm, rm, xi, xj, xk);
+      features(rm, xi, xj, xk);          // prologue: the angular MMA of the first tile
+      const float* prow = Pc + (size_t)max(rm.x, 0) * H + s * 32;
+#pragma unroll
+      for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+      const int e0 = min(blockIdx.x * 4 + q, a.n_bonds - 1);
+      wq[lane] = __ldg(Qc + (size_t)e0 * H + s * 32 + lane);
+    }
+    TL_DECL
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      TL_MARK(0);
       const int e = tile * 4 + q;
       const bool gvalid = e < a.n_bonds;
-      const bool rvalid = rm.x >= 0, rowok = rm.y >= 0;          // rowok: valid and k != i (:117-118)
-      // all global loads of this row are requested up front (P[kj] slice, Q[ji] slice, the LayerNorm shift, the query)
-      float z[32];
+      const bool rowok = rm.y >= 0;          // valid and k != i (:117-118)
+      // requests for later: the Q slice of the next tile, the query slice of this one, metadata two tiles ahead
+      const int e_next = min(e + 4 * (int)gridDim.x, a.n_bonds - 1);
+      const float q_next = __ldg(Qc + (size_t)e_next * H + s * 32 + lane);
+      float qry_v = 0.f;
+      if (!VPASS) qry_v = __ldg(a.q + (size_t)min(e, a.n_bonds - 1) * a.ldq + s * 32 + lane);
+      int2 gm_nn, rm_nn;
+      load_meta(tile + 2 * gridDim.x, gm_nn, rm_nn);
+      float4 nxi, nxj, nxk;
+      load_xyz(gm_n, rm_n, nxi, nxj, nxk);
+      const int tb = __ldg(a.trip_base + min(e, a.n_bonds - 1));
+      // ---- first Linear: z = P'[kj] (prefetched) + Q'[ji] (staged) + D2 (angular MMA, issued one iteration ago)
+      float2 z[16];
       {
-        const float* prow = side.P + (size_t)(rvalid ? rm.x : 0) * H + s * 32;
-        const float* qrow = side.Q + (size_t)(gvalid ? e : 0) * H + s * 32;
-        float4 pv[8], qv[8];
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) pv[i4] = rvalid ? ldg4(prow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) qv[i4] = gvalid ? ldg4(qrow + i4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float shift = (gvalid ? __ldg(side.Qm + e) : 0.f) + (rvalid ? __ldg(side.Pm + rm.x) : 0.f);
-        float qry_v = 0.f;
-        if (!VPASS && gvalid) qry_v = __ldg(a.q + (size_t)e * a.ldq + s * 32 + lane);
-        // metadata two tiles ahead
-        int2 gm_nn, rm_nn;
-        load_meta(tile + 2 * gridDim.x, gm_nn, rm_nn);
-        // ---- D2 of this tile was issued one iteration ago
         mbar_wait(bar_ang, it & 1);
+        TL_MARK(1);
         tc_fence_after();
+        __syncwarp();
+        const float* qs = wq + (it & 1) * 32;
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 qv = ld4(qs + i4 * 4);
+          z[i4 * 2] = __fadd2_rn(f2(pv[i4].x, pv[i4].y), f2(qv.x, qv.y));
+          z[i4 * 2 + 1] = __fadd2_rn(f2(pv[i4].z, pv[i4].w), f2(qv.z, qv.w));
+        }
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TT_COL_D2 + s * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!VPASS) sm.qry[((it & 3) * 4 + q) * H + s * 32 + lane] = qry_v;
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          z[i4 * 4 + 0] = ((pv[i4].x + qv[i4].x) - shift) + __uint_as_float(v[i4 * 4 + 0]);
-          z[i4 * 4 + 1] = ((pv[i4].y + qv[i4].y) - shift) + __uint_as_float(v[i4 * 4 + 1]);
-          z[i4 * 4 + 2] = ((pv[i4].z + qv[i4].z) - shift) + __uint_as_float(v[i4 * 4 + 2]);
-          z[i4 * 4 + 3] = ((pv[i4].w + qv[i4].w) - shift) + __uint_as_float(v[i4 * 4 + 3]);
-        }
-        // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
-        if (tile + gridDim.x < n_tiles) features(gm_n, rm_n);
-        gm = gm_n; rm = rm_n; gm_n = gm_nn; rm_n = rm_nn;
+        for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], u2f(v[2 * i], v[2 * i + 1]));
       }
-      // ---- LayerNorm with ONE exchange: the row statistics are taken about the shift Pm[kj] + Qm[ji] (known to every
-      // slice without communication), then ReLU
+      // ---- prefetch the P' rows of the next tile (consumed one iteration from now), stage its Q slice and this tile's query
+      const float* prow_next = Pc + (size_t)max(rm_n.x, 0) * H + s * 32;
       {
-        float s1 = 0.f, s2 = 0.f;
+        if (TT_EARLY_PREFETCH && !VPASS) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { s1 += z[i]; s2 = fmaf(z[i], z[i], s2); }
+          for (int i8 = 0; i8 < 4; ++i8) ldg8(prow_next + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+        }
+        wq[((it + 1) & 1) * 32 + lane] = q_next;
+        if (!VPASS) wqry[(it & 3) * 32 + lane] = qry_v;
+      }
+      TL_MARK(2);
+      // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
+      if (tile + gridDim.x < n_tiles) features(rm_n, nxi, nxj, nxk);
+      TL_MARK(3);
+      gm = gm_n; rm = rm_n; gm_n = gm_nn; rm_n = rm_nn;
+      // ---- LayerNorm with ONE exchange (single-pass statistics: the rows are centred up to the small angular term), ReLU
+      {
+        float2 s1 = f2(0.f, 0.f), s2 = f2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { s1 = __fadd2_rn(s1, z[i]); s2 = __ffma2_rn(z[i], z[i], s2); }
         float2* st = sm.stat + ((it & 1) * 128 + r) * 4;
-        st[s] = make_float2(s1, s2);
+        st[s] = make_float2(s1.x + s1.y, s2.x + s2.y);
+        TL_MARK(4);
         quad_barrier(q);
+        TL_MARK(5);
         const float4 t01 = *reinterpret_cast<const float4*>(st), t23 = *reinterpret_cast<const float4*>(st + 2);
         const float mu = ((t01.x + t01.z) + (t23.x + t23.z)) * (1.0f / H);
         const float var = fmaxf(((t01.y + t01.w) + (t23.y + t23.w)) * (1.0f / H) - mu * mu, 0.f);
         const float rstd = 1.0f / sqrtf(var + LN_EPS);
+        const float2 rs2 = f2(rstd, rstd), nm2 = f2(-mu * rstd, -mu * rstd);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 g = ld4(sm.gamma + s * 32 + i4 * 4), b = ld4(sm.beta + s * 32 + i4 * 4);
-          z[i4 * 4 + 0] = fmaxf(fmaf((z[i4 * 4 + 0] - mu) * rstd, g.x, b.x), 0.f);
-          z[i4 * 4 + 1] = fmaxf(fmaf((z[i4 * 4 + 1] - mu) * rstd, g.y, b.y), 0.f);
-          z[i4 * 4 + 2] = fmaxf(fmaf((z[i4 * 4 + 2] - mu) * rstd, g.z, b.z), 0.f);
-          z[i4 * 4 + 3] = fmaxf(fmaf((z[i4 * 4 + 3] - mu) * rstd, g.w, b.w), 0.f);
+          float2 u0 = __ffma2_rn(z[i4 * 2], rs2, nm2), u1 = __ffma2_rn(z[i4 * 2 + 1], rs2, nm2);      // (z - mu) * rstd
+          u0 = __ffma2_rn(u0, f2(g.x, g.y), f2(b.x, b.y));
+          u1 = __ffma2_rn(u1, f2(g.z, g.w), f2(b.z, b.w));
+          z[i4 * 2] = f2(fmaxf(u0.x, 0.f), fmaxf(u0.y, 0.f));
+          z[i4 * 2 + 1] = f2(fmaxf(u1.x, 0.f), fmaxf(u1.y, 0.f));
         }
       }
-      // ---- epilogue of the previous tile (its main MMA has had this tile's loads / features / LayerNorm to finish)
+      // ---- drain D of the previous tile into registers (its main MMA had this tile's first Linear / LayerNorm to finish)
+      float lg[4] = {0.f, 0.f, 0.f, 0.f};
+      float val[32];
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float hb_in = 0.f;
+      if (VPASS && it > 0) {      // requested before the wait on the tensor core: attention weights of this thread's row, residual input
+        if (prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
+        if (prev_e >= 0) hb_in = __ldg(a.h_bond_in + (size_t)prev_e * H + s * 32 + lane);
+      }
+      TL_MARK(6);
       if (it > 0) {
         mbar_wait(bar_mma, (it - 1) & 1);
+        TL_MARK(7);
         tc_fence_after();
-        trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 3, prev_e, prev_ok, prev_nvalid);
-      }
-      // ---- hidden activations -> TMEM; the issuer warp starts the main MMA once every worker has arrived
-      {
-        uint32_t hi[32], lo[32];
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!VPASS) {
+          const float* qr = wqry + ((it - 1) & 3) * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tf32_split(rowok ? z[i] : 0.f, hi[i], lo[i]);
+          for (int hh = 0; hh < 4; ++hh) {
+            const float4 q0 = ld4(qr + hh * 8), q1 = ld4(qr + hh * 8 + 4);
+            float2 acc = __fmul2_rn(f2(q0.x, q0.y), u2f(v[hh * 8], v[hh * 8 + 1]));
+            acc = __ffma2_rn(f2(q0.z, q0.w), u2f(v[hh * 8 + 2], v[hh * 8 + 3]), acc);
+            acc = __ffma2_rn(f2(q1.x, q1.y), u2f(v[hh * 8 + 4], v[hh * 8 + 5]), acc);
+            acc = __ffma2_rn(f2(q1.z, q1.w), u2f(v[hh * 8 + 6], v[hh * 8 + 7]), acc);
+            lg[hh] = prev_ok ? acc.x + acc.y : -INFINITY;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;
+            val[i] = wh * __uint_as_float(v[i]);
+          }
+        }
+      }
+      // ---- hidden activations -> TMEM (D is in registers, so the issuer may start the main MMA right away)
+      {
+        // hi = z truncated to TF32, lo = z - hi (exact); 16 columns at a time keeps the register peak low
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        tmem_st32(lane_addr + ATC_COL_AHI + s * 32, hi);
-        tmem_st32(lane_addr + ATC_COL_ALO + s * 32, lo);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 zz = z[half * 8 + i];
+            hi[2 * i] = __float_as_uint(zz.x) & 0xffffe000u;
+            hi[2 * i + 1] = __float_as_uint(zz.y) & 0xffffe000u;
+            const float2 l = __fadd2_rn(zz, f2(-__uint_as_float(hi[2 * i]), -__uint_as_float(hi[2 * i + 1])));
+            lo[2 * i] = __float_as_uint(l.x); lo[2 * i + 1] = __float_as_uint(l.y);
+          }
+          tmem_st16(lane_addr + ATC_COL_AHI + s * 32 + half * 16, hi);
+          tmem_st16(lane_addr + ATC_COL_ALO + s * 32 + half * 16, lo);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-        named_arrive(BAR_A_READY, TT_THREADS);
+        TL_MARK(8);
+        hand_over_a();
+        TL_MARK(9);
       }
-      prev_e = gvalid ? e : -1; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok));
+      if (VPASS || !TT_EARLY_PREFETCH) {      // register budget: the prefetch of the next tile's rows starts after the hand-over
+#pragma unroll
+        for (int i8 = 0; i8 < 4; ++i8) ldg8(prow_next + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+      }
+      // ---- finish the epilogue of the previous tile from registers while the tensor core works
+      if (it > 0) {
+        if (!VPASS) {
+          // softmax over the 32 rows of the group, 4 heads at once: max by one REDUX each, sums by a transposed all-reduce
+          float ex[4];
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            float m;
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(lg[hh]));
+            ex[hh] = prev_ok ? expf(lg[hh] - m) : 0.f;
+          }
+          float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
+          warp_allreduce4(sum, lane);
+          float w[4];
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? ex[hh] * __frcp_rn(sum[hh]) : 0.f;
+          if (prev_e >= 0) st4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
+        } else {
+          warp_reduce_scatter<32>(val, lane);
+          if (prev_e >= 0) {
+            const int c = s * 32 + lane;
+            const float upd = prev_nvalid > 0 ? val[0] + sm.b2[c] : 0.f;
+            a.h_bond_out[(size_t)prev_e * H + c] = hb_in + upd;      // :274
+          }
+        }
+      }
+      prev_e = gvalid ? e : -1; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok)); prev_tb = tb;
+      TL_MARK(10);
     }
+    TL_FLUSH(VPASS ? 1 : 0);
+    // ---- epilogue of the last tile
     if (it > 0) {
       mbar_wait(bar_mma, (it - 1) & 1);
       tc_fence_after();
-      trip_epilogue<VPASS>(a, sm, tmem_base, q, s, lane, (it - 1) & 3, prev_e, prev_ok, prev_nvalid);
+      if (!VPASS) {
+        float4 w4 = atc_logits_softmax(tmem_base, q, s, wqry + ((it - 1) & 3) * 32 - s * 32, prev_ok);
+        if (prev_e >= 0) st4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4, w4);
+      } else {
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
+        float tot = atc_weighted_colsum(tmem_base, q, s, lane, w4);
+        if (prev_e >= 0) {
+          const int c = s * 32 + lane;
+          float upd = prev_nvalid > 0 ? tot + sm.b2[c] : 0.f;
+          a.h_bond_out[(size_t)prev_e * H + c] = a.h_bond_in[(size_t)prev_e * H + c] + upd;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -280,6 +413,12 @@ void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t str
   if (vpass) trip_tc_kernel<true><<<grid, TT_THREADS, bytes, stream>>>(a);
   else trip_tc_kernel<false><<<grid, TT_THREADS, bytes, stream>>>(a);
 }
+
+#ifdef DDB_TIMELINE
+extern "C" int ddb_debug_trip_timeline(unsigned long long* out /* 2*2*16 */) {
+  return (int)cudaMemcpyFromSymbol(out, g_trip_timeline, sizeof(unsigned long long) * 64);
+}
+#endif
 
 // host-side packing of Wa[13][128] (first-Linear columns of the angular encoding, transposed) into the B operand of the
 // angular MMA: rows n = output channel, K = 16 features (13 used), hi | lo, 128-byte rows with the 128B swizzle
