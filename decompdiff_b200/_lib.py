@@ -42,11 +42,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get('DDB_LIB_PATH', LIB_PATH)      # A/B testing of kernel variants; the default is the in-tree build
+    if not os.path.exists(path):
         raise RuntimeError(
-            f'{LIB_PATH} is missing - the CUDA extension is required (no CPU fallback). '
+            f'{path} is missing - the CUDA extension is required (no CPU fallback). '
             'Build it with `python -m decompdiff_b200.build`.')
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     L.ddb_last_error.restype = C.c_char_p
     L.ddb_version.restype = C.c_char_p

@@ -38,7 +38,7 @@ struct Blob {
 };
 
 struct Mlp2 { size_t gamma, beta, W2, b2, W2tc; };   // offsets: LayerNorm affine + second Linear (natural layout) + tensor-core image
-struct KnnMlpOff { size_t Wg, Wt; Mlp2 m; };
+struct KnnMlpOff { size_t Wg, Wt, B2tc[2]; Mlp2 m; };
 struct TripOff { size_t Wd, Wc, Wa, Watc; Mlp2 m; };
 struct GemmW { size_t Wt, bias, Wtc; int N; };     // K-major weight (128 x N) + bias (N) + tensor-core image (2*128*N)
 
@@ -138,6 +138,11 @@ struct Packer {
     KnnMlpOff r;
     r.Wg = cols_t(pre + ".net.0.weight", 340, 0, 80);     // [type*20+g][128]
     r.Wt = cols_t(pre + ".net.0.weight", 340, 80, 4);
+    for (int cls = 0; cls < 2; ++cls) {          // distance-term weights per destination class (tensor-core kernels)
+      r.B2tc[cls] = m.blob.alloc((size_t)2 * 5120);
+      std::vector<float> wg(m.blob.data.begin() + r.Wg, m.blob.data.begin() + r.Wg + (size_t)80 * H);
+      pack_wg_tc(wg.data(), cls ? 2 : 3, cls ? 0 : 1, m.blob.data.data() + r.B2tc[cls]);
+    }
     r.m = mlp2(pre, out_dim, scale);
     return r;
   }
@@ -324,7 +329,8 @@ struct ddb_batch {
   float *PL = nullptr, *qNB = nullptr, *PLx = nullptr, *qXe = nullptr, *qXb = nullptr;
   float *hbA = nullptr, *hbB = nullptr, *PB = nullptr, *qE = nullptr, *Pk = nullptr, *Pv = nullptr, *PBx = nullptr;
   float *Qk = nullptr, *Qv = nullptr, *Pmk = nullptr, *Pmv = nullptr, *Qmk = nullptr, *Qmv = nullptr;
-  float *wb_knn = nullptr, *wb_bond = nullptr, *wb_trip = nullptr, *e_w = nullptr, *dx_edge = nullptr;
+  float *wb_knn = nullptr, *wb_bond = nullptr, *wb_trip = nullptr, *e_w = nullptr, *dx_edge = nullptr, *dist = nullptr;
+  int* dst_sorted = nullptr; int n_slots_all = 0, n_slots_prot = 0;   // destinations by class (protein first), padded to tiles of 4
   int *nbr = nullptr, *deg = nullptr, *nlig = nullptr;
   float *hid_v = nullptr, *v_logits = nullptr, *b_logits = nullptr, *x0 = nullptr, *grad = nullptr;
   // results of the last forward
@@ -511,6 +517,15 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   }
   std::vector<uint8_t> upd(NL, 1);
   if (ligand_atom_mask) for (int i = 0; i < NL; ++i) upd[i] = ligand_atom_mask[i] ? 1 : 0;
+  {   // destinations of the kNN node update grouped by class (tiles of 4 never mix protein and ligand destinations)
+    std::vector<int> sorted;
+    for (int i = 0; i < N; ++i) if (!is_lig[i]) sorted.push_back(i);
+    while (sorted.size() % 4) sorted.push_back(-1);
+    b->n_slots_prot = (int)sorted.size();
+    for (int i = 0; i < N; ++i) if (is_lig[i]) sorted.push_back(i);
+    b->n_slots_all = (int)sorted.size();
+    DDB_TRY(b->upload(&b->dst_sorted, sorted));
+  }
 
   DDB_TRY(b->upload(&b->node_ptr, node_ptr)); DDB_TRY(b->upload(&b->graph_of, graph_of));
   DDB_TRY(b->upload(&b->lig_idx, lig_idx)); DDB_TRY(b->upload(&b->lig_ptr, lig_ptr));
@@ -534,7 +549,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   DDB_TRY(b->dalloc(&b->Pmk, eb)); DDB_TRY(b->dalloc(&b->Pmv, eb)); DDB_TRY(b->dalloc(&b->Qmk, eb)); DDB_TRY(b->dalloc(&b->Qmv, eb));
   DDB_TRY(b->dalloc(&b->wb_knn, n * KNN * NH)); DDB_TRY(b->dalloc(&b->wb_bond, eb * NH));
   DDB_TRY(b->dalloc(&b->wb_trip, (size_t)slots * NH));
-  DDB_TRY(b->dalloc(&b->e_w, n * KNN)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4));
+  DDB_TRY(b->dalloc(&b->e_w, n * KNN)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4)); DDB_TRY(b->dalloc(&b->dist, n * KNN));
   DDB_TRY(b->dalloc(&b->nbr, n * KNN)); DDB_TRY(b->dalloc(&b->deg, n)); DDB_TRY(b->dalloc(&b->nlig, n));
   DDB_TRY(b->dalloc(&b->hid_v, nl * H)); DDB_TRY(b->dalloc(&b->v_logits, nl * c.num_classes));
   DDB_TRY(b->dalloc(&b->b_logits, eb * c.num_bond_classes)); DDB_TRY(b->dalloc(&b->x0, nl * 3));
@@ -666,8 +681,15 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ka.n_dst = N; ka.Hi = b->PN; ka.ldhi = 5 * H; ka.Hj = b->PN + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
     ka.x4 = x_in; ka.nbr = b->nbr; ka.deg = b->deg; ka.nlig = b->nlig; ka.is_lig = b->is_lig; ka.e_w = b->e_w;
     ka.wbuf = b->wb_knn; ka.w = knn_w(m, L.ne_k); ka.W2tc = m->p(L.ne_k.m.W2tc);
+    if (b->tc_attn & 12) { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn_dist(x_in, b->nbr, b->deg, N, b->dist, s); b->launches += 1; }
+    auto tc_dsts = [&](KnnAttnArgs& k, const KnnMlpOff& o, bool on) {      // the tensor-core kernels walk destinations by class
+      k.dist = b->dist; k.B2tc[0] = m->p(o.B2tc[0]); k.B2tc[1] = m->p(o.B2tc[1]);
+      k.n_dst = on ? b->n_slots_all : N; k.dst_list = on ? b->dst_sorted : nullptr; k.n_slots_prot = on ? b->n_slots_prot : 0;
+    };
+    tc_dsts(ka, L.ne_k, b->tc_attn & 4);
     { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, false, sms, s); else launch_knn_attn_k(ka, sms, s); }
     ka.Hi = b->PN + 2 * H; ka.Hj = b->PN + 3 * H; ka.w = knn_w(m, L.ne_v); ka.W2tc = m->p(L.ne_v.m.W2tc); ka.out_h = b->h1; ka.ldo = H;
+    tc_dsts(ka, L.ne_v, b->tc_attn & 8);
     { ProfScope ps(b, s, PC_KNN_ATTN_V); if (b->tc_attn & 8) launch_knn_tc(ka, true, sms, s); else launch_knn_attn_v_node(ka, sms, s); }
     // --- node update over bond edges -> h1[ligand rows] +=
     BondAttnArgs ba;
@@ -706,6 +728,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     kp.Hj = b->PNx; kp.ldhj = 2 * H; kp.q = b->qXe; kp.ldq = H; kp.q_by_slot = 1;
     kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
     kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k); kp.W2tc = m->p(L.pe_k.m.W2tc);
+    kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_prot = 0;      // ligand destinations only
     { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, false, sms, s); else launch_knn_attn_k(kp, sms, s); }
     kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
     { ProfScope ps(b, s, PC_KNN_POS_V); launch_knn_attn_v_pos(kp, sms, s); }

@@ -1,104 +1,375 @@
-// Tensor-core attention over the kNN(32) edges (see attn_tc.cuh for the structure shared with the triplet kernels).
+// Tensor-core attention over the kNN(32) edges: NodeUpdateLayer / PosUpdateLayer key pass and the node value pass
+// (uni_transformer_edge.py:42-74, 188-210).  Structure shared with the triplet kernel (attn_tc.cuh, attn_tc_trip.cu):
+//   rows   : one kNN edge each; 32 rows = the incoming edges of one destination node = one softmax group = one TMEM lane
+//            quadrant; 4 destinations form a 128-row tile; thread = (row, 32-channel slice)
+//   GEMM 1 : the distance term of the first Linear, sum_g gauss_g(d) Wg[type][g][:], on tcgen05: A2 = Gaussian features of the
+//            row placed in the column block of its source class (protein | ligand source, 2 x 20 columns, hi/lo TF32 split,
+//            SWIZZLE_32B K-major tile written by the workers), B2 = the two matching type blocks of Wg for the destination
+//            class of the tile (destinations are visited protein class first; B2 is swapped once at the class boundary)
+//   SIMT   : z = D2 + P_src[j] (row gather, LDG.256) + (P_dst[i] + Wt[type]) (staged per warp), LayerNorm, ReLU, TF32 split
+//   GEMM 2 : second Linear, A = hidden activations in TMEM, B = W2 hi/lo resident in shared memory (3xTF32)
+//   k pass : logits = <q_i[head], D[row, head]>, softmax over the 32 rows, times e_w -> wbuf
+//   v pass : out_h[i] = sum_rows w[row, head(c)] D[row, c] + b2[c] sum_rows w[row, head(c)]
+// A dedicated warp issues the MMAs (the angular... distance MMA one tile ahead); setmaxnreg moves its registers to the workers.
 #include "attn_tc.cuh"
 
 namespace ddb {
 
-// ================================================================================================ kNN edges
+constexpr int KT_THREADS = ATC_THREADS + 128;     // 16 worker warps + the issuing warpgroup
+constexpr int KT_SYNC = ATC_THREADS + 32;         // participants of the hand-over barriers
+constexpr int KT_KB = 5;                          // 40 feature columns = 5 k-steps of 8
+constexpr int KT_IMG = KT_KB * 128 * 32;          // one TF32 image of a [128 rows][40 cols] SWIZZLE_32B operand: 20480 bytes
+constexpr int KT_COL_D2 = 384;
+constexpr int KBAR_A2_READY = 5, KBAR_A_READY = 6;
+
 struct KnnTcSmem {
-  uint8_t* W2; float *Wg, *Wt, *gamma, *beta, *b2, *G, *Hi, *qry, *statA, *statB; uint64_t* bars; uint32_t* tmem_slot;
+  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *hit, *qry; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
   __device__ explicit KnnTcSmem(uint8_t* raw) {
     uint8_t* p = raw;
     W2 = p; p += ATC_W2_BYTES;
-    Wg = reinterpret_cast<float*>(p); p += 4 * NG * H * 4;
-    Wt = reinterpret_cast<float*>(p); p += 4 * H * 4;
+    B2 = p; p += 2 * KT_IMG;
+    A2 = p; p += 2 * KT_IMG;
     gamma = reinterpret_cast<float*>(p); p += H * 4;
     beta = reinterpret_cast<float*>(p); p += H * 4;
     b2 = reinterpret_cast<float*>(p); p += H * 4;
-    G = reinterpret_cast<float*>(p); p += 128 * NG * 4;
-    Hi = reinterpret_cast<float*>(p); p += 4 * H * 4;
-    qry = reinterpret_cast<float*>(p); p += 2 * 4 * H * 4;
-    statA = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
-    statB = reinterpret_cast<float*>(p); p += 128 * 4 * 4;
-    bars = reinterpret_cast<uint64_t*>(p); p += 16;
+    hit = reinterpret_cast<float*>(p); p += 16 * 64 * 4;        // per warp: dst-side row slice + Wt[type], for protein | ligand sources
+    qry = reinterpret_cast<float*>(p); p += 16 * 64 * 4;        // per warp: 2-deep ring of 32-float query slices
+    stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;  // [parity][row][slice] {sum, sum of squares}
+    bars = reinterpret_cast<uint64_t*>(p); p += 32;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() {
-    return ATC_W2_BYTES + (4 * NG * H + 4 * H + 3 * H + 128 * NG + 4 * H + 8 * H + 2 * 128 * 4) * 4 + 64;
-  }
+  static constexpr int bytes() { return ATC_W2_BYTES + 4 * KT_IMG + (3 * H + 16 * 64 * 2 + 2 * 128 * 4 * 2) * 4 + 64; }
 };
 static_assert(KnnTcSmem::bytes() <= 232448, "shared memory budget");
 
+// K-major SWIZZLE_32B shared-memory matrix descriptor: rows of 32 bytes (8 tf32), 8-row groups 256 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+// byte offset of the 16-byte chunk holding columns [4*c4, 4*c4+4) of row r inside one image
+__device__ __forceinline__ int kt_chunk_off(int r, int c4) { return (c4 >> 1) * 4096 + r * 32 + (((c4 & 1) ^ ((r >> 2) & 1)) << 4); }
+
+__device__ __forceinline__ float2 kf2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 ku2f(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+__device__ __forceinline__ void knamed_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void knamed_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// distances of all kNN edges at layer entry: dist[node][lane] = |x_i - x_j| (rel_x of uni_transformer_edge.py:263-265)
+__global__ void __launch_bounds__(256) knn_dist_kernel(const float* __restrict__ x4, const int* __restrict__ nbr, const int* __restrict__ deg,
+                                                       int n, float* __restrict__ dist) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int node = idx >> 5, lane = idx & 31;
+  if (node >= n) return;
+  float d = 0.f;
+  if (lane < deg[node]) {
+    const float4 xi = ldg4(x4 + (size_t)node * 4), xj = ldg4(x4 + (size_t)__ldg(nbr + idx) * 4);
+    const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+    d = sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  dist[idx] = d;
+}
+void launch_knn_dist(const float* x4, const int* nbr, const int* deg, int n, float* dist, cudaStream_t stream) {
+  if (n <= 0) return;
+  knn_dist_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(x4, nbr, deg, n, dist);
+}
+
 template <bool VPASS>
-__global__ void __launch_bounds__(ATC_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) {
+__global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   KnnTcSmem sm(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = warp >> 2, r = q * 32 + lane;
-  const uint32_t tmem_base = atc_setup(sm.W2, a.W2tc, sm.bars, sm.tmem_slot);
-  cta_copy_f4(sm.Wg, a.w.Wg, 4 * NG * H);
-  cta_copy_f4(sm.Wt, a.w.Wt, 4 * H);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
+  // barriers: [0] W2 (+ first B2) landed, [1] main MMA retired, [2] distance MMA retired, [3] B2 of the second class landed
+  if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&sm.bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const int n_tiles = (a.n_dst + 3) / 4;
+  const int tile_class1 = a.n_slots_prot / 4;          // tiles >= this hold ligand destinations
+  if (tid == 0) {
+    const uint32_t bar = smem_u32(&sm.bars[0]);
+    mbar_expect_tx(bar, ATC_W2_BYTES + 2 * KT_IMG);
+    bulk_g2s(smem_u32(sm.W2), a.W2tc, ATC_W2_BYTES / 2, bar);
+    bulk_g2s(smem_u32(sm.W2) + ATC_W2_BYTES / 2, a.W2tc + ATC_W2_BYTES / 8, ATC_W2_BYTES / 2, bar);
+    bulk_g2s(smem_u32(sm.B2), a.B2tc[(int)blockIdx.x >= tile_class1 ? 1 : 0], 2 * KT_IMG, bar);
+  }
+  const uint32_t tmem_base = *sm.tmem_slot;
   cta_copy_f4(sm.gamma, a.w.gamma, H);
   cta_copy_f4(sm.beta, a.w.beta, H);
   if (VPASS) cta_copy_f4(sm.b2, a.w.b2, H);
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
-  const uint32_t bar_mma = smem_u32(&sm.bars[1]), w2_smem = smem_u32(sm.W2);
+  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_d2 = smem_u32(&sm.bars[2]);
+  const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
 
-  const int n_tiles = (a.n_dst + 3) / 4;
-  int it = 0;
-  int prev_node = -1; bool prev_ok = false; float prev_ew = 0.f;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    // ---- P0: group = destination node, row = one of its (<= 32) incoming kNN edges
-    const int slot = tile * 4 + q;
-    const bool gvalid = slot < a.n_dst;
-    int node = 0, deg = 0, nlig = 0; bool lig_dst = false;
-    if (gvalid) { node = a.dst_list ? a.dst_list[slot] : slot; deg = a.deg[node]; nlig = a.nlig[node]; lig_dst = a.is_lig[node]; }
-    const bool rowok = gvalid && lane < deg;
-    const int j = rowok ? __ldg(a.nbr + (size_t)node * KNN + lane) : node;
-    const int type = lig_dst ? (lane < nlig ? 0 : 2) : (lane < nlig ? 1 : 3);       // uni_transformer_edge.py:371-377
-    {
-      const float4 xi = ldg4(a.x4 + (size_t)node * 4), xj = ldg4(a.x4 + (size_t)j * 4);
-      float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-      float d = sqrtf(dx * dx + dy * dy + dz * dz);
-#pragma unroll
-      for (int g = 0; g < NG / 4; ++g) sm.G[r * NG + s * (NG / 4) + g] = gauss_feat(d, s * (NG / 4) + g);
-      sm.Hi[q * H + s * 32 + lane] = gvalid ? __ldg(a.Hi + (size_t)(a.hi_by_slot ? slot : node) * a.ldhi + s * 32 + lane) : 0.f;
-      if (!VPASS) sm.qry[((it & 1) * 4 + q) * H + s * 32 + lane] =
-          gvalid ? __ldg(a.q + (size_t)(a.q_by_slot ? slot : node) * a.ldq + s * 32 + lane) : 0.f;
-    }
-    quad_barrier(q);
-    // ---- P1
-    float z[32];
-    {
-      const float* hj = a.Hj + (size_t)j * a.ldhj + s * 32;
-      const float* wt = sm.Wt + type * H + s * 32;
-#pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
-        const float4 p = ldg4(hj + i4 * 4), hh = ld4(sm.Hi + q * H + s * 32 + i4 * 4), t = ld4(wt + i4 * 4);
-        z[i4 * 4] = (p.x + hh.x) + t.x; z[i4 * 4 + 1] = (p.y + hh.y) + t.y; z[i4 * 4 + 2] = (p.z + hh.z) + t.z; z[i4 * 4 + 3] = (p.w + hh.w) + t.w;
+  if (warp >= 16) {
+    // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
+#ifndef DDB_NO_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+#endif
+    if (warp == 16) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int cur_class = (int)blockIdx.x >= tile_class1 ? 1 : 0;
+      auto issue_d2 = [&](int tile) {
+        knamed_sync(KBAR_A2_READY, KT_SYNC);          // every worker has written its A2 features and has read D2 of the tile before
+        if (lane == 0) {
+          tc_fence_after();
+          const int cls = tile >= tile_class1 ? 1 : 0;
+          if (cls != cur_class) {                     // class boundary: every distance MMA issued so far has retired (workers
+            cur_class = cls;                          // waited on it), so B2 can be replaced
+            const uint32_t bar = smem_u32(&sm.bars[3]);
+            mbar_expect_tx(bar, 2 * KT_IMG);
+            bulk_g2s(b2_smem, a.B2tc[cls], 2 * KT_IMG, bar);
+            mbar_wait(bar, 0);
+          }
+          const uint64_t a_hi = umma_desc_sw32(a2_smem), a_lo = umma_desc_sw32(a2_smem + KT_IMG);
+          const uint64_t b_hi = umma_desc_sw32(b2_smem), b_lo = umma_desc_sw32(b2_smem + KT_IMG);
+#pragma unroll 1
+          for (int kb = 0; kb < KT_KB; ++kb) {
+            const uint64_t o = (uint64_t)((kb * 4096) >> 4);
+            umma_tf32_ss(tmem_base + KT_COL_D2, a_hi + o, b_hi + o, idesc, kb ? 1u : 0u);
+            umma_tf32_ss(tmem_base + KT_COL_D2, a_lo + o, b_hi + o, idesc, 1u);
+            umma_tf32_ss(tmem_base + KT_COL_D2, a_hi + o, b_lo + o, idesc, 1u);
+          }
+          umma_commit(bar_d2);
+        }
+        __syncwarp();
+      };
+      if ((int)blockIdx.x < n_tiles) issue_d2(blockIdx.x);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tile + (int)gridDim.x < n_tiles) issue_d2(tile + gridDim.x);
+        knamed_sync(KBAR_A_READY, KT_SYNC);           // hidden activations are in TMEM, D of the previous tile is in registers
+        if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
+        __syncwarp();
       }
-      const float* wg = sm.Wg + (size_t)type * NG * H + s * 32;
+    }
+  } else {
+#ifndef DDB_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+#endif
+    // ---------------------------------------------------------------- 16 worker warps: thread = (row r, channel slice s)
+    struct Grp { int node, hidx, deg, nlig; bool lig_dst, valid; };
+    auto load_group = [&](int tile) {
+      Grp g; g.node = 0; g.hidx = 0; g.deg = 0; g.nlig = 0; g.lig_dst = false; g.valid = false;
+      const int slot = tile * 4 + q;
+      if (tile < n_tiles && slot < a.n_dst) {
+        const int node = a.dst_list ? __ldg(a.dst_list + slot) : slot;
+        if (node >= 0) {
+          g.node = node; g.valid = true; g.hidx = a.hi_by_slot ? slot : node;
+          g.deg = __ldg(a.deg + node); g.nlig = __ldg(a.nlig + node); g.lig_dst = __ldg(a.is_lig + node) != 0;
+        }
+      }
+      return g;
+    };
+    // Gaussian features of this thread's row -> A2.  Slice-warp s owns the 4-column chunks {s} (and {4} for s == 0); a chunk goes
+    // to the column block of the row's source class, the other block gets zeros.
+    auto features = [&](float d, bool src_lig) {
 #pragma unroll
-      for (int gb = 0; gb < NG / 4; ++gb) {
-        const float4 g4 = ld4(sm.G + r * NG + gb * 4);
+      for (int rep = 0; rep < 2; ++rep) {
+        if (rep == 1 && s != 0) break;
+        const int c = rep == 0 ? s : 4;
+        float g[4];
 #pragma unroll
-        for (int gc = 0; gc < 4; ++gc) {
-          const float gv = sel4(g4, gc);
+        for (int i = 0; i < 4; ++i) { const float t = d - c_gauss_offset[c * 4 + i]; g[i] = expf(-0.5f * t * t); }
+        uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 w = ld4(wg + (gb * 4 + gc) * H + i4 * 4);
-            z[i4 * 4] = fmaf(gv, w.x, z[i4 * 4]); z[i4 * 4 + 1] = fmaf(gv, w.y, z[i4 * 4 + 1]);
-            z[i4 * 4 + 2] = fmaf(gv, w.z, z[i4 * 4 + 2]); z[i4 * 4 + 3] = fmaf(gv, w.w, z[i4 * 4 + 3]);
+        for (int i = 0; i < 4; ++i) tf32_split(g[i], hi[i], lo[i]);
+        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]), z4 = make_uint4(0u, 0u, 0u, 0u);
+        const int off_p = kt_chunk_off(r, c), off_l = kt_chunk_off(r, 5 + c);
+        *reinterpret_cast<uint4*>(sm.A2 + off_p) = src_lig ? z4 : vh;
+        *reinterpret_cast<uint4*>(sm.A2 + KT_IMG + off_p) = src_lig ? z4 : vl;
+        *reinterpret_cast<uint4*>(sm.A2 + off_l) = src_lig ? vh : z4;
+        *reinterpret_cast<uint4*>(sm.A2 + KT_IMG + off_l) = src_lig ? vl : z4;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
+      tc_fence_before();
+      knamed_arrive(KBAR_A2_READY, KT_SYNC);
+    };
+    float* const whit = sm.hit + warp * 64;         // [2 source classes][32]
+    float* const wqry = sm.qry + warp * 64;         // [2-deep ring][32]
+    const int step = gridDim.x;
+
+    int it = 0;
+    Grp g = load_group(blockIdx.x), g_n = load_group(blockIdx.x + step);
+    // row state of the current tile
+    int j = g.valid && lane < g.deg ? __ldg(a.nbr + (size_t)g.node * KNN + lane) : 0;
+    float hi_cur = g.valid ? __ldg(a.Hi + (size_t)g.hidx * a.ldhi + s * 32 + lane) : 0.f;
+    float4 pv[8];
+    if ((int)blockIdx.x < n_tiles) {
+      const float d0 = g.valid ? __ldg(a.dist + (size_t)g.node * KNN + lane) : 0.f;
+      features(d0, lane < g.nlig);                  // prologue: the distance MMA of the first tile
+      const float* prow = a.Hj + (size_t)j * a.ldhj + s * 32;
+#pragma unroll
+      for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+    }
+    int prev_node = -1; bool prev_ok = false; float prev_ew = 0.f;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += step, ++it) {
+      const bool rowok = g.valid && lane < g.deg;
+      // ---- requests for later: rows of the next tile, group metadata two tiles ahead, this tile's query / edge weight
+      const int j_n = g_n.valid && lane < g_n.deg ? __ldg(a.nbr + (size_t)g_n.node * KNN + lane) : 0;
+      const float d_n = g_n.valid ? __ldg(a.dist + (size_t)g_n.node * KNN + lane) : 0.f;
+      const float hi_n = g_n.valid ? __ldg(a.Hi + (size_t)g_n.hidx * a.ldhi + s * 32 + lane) : 0.f;
+      const Grp g_nn = load_group(tile + 2 * step);
+      float qry_v = 0.f, ew = 0.f;
+      if (!VPASS) {
+        if (g.valid) qry_v = __ldg(a.q + (size_t)(a.q_by_slot ? tile * 4 + q : g.node) * a.ldq + s * 32 + lane);
+        if (rowok) ew = __ldg(a.e_w + (size_t)g.node * KNN + lane);
+      }
+      // dst-side term of the first Linear + type bias, for protein and for ligand sources (uni_transformer_edge.py:371-377)
+      {
+        const int tp = g.lig_dst ? 2 : 3, tl = g.lig_dst ? 0 : 1;
+        whit[lane] = hi_cur + __ldg(a.w.Wt + tp * H + s * 32 + lane);
+        whit[32 + lane] = hi_cur + __ldg(a.w.Wt + tl * H + s * 32 + lane);
+        if (!VPASS) wqry[(it & 1) * 32 + lane] = qry_v;
+      }
+      // ---- first Linear: z = P_src[j] (prefetched) + (P_dst[i] + Wt) (staged) + D2 (distance MMA, issued one iteration ago)
+      float2 z[16];
+      {
+        mbar_wait(bar_d2, it & 1);
+        tc_fence_after();
+        __syncwarp();
+        const float* hs = whit + (lane < g.nlig ? 32 : 0);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 hv = ld4(hs + i4 * 4);
+          z[i4 * 2] = __fadd2_rn(kf2(pv[i4].x, pv[i4].y), kf2(hv.x, hv.y));
+          z[i4 * 2 + 1] = __fadd2_rn(kf2(pv[i4].z, pv[i4].w), kf2(hv.z, hv.w));
+        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + KT_COL_D2 + s * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], ku2f(v[2 * i], v[2 * i + 1]));
+      }
+      // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
+      if (tile + step < n_tiles) features(d_n, lane < g_n.nlig);
+      // ---- LayerNorm with one exchange between the 4 slice-warps of the quadrant, ReLU
+      {
+        float2 s1 = kf2(0.f, 0.f), s2 = kf2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s1 = __fadd2_rn(s1, z[i]);
+        const float part = s1.x + s1.y;
+        // two-pass statistics need two exchanges; a one-pass variance about the slice mean needs only one: exchange
+        // {sum, centred sum of squares} and combine with the parallel-variance formula
+        const float mu_s = part * (1.0f / 32.0f);
+        const float2 nm = kf2(-mu_s, -mu_s);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float2 dz = __fadd2_rn(z[i], nm); s2 = __ffma2_rn(dz, dz, s2); }
+        float2* st = sm.stat + ((it & 1) * 128 + r) * 4;
+        st[s] = make_float2(part, s2.x + s2.y);
+        quad_barrier(q);
+        const float4 t01 = *reinterpret_cast<const float4*>(st), t23 = *reinterpret_cast<const float4*>(st + 2);
+        const float mu = ((t01.x + t01.z) + (t23.x + t23.z)) * (1.0f / H);
+        const float d0 = t01.x * (1.0f / 32.0f) - mu, d1 = t01.z * (1.0f / 32.0f) - mu, d2 = t23.x * (1.0f / 32.0f) - mu, d3 = t23.z * (1.0f / 32.0f) - mu;
+        const float m2 = ((t01.y + t01.w) + (t23.y + t23.w)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+        const float rstd = 1.0f / sqrtf(m2 * (1.0f / H) + LN_EPS);
+        const float2 rs2 = kf2(rstd, rstd), nm2 = kf2(-mu * rstd, -mu * rstd);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 gm = ld4(sm.gamma + s * 32 + i4 * 4), bt = ld4(sm.beta + s * 32 + i4 * 4);
+          float2 u0 = __ffma2_rn(z[i4 * 2], rs2, nm2), u1 = __ffma2_rn(z[i4 * 2 + 1], rs2, nm2);      // (z - mu) * rstd
+          u0 = __ffma2_rn(u0, kf2(gm.x, gm.y), kf2(bt.x, bt.y));
+          u1 = __ffma2_rn(u1, kf2(gm.z, gm.w), kf2(bt.z, bt.w));
+          z[i4 * 2] = kf2(fmaxf(u0.x, 0.f), fmaxf(u0.y, 0.f));
+          z[i4 * 2 + 1] = kf2(fmaxf(u1.x, 0.f), fmaxf(u1.y, 0.f));
+        }
+      }
+      // ---- drain D of the previous tile into registers
+      float lg[4] = {0.f, 0.f, 0.f, 0.f};
+      float val[32];
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (VPASS && it > 0 && prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
+      if (it > 0) {
+        mbar_wait(bar_mma, (it - 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!VPASS) {
+          const float* qr = wqry + ((it - 1) & 1) * 32;
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            const float4 q0 = ld4(qr + hh * 8), q1 = ld4(qr + hh * 8 + 4);
+            float2 acc = __fmul2_rn(kf2(q0.x, q0.y), ku2f(v[hh * 8], v[hh * 8 + 1]));
+            acc = __ffma2_rn(kf2(q0.z, q0.w), ku2f(v[hh * 8 + 2], v[hh * 8 + 3]), acc);
+            acc = __ffma2_rn(kf2(q1.x, q1.y), ku2f(v[hh * 8 + 4], v[hh * 8 + 5]), acc);
+            acc = __ffma2_rn(kf2(q1.z, q1.w), ku2f(v[hh * 8 + 6], v[hh * 8 + 7]), acc);
+            lg[hh] = prev_ok ? acc.x + acc.y : -INFINITY;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;
+            val[i] = wh * __uint_as_float(v[i]);
           }
         }
       }
+      // ---- hidden activations -> TMEM, 16 columns at a time (hi = z truncated to TF32, lo = z - hi, exact)
+      {
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float2 zz = z[half * 8 + i];
+            hi[2 * i] = __float_as_uint(zz.x) & 0xffffe000u;
+            hi[2 * i + 1] = __float_as_uint(zz.y) & 0xffffe000u;
+            const float2 l = __fadd2_rn(zz, kf2(-__uint_as_float(hi[2 * i]), -__uint_as_float(hi[2 * i + 1])));
+            lo[2 * i] = __float_as_uint(l.x); lo[2 * i + 1] = __float_as_uint(l.y);
+          }
+          tmem_st16(lane_addr + ATC_COL_AHI + s * 32 + half * 16, hi);
+          tmem_st16(lane_addr + ATC_COL_ALO + s * 32 + half * 16, lo);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        knamed_arrive(KBAR_A_READY, KT_SYNC);
+      }
+      // ---- row gather of the next tile (consumed one iteration from now)
+      {
+        const float* prow = a.Hj + (size_t)j_n * a.ldhj + s * 32;
+#pragma unroll
+        for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+      }
+      // ---- finish the epilogue of the previous tile from registers while the tensor core works
+      if (it > 0) {
+        if (!VPASS) {
+          float ex[4];
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            float m;
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(lg[hh]));
+            ex[hh] = prev_ok ? expf(lg[hh] - m) : 0.f;
+          }
+          float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
+          warp_allreduce4(sum, lane);
+          float w[4];
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? ex[hh] * __frcp_rn(sum[hh]) * prev_ew : 0.f;
+          if (prev_ok) st4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
+        } else {
+          float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+          warp_allreduce4(ws, lane);
+          warp_reduce_scatter<32>(val, lane);
+          if (prev_node >= 0) {
+            const int c = s * 32 + lane;
+            a.out_h[(size_t)prev_node * a.ldo + c] = val[0] + sm.b2[c] * ws[lane >> 3];
+          }
+        }
+      }
+      prev_node = g.valid ? g.node : -1; prev_ok = rowok; prev_ew = ew;
+      g = g_n; g_n = g_nn; j = j_n; hi_cur = hi_n;
     }
-    atc_ln_relu(z, sm.statA, sm.statB, r, s, q, sm.gamma, sm.beta);
-    // ---- epilogue of the previous tile
+    // ---- epilogue of the last tile
     if (it > 0) {
       mbar_wait(bar_mma, (it - 1) & 1);
       tc_fence_after();
       if (!VPASS) {
-        float4 w4 = atc_logits_softmax(tmem_base, q, s, sm.qry + (((it - 1) & 1) * 4 + q) * H, prev_ok);
+        float4 w4 = atc_logits_softmax(tmem_base, q, s, wqry + ((it - 1) & 1) * 32 - s * 32, prev_ok);
         if (prev_ok) st4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4,
                          make_float4(w4.x * prev_ew, w4.y * prev_ew, w4.z * prev_ew, w4.w * prev_ew));
       } else {
@@ -110,27 +381,6 @@ __global__ void __launch_bounds__(ATC_THREADS, 1) knn_tc_kernel(const KnnAttnArg
           const int c = s * 32 + lane;
           a.out_h[(size_t)prev_node * a.ldo + c] = tot + sm.b2[c] * sel4(ws, lane >> 3);
         }
-      }
-    }
-    atc_store_and_mma(z, rowok, tmem_base, q, s, w2_smem, bar_mma);
-    prev_node = gvalid ? node : -1; prev_ok = rowok;
-    prev_ew = (!VPASS && rowok) ? __ldg(a.e_w + (size_t)node * KNN + lane) : 0.f;
-  }
-  if (it > 0) {
-    mbar_wait(bar_mma, (it - 1) & 1);
-    tc_fence_after();
-    if (!VPASS) {
-      float4 w4 = atc_logits_softmax(tmem_base, q, s, sm.qry + (((it - 1) & 1) * 4 + q) * H, prev_ok);
-      if (prev_ok) st4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4,
-                       make_float4(w4.x * prev_ew, w4.y * prev_ew, w4.z * prev_ew, w4.w * prev_ew));
-    } else {
-      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
-      float tot = atc_weighted_colsum(tmem_base, q, s, lane, w4);
-      float4 ws = make_float4(warp_sum(w4.x), warp_sum(w4.y), warp_sum(w4.z), warp_sum(w4.w));
-      if (prev_node >= 0) {
-        const int c = s * 32 + lane;
-        a.out_h[(size_t)prev_node * a.ldo + c] = tot + sm.b2[c] * sel4(ws, lane >> 3);
       }
     }
   }
@@ -149,8 +399,24 @@ void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t s
     once = true;
   }
   const int grid = atc_grid((a.n_dst + 3) / 4, num_sms);
-  if (vpass) knn_tc_kernel<true><<<grid, ATC_THREADS, bytes, stream>>>(a);
-  else knn_tc_kernel<false><<<grid, ATC_THREADS, bytes, stream>>>(a);
+  if (vpass) knn_tc_kernel<true><<<grid, KT_THREADS, bytes, stream>>>(a);
+  else knn_tc_kernel<false><<<grid, KT_THREADS, bytes, stream>>>(a);
+}
+
+// host-side packing of the distance-term weights for one destination class: B2[n = channel][k], k < 20: Wg[type_p][k][n],
+// 20 <= k < 40: Wg[type_l][k-20][n]; hi | lo images in the SWIZZLE_32B K-major layout of the kernel
+void pack_wg_tc(const float* Wg /* [4*20][128] */, int type_p, int type_l, float* out /* 2 * KT_IMG / 4 floats */) {
+  for (int i = 0; i < 2 * KT_IMG / 4; ++i) out[i] = 0.f;
+  float* hi = out;
+  float* lo = out + KT_IMG / 4;
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 40; ++k) {
+      const int type = k < 20 ? type_p : type_l, g = k < 20 ? k : k - 20;
+      const float w = Wg[(size_t)(type * NG + g) * H + n];
+      const float h = host_tf32_rna(w), l = host_tf32_rna(w - h);
+      const int off = ((k >> 3) * 4096 + n * 32 + ((((k >> 2) & 1) ^ ((n >> 2) & 1)) << 4) + (k & 3) * 4) / 4;
+      hi[off] = h; lo[off] = l;
+    }
 }
 
 // host-side packing of a second-Linear weight W2[128 out][128 in] (already scaled) into the hi | lo swizzled image

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
 
   if (warp >= 16) {
     // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+#endif
     if (warp == TT_ISSUER) {
       // tensor-pipe order: ang(t0), [ang(t1), main(t0)], [ang(t2), main(t1)], ...  - the angular MMA runs one tile ahead
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -133,7 +135,9 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       }
     }
   } else {
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+#endif
     auto hand_over_a2 = [&]() { named_arrive(BAR_A2_READY, TT_SYNC); };
     auto hand_over_a = [&]() { named_arrive(BAR_A_READY, TT_SYNC); };
     // ---------------------------------------------------------------- 16 warps: thread = (row r, channel slice s)

@@ -38,6 +38,12 @@ struct KnnAttnArgs {
   float* wbuf = nullptr;              // (N*32,16) logits -> alpha * e_w
   KnnMlpW w;
   const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 for the tensor-core kernels (attn_tc.cu)
+  // tensor-core kernels only: distances at layer entry (N,32), the distance-term weights per destination class
+  // (0 = protein, 1 = ligand destinations; pack_wg_tc) and the number of leading slots of dst_list that are protein
+  // destinations (a multiple of 4; padding slots hold -1)
+  const float* dist = nullptr;
+  const float* B2tc[2] = {nullptr, nullptr};
+  int n_slots_prot = 0;
   // v pass outputs
   float* out_h = nullptr; int ldo = 0;          // node variant: (N,128) rows by node id
   float* out_dx = nullptr;                      // pos variant: (n_dst,4) by slot
@@ -119,7 +125,9 @@ void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
 // ---- tensor-core variants (attn_tc.cu): same arguments, wbuf rows of a group are 32 apart; groups of <= 32 rows only
 void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t stream);
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
+void launch_knn_dist(const float* x4, const int* nbr, const int* deg, int n, float* dist, cudaStream_t stream);
 void pack_w2_tc(const float* W2, float* out);
+void pack_wg_tc(const float* Wg, int type_p, int type_l, float* out /* 2 * 5120 floats */);
 void pack_wa_tc(const float* Wa, float* out);
 
 // ---- embeddings, heads, reverse step, guidance (step.cu) -----------------------------------------
