@@ -64,6 +64,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_first(self, timeout_s: float):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
@@ -220,7 +225,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     wl = WORKLOADS[args.workload]
     warmup = max(args.warmup, 3)
-    if warmup + args.steps + 8 > T_FULL:
+    if warmup + args.steps + 64 > T_FULL:
         raise SystemExit('warmup + steps must stay below T=1000')
 
     model = ddb.DecompScorePosNet3D(syn.DEFAULT_MODEL_CONFIG, syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
@@ -236,12 +241,22 @@ def main():
 
     # ---------------------------------------------------------------- device-resident steps (value)
     run = model.begin_sampling(**kw, num_steps=T_FULL, center_pos_mode='protein', energy_drift_opt=drift)
-    run.advance(warmup)
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi's own start-up (NVML initialisation) disturbs a running GPU for
+    # a few hundred ms and must not fall into the timed region
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first(5.0)
+    run.advance(warmup)
+    # W warm-up steps are the contract's minimum; keep stepping (untimed) until the GPU has been busy for ~0.5 s so that the
+    # timed steps run at steady-state clocks with an instantiated graph
     torch.cuda.synchronize()
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.5 and warmup + args.steps + 16 < T_FULL:
+        run.advance(4)
+        warmup += 4
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
