@@ -317,6 +317,8 @@ class DecompScorePosNet3D(nn.Module):
             ligand_decomp_batch, ligand_decomp_index, ligand_atom_mask, ligand_fc_bond_index, init_ligand_fc_bond_type,
             batch_ligand_bond, num_steps, center_pos_mode, energy_drift_opt, full_protein_pos, full_batch_protein,
             keep_traj)
+        if keep_traj and not traj_on_device:      # the reference's trajectories are CPU tensors whatever the input device
+            run.enable_host_streaming()
         run.advance(run.num_steps, noise=noise)
         return run.finish(traj_on_device=traj_on_device)
 
@@ -350,6 +352,28 @@ class SamplingRun:
                ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj', 'bond_traj', 'bt_traj')})
         self.done = 0
         self.graph = None
+        # trajectories stream to pinned host memory while later steps run (side stream, every STREAM_CHUNK steps), so the end
+        # of a run only waits for the last chunk instead of a 1.7 GB device->host copy (cfg 2)
+        self.host_traj, self.copied, self.copy_stream = None, 0, None
+
+    STREAM_CHUNK = 64
+
+    def enable_host_streaming(self):
+        if self.keep_traj and self.host_traj is None and self.num_steps > 0:
+            self.host_traj = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.traj.items()}
+            self.copy_stream = torch.cuda.Stream(device=self.eb.device)
+        return self
+
+    def _stream_out(self, force: bool = False):
+        if self.host_traj is None or self.done == self.copied or (not force and self.done - self.copied < self.STREAM_CHUNK):
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.copy_stream.wait_event(ev)
+        with torch.cuda.stream(self.copy_stream):
+            for k, v in self.traj.items():
+                self.host_traj[k][self.copied:self.done].copy_(v[self.copied:self.done], non_blocking=True)
+        self.copied = self.done
 
     def _draw(self):
         # the three draws of the reference: same order, shapes and generator
@@ -375,10 +399,12 @@ class SamplingRun:
                 raise ValueError('noise list shorter than the requested steps')
             for _ in range(k):
                 self.step_eager(noise[self.done])
+                self._stream_out()
             return self
         if not self.model.use_cuda_graph or (self.graph is None and k < 4):
             for _ in range(k):
                 self.step_eager()
+                self._stream_out()
             return self
         if self.graph is None:
             self.step_eager()                                # lazy initialisation outside the capture
@@ -390,7 +416,8 @@ class SamplingRun:
                 self.eb.reverse_step(self.io)
         for _ in range(k):
             self.graph.replay()
-        self.done += k
+            self.done += 1
+            self._stream_out()
         return self
 
     @property
@@ -407,6 +434,13 @@ class SamplingRun:
                 result[key] = []
             elif traj_on_device:
                 result[key] = self.traj[key][:self.done]
+            elif self.host_traj is not None:      # streamed while the loop ran; only the tail is still in flight
+                result[key] = None
             else:   # reference: python lists of per-step CPU tensors (:624-636, :688-689); one D2H per array here
                 result[key] = list(self.traj[key][:self.done].cpu().unbind(0))
+        if self.keep_traj and not traj_on_device and self.host_traj is not None:
+            self._stream_out(force=True)
+            self.copy_stream.synchronize()
+            for key in self.traj:
+                result[key] = list(self.host_traj[key][:self.done].unbind(0))
         return result
