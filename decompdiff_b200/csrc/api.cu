@@ -330,7 +330,8 @@ struct ddb_batch {
   float *hbA = nullptr, *hbB = nullptr, *PB = nullptr, *qE = nullptr, *Pk = nullptr, *Pv = nullptr, *PBx = nullptr;
   float *Qk = nullptr, *Qv = nullptr, *Pmk = nullptr, *Pmv = nullptr, *Qmk = nullptr, *Qmv = nullptr;
   float *wb_knn = nullptr, *wb_bond = nullptr, *wb_trip = nullptr, *e_w = nullptr, *dx_edge = nullptr, *dist = nullptr;
-  int* dst_sorted = nullptr; int n_slots_all = 0, n_slots_prot = 0;   // destinations by class (protein first), padded to tiles of 4
+  int* dst_sorted = nullptr; int n_slots_all = 0, n_slots_prot = 0;
+  int2 *slot_meta_all = nullptr, *slot_meta_lig = nullptr;   // destinations by class (protein first), padded to tiles of 4
   int *nbr = nullptr, *deg = nullptr, *nlig = nullptr;
   float *hid_v = nullptr, *v_logits = nullptr, *b_logits = nullptr, *x0 = nullptr, *grad = nullptr;
   // results of the last forward
@@ -525,6 +526,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     for (int i = 0; i < N; ++i) if (is_lig[i]) sorted.push_back(i);
     b->n_slots_all = (int)sorted.size();
     DDB_TRY(b->upload(&b->dst_sorted, sorted));
+    DDB_TRY(b->dalloc(&b->slot_meta_all, sorted.size())); DDB_TRY(b->dalloc(&b->slot_meta_lig, (size_t)NL));
   }
 
   DDB_TRY(b->upload(&b->node_ptr, node_ptr)); DDB_TRY(b->upload(&b->graph_of, graph_of));
@@ -663,6 +665,12 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   { ProfScope ps(b, s, PC_EDGE_WEIGHT); launch_edge_weight(b->x4_0, b->nbr, b->deg, N, m->p(m->ew_W1t), m->p(m->ew_b1), m->p(m->ew_gamma), m->p(m->ew_beta),
                      m->p(m->ew_w2), m->ew_b2, b->e_w, s); }
   b->launches += 5;
+  if (b->tc_attn & 12) {
+    ProfScope ps(b, s, PC_KNN_GRAPH);
+    launch_knn_slot_meta(b->dst_sorted, b->n_slots_all, b->deg, b->nlig, b->is_lig, b->slot_meta_all, s);
+    launch_knn_slot_meta(b->lig_idx, NL, b->deg, b->nlig, b->is_lig, b->slot_meta_lig, s);
+    b->launches += 2;
+  }
   float *h_in = b->h0, *x_in = b->x4_0, *hb_in = b->hbA;
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerOff& L = m->layers[l];
@@ -685,6 +693,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     auto tc_dsts = [&](KnnAttnArgs& k, const KnnMlpOff& o, bool on) {      // the tensor-core kernels walk destinations by class
       k.dist = b->dist; k.B2tc[0] = m->p(o.B2tc[0]); k.B2tc[1] = m->p(o.B2tc[1]);
       k.n_dst = on ? b->n_slots_all : N; k.dst_list = on ? b->dst_sorted : nullptr; k.n_slots_prot = on ? b->n_slots_prot : 0;
+      k.slot_meta = b->slot_meta_all;
     };
     tc_dsts(ka, L.ne_k, b->tc_attn & 4);
     { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, false, sms, s); else launch_knn_attn_k(ka, sms, s); }
@@ -728,7 +737,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     kp.Hj = b->PNx; kp.ldhj = 2 * H; kp.q = b->qXe; kp.ldq = H; kp.q_by_slot = 1;
     kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
     kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k); kp.W2tc = m->p(L.pe_k.m.W2tc);
-    kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_prot = 0;      // ligand destinations only
+    kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_prot = 0; kp.slot_meta = b->slot_meta_lig;      // ligand destinations only
     { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, false, sms, s); else launch_knn_attn_k(kp, sms, s); }
     kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
     { ProfScope ps(b, s, PC_KNN_POS_V); launch_knn_attn_v_pos(kp, sms, s); }

@@ -73,6 +73,22 @@ void launch_knn_dist(const float* x4, const int* nbr, const int* deg, int n, flo
   knn_dist_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(x4, nbr, deg, n, dist);
 }
 
+// per-slot metadata of a destination list, packed so that the attention kernels need ONE load per group and no dependent chain:
+// {node id or -1 (padding), deg | nlig << 8 | is_ligand << 16}
+__global__ void __launch_bounds__(256) knn_slot_meta_kernel(const int* __restrict__ dst_list, int n_slots, const int* __restrict__ deg,
+                                                            const int* __restrict__ nlig, const uint8_t* __restrict__ is_lig,
+                                                            int2* __restrict__ out) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  const int node = dst_list ? dst_list[slot] : slot;
+  out[slot] = node < 0 ? make_int2(-1, 0) : make_int2(node, deg[node] | (nlig[node] << 8) | ((int)is_lig[node] << 16));
+}
+void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, const int* nlig, const uint8_t* is_lig, int2* out,
+                          cudaStream_t stream) {
+  if (n_slots <= 0) return;
+  knn_slot_meta_kernel<<<(n_slots + 255) / 256, 256, 0, stream>>>(dst_list, n_slots, deg, nlig, is_lig, out);
+}
+
 template <bool VPASS>
 __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -128,8 +144,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
           }
           const uint64_t a_hi = umma_desc_sw32(a2_smem), a_lo = umma_desc_sw32(a2_smem + KT_IMG);
           const uint64_t b_hi = umma_desc_sw32(b2_smem), b_lo = umma_desc_sw32(b2_smem + KT_IMG);
+          // tiles without a ligand source (most protein destinations): the ligand column block is all zero, 3 of the 5 k-steps
+          // cover the protein block (columns 20..23 of k-step 2 are zeros written by the workers)
+          int any_lig = 0;
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const int slot = tile * 4 + g4;
+            if (slot < a.n_dst) any_lig |= (__ldg(a.slot_meta + slot).y >> 8) & 0xff;
+          }
+          const int n_kb = any_lig ? KT_KB : 3;
 #pragma unroll 1
-          for (int kb = 0; kb < KT_KB; ++kb) {
+          for (int kb = 0; kb < n_kb; ++kb) {
             const uint64_t o = (uint64_t)((kb * 4096) >> 4);
             umma_tf32_ss(tmem_base + KT_COL_D2, a_hi + o, b_hi + o, idesc, kb ? 1u : 0u);
             umma_tf32_ss(tmem_base + KT_COL_D2, a_lo + o, b_hi + o, idesc, 1u);
@@ -152,17 +176,17 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
 #endif
     // ---------------------------------------------------------------- 16 worker warps: thread = (row r, channel slice s)
-    struct Grp { int node, hidx, deg, nlig; bool lig_dst, valid; };
+    struct Grp {            // one destination group, 2 registers: node id (-1: padding) and deg | nlig << 8 | is_ligand << 16
+      int node, pk;
+      __device__ bool valid() const { return node >= 0; }
+      __device__ int deg() const { return pk & 0xff; }
+      __device__ int nlig() const { return (pk >> 8) & 0xff; }
+      __device__ bool lig_dst() const { return (pk >> 16) != 0; }
+    };
     auto load_group = [&](int tile) {
-      Grp g; g.node = 0; g.hidx = 0; g.deg = 0; g.nlig = 0; g.lig_dst = false; g.valid = false;
+      Grp g; g.node = -1; g.pk = 0;
       const int slot = tile * 4 + q;
-      if (tile < n_tiles && slot < a.n_dst) {
-        const int node = a.dst_list ? __ldg(a.dst_list + slot) : slot;
-        if (node >= 0) {
-          g.node = node; g.valid = true; g.hidx = a.hi_by_slot ? slot : node;
-          g.deg = __ldg(a.deg + node); g.nlig = __ldg(a.nlig + node); g.lig_dst = __ldg(a.is_lig + node) != 0;
-        }
-      }
+      if (tile < n_tiles && slot < a.n_dst) { const int2 m = __ldg(a.slot_meta + slot); g.node = m.x; g.pk = m.y; }
       return g;
     };
     // Gaussian features of this thread's row -> A2.  Slice-warp s owns the 4-column chunks {s} (and {4} for s == 0); a chunk goes
@@ -196,32 +220,33 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
     int it = 0;
     Grp g = load_group(blockIdx.x), g_n = load_group(blockIdx.x + step);
     // row state of the current tile
-    int j = g.valid && lane < g.deg ? __ldg(a.nbr + (size_t)g.node * KNN + lane) : 0;
-    float hi_cur = g.valid ? __ldg(a.Hi + (size_t)g.hidx * a.ldhi + s * 32 + lane) : 0.f;
+    auto hidx = [&](const Grp& gg, int tile) { return a.hi_by_slot ? tile * 4 + q : gg.node; };
+    int j = lane < g.deg() ? __ldg(a.nbr + (size_t)g.node * KNN + lane) : 0;
+    float hi_cur = g.valid() ? __ldg(a.Hi + (size_t)hidx(g, blockIdx.x) * a.ldhi + s * 32 + lane) : 0.f;
     float4 pv[8];
     if ((int)blockIdx.x < n_tiles) {
-      const float d0 = g.valid ? __ldg(a.dist + (size_t)g.node * KNN + lane) : 0.f;
-      features(d0, lane < g.nlig);                  // prologue: the distance MMA of the first tile
+      const float d0 = g.valid() ? __ldg(a.dist + (size_t)g.node * KNN + lane) : 0.f;
+      features(d0, lane < g.nlig());                // prologue: the distance MMA of the first tile
       const float* prow = a.Hj + (size_t)j * a.ldhj + s * 32;
 #pragma unroll
       for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
     }
     int prev_node = -1; bool prev_ok = false; float prev_ew = 0.f;
     for (int tile = blockIdx.x; tile < n_tiles; tile += step, ++it) {
-      const bool rowok = g.valid && lane < g.deg;
+      const bool rowok = lane < g.deg();            // deg is 0 for padding groups
       // ---- requests for later: rows of the next tile, group metadata two tiles ahead, this tile's query / edge weight
-      const int j_n = g_n.valid && lane < g_n.deg ? __ldg(a.nbr + (size_t)g_n.node * KNN + lane) : 0;
-      const float d_n = g_n.valid ? __ldg(a.dist + (size_t)g_n.node * KNN + lane) : 0.f;
-      const float hi_n = g_n.valid ? __ldg(a.Hi + (size_t)g_n.hidx * a.ldhi + s * 32 + lane) : 0.f;
+      const int j_n = lane < g_n.deg() ? __ldg(a.nbr + (size_t)g_n.node * KNN + lane) : 0;
+      const float d_n = g_n.valid() ? __ldg(a.dist + (size_t)g_n.node * KNN + lane) : 0.f;
+      const float hi_n = g_n.valid() ? __ldg(a.Hi + (size_t)hidx(g_n, tile + step) * a.ldhi + s * 32 + lane) : 0.f;
       const Grp g_nn = load_group(tile + 2 * step);
       float qry_v = 0.f, ew = 0.f;
       if (!VPASS) {
-        if (g.valid) qry_v = __ldg(a.q + (size_t)(a.q_by_slot ? tile * 4 + q : g.node) * a.ldq + s * 32 + lane);
+        if (g.valid()) qry_v = __ldg(a.q + (size_t)(a.q_by_slot ? tile * 4 + q : g.node) * a.ldq + s * 32 + lane);
         if (rowok) ew = __ldg(a.e_w + (size_t)g.node * KNN + lane);
       }
       // dst-side term of the first Linear + type bias, for protein and for ligand sources (uni_transformer_edge.py:371-377)
       {
-        const int tp = g.lig_dst ? 2 : 3, tl = g.lig_dst ? 0 : 1;
+        const int tp = g.lig_dst() ? 2 : 3, tl = g.lig_dst() ? 0 : 1;
         whit[lane] = hi_cur + __ldg(a.w.Wt + tp * H + s * 32 + lane);
         whit[32 + lane] = hi_cur + __ldg(a.w.Wt + tl * H + s * 32 + lane);
         if (!VPASS) wqry[(it & 1) * 32 + lane] = qry_v;
@@ -232,7 +257,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         mbar_wait(bar_d2, it & 1);
         tc_fence_after();
         __syncwarp();
-        const float* hs = whit + (lane < g.nlig ? 32 : 0);
+        const float* hs = whit + (lane < g.nlig() ? 32 : 0);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 hv = ld4(hs + i4 * 4);
@@ -246,7 +271,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], ku2f(v[2 * i], v[2 * i + 1]));
       }
       // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
-      if (tile + step < n_tiles) features(d_n, lane < g_n.nlig);
+      if (tile + step < n_tiles) features(d_n, lane < g_n.nlig());
       // ---- LayerNorm with one exchange between the 4 slice-warps of the quadrant, ReLU
       {
         float2 s1 = kf2(0.f, 0.f), s2 = kf2(0.f, 0.f);
@@ -361,7 +386,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
           }
         }
       }
-      prev_node = g.valid ? g.node : -1; prev_ok = rowok; prev_ew = ew;
+      prev_node = g.node; prev_ok = rowok; prev_ew = ew;
       g = g_n; g_n = g_nn; j = j_n; hi_cur = hi_n;
     }
     // ---- epilogue of the last tile

@@ -42,6 +42,7 @@ struct KnnAttnArgs {
   // (0 = protein, 1 = ligand destinations; pack_wg_tc) and the number of leading slots of dst_list that are protein
   // destinations (a multiple of 4; padding slots hold -1)
   const float* dist = nullptr;
+  const int2* slot_meta = nullptr;    // (n_dst) {node or -1, deg | nlig << 8 | is_ligand << 16} per slot (launch_knn_slot_meta)
   const float* B2tc[2] = {nullptr, nullptr};
   int n_slots_prot = 0;
   // v pass outputs
@@ -125,6 +126,8 @@ void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
 // ---- tensor-core variants (attn_tc.cu): same arguments, wbuf rows of a group are 32 apart; groups of <= 32 rows only
 void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t stream);
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
+void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, const int* nlig, const uint8_t* is_lig, int2* out,
+                          cudaStream_t stream);
 void launch_knn_dist(const float* x4, const int* nbr, const int* deg, int n, float* dist, cudaStream_t stream);
 void pack_w2_tc(const float* W2, float* out);
 void pack_wg_tc(const float* Wg, int type_p, int type_l, float* out /* 2 * 5120 floats */);
