@@ -319,7 +319,7 @@ struct ddb_batch {
   int *node_ptr = nullptr, *graph_of = nullptr, *lig_idx = nullptr, *lig_ptr = nullptr;
   uint8_t *is_lig = nullptr, *upd_mask = nullptr;
   int *bsrc = nullptr, *bdst = nullptr, *in_ptr = nullptr, *in_eid = nullptr, *in_src = nullptr, *trip_base = nullptr;
-  int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr;
+  int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr; int* trip_grp_order = nullptr;
   float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
   // evolving state
   float* x_lig = nullptr; int64_t* v = nullptr; int64_t* bond = nullptr; bool has_state = false;
@@ -331,7 +331,8 @@ struct ddb_batch {
   float *Qk = nullptr, *Qv = nullptr, *Pmk = nullptr, *Pmv = nullptr, *Qmk = nullptr, *Qmv = nullptr;
   float *wb_knn = nullptr, *wb_bond = nullptr, *wb_trip = nullptr, *e_w = nullptr, *dx_edge = nullptr, *dist = nullptr;
   int* dst_sorted = nullptr; int n_slots_all = 0, n_slots_prot = 0;
-  int2 *slot_meta_all = nullptr, *slot_meta_lig = nullptr;   // destinations by class (protein first), padded to tiles of 4
+  int2 *slot_meta_all = nullptr, *slot_meta_lig = nullptr;
+  float* ew_table = nullptr; long long* ew_table_base = nullptr; int* n_protein_of = nullptr;     // EdgeWeightCache   // destinations by class (protein first), padded to tiles of 4
   int *nbr = nullptr, *deg = nullptr, *nlig = nullptr;
   float *hid_v = nullptr, *v_logits = nullptr, *b_logits = nullptr, *x0 = nullptr, *grad = nullptr;
   // results of the last forward
@@ -515,9 +516,23 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
       }
     }
     DDB_TRY(b->upload(&b->trip_row_meta, row_meta)); DDB_TRY(b->upload(&b->trip_grp_meta, grp_meta));
+    std::vector<int> order(Eb);
+    for (int e = 0; e < Eb; ++e) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bsrc[x] != bsrc[y] ? bsrc[x] < bsrc[y] : bdst[x] < bdst[y]; });
+    DDB_TRY(b->upload(&b->trip_grp_order, order));
   }
   std::vector<uint8_t> upd(NL, 1);
   if (ligand_atom_mask) for (int i = 0; i < NL; ++i) upd[i] = ligand_atom_mask[i] ? 1 : 0;
+  {   // memo table of e_w for protein-protein pairs (skipped when it would exceed 1 GB)
+    std::vector<long long> base(B); std::vector<int> npg(B);
+    long long total = 0;
+    for (int g = 0; g < B; ++g) { base[g] = total; npg[g] = cnt_p[g]; total += (long long)cnt_p[g] * cnt_p[g]; }
+    if (total > 0 && total <= (1ll << 28) && !getenv("DDB_NO_EW_CACHE")) {
+      DDB_TRY(b->dalloc(&b->ew_table, (size_t)total));
+      cudaMemset(b->ew_table, 0xff, (size_t)total * sizeof(float));      // all-ones bit pattern = NaN = empty
+      DDB_TRY(b->upload(&b->ew_table_base, base)); DDB_TRY(b->upload(&b->n_protein_of, npg));
+    }
+  }
   {   // destinations of the kNN node update grouped by class (tiles of 4 never mix protein and ligand destinations)
     std::vector<int> sorted;
     for (int i = 0; i < N; ++i) if (!is_lig[i]) sorted.push_back(i);
@@ -662,8 +677,10 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   { ProfScope ps(b, s, PC_SETUP); launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s); }
   { ProfScope ps(b, s, PC_SETUP); launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s); }
   { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s); }
+  EdgeWeightCache ewc;
+  ewc.table = b->ew_table; ewc.table_base = b->ew_table_base; ewc.n_protein = b->n_protein_of; ewc.node_ptr = b->node_ptr; ewc.graph_of = b->graph_of;
   { ProfScope ps(b, s, PC_EDGE_WEIGHT); launch_edge_weight(b->x4_0, b->nbr, b->deg, N, m->p(m->ew_W1t), m->p(m->ew_b1), m->p(m->ew_gamma), m->p(m->ew_beta),
-                     m->p(m->ew_w2), m->ew_b2, b->e_w, s); }
+                     m->p(m->ew_w2), m->ew_b2, b->e_w, ewc, s); }
   b->launches += 5;
   if (b->tc_attn & 12) {
     ProfScope ps(b, s, PC_KNN_GRAPH);
@@ -711,7 +728,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     // --- bond update over triplets -> hb_out
     TripArgs ta;
     ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
-    ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.row_meta = b->trip_row_meta; ta.grp_meta = b->trip_grp_meta; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
+    ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.row_meta = b->trip_row_meta; ta.grp_meta = b->trip_grp_meta; ta.grp_order = b->trip_grp_order; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
     ta.k.Pe = b->PB + 2 * H; ta.k.Hk = b->PL + 5 * H; ta.k.Hj = b->PL + 6 * H; ta.k.Wd = m->p(L.bl_k.Wd);
     ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m); ta.k.W2tc = m->p(L.bl_k.m.W2tc); ta.k.Watc = m->p(L.bl_k.Watc);
     if (b->tc_attn & 1) { ta.k.Q = b->Qk; ta.k.Pm = b->Pmk; ta.k.Qm = b->Qmk; }

@@ -239,42 +239,68 @@ void launch_bond_attn_pos(const BondAttnArgs& a, int num_sms, cudaStream_t strea
 }
 
 // ---------------------------------------------------------------------------------------- triplets
-// prep: P[e] = Pe[e] + Hk[src(e)] + Hj[dst(e)] + Wd . gauss(d_e)   for the k and the v MLP (one warp per edge)
+// prep: P[e] = Pe[e] + Hk[src(e)] + Hj[dst(e)] + Wd . gauss(d_e)   for the k and the v MLP.  One warp handles PREP_EDGES edges at
+// a time (lane = 4 channels) so that every weight row fetched from L1 feeds several edges - the kernel is bound by the L1
+// wavefronts of the Wd / Wc reads otherwise.
+constexpr int PREP_EDGES = 4;
 __global__ void __launch_bounds__(256) trip_prep_kernel(const TripArgs a) {
   const int lane = threadIdx.x & 31;
-  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (e >= a.n_bonds) return;
-  const int k = a.bsrc[e], j = a.bdst[e];
-  float4 xk = ldg4(a.x4 + (size_t)a.lig_idx[k] * 4), xj = ldg4(a.x4 + (size_t)a.lig_idx[j] * 4);
-  float dx = xj.x - xk.x, dy = xj.y - xk.y, dz = xj.z - xk.z;
-  float d = sqrtf(dx * dx + dy * dy + dz * dz);       // (pos[i]-pos[j]).pow(2).sum(-1).sqrt()  (:130)
-  float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
+  const int e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PREP_EDGES;
+  if (e0 >= a.n_bonds) return;
+  int ks[PREP_EDGES], js[PREP_EDGES], es[PREP_EDGES];
+  float gl[PREP_EDGES];
+#pragma unroll
+  for (int u = 0; u < PREP_EDGES; ++u) {
+    es[u] = min(e0 + u, a.n_bonds - 1);
+    ks[u] = a.bsrc[es[u]]; js[u] = a.bdst[es[u]];
+    float4 xk = ldg4(a.x4 + (size_t)a.lig_idx[ks[u]] * 4), xj = ldg4(a.x4 + (size_t)a.lig_idx[js[u]] * 4);
+    float dx = xj.x - xk.x, dy = xj.y - xk.y, dz = xj.z - xk.z;
+    float d = sqrtf(dx * dx + dy * dy + dz * dz);       // (pos[i]-pos[j]).pow(2).sum(-1).sqrt()  (:130)
+    gl[u] = lane < NG ? gauss_feat(d, lane) : 0.f;
+  }
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     const TripSide& t = side ? a.v : a.k;
-    float4 z = add4(add4(ldg4(t.Pe + (size_t)e * a.ldpe + lane * 4), ldg4(t.Hk + (size_t)k * a.ldh + lane * 4)),
-                    ldg4(t.Hj + (size_t)j * a.ldh + lane * 4));
-    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 z[PREP_EDGES], qv[PREP_EDGES];
+#pragma unroll
+    for (int u = 0; u < PREP_EDGES; ++u) {
+      z[u] = add4(add4(ldg4(t.Pe + (size_t)es[u] * a.ldpe + lane * 4), ldg4(t.Hk + (size_t)ks[u] * a.ldh + lane * 4)),
+                  ldg4(t.Hj + (size_t)js[u] * a.ldh + lane * 4));
+      qv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      const float gg = __shfl_sync(FULL, gl, g);
-      z = fma4(gg, ldg4(t.Wd + g * H + lane * 4), z);
-      if (t.Q) qv = fma4(gg, ldg4(t.Wc + g * H + lane * 4), qv);
+      const float4 wd = ldg4(t.Wd + g * H + lane * 4);
+      float4 wc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t.Q) wc = ldg4(t.Wc + g * H + lane * 4);
+#pragma unroll
+      for (int u = 0; u < PREP_EDGES; ++u) {
+        const float gg = __shfl_sync(FULL, gl[u], g);
+        z[u] = fma4(gg, wd, z[u]);
+        if (t.Q) qv[u] = fma4(gg, wc, qv[u]);
+      }
     }
-    if (t.Q) {      // tensor-core kernels: rows are stored CENTRED (LayerNorm is invariant to a per-row shift, and centred rows
-      // keep its single-pass statistics well conditioned); Q = Wc . gauss(d) is the same edge seen as j->i
-      const float pm = warp_sum((z.x + z.y) + (z.z + z.w)) * (1.0f / H), qm = warp_sum((qv.x + qv.y) + (qv.z + qv.w)) * (1.0f / H);
-      st4(t.P + (size_t)e * H + lane * 4, make_float4(z.x - pm, z.y - pm, z.z - pm, z.w - pm));
-      st4(t.Q + (size_t)e * H + lane * 4, make_float4(qv.x - qm, qv.y - qm, qv.z - qm, qv.w - qm));
-    } else {
-      st4(t.P + (size_t)e * H + lane * 4, z);
+#pragma unroll
+    for (int u = 0; u < PREP_EDGES; ++u) {
+      if (t.Q) {      // tensor-core kernels: rows are stored CENTRED (LayerNorm is invariant to a per-row shift, and centred rows
+        // keep its single-pass statistics well conditioned); Q = Wc . gauss(d) is the same edge seen as j->i
+        const float pm = warp_sum((z[u].x + z[u].y) + (z[u].z + z[u].w)) * (1.0f / H);
+        const float qm = warp_sum((qv[u].x + qv[u].y) + (qv[u].z + qv[u].w)) * (1.0f / H);
+        if (e0 + u < a.n_bonds) {
+          st4(t.P + (size_t)es[u] * H + lane * 4, make_float4(z[u].x - pm, z[u].y - pm, z[u].z - pm, z[u].w - pm));
+          st4(t.Q + (size_t)es[u] * H + lane * 4, make_float4(qv[u].x - qm, qv[u].y - qm, qv[u].z - qm, qv[u].w - qm));
+        }
+      } else if (e0 + u < a.n_bonds) {
+        st4(t.P + (size_t)es[u] * H + lane * 4, z[u]);
+      }
     }
   }
 }
 
 void launch_trip_prep(const TripArgs& a, cudaStream_t stream) {
   if (a.n_bonds <= 0) return;
-  trip_prep_kernel<<<(a.n_bonds + 7) / 8, 256, 0, stream>>>(a);
+  const int per_block = 8 * PREP_EDGES;
+  trip_prep_kernel<<<(a.n_bonds + per_block - 1) / per_block, 256, 0, stream>>>(a);
 }
 
 struct TripSmem {

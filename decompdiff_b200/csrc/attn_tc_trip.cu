@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]);
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
-  const int n_tiles = (a.n_bonds + 3) / 4;
+  // Work distribution: the groups (bond edges j->i) are visited in SOURCE-major order (a.grp_order) and every (CTA, quadrant)
+  // pair walks one contiguous chunk of that order.  All groups with the same source j read the same rows P'[k->j], so a thread
+  // keeps its row slice in registers and gathers again only when j changes (once per ~n_lig groups).
+  const int per = (a.n_bonds + 4 * (int)gridDim.x - 1) / (4 * (int)gridDim.x);      // iterations of every CTA
 
   if (warp >= 16) {
     // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
@@ -126,9 +129,9 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         }
         __syncwarp();
       };
-      if (blockIdx.x < n_tiles) issue_ang();
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (tile + gridDim.x < n_tiles) issue_ang();
+      if (per > 0) issue_ang();
+      for (int it = 0; it < per; ++it) {
+        if (it + 1 < per) issue_ang();
         named_sync(BAR_A_READY, TT_SYNC);           // hidden activations are in TMEM, D of the previous tile is in registers
         if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
         __syncwarp();
@@ -184,10 +187,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     };
     // metadata of a tile: clamped so that every load below is unconditional (padding rows read edge 0 / node 0; their
     // results are never stored and they get zero attention weight)
-    auto load_meta = [&](int tile, int2& gm, int2& rm) {
-      gm = make_int2(0, 0); rm = make_int2(0, -1);
-      const int en = tile * 4 + q;
-      if (tile < n_tiles && en < a.n_bonds) { gm = __ldg(a.grp_meta + en); rm = __ldg(a.row_meta + (size_t)en * 32 + lane); }
+    const int g_begin = ((int)blockIdx.x * 4 + q) * per, g_end = min(a.n_bonds, g_begin + per);
+    auto load_meta = [&](int i, int& e, int2& gm, int2& rm) {
+      e = -1; gm = make_int2(0, 0); rm = make_int2(-1, -1);
+      if (g_begin + i < g_end) {
+        e = __ldg(a.grp_order + g_begin + i);
+        gm = __ldg(a.grp_meta + e); rm = __ldg(a.row_meta + (size_t)e * 32 + lane);
+      }
     };
     float* const wq = sm.qrow + warp * 64;          // this warp's private staging: [parity][32] slice of the Q row
     float* const wqry = sm.qry + warp * 128;        // k pass: [4-deep ring][32] slice of the query row
@@ -197,36 +203,35 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     int it = 0;
     int prev_e = -1, prev_tb = 0; bool prev_ok = false; int prev_nvalid = 0;
     int2 gm, rm, gm_n, rm_n;
-    load_meta(blockIdx.x, gm, rm);
-    load_meta(blockIdx.x + gridDim.x, gm_n, rm_n);
+    int e, e_n;
+    load_meta(0, e, gm, rm);
+    load_meta(1, e_n, gm_n, rm_n);
     float4 pv[8];
-    if (blockIdx.x < n_tiles) {
+    if (per > 0) {
       float4 xi, xj, xk;
       load_xyz(gm, rm, xi, xj, xk);
       features(rm, xi, xj, xk);          // prologue: the angular MMA of the first tile
       const float* prow = Pc + (size_t)max(rm.x, 0) * H + s * 32;
 #pragma unroll
       for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
-      const int e0 = min(blockIdx.x * 4 + q, a.n_bonds - 1);
-      wq[lane] = __ldg(Qc + (size_t)e0 * H + s * 32 + lane);
+      wq[lane] = __ldg(Qc + (size_t)max(e, 0) * H + s * 32 + lane);
     }
     TL_DECL
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (; it < per; ++it) {
       TL_MARK(0);
-      const int e = tile * 4 + q;
-      const bool gvalid = e < a.n_bonds;
+      const bool gvalid = e >= 0;
       const bool rowok = rm.y >= 0;          // valid and k != i (:117-118)
-      // requests for later: the Q slice of the next tile, the query slice of this one, metadata two tiles ahead
-      const int e_next = min(e + 4 * (int)gridDim.x, a.n_bonds - 1);
-      const float q_next = __ldg(Qc + (size_t)e_next * H + s * 32 + lane);
+      // requests for later: the Q slice of the next group, the query slice of this one, metadata two groups ahead
+      const float q_next = __ldg(Qc + (size_t)max(e_n, 0) * H + s * 32 + lane);
       float qry_v = 0.f;
-      if (!VPASS) qry_v = __ldg(a.q + (size_t)min(e, a.n_bonds - 1) * a.ldq + s * 32 + lane);
+      if (!VPASS) qry_v = __ldg(a.q + (size_t)max(e, 0) * a.ldq + s * 32 + lane);
       int2 gm_nn, rm_nn;
-      load_meta(tile + 2 * gridDim.x, gm_nn, rm_nn);
+      int e_nn;
+      load_meta(it + 2, e_nn, gm_nn, rm_nn);
       float4 nxi, nxj, nxk;
       load_xyz(gm_n, rm_n, nxi, nxj, nxk);
-      const int tb = __ldg(a.trip_base + min(e, a.n_bonds - 1));
-      // ---- first Linear: z = P'[kj] (prefetched) + Q'[ji] (staged) + D2 (angular MMA, issued one iteration ago)
+      const int tb = __ldg(a.trip_base + max(e, 0));
+      // ---- first Linear: z = P'[kj] (in registers) + Q'[ji] (staged) + D2 (angular MMA, issued one iteration ago)
       float2 z[16];
       {
         mbar_wait(bar_ang, it & 1);
@@ -247,20 +252,20 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], u2f(v[2 * i], v[2 * i + 1]));
       }
       // ---- prefetch the P' rows of the next tile (consumed one iteration from now), stage its Q slice and this tile's query
-      const float* prow_next = Pc + (size_t)max(rm_n.x, 0) * H + s * 32;
-      {
-        if (TT_EARLY_PREFETCH && !VPASS) {
+      // ---- the next group reads other rows only when its source atom differs: gather them now, consumed one iteration later
+      if (__any_sync(FULL, rm_n.x != rm.x)) {
+        const float* prow_next = Pc + (size_t)max(rm_n.x, 0) * H + s * 32;
 #pragma unroll
-          for (int i8 = 0; i8 < 4; ++i8) ldg8(prow_next + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
-        }
+        for (int i8 = 0; i8 < 4; ++i8) ldg8(prow_next + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+      }
+      {
         wq[((it + 1) & 1) * 32 + lane] = q_next;
         if (!VPASS) wqry[(it & 3) * 32 + lane] = qry_v;
       }
       TL_MARK(2);
       // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
-      if (tile + gridDim.x < n_tiles) features(rm_n, nxi, nxj, nxk);
+      if (it + 1 < per) features(rm_n, nxi, nxj, nxk);
       TL_MARK(3);
-      gm = gm_n; rm = rm_n; gm_n = gm_nn; rm_n = rm_nn;
       // ---- LayerNorm with ONE exchange (single-pass statistics: the rows are centred up to the small angular term), ReLU
       {
         float2 s1 = f2(0.f, 0.f), s2 = f2(0.f, 0.f);
@@ -346,10 +351,6 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         hand_over_a();
         TL_MARK(9);
       }
-      if (VPASS || !TT_EARLY_PREFETCH) {      // register budget: the prefetch of the next tile's rows starts after the hand-over
-#pragma unroll
-        for (int i8 = 0; i8 < 4; ++i8) ldg8(prow_next + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
-      }
       // ---- finish the epilogue of the previous tile from registers while the tensor core works
       if (it > 0) {
         if (!VPASS) {
@@ -376,7 +377,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
           }
         }
       }
-      prev_e = gvalid ? e : -1; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok)); prev_tb = tb;
+      prev_e = e; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok)); prev_tb = tb;
+      e = e_n; gm = gm_n; rm = rm_n; e_n = e_nn; gm_n = gm_nn; rm_n = rm_nn;
       TL_MARK(10);
     }
     TL_FLUSH(VPASS ? 1 : 0);

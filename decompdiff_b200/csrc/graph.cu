@@ -100,42 +100,63 @@ void launch_knn(const float* x4, const int* node_ptr, const int* graph_of, const
 
 // e_w = sigmoid(MLP_{20->128->1}(gauss(d)))  (uni_transformer_edge.py:422-427), one warp per destination node,
 // lane = 4 hidden channels, first-layer weights (20 x 128) held in registers.
+//
+// e_w depends on the distance only, and protein atoms never move during a sampling run: the value of every protein-protein
+// pair is memoised in a per-graph table (NaN = not yet computed), filled on first use by the same arithmetic, so later steps
+// only evaluate the MLP for edges that touch a ligand atom (a cache hit returns the bits a recomputation would produce).
 __global__ void __launch_bounds__(256) edge_weight_kernel(const float* __restrict__ x4, const int* __restrict__ nbr,
                                                           const int* __restrict__ deg, int n,
                                                           const float* __restrict__ W1t /*[20][128]*/,
                                                           const float* __restrict__ b1, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ w2,
-                                                          float b2, float* __restrict__ e_w) {
+                                                          float b2, float* __restrict__ e_w, EdgeWeightCache c) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
-  float4 w[NG];
-#pragma unroll
-  for (int g = 0; g < NG; ++g) w[g] = ldg4(W1t + g * H + lane * 4);
-  const float4 bb = ldg4(b1 + lane * 4), gm = ldg4(gamma + lane * 4), bt = ldg4(beta + lane * 4), w2v = ldg4(w2 + lane * 4);
   const float4 xi = ldg4(x4 + (size_t)i * 4);
   const int d_i = deg[i];
-  for (int e = 0; e < d_i; ++e) {
-    int j = nbr[(size_t)i * KNN + e];
-    float4 xj = ldg4(x4 + (size_t)j * 4);
-    float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-    float d = sqrtf(dx * dx + dy * dy + dz * dz);
-    float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
-    float4 z[1] = {bb};
-#pragma unroll
-    for (int g = 0; g < NG; ++g) z[0] = fma4(__shfl_sync(FULL, gl, g), w[g], z[0]);
-    ln_relu_rows<1>(z, gm, bt, lane);
-    float logit = warp_sum(dot4(z[0], w2v)) + b2;
-    if (lane == 0) e_w[(size_t)i * KNN + e] = 1.0f / (1.0f + expf(-logit));
+  // ---- lookup phase: lane = edge
+  const int j = lane < d_i ? nbr[(size_t)i * KNN + lane] : i;
+  const float4 xj = ldg4(x4 + (size_t)j * 4);
+  float val = __int_as_float(0x7fc00000);
+  long long slot = -1;
+  if (c.table != nullptr && lane < d_i) {
+    const int g = c.graph_of[i], base = c.node_ptr[g], np = c.n_protein[g];
+    const int il = i - base, jl = j - base;
+    if (il < np && jl < np) { slot = c.table_base[g] + (long long)il * np + jl; val = __ldcg(c.table + slot); }
   }
+  unsigned todo = __ballot_sync(FULL, lane < d_i && val != val);
+  if (todo) {
+    // ---- evaluation phase: the warp computes the missing edges one at a time
+    float4 w[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) w[g] = ldg4(W1t + g * H + lane * 4);
+    const float4 bb = ldg4(b1 + lane * 4), gm = ldg4(gamma + lane * 4), bt = ldg4(beta + lane * 4), w2v = ldg4(w2 + lane * 4);
+    while (todo) {
+      const int e = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float xjx = __shfl_sync(FULL, xj.x, e), xjy = __shfl_sync(FULL, xj.y, e), xjz = __shfl_sync(FULL, xj.z, e);
+      const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
+      const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+      const float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
+      float4 z[1] = {bb};
+#pragma unroll
+      for (int g = 0; g < NG; ++g) z[0] = fma4(__shfl_sync(FULL, gl, g), w[g], z[0]);
+      ln_relu_rows<1>(z, gm, bt, lane);
+      const float logit = warp_sum(dot4(z[0], w2v)) + b2;
+      const float r = 1.0f / (1.0f + expf(-logit));
+      if (lane == e) { val = r; if (slot >= 0) c.table[slot] = r; }
+    }
+  }
+  if (lane < d_i) e_w[(size_t)i * KNN + lane] = val;
 }
 
 void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, const float* W1t, const float* b1,
                         const float* gamma, const float* beta, const float* w2, float b2, float* e_w,
-                        cudaStream_t stream) {
+                        const EdgeWeightCache& cache, cudaStream_t stream) {
   if (n <= 0) return;
   const int wpb = 8;
-  edge_weight_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, stream>>>(x4, nbr, deg, n, W1t, b1, gamma, beta, w2, b2, e_w);
+  edge_weight_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, stream>>>(x4, nbr, deg, n, W1t, b1, gamma, beta, w2, b2, e_w, cache);
 }
 
 }  // namespace ddb

@@ -8,9 +8,17 @@ namespace ddb {
 // ---- K1 graph build ---------------------------------------------------------------------------
 void launch_knn(const float* x4, const int* node_ptr, const int* graph_of, const uint8_t* is_lig, int n, int k,
                 int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream);
+// memo table of the global edge weight for protein-protein pairs (positions of protein atoms are constant over a run)
+struct EdgeWeightCache {
+  float* table = nullptr;               // sum_g n_protein[g]^2 entries, NaN = empty; null disables the cache
+  const long long* table_base = nullptr;   // (B) first entry of graph g
+  const int* n_protein = nullptr;       // (B)
+  const int* node_ptr = nullptr;        // (B+1) merged-node offsets (protein atoms of a graph come first)
+  const int* graph_of = nullptr;        // (N)
+};
 void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, const float* W1t, const float* b1,
                         const float* gamma, const float* beta, const float* w2, float b2, float* e_w,
-                        cudaStream_t stream);
+                        const EdgeWeightCache& cache, cudaStream_t stream);
 
 // Weights of one attention MLP whose first Linear acts on kNN-edge features (NodeUpdateLayer /
 // PosUpdateLayer with edge_feat = [type (x) gauss(d) | type]), re-packed by api.cu:
@@ -112,6 +120,7 @@ struct TripArgs {
   // static row metadata for the tensor-core kernels (groups of <= 32 rows): row_meta[e*32+p] = {edge id k->j or -1,
   // merged node id of k or -1 when k == i}; grp_meta[e] = {merged node id of i, of j}
   const int2* row_meta = nullptr; const int2* grp_meta = nullptr;
+  const int* grp_order = nullptr;     // (Eb) edge ids sorted by (source atom, destination atom): the visiting order of the tensor-core kernels
   const float* x4 = nullptr;
   int ldh = 0, ldpe = 0;
   TripSide k, v;
