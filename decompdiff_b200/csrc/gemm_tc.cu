@@ -5,16 +5,20 @@
 // the 3xTF32 split  a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi)), three
 // MMAs into the same fp32 accumulator; the dropped a_lo*b_lo term is O(2^-22).
 //
-// Structure (one CTA = 16 worker warps + 1 MMA-issuing warp per 128-row tile x a slice of the N columns):
+// Structure (one CTA = 16 worker warps + 1 MMA-issuing warp + 1 weight-producer warp, per 128-row tile x a range of 128-column
+// output tiles):
 //   * worker thread (row r = 32q + lane, channel slice s) of warp w = 4s + q stages 32 channels of one row: gather / add /
 //     LayerNorm+ReLU prologue (row statistics exchanged through smem between the 4 warps of a quadrant), hi/lo split,
 //     tcgen05.st into TMEM (A_hi columns 0..127, A_lo columns 128..255; row -> lane, k -> column)
-//   * B is pre-split and pre-swizzled on the host into 32-column chunks of 32 KB (hi | lo, K-major, 128B swizzle); a chunk
-//     is ONE cp.async.bulk (TMA engine, mbarrier complete_tx) into a 4-stage ring
-//   * the issuer warp waits for a chunk and a free accumulator, issues 48 tcgen05.mma (M128 N32 K8, A from TMEM) and
-//     commits to an mbarrier - no CTA-wide barrier inside the chunk loop
-//   * chunk c is drained by the 4 warps of slice c % 4: tcgen05.ld, release the accumulator, refill the ring stage with
-//     chunk c + 4, smem transpose, bias / residual / activation, coalesced global stores
+//   * B is pre-split and pre-swizzled on the host into K-blocks: for every 128-column output tile, 4 blocks of 32 k-values,
+//     each 32 KB (hi | lo, [128 n-rows][128 B], K-major, 128B swizzle); the producer warp streams them with ONE cp.async.bulk
+//     each into a 4-stage ring (mbarrier complete_tx), re-using a stage as soon as the MMAs that read it have retired
+//   * the issuer warp waits for a stage, issues 12 tcgen05.mma (M128 N128 K8, A from TMEM, 64 tensor cycles each - wide enough
+//     to hide the issue cost of a single thread, which N=32 tiles did not) and commits to the stage's "empty" barrier;
+//     after the 4th K-block it also commits the accumulator's "full" barrier.  Two accumulators (TMEM columns 256..511)
+//     alternate, so the epilogue of tile t overlaps the MMAs of tile t+1.  No CTA-wide barrier inside the tile loop.
+//   * epilogue: warp (s, q) drains rows 32q.. of columns 32s.. of the accumulator: tcgen05.ld, release, smem transpose, bias /
+//     residual / activation, coalesced global stores
 #include <cstring>
 
 #include "gemm.cuh"
@@ -23,18 +27,17 @@
 namespace ddb {
 
 constexpr int TC_BM = 128;              // rows per CTA (UMMA M)
-constexpr int TC_BN = 32;               // columns per chunk (UMMA N)
-constexpr int TC_STAGES = 4;            // B ring depth == accumulator ring depth == number of epilogue warp groups
-constexpr int TC_B_KB = TC_BN * 128;                    // 4 KB per K-block (32 tf32 along K) of a B chunk
-constexpr int TC_B_PART = 4 * TC_B_KB;                  // 16 KB (hi or lo)
-constexpr int TC_B_CHUNK = 2 * TC_B_PART;               // 32 KB per chunk (hi | lo)
+constexpr int TC_BN = 128;              // columns per output tile (UMMA N)
+constexpr int TC_STAGES = 4;            // weight ring depth (K-blocks in flight)
+constexpr int TC_B_PART = TC_BN * 128;                  // 16 KB: [128 n-rows][32 tf32 = 128 B] hi or lo
+constexpr int TC_B_STAGE = 2 * TC_B_PART;               // 32 KB per K-block (hi | lo)
 constexpr int TC_WORKERS = 512;                         // 16 staging / epilogue warps
-constexpr int TC_THREADS = TC_WORKERS + 32;             // + 1 MMA-issuing warp
+constexpr int TC_THREADS = TC_WORKERS + 64;             // + MMA-issuing warp + weight-producer warp
 constexpr int TC_EPI_LD = 36;                           // padded row of a per-warp 32x32 transpose tile (floats)
 constexpr int TC_EPI_BYTES = 16 * 32 * TC_EPI_LD * 4;   // 72 KB
 constexpr int TC_STAT_BYTES = 2 * 128 * 4 * 4;          // LayerNorm partial sums [row][slice] x {sum, centred squares}
-constexpr int TC_SMEM = TC_STAGES * TC_B_CHUNK + TC_EPI_BYTES + TC_STAT_BYTES + 128 /*barriers*/;
-constexpr int TC_COL_AHI = 0, TC_COL_ALO = 128, TC_COL_D = 256;   // TMEM column map (512 allocated)
+constexpr int TC_SMEM = TC_STAGES * TC_B_STAGE + TC_EPI_BYTES + TC_STAT_BYTES + 128 /*barriers*/;
+constexpr int TC_COL_AHI = 0, TC_COL_ALO = 128, TC_COL_D = 256;   // TMEM column map (512 allocated): D0 256.., D1 384..
 constexpr int TC_BAR_A_READY = 5;
 static_assert(TC_SMEM <= 232448, "shared memory budget");
 
@@ -43,26 +46,27 @@ __device__ __forceinline__ void tc_quad_barrier(int q) { asm volatile("bar.sync 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArgs a, const float* __restrict__ Wtc,
-                                                                   int chunks_per_cta) {
+                                                                   int tiles_per_cta) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sB = smem_raw;                                                // TC_STAGES x (hi | lo)
-  float* sEpi = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_CHUNK);   // per-warp 32 x 36 transpose tiles
+  float* sEpi = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_STAGE);   // per-warp 32 x 36 transpose tiles
   float* sStatA = sEpi + 16 * 32 * TC_EPI_LD;
   float* sStatB = sStatA + 128 * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStatB + 128 * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * TC_BM;
-  const int chunk0 = blockIdx.y * chunks_per_cta;
-  const int n_chunks = min(chunks_per_cta, a.N / TC_BN - chunk0);
-  auto bar_b = [&](int i) { return smem_u32(&bars[i]); };                     // B chunk landed in stage i
-  auto bar_m = [&](int i) { return smem_u32(&bars[TC_STAGES + i]); };         // MMAs into accumulator i retired
-  auto bar_f = [&](int i) { return smem_u32(&bars[2 * TC_STAGES + i]); };     // accumulator i drained (4 warp arrivals)
+  const int tile0 = blockIdx.y * tiles_per_cta;
+  const int n_tiles = min(tiles_per_cta, a.N / TC_BN - tile0);
+  auto bar_full = [&](int i) { return smem_u32(&bars[i]); };                        // K-block landed in stage i
+  auto bar_empty = [&](int i) { return smem_u32(&bars[TC_STAGES + i]); };           // MMAs reading stage i retired
+  auto bar_dfull = [&](int i) { return smem_u32(&bars[2 * TC_STAGES + i]); };       // accumulator i complete
+  auto bar_dempty = [&](int i) { return smem_u32(&bars[2 * TC_STAGES + 2 + i]); };  // accumulator i drained (16 warp arrivals)
 
   if ((smem_u32(sB) & 1023u) != 0u) __trap();      // SWIZZLE_128B operands need a 1024-byte aligned base
   if (tid == 0) {
-    for (int i = 0; i < 2 * TC_STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
-    for (int i = 0; i < TC_STAGES; ++i) mbar_init(bar_f(i), 4);
+    for (int i = 0; i < 2 * TC_STAGES + 2; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_dempty(i), 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 512); }
@@ -70,36 +74,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_blocks = n_tiles * 4;                 // K-blocks this CTA consumes
 
-  if (warp == 16) {
-    // ------------------------------------------------------------------------------------ MMA issuer warp
+  if (warp == 17) {
+    // ------------------------------------------------------------------------------------ weight producer warp
     if (lane == 0) {
-      for (int c = 0; c < min(TC_STAGES, n_chunks); ++c) {      // fill the weight ring while the A tile is being staged
-        mbar_expect_tx(bar_b(c), TC_B_CHUNK);
-        bulk_g2s(smem_u32(sB + c * TC_B_CHUNK), Wtc + (size_t)(chunk0 + c) * (TC_B_CHUNK / 4), TC_B_CHUNK, bar_b(c));
+      const float* src = Wtc + (size_t)tile0 * 4 * (TC_B_STAGE / 4);
+      for (int i = 0; i < n_blocks; ++i) {
+        const int st = i % TC_STAGES, use = i / TC_STAGES;
+        if (use > 0) mbar_wait(bar_empty(st), (use - 1) & 1);
+        mbar_expect_tx(bar_full(st), TC_B_STAGE);
+        bulk_g2s(smem_u32(sB + st * TC_B_STAGE), src + (size_t)i * (TC_B_STAGE / 4), TC_B_STAGE, bar_full(st));
       }
     }
-    asm volatile("bar.sync %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_THREADS) : "memory");   // A tile is in TMEM
+    __syncwarp();
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------------------------ MMA issuer warp
+    asm volatile("bar.sync %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_WORKERS + 32) : "memory");   // A tile is in TMEM
     if (lane == 0) {
       tc_fence_after();
-      // instruction descriptor: D=F32, A=B=TF32, both K-major, N=32, M=128 (cute::UMMA::InstrDescriptor)
+      // instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint64_t desc0 = umma_desc_sw128(smem_u32(sB));     // descriptors of other addresses differ in the low field only
-      for (int c = 0; c < n_chunks; ++c) {
-        const int st = c % TC_STAGES, use = c / TC_STAGES;
-        mbar_wait(bar_b(st), use & 1);
-        if (use > 0) mbar_wait(bar_f(st), (use - 1) & 1);       // accumulator st drained by the epilogue of chunk c - 4
-        tc_fence_after();
-        const uint64_t d_hi = desc0 + (uint64_t)((st * TC_B_CHUNK) >> 4), d_lo = d_hi + (uint64_t)(TC_B_PART >> 4);
-        const uint32_t d = tmem_base + TC_COL_D + st * TC_BN;
+      int i = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int db = t & 1;
+        if (t >= 2) mbar_wait(bar_dempty(db), ((t >> 1) - 1) & 1);      // the epilogue of tile t - 2 has drained this accumulator
+        const uint32_t d = tmem_base + TC_COL_D + db * TC_BN;
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb, ++i) {
+          const int st = i % TC_STAGES;
+          mbar_wait(bar_full(st), (i / TC_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t d_hi = desc0 + (uint64_t)((st * TC_B_STAGE) >> 4), d_lo = d_hi + (uint64_t)(TC_B_PART >> 4);
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {   // UMMA K = 8 tf32: 8 TMEM columns of A, 32 bytes inside the 128-byte swizzle atom of B
-          const uint64_t bo = (uint64_t)(((kk >> 2) * TC_B_KB + (kk & 3) * 32) >> 4);
-          umma_tf32_ts(d, tmem_base + TC_COL_AHI + kk * 8, d_hi + bo, idesc, kk ? 1u : 0u);
-          umma_tf32_ts(d, tmem_base + TC_COL_ALO + kk * 8, d_hi + bo, idesc, 1u);
-          umma_tf32_ts(d, tmem_base + TC_COL_AHI + kk * 8, d_lo + bo, idesc, 1u);
+          for (int kk = 0; kk < 4; ++kk) {   // UMMA K = 8 tf32: 8 TMEM columns of A, 32 bytes inside the 128-byte swizzle atom of B
+            const uint32_t acol = kb * 32 + kk * 8;
+            umma_tf32_ts(d, tmem_base + TC_COL_AHI + acol, d_hi + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+            umma_tf32_ts(d, tmem_base + TC_COL_ALO + acol, d_hi + (uint64_t)(kk * 2), idesc, 1u);
+            umma_tf32_ts(d, tmem_base + TC_COL_AHI + acol, d_lo + (uint64_t)(kk * 2), idesc, 1u);
+          }
+          umma_commit(bar_empty(st));           // stage st may be refilled once these MMAs retire
         }
-        umma_commit(bar_m(st));             // implies tcgen05.fence::before_thread_sync
+        umma_commit(bar_dfull(db));             // accumulator complete (implies tcgen05.fence::before_thread_sync)
       }
     }
     __syncwarp();
@@ -157,32 +174,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
       tmem_st32(lane_addr + TC_COL_ALO + s * 32, lo);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
-      asm volatile("bar.arrive %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_THREADS) : "memory");
+      asm volatile("bar.arrive %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_WORKERS + 32) : "memory");
     }
-    // ---- epilogue: slice group s drains chunks s, s+4, s+8, ...
+    // ---- epilogue: warp (s, q) drains rows 32q.., columns 32s.. of every output tile
     float* tile = sEpi + warp * 32 * TC_EPI_LD;
-    for (int c = s; c < n_chunks; c += TC_STAGES) {
-      const int st = s, use = c / TC_STAGES;                // c % TC_STAGES == s
-      mbar_wait(bar_m(st), use & 1);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int db = t & 1;
+      mbar_wait(bar_dfull(db), (t >> 1) & 1);
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TC_COL_D + st * TC_BN, v);
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TC_COL_D + db * TC_BN + s * 32, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_f(st));                             // accumulator st may be overwritten
-        if (q == 0 && c + TC_STAGES < n_chunks) {           // MMAs of chunk c retired -> ring stage st is free: refill it
-          mbar_expect_tx(bar_b(st), TC_B_CHUNK);
-          bulk_g2s(smem_u32(sB + st * TC_B_CHUNK), Wtc + (size_t)(chunk0 + c + TC_STAGES) * (TC_B_CHUNK / 4), TC_B_CHUNK, bar_b(st));
-        }
-      }
+      if (lane == 0) mbar_arrive(bar_dempty(db));           // this warp's part of the accumulator may be overwritten
       // thread = row -> transpose through smem so that 8 lanes write one 128-byte segment of a row
 #pragma unroll
-      for (int j = 0; j < TC_BN; j += 4)
+      for (int j = 0; j < 32; j += 4)
         st4(tile + lane * TC_EPI_LD + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
       __syncwarp();
-      const int n0 = (chunk0 + c) * TC_BN + (lane & 7) * 4;
+      const int n0 = (tile0 + t) * TC_BN + s * 32 + (lane & 7) * 4;
       const float4 bias4 = a.bias ? ldg4(a.bias + n0) : make_float4(0, 0, 0, 0);
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -211,38 +222,39 @@ void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStr
     cudaFuncSetAttribute(gemm128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     attr_set = true;
   }
-  const int row_tiles = (a.M + TC_BM - 1) / TC_BM, chunks = a.N / TC_BN;
-  // Split the N chunks over `nsplit` CTAs per row tile.  Cost model in units of one chunk of MMA work: every CTA pays ~3
-  // units to stage its A tile, then chunks/nsplit units; CTAs run in waves of num_sms (1 CTA per SM).
+  const int row_tiles = (a.M + TC_BM - 1) / TC_BM, tiles = a.N / TC_BN;
+  // Split the output tiles over `nsplit` CTAs per row tile.  Cost model in units of one output tile of MMA work: every CTA
+  // pays ~1.5 units to stage its A tile, then tiles/nsplit units; CTAs run in waves of num_sms (1 CTA per SM).
   int best = 1; double best_cost = 1e30;
-  for (int ns = 1; ns <= chunks; ++ns) {
-    if (chunks % ns) continue;
+  for (int ns = 1; ns <= tiles; ++ns) {
+    if (tiles % ns) continue;
     long ctas = (long)row_tiles * ns;
     double waves = (double)((ctas + num_sms - 1) / num_sms);
-    double cost = waves * (3.0 + (double)chunks / ns);
+    double cost = waves * (1.5 + (double)tiles / ns);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
-  const int per = chunks / best;
-  dim3 grid(row_tiles, (chunks + per - 1) / per);
+  const int per = tiles / best;
+  dim3 grid(row_tiles, (tiles + per - 1) / per);
   gemm128_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(a, Wtc, per);
 }
 
-// host-side packing of a K-major weight Wt[128][N] into the chunked, hi/lo-split, 128B-swizzled image the kernel copies
+// host-side packing of a K-major weight Wt[128][N] into the image the kernel streams: for every 128-column output tile, 4
+// K-blocks of 32 k-values, each hi | lo with rows = output column n (128 of them), 128-byte rows, 128B swizzle
 void pack_gemm_tc(const float* Wt, int N, float* out /* N*128*2 floats */) {
-  const int chunks = N / TC_BN;
-  for (int c = 0; c < chunks; ++c) {
-    float* hi = out + (size_t)c * (TC_B_CHUNK / 4);
-    float* lo = hi + TC_B_PART / 4;
-    for (int nl = 0; nl < TC_BN; ++nl) {
-      for (int k = 0; k < H; ++k) {
-        float w = Wt[(size_t)k * N + c * TC_BN + nl];
-        float h = host_tf32_rna(w), l = host_tf32_rna(w - h);
-        int off = sw128_offset_bytes(nl, k, TC_BN) / 4;
-        hi[off] = h;
-        lo[off] = l;
-      }
+  const int tiles = N / TC_BN;
+  for (int t = 0; t < tiles; ++t)
+    for (int kb = 0; kb < 4; ++kb) {
+      float* hi = out + (size_t)(t * 4 + kb) * (TC_B_STAGE / 4);
+      float* lo = hi + TC_B_PART / 4;
+      for (int nl = 0; nl < TC_BN; ++nl)
+        for (int kk = 0; kk < 32; ++kk) {
+          const float w = Wt[(size_t)(kb * 32 + kk) * N + t * TC_BN + nl];
+          const float h = host_tf32_rna(w), l = host_tf32_rna(w - h);
+          const int off = (nl * 128 + (((kk >> 2) ^ (nl & 7)) << 4) + (kk & 3) * 4) / 4;
+          hi[off] = h;
+          lo[off] = l;
+        }
     }
-  }
 }
 
 }  // namespace ddb
