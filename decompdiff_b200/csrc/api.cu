@@ -506,19 +506,19 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   }
   b->trip_slots = slots;
   if (b->max_indeg <= 32) {      // static per-row metadata of the tensor-core triplet kernels
+    std::vector<int> order(Eb);      // groups are visited source-major: consecutive groups read the same rows P[k->j]
+    for (int e = 0; e < Eb; ++e) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bsrc[x] != bsrc[y] ? bsrc[x] < bsrc[y] : bdst[x] < bdst[y]; });
     std::vector<int2> row_meta((size_t)Eb * 32, make_int2(-1, -1)), grp_meta(Eb);
-    for (int e = 0; e < Eb; ++e) {
-      const int j = bsrc[e], i = bdst[e];
-      grp_meta[e] = make_int2(lig_idx[i], lig_idx[j]);
+    for (int pos = 0; pos < Eb; ++pos) {
+      const int e = order[pos], j = bsrc[e], i = bdst[e];
+      grp_meta[pos] = make_int2(lig_idx[i], lig_idx[j]);
       for (int p = in_ptr[j]; p < in_ptr[j + 1]; ++p) {
         const int k = in_src[p];
-        row_meta[(size_t)e * 32 + (p - in_ptr[j])] = make_int2(in_eid[p], k == i ? -1 : lig_idx[k]);
+        row_meta[(size_t)pos * 32 + (p - in_ptr[j])] = make_int2(in_eid[p], k == i ? -1 : lig_idx[k]);
       }
     }
     DDB_TRY(b->upload(&b->trip_row_meta, row_meta)); DDB_TRY(b->upload(&b->trip_grp_meta, grp_meta));
-    std::vector<int> order(Eb);
-    for (int e = 0; e < Eb; ++e) order[e] = e;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bsrc[x] != bsrc[y] ? bsrc[x] < bsrc[y] : bdst[x] < bdst[y]; });
     DDB_TRY(b->upload(&b->trip_grp_order, order));
   }
   std::vector<uint8_t> upd(NL, 1);

@@ -20,6 +20,19 @@
 
 namespace ddb {
 
+// Optional in-kernel timeline (compile with -DDDB_TIMELINE): CTA 0, lane 0 of warps 0 and 13 add the SM cycles spent in each
+// phase of the tile loop to g_timeline[pass][warp slot][phase]; read with ddb_debug_timeline_{trip,knn}() (profiles/timeline.py).
+#ifdef DDB_TIMELINE
+static __device__ unsigned long long g_timeline[2][2][16];      // one copy per translation unit: [pass][warp slot][phase]
+#define TL_DECL unsigned long long tl_t = clock64(), tl_acc[12] = {0}; const bool tl_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 13);
+#define TL_MARK(i) do { if (tl_on) { unsigned long long n_ = clock64(); tl_acc[i] += n_ - tl_t; tl_t = n_; } } while (0)
+#define TL_FLUSH(kid) do { if (tl_on) { for (int i_ = 0; i_ < 12; ++i_) g_timeline[kid][warp == 0 ? 0 : 1][i_] = tl_acc[i_]; g_timeline[kid][warp == 0 ? 0 : 1][12] = it; } } while (0)
+#else
+#define TL_DECL
+#define TL_MARK(i)
+#define TL_FLUSH(kid)
+#endif
+
 constexpr int ATC_THREADS = 512;
 constexpr int ATC_W2_BYTES = 2 * 128 * 128 * 4;                       // hi | lo image of W2
 constexpr int ANG_LD = 20;              // padded row of the per-tile angular features (bank-conflict-free float4 reads)

@@ -216,6 +216,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
     float* const whit = sm.hit + warp * 64;         // [2 source classes][32]
     float* const wqry = sm.qry + warp * 64;         // [2-deep ring][32]
     const int step = gridDim.x;
+    // type bias of the first Linear for this thread's channel, all four edge types (L1 is a few KB next to 226 KB of shared
+    // memory, so a per-tile __ldg would be an L2 round trip)
+    const float wt0 = __ldg(a.w.Wt + 0 * H + s * 32 + lane), wt1 = __ldg(a.w.Wt + 1 * H + s * 32 + lane),
+                wt2 = __ldg(a.w.Wt + 2 * H + s * 32 + lane), wt3 = __ldg(a.w.Wt + 3 * H + s * 32 + lane);
 
     int it = 0;
     Grp g = load_group(blockIdx.x), g_n = load_group(blockIdx.x + step);
@@ -232,7 +236,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
       for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
     }
     int prev_node = -1; bool prev_ok = false; float prev_ew = 0.f;
+    TL_DECL
     for (int tile = blockIdx.x; tile < n_tiles; tile += step, ++it) {
+      TL_MARK(0);
       const bool rowok = lane < g.deg();            // deg is 0 for padding groups
       // ---- requests for later: rows of the next tile, group metadata two tiles ahead, this tile's query / edge weight
       const int j_n = lane < g_n.deg() ? __ldg(a.nbr + (size_t)g_n.node * KNN + lane) : 0;
@@ -246,15 +252,17 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
       }
       // dst-side term of the first Linear + type bias, for protein and for ligand sources (uni_transformer_edge.py:371-377)
       {
-        const int tp = g.lig_dst() ? 2 : 3, tl = g.lig_dst() ? 0 : 1;
-        whit[lane] = hi_cur + __ldg(a.w.Wt + tp * H + s * 32 + lane);
-        whit[32 + lane] = hi_cur + __ldg(a.w.Wt + tl * H + s * 32 + lane);
+        const bool ld = g.lig_dst();
+        whit[lane] = hi_cur + (ld ? wt2 : wt3);            // protein sources: type 2 into a ligand, 3 into a protein destination
+        whit[32 + lane] = hi_cur + (ld ? wt0 : wt1);       // ligand sources:  type 0 / 1
         if (!VPASS) wqry[(it & 1) * 32 + lane] = qry_v;
       }
       // ---- first Linear: z = P_src[j] (prefetched) + (P_dst[i] + Wt) (staged) + D2 (distance MMA, issued one iteration ago)
       float2 z[16];
       {
+        TL_MARK(1);
         mbar_wait(bar_d2, it & 1);
+        TL_MARK(2);
         tc_fence_after();
         __syncwarp();
         const float* hs = whit + (lane < g.nlig() ? 32 : 0);
@@ -271,7 +279,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], ku2f(v[2 * i], v[2 * i + 1]));
       }
       // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
+      TL_MARK(3);
       if (tile + step < n_tiles) features(d_n, lane < g_n.nlig());
+      TL_MARK(4);
       // ---- LayerNorm with one exchange between the 4 slice-warps of the quadrant, ReLU
       {
         float2 s1 = kf2(0.f, 0.f), s2 = kf2(0.f, 0.f);
@@ -286,7 +296,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         for (int i = 0; i < 16; ++i) { const float2 dz = __fadd2_rn(z[i], nm); s2 = __ffma2_rn(dz, dz, s2); }
         float2* st = sm.stat + ((it & 1) * 128 + r) * 4;
         st[s] = make_float2(part, s2.x + s2.y);
+        TL_MARK(5);
         quad_barrier(q);
+        TL_MARK(6);
         const float4 t01 = *reinterpret_cast<const float4*>(st), t23 = *reinterpret_cast<const float4*>(st + 2);
         const float mu = ((t01.x + t01.z) + (t23.x + t23.z)) * (1.0f / H);
         const float d0 = t01.x * (1.0f / 32.0f) - mu, d1 = t01.z * (1.0f / 32.0f) - mu, d2 = t23.x * (1.0f / 32.0f) - mu, d3 = t23.z * (1.0f / 32.0f) - mu;
@@ -308,8 +320,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
       float val[32];
       float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (VPASS && it > 0 && prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
+      TL_MARK(7);
       if (it > 0) {
         mbar_wait(bar_mma, (it - 1) & 1);
+        TL_MARK(8);
         tc_fence_after();
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
@@ -353,6 +367,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         knamed_arrive(KBAR_A_READY, KT_SYNC);
+        TL_MARK(9);
       }
       // ---- row gather of the next tile (consumed one iteration from now)
       {
@@ -388,7 +403,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
       }
       prev_node = g.node; prev_ok = rowok; prev_ew = ew;
       g = g_n; g_n = g_nn; j = j_n; hi_cur = hi_n;
+      TL_MARK(10);
     }
+    TL_FLUSH(VPASS ? 1 : 0);
     // ---- epilogue of the last tile
     if (it > 0) {
       mbar_wait(bar_mma, (it - 1) & 1);
@@ -427,6 +444,12 @@ void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t s
   if (vpass) knn_tc_kernel<true><<<grid, KT_THREADS, bytes, stream>>>(a);
   else knn_tc_kernel<false><<<grid, KT_THREADS, bytes, stream>>>(a);
 }
+
+#ifdef DDB_TIMELINE
+extern "C" int ddb_debug_timeline_knn(unsigned long long* out /* 2*2*16 */) {
+  return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * 64);
+}
+#endif
 
 // host-side packing of the distance-term weights for one destination class: B2[n = channel][k], k < 20: Wg[type_p][k][n],
 // 20 <= k < 40: Wg[type_l][k-20][n]; hi | lo images in the SWIZZLE_32B K-major layout of the kernel

@@ -11,7 +11,7 @@ constexpr int TT_A2_BYTES = 2 * 128 * 128;        // hi | lo, [128 rows][128 B] 
 constexpr int TT_COL_D2 = 384;
 
 struct TripTcSmem {
-  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *qry, *qrow; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
+  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *qry, *qrow, *xyz; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
   __device__ explicit TripTcSmem(uint8_t* raw) {
     uint8_t* p = raw;      // purely additive carving keeps everything in the shared address space (LDS / STS)
     W2 = p; p += ATC_W2_BYTES;
@@ -22,11 +22,12 @@ struct TripTcSmem {
     b2 = reinterpret_cast<float*>(p); p += H * 4;
     qry = reinterpret_cast<float*>(p); p += 16 * 128 * 4;       // per warp: 4-deep ring of 32-float query slices
     qrow = reinterpret_cast<float*>(p); p += 16 * 64 * 4;       // per warp: 2 x 32-float slices of the centred Q row
+    xyz = reinterpret_cast<float*>(p); p += 16 * 34 * 16;       // per warp: positions x_k of its 32 rows, x_i, x_j (cp.async staging)
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][row][slice] {sum, sum of squares}
     bars = reinterpret_cast<uint64_t*>(p); p += 32;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 2 * 2 * 128 * 4) * 4 + 64; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 16 * 34 * 4 + 2 * 2 * 128 * 4) * 4 + 64; }
 };
 static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -55,19 +56,6 @@ constexpr int TT_SYNC = ATC_THREADS + 32;       // participants of the hand-over
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 constexpr int BAR_A2_READY = 5, BAR_A_READY = 6;  // named barriers: every warp arrives, the issuing warp waits on them
-
-// Optional in-kernel timeline (compile with -DDDB_TIMELINE): CTA 0, lane 0 of warps 0 and TT_ISSUER add the SM cycles spent in
-// each phase of the tile loop to g_trip_timeline[VPASS][warp slot][phase]; read with ddb_debug_trip_timeline().
-#ifdef DDB_TIMELINE
-__device__ unsigned long long g_trip_timeline[2][2][16];
-#define TL_DECL unsigned long long tl_t = clock64(), tl_acc[12] = {0}; const bool tl_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 13);
-#define TL_MARK(i) do { if (tl_on) { unsigned long long n_ = clock64(); tl_acc[i] += n_ - tl_t; tl_t = n_; } } while (0)
-#define TL_FLUSH(vp) do { if (tl_on) { for (int i_ = 0; i_ < 12; ++i_) g_trip_timeline[vp][warp == 0 ? 0 : 1][i_] = tl_acc[i_]; g_trip_timeline[vp][warp == 0 ? 0 : 1][12] = it; } } while (0)
-#else
-#define TL_DECL
-#define TL_MARK(i)
-#define TL_FLUSH(vp)
-#endif
 
 template <bool VPASS>
 __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a) {
@@ -145,10 +133,22 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     auto hand_over_a = [&]() { named_arrive(BAR_A_READY, TT_SYNC); };
     // ---------------------------------------------------------------- 16 warps: thread = (row r, channel slice s)
     // geometry of a row -> angular features -> A2 (the 13 features are split over the 4 slice-warps), then hand A2 over
-    // positions for the features of a tile: requested one phase early (gathers through L2), consumed in features()
-    auto load_xyz = [&](int2 gm, int2 rm, float4& xi, float4& xj, float4& xk) {
-      xi = ldg4(a.x4 + (size_t)gm.x * 4); xj = ldg4(a.x4 + (size_t)gm.y * 4);
-      xk = ldg4(a.x4 + (size_t)(rm.y >= 0 ? rm.y : gm.y) * 4);      // excluded rows: k := j, theta = 0
+    // positions for the features of a tile: requested one phase early with cp.async (gathers through L2 that hold no registers
+    // while in flight) into this warp's staging rows, consumed in features()
+    float* const wxyz = sm.xyz + warp * (34 * 4);
+    auto cp16 = [](float* dst, const float* src) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    };
+    auto request_xyz = [&](int2 gm, int2 rm) {
+      cp16(wxyz + lane * 4, a.x4 + (size_t)(rm.y >= 0 ? rm.y : gm.y) * 4);      // excluded rows: k := j, theta = 0
+      if (lane < 2) cp16(wxyz + (32 + lane) * 4, a.x4 + (size_t)(lane == 0 ? gm.x : gm.y) * 4);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto fetch_xyz = [&](float4& xi, float4& xj, float4& xk) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      xk = ld4(wxyz + lane * 4); xi = ld4(wxyz + 32 * 4); xj = ld4(wxyz + 33 * 4);
+      __syncwarp();
     };
     auto features = [&](int2 rm, float4 xi, float4 xj, float4 xk) {
       const bool rowok = rm.y >= 0;
@@ -188,12 +188,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     // metadata of a tile: clamped so that every load below is unconditional (padding rows read edge 0 / node 0; their
     // results are never stored and they get zero attention weight)
     const int g_begin = ((int)blockIdx.x * 4 + q) * per, g_end = min(a.n_bonds, g_begin + per);
-    auto load_meta = [&](int i, int& e, int2& gm, int2& rm) {
+    auto load_meta = [&](int i, int& e, int2& gm, int2& rm) {      // metadata is stored in visiting order: three independent loads
       e = -1; gm = make_int2(0, 0); rm = make_int2(-1, -1);
-      if (g_begin + i < g_end) {
-        e = __ldg(a.grp_order + g_begin + i);
-        gm = __ldg(a.grp_meta + e); rm = __ldg(a.row_meta + (size_t)e * 32 + lane);
-      }
+      const int pos = g_begin + i;
+      if (pos < g_end) { e = __ldg(a.grp_order + pos); gm = __ldg(a.grp_meta + pos); rm = __ldg(a.row_meta + (size_t)pos * 32 + lane); }
     };
     float* const wq = sm.qrow + warp * 64;          // this warp's private staging: [parity][32] slice of the Q row
     float* const wqry = sm.qry + warp * 128;        // k pass: [4-deep ring][32] slice of the query row
@@ -209,7 +207,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     float4 pv[8];
     if (per > 0) {
       float4 xi, xj, xk;
-      load_xyz(gm, rm, xi, xj, xk);
+      request_xyz(gm, rm);
+      fetch_xyz(xi, xj, xk);
       features(rm, xi, xj, xk);          // prologue: the angular MMA of the first tile
       const float* prow = Pc + (size_t)max(rm.x, 0) * H + s * 32;
 #pragma unroll
@@ -228,8 +227,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       int2 gm_nn, rm_nn;
       int e_nn;
       load_meta(it + 2, e_nn, gm_nn, rm_nn);
-      float4 nxi, nxj, nxk;
-      load_xyz(gm_n, rm_n, nxi, nxj, nxk);
+      request_xyz(gm_n, rm_n);
       const int tb = __ldg(a.trip_base + max(e, 0));
       // ---- first Linear: z = P'[kj] (in registers) + Q'[ji] (staged) + D2 (angular MMA, issued one iteration ago)
       float2 z[16];
@@ -264,7 +262,11 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       }
       TL_MARK(2);
       // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
-      if (it + 1 < per) features(rm_n, nxi, nxj, nxk);
+      if (it + 1 < per) {
+        float4 nxi, nxj, nxk;
+        fetch_xyz(nxi, nxj, nxk);
+        features(rm_n, nxi, nxj, nxk);
+      }
       TL_MARK(3);
       // ---- LayerNorm with ONE exchange (single-pass statistics: the rows are centred up to the small angular term), ReLU
       {
@@ -421,8 +423,8 @@ void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t str
 }
 
 #ifdef DDB_TIMELINE
-extern "C" int ddb_debug_trip_timeline(unsigned long long* out /* 2*2*16 */) {
-  return (int)cudaMemcpyFromSymbol(out, g_trip_timeline, sizeof(unsigned long long) * 64);
+extern "C" int ddb_debug_timeline_trip(unsigned long long* out /* 2*2*16: {k, v} x {warp 0, warp 13} x phase */) {
+  return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * 64);
 }
 #endif
 

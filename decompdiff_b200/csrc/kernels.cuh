@@ -117,8 +117,9 @@ struct TripArgs {
   const int* lig_idx = nullptr;
   const int* in_ptr = nullptr; const int* in_eid = nullptr; const int* in_src = nullptr;
   const int* trip_base = nullptr;     // (Eb) offset of edge e's triplet slots in wbuf (one per edge entering src(e))
-  // static row metadata for the tensor-core kernels (groups of <= 32 rows): row_meta[e*32+p] = {edge id k->j or -1,
-  // merged node id of k or -1 when k == i}; grp_meta[e] = {merged node id of i, of j}
+  // static row metadata for the tensor-core kernels (groups of <= 32 rows), stored in VISITING order (position pos of
+  // grp_order, e = grp_order[pos]): row_meta[pos*32+p] = {edge id k->j or -1, merged node id of k or -1 when k == i};
+  // grp_meta[pos] = {merged node id of i, of j}
   const int2* row_meta = nullptr; const int2* grp_meta = nullptr;
   const int* grp_order = nullptr;     // (Eb) edge ids sorted by (source atom, destination atom): the visiting order of the tensor-core kernels
   const float* x4 = nullptr;
