@@ -187,10 +187,31 @@ def run_reference_arm(args, rank, world):
         'e2e': {'value': value, 'unit': 'molecules/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to stdout) are sent to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -354,7 +375,7 @@ def main():
             'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps), 'launches_per_step': launches_per_step,
             'clocks': clocks, 'roofline': roof, 'kernels': kernels, 'kernel_categories': prof_raw, 'cpu_baseline': cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
