@@ -123,6 +123,10 @@ struct Packer {
       r.W2tc = m.blob.alloc((size_t)2 * H * H);
       std::vector<float> w2(m.blob.data.begin() + r.W2, m.blob.data.begin() + r.W2 + (size_t)H * H);
       pack_w2_tc(w2.data(), m.blob.data.data() + r.W2tc);
+    } else if (out_dim == NH) {      // the 16-output value MLP of the position layers
+      r.W2tc = m.blob.alloc((size_t)2 * NH * H);
+      std::vector<float> w2(m.blob.data.begin() + r.W2, m.blob.data.begin() + r.W2 + (size_t)NH * H);
+      pack_w2x_tc(w2.data(), m.blob.data.data() + r.W2tc);
     }
     return r;
   }
@@ -343,7 +347,7 @@ struct ddb_batch {
   long long launches = 0;
   long long h2d_bytes = 0;
   bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
-  int tc_attn = 15;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v: tensor-core attention kernels (DDB_TC_ATTN=<mask>)
+  int tc_attn = 31;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels (DDB_TC_ATTN=<mask>)
   int max_indeg = 0;
   // optional per-kernel timing (CUDA events on the launch stream; eager passes only, never under graph capture)
   bool profiling = false;
@@ -496,7 +500,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     for (int s = 0; s < Eb; ++s) { in_eid[s] = order[s]; in_src[s] = bsrc[order[s]]; }
   }
   for (int a = 0; a < NL; ++a) b->max_indeg = std::max(b->max_indeg, in_ptr[a + 1] - in_ptr[a]);
-  if (b->max_indeg > 32) b->tc_attn &= ~3;     // triplet groups of more than 32 rows: fp32 FMA kernels
+  if (b->max_indeg > 32) b->tc_attn &= ~(3 | 16);     // triplet groups of more than 32 rows: fp32 FMA kernels
   long long slots = 0;
   for (int e = 0; e < Eb; ++e) {
     if (slots > 2000000000LL) { ddb_batch_destroy(b); return fail(DDB_ERR_INVALID, "too many bond triplets"); }
@@ -724,7 +728,8 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ba.k.Hi = b->PL; ba.k.Hj = b->PL + H; ba.k.Pe = b->PB; ba.k.w = bond_w(m, L.nb_k);
     ba.v.Hi = b->PL + 2 * H; ba.v.Hj = b->PL + 3 * H; ba.v.Pe = b->PB + H; ba.v.w = bond_w(m, L.nb_v);
     ba.q = b->qNB; ba.ldq = H; ba.x4 = x_in; ba.wbuf = b->wb_bond; ba.out_h = b->h1; ba.ldo = H;
-    { ProfScope ps(b, s, PC_BOND_NODE); launch_bond_attn_node(ba, sms, s); }
+    ba.k.W2tc = m->p(L.nb_k.W2tc); ba.v.W2tc = m->p(L.nb_v.W2tc);
+    { ProfScope ps(b, s, PC_BOND_NODE); if (b->tc_attn & 16) { launch_bond_tc(ba, false, sms, s); b->launches += 1; } else launch_bond_attn_node(ba, sms, s); }
     // --- bond update over triplets -> hb_out
     TripArgs ta;
     ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
@@ -766,7 +771,8 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     bp.v.Hi = b->PLx + 5 * H; bp.v.Hj = b->PLx + 6 * H; bp.v.Pe = b->PBx + H; bp.v.w = bond_w(m, L.pb_v);
     bp.q = b->qXb; bp.ldq = H; bp.x4 = x_in; bp.wbuf = b->wb_bond; bp.dx_edge = b->dx_edge; bp.upd_mask = b->upd_mask;
     bp.x4_out = x_out;
-    { ProfScope ps(b, s, PC_BOND_POS); launch_bond_attn_pos(bp, sms, s); }
+    bp.k.W2tc = m->p(L.pb_k.W2tc); bp.v.W2tc = m->p(L.pb_v.W2tc);
+    { ProfScope ps(b, s, PC_BOND_POS); if (b->tc_attn & 16) { launch_bond_tc(bp, true, sms, s); b->launches += 1; } else launch_bond_attn_pos(bp, sms, s); }
     b->launches += 3;
     h_in = h_out; x_in = x_out; hb_in = hb_out;
   }

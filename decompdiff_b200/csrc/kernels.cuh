@@ -75,6 +75,7 @@ struct BondSide {
   const float* Hj = nullptr;          // (n_lig, ldh) src-side projection, by ligand atom
   const float* Pe = nullptr;          // (Eb, ldpe) projection of h_bond, by edge id
   BondMlpW w;
+  const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 (tensor-core kernels; 128 or 16 output rows)
 };
 struct BondAttnArgs {
   int n_lig = 0;
@@ -139,7 +140,9 @@ void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t str
 void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, const int* nlig, const uint8_t* is_lig, int2* out,
                           cudaStream_t stream);
 void launch_knn_dist(const float* x4, const int* nbr, const int* deg, int n, float* dist, cudaStream_t stream);
+void launch_bond_tc(const BondAttnArgs& a, bool pos, int num_sms, cudaStream_t stream);      // attn_tc_bond.cu (groups of <= 32 edges)
 void pack_w2_tc(const float* W2, float* out);
+void pack_w2x_tc(const float* W2 /* [16][128] */, float* out /* 2*16*128 floats */);
 void pack_wg_tc(const float* Wg, int type_p, int type_l, float* out /* 2 * 5120 floats */);
 void pack_wa_tc(const float* Wa, float* out);
 
