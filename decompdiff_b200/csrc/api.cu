@@ -717,10 +717,10 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
       k.slot_meta = b->slot_meta_all;
     };
     tc_dsts(ka, L.ne_k, b->tc_attn & 4);
-    { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, false, sms, s); else launch_knn_attn_k(ka, sms, s); }
+    { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, 0, sms, s); else launch_knn_attn_k(ka, sms, s); }
     ka.Hi = b->PN + 2 * H; ka.Hj = b->PN + 3 * H; ka.w = knn_w(m, L.ne_v); ka.W2tc = m->p(L.ne_v.m.W2tc); ka.out_h = b->h1; ka.ldo = H;
     tc_dsts(ka, L.ne_v, b->tc_attn & 8);
-    { ProfScope ps(b, s, PC_KNN_ATTN_V); if (b->tc_attn & 8) launch_knn_tc(ka, true, sms, s); else launch_knn_attn_v_node(ka, sms, s); }
+    { ProfScope ps(b, s, PC_KNN_ATTN_V); if (b->tc_attn & 8) launch_knn_tc(ka, 1, sms, s); else launch_knn_attn_v_node(ka, sms, s); }
     // --- node update over bond edges -> h1[ligand rows] +=
     BondAttnArgs ba;
     ba.n_lig = NL; ba.lig_idx = b->lig_idx; ba.in_ptr = b->in_ptr; ba.in_eid = b->in_eid; ba.in_src = b->in_src;
@@ -760,9 +760,10 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
     kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k); kp.W2tc = m->p(L.pe_k.m.W2tc);
     kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_prot = 0; kp.slot_meta = b->slot_meta_lig;      // ligand destinations only
-    { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, false, sms, s); else launch_knn_attn_k(kp, sms, s); }
+    { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, 0, sms, s); else launch_knn_attn_k(kp, sms, s); }
     kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
-    { ProfScope ps(b, s, PC_KNN_POS_V); launch_knn_attn_v_pos(kp, sms, s); }
+    kp.W2tc = m->p(L.pe_v.m.W2tc); kp.B2tc[0] = m->p(L.pe_v.B2tc[0]); kp.B2tc[1] = m->p(L.pe_v.B2tc[1]);
+    { ProfScope ps(b, s, PC_KNN_POS_V); if (b->tc_attn & 8) launch_knn_tc(kp, 2, sms, s); else launch_knn_attn_v_pos(kp, sms, s); }
     // --- position update over bond edges + x_out = x_in + (dx_edge + dx_bond) * mask   (:280-285)
     BondAttnArgs bp;
     bp.n_lig = NL; bp.lig_idx = b->lig_idx; bp.in_ptr = b->in_ptr; bp.in_eid = b->in_eid; bp.in_src = b->in_src;

@@ -63,6 +63,29 @@ __device__ __forceinline__ void atc_issue_mma(uint32_t tmem_base, uint32_t w2_sm
   umma_commit(bar);
 }
 
+// same with N output columns (W2 image: hi | lo, each 4 K-blocks of [N rows][128 B]); N = 16 serves the position value MLPs
+template <int N>
+__device__ __forceinline__ void atc_issue_mma_n(uint32_t tmem_base, uint32_t w2_smem, uint32_t bar) {
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t d = tmem_base + ATC_COL_D;
+  const uint64_t b_hi0 = umma_desc_sw128(w2_smem), b_lo0 = umma_desc_sw128(w2_smem + 4 * N * 128);
+#pragma unroll 1
+  for (int kk = 0; kk < 16; ++kk) {
+    const uint64_t bo = (uint64_t)(((kk >> 2) * (N * 128) + (kk & 3) * 32) >> 4);
+    umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, b_hi0 + bo, idesc, kk ? 1u : 0u);
+    umma_tf32_ts(d, tmem_base + ATC_COL_ALO + kk * 8, b_hi0 + bo, idesc, 1u);
+    umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, b_lo0 + bo, idesc, 1u);
+  }
+  umma_commit(bar);
+}
+// 16 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+
 // LayerNorm(128) + ReLU on a row whose 128 channels are spread over the 4 slice-warps of quadrant q
 __device__ __forceinline__ void atc_ln_relu(float (&z)[32], float* statA, float* statB, int r, int s, int q,
                                             const float* sGamma, const float* sBeta) {

@@ -89,8 +89,11 @@ void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, cons
   knn_slot_meta_kernel<<<(n_slots + 255) / 256, 256, 0, stream>>>(dst_list, n_slots, deg, nlig, is_lig, out);
 }
 
-template <bool VPASS>
+// PASS: 0 = key pass, 1 = node value pass, 2 = position value pass (16-output second Linear, dx per destination slot)
+template <int PASS>
 __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) {
+  constexpr bool VPASS = PASS != 0, VPOS = PASS == 2;
+  constexpr int W2_BYTES = VPOS ? 2 * NH * 128 * 4 : ATC_W2_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   KnnTcSmem sm(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
@@ -108,15 +111,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   const int tile_class1 = a.n_slots_prot / 4;          // tiles >= this hold ligand destinations
   if (tid == 0) {
     const uint32_t bar = smem_u32(&sm.bars[0]);
-    mbar_expect_tx(bar, ATC_W2_BYTES + 2 * KT_IMG);
-    bulk_g2s(smem_u32(sm.W2), a.W2tc, ATC_W2_BYTES / 2, bar);
-    bulk_g2s(smem_u32(sm.W2) + ATC_W2_BYTES / 2, a.W2tc + ATC_W2_BYTES / 8, ATC_W2_BYTES / 2, bar);
+    mbar_expect_tx(bar, W2_BYTES + 2 * KT_IMG);
+    bulk_g2s(smem_u32(sm.W2), a.W2tc, W2_BYTES / 2, bar);
+    bulk_g2s(smem_u32(sm.W2) + W2_BYTES / 2, a.W2tc + W2_BYTES / 8, W2_BYTES / 2, bar);
     bulk_g2s(smem_u32(sm.B2), a.B2tc[(int)blockIdx.x >= tile_class1 ? 1 : 0], 2 * KT_IMG, bar);
   }
   const uint32_t tmem_base = *sm.tmem_slot;
   cta_copy_f4(sm.gamma, a.w.gamma, H);
   cta_copy_f4(sm.beta, a.w.beta, H);
-  if (VPASS) cta_copy_f4(sm.b2, a.w.b2, H);
+  if (VPASS && !VPOS) cta_copy_f4(sm.b2, a.w.b2, H);
+  if (VPOS && tid < NH) sm.b2[tid] = a.w.b2[tid];
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_d2 = smem_u32(&sm.bars[2]);
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (tile + (int)gridDim.x < n_tiles) issue_d2(tile + gridDim.x);
         knamed_sync(KBAR_A_READY, KT_SYNC);           // hidden activations are in TMEM, D of the previous tile is in registers
-        if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
+        if (lane == 0) { tc_fence_after(); if (VPOS) atc_issue_mma_n<NH>(tmem_base, w2_smem, bar_mma); else atc_issue_mma(tmem_base, w2_smem, bar_mma); }
         __syncwarp();
       }
     }
@@ -235,7 +239,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
 #pragma unroll
       for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
     }
-    int prev_node = -1; bool prev_ok = false; float prev_ew = 0.f;
+    int prev_node = -1, prev_slot = 0; bool prev_ok = false; float prev_ew = 0.f;
+    float4 prev_rel = make_float4(0.f, 0.f, 0.f, 0.f);
     TL_DECL
     for (int tile = blockIdx.x; tile < n_tiles; tile += step, ++it) {
       TL_MARK(0);
@@ -245,6 +250,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
       const float d_n = g_n.valid() ? __ldg(a.dist + (size_t)g_n.node * KNN + lane) : 0.f;
       const float hi_n = g_n.valid() ? __ldg(a.Hi + (size_t)hidx(g_n, tile + step) * a.ldhi + s * 32 + lane) : 0.f;
       const Grp g_nn = load_group(tile + 2 * step);
+      float4 rel = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (VPOS && s == 0 && rowok) {          // x_i - x_j of this thread's edge (rel_x, :198-199)
+        const float4 xi = ldg4(a.x4 + (size_t)g.node * 4), xj = ldg4(a.x4 + (size_t)j * 4);
+        rel = make_float4(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z, 0.f);
+      }
       float qry_v = 0.f, ew = 0.f;
       if (!VPASS) {
         if (g.valid()) qry_v = __ldg(a.q + (size_t)(a.q_by_slot ? tile * 4 + q : g.node) * a.ldq + s * 32 + lane);
@@ -319,16 +329,38 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
       float lg[4] = {0.f, 0.f, 0.f, 0.f};
       float val[32];
       float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (VPASS && it > 0 && prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
+      if (VPASS && !VPOS && it > 0 && prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
+      float4 wpos[4];
+      float cpos = 0.f;
+      if (VPOS && it > 0 && s == 0) {
+#pragma unroll
+        for (int h4 = 0; h4 < 4; ++h4) wpos[h4] = prev_ok ? ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + h4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       TL_MARK(7);
       if (it > 0) {
         mbar_wait(bar_mma, (it - 1) & 1);
         TL_MARK(8);
         tc_fence_after();
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!VPASS) {
+        if (VPOS) {
+          if (s == 0) {           // 16 head outputs of this row; c = sum_h (alpha e_w)[h] (D[h] + b2[h])   (:199-208)
+            uint32_t v16[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D, v16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int h4 = 0; h4 < 4; ++h4) {
+              cpos = fmaf(wpos[h4].x, __uint_as_float(v16[h4 * 4 + 0]) + sm.b2[h4 * 4 + 0], cpos);
+              cpos = fmaf(wpos[h4].y, __uint_as_float(v16[h4 * 4 + 1]) + sm.b2[h4 * 4 + 1], cpos);
+              cpos = fmaf(wpos[h4].z, __uint_as_float(v16[h4 * 4 + 2]) + sm.b2[h4 * 4 + 2], cpos);
+              cpos = fmaf(wpos[h4].w, __uint_as_float(v16[h4 * 4 + 3]) + sm.b2[h4 * 4 + 3], cpos);
+            }
+          }
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (VPOS) {
+        } else if (!VPASS) {
           const float* qr = wqry + ((it - 1) & 1) * 32;
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) {
@@ -391,6 +423,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? ex[hh] * __frcp_rn(sum[hh]) * prev_ew : 0.f;
           if (prev_ok) st4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
+        } else if (VPOS) {
+          if (s == 0) {
+            const float ax = warp_sum(cpos * prev_rel.x), ay = warp_sum(cpos * prev_rel.y), az = warp_sum(cpos * prev_rel.z);
+            if (lane == 0 && prev_node >= 0) st4(a.out_dx + (size_t)prev_slot * 4, make_float4(ax * (1.f / NH), ay * (1.f / NH), az * (1.f / NH), 0.f));
+          }
         } else {
           float ws[4] = {w4.x, w4.y, w4.z, w4.w};
           warp_allreduce4(ws, lane);
@@ -401,11 +438,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
           }
         }
       }
-      prev_node = g.node; prev_ok = rowok; prev_ew = ew;
+      prev_node = g.node; prev_ok = rowok; prev_ew = ew; prev_rel = rel; prev_slot = tile * 4 + q;
       g = g_n; g_n = g_nn; j = j_n; hi_cur = hi_n;
       TL_MARK(10);
     }
-    TL_FLUSH(VPASS ? 1 : 0);
+    TL_FLUSH(PASS == 1 ? 1 : 0);
     // ---- epilogue of the last tile
     if (it > 0) {
       mbar_wait(bar_mma, (it - 1) & 1);
@@ -414,6 +451,19 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         float4 w4 = atc_logits_softmax(tmem_base, q, s, wqry + ((it - 1) & 1) * 32 - s * 32, prev_ok);
         if (prev_ok) st4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4,
                          make_float4(w4.x * prev_ew, w4.y * prev_ew, w4.z * prev_ew, w4.w * prev_ew));
+      } else if (VPOS) {
+        if (s == 0) {
+          uint32_t v16[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D, v16);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float cpos = 0.f;
+          if (prev_ok) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) cpos = fmaf(__ldg(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + h), __uint_as_float(v16[h]) + sm.b2[h], cpos);
+          }
+          const float ax = warp_sum(cpos * prev_rel.x), ay = warp_sum(cpos * prev_rel.y), az = warp_sum(cpos * prev_rel.z);
+          if (lane == 0 && prev_node >= 0) st4(a.out_dx + (size_t)prev_slot * 4, make_float4(ax * (1.f / NH), ay * (1.f / NH), az * (1.f / NH), 0.f));
+        }
       } else {
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
@@ -431,18 +481,20 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t stream) {
+void launch_knn_tc(const KnnAttnArgs& a, int pass, int num_sms, cudaStream_t stream) {      // pass: 0 key, 1 node value, 2 position value
   if (a.n_dst <= 0) return;
   static bool once = false;
   const int bytes = KnnTcSmem::bytes();
   if (!once) {
-    cudaFuncSetAttribute(knn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(knn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(knn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(knn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     once = true;
   }
   const int grid = atc_grid((a.n_dst + 3) / 4, num_sms);
-  if (vpass) knn_tc_kernel<true><<<grid, KT_THREADS, bytes, stream>>>(a);
-  else knn_tc_kernel<false><<<grid, KT_THREADS, bytes, stream>>>(a);
+  if (pass == 2) knn_tc_kernel<2><<<grid, KT_THREADS, bytes, stream>>>(a);
+  else if (pass == 1) knn_tc_kernel<1><<<grid, KT_THREADS, bytes, stream>>>(a);
+  else knn_tc_kernel<0><<<grid, KT_THREADS, bytes, stream>>>(a);
 }
 
 #ifdef DDB_TIMELINE

@@ -135,7 +135,7 @@ void launch_trip_k(const TripArgs& a, int num_sms, cudaStream_t stream);
 void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
 
 // ---- tensor-core variants (attn_tc.cu): same arguments, wbuf rows of a group are 32 apart; groups of <= 32 rows only
-void launch_knn_tc(const KnnAttnArgs& a, bool vpass, int num_sms, cudaStream_t stream);
+void launch_knn_tc(const KnnAttnArgs& a, int pass /* 0 key, 1 node value, 2 position value */, int num_sms, cudaStream_t stream);
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
 void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, const int* nlig, const uint8_t* is_lig, int2* out,
                           cudaStream_t stream);
