@@ -335,7 +335,10 @@ struct ddb_batch {
   float *Qk = nullptr, *Qv = nullptr, *Pmk = nullptr, *Pmv = nullptr, *Qmk = nullptr, *Qmv = nullptr;
   float *wb_knn = nullptr, *wb_bond = nullptr, *wb_trip = nullptr, *e_w = nullptr, *dx_edge = nullptr, *dist = nullptr;
   int* dst_sorted = nullptr; int n_slots_all = 0, n_slots_prot = 0;
-  int2 *slot_meta_all = nullptr, *slot_meta_lig = nullptr;
+  int2 *slot_meta_all = nullptr, *slot_meta_lig = nullptr, *slot_meta_lvl = nullptr;
+  // exact receptive-field pruning (launch_receptive_field): hop level per node, [ligand block | protein nodes by level], per-layer counts
+  bool prune = false; int lig_block = 0;
+  int *level = nullptr, *lvl_hist = nullptr, *lvl_counts = nullptr, *dst_lvl = nullptr;
   float* ew_table = nullptr; long long* ew_table_base = nullptr; int* n_protein_of = nullptr;     // EdgeWeightCache   // destinations by class (protein first), padded to tiles of 4
   int *nbr = nullptr, *deg = nullptr, *nlig = nullptr;
   float *hid_v = nullptr, *v_logits = nullptr, *b_logits = nullptr, *x0 = nullptr, *grad = nullptr;
@@ -531,10 +534,11 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     std::vector<long long> base(B); std::vector<int> npg(B);
     long long total = 0;
     for (int g = 0; g < B; ++g) { base[g] = total; npg[g] = cnt_p[g]; total += (long long)cnt_p[g] * cnt_p[g]; }
+    DDB_TRY(b->upload(&b->n_protein_of, npg));
     if (total > 0 && total <= (1ll << 28) && !getenv("DDB_NO_EW_CACHE")) {
       DDB_TRY(b->dalloc(&b->ew_table, (size_t)total));
       cudaMemset(b->ew_table, 0xff, (size_t)total * sizeof(float));      // all-ones bit pattern = NaN = empty
-      DDB_TRY(b->upload(&b->ew_table_base, base)); DDB_TRY(b->upload(&b->n_protein_of, npg));
+      DDB_TRY(b->upload(&b->ew_table_base, base));
     }
   }
   {   // destinations of the kNN node update grouped by class (tiles of 4 never mix protein and ligand destinations)
@@ -546,6 +550,14 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     b->n_slots_all = (int)sorted.size();
     DDB_TRY(b->upload(&b->dst_sorted, sorted));
     DDB_TRY(b->dalloc(&b->slot_meta_all, sorted.size())); DDB_TRY(b->dalloc(&b->slot_meta_lig, (size_t)NL));
+    b->prune = b->use_tc && (b->tc_attn & 12) == 12 && !getenv("DDB_NO_PRUNE");
+    std::vector<int> lvl;
+    for (int i = 0; i < N; ++i) if (is_lig[i]) lvl.push_back(i);
+    while (lvl.size() % 4) lvl.push_back(-1);
+    b->lig_block = (int)lvl.size();
+    lvl.resize(lvl.size() + (size_t)NP, -1);            // the protein part is rewritten every step
+    DDB_TRY(b->upload(&b->dst_lvl, lvl)); DDB_TRY(b->dalloc(&b->slot_meta_lvl, lvl.size()));
+    DDB_TRY(b->dalloc(&b->level, (size_t)N)); DDB_TRY(b->dalloc(&b->lvl_hist, (size_t)8 * B)); DDB_TRY(b->dalloc(&b->lvl_counts, (size_t)2 * m->cfg.num_layers + 1));
   }
 
   DDB_TRY(b->upload(&b->node_ptr, node_ptr)); DDB_TRY(b->upload(&b->graph_of, graph_of));
@@ -655,13 +667,13 @@ void prof_collect(ddb_batch* b, cudaStream_t s) {
 
 void gemm(ddb_batch* b, cudaStream_t s, int cat, const float* A, int lda, const int* a_rows, int M, const GemmW& w, float* C, int ldc,
           const Mlp2* ln = nullptr, const float* A2 = nullptr, int lda2 = 0, const int* a2_rows = nullptr,
-          const float* R = nullptr, int ldr = 0, const int* c_rows = nullptr, int act = 0) {
+          const float* R = nullptr, int ldr = 0, const int* c_rows = nullptr, int act = 0, const int* M_dev = nullptr) {
   const ddb_model* m = b->m;
   GemmArgs g;
   g.A = A; g.lda = lda; g.a_rows = a_rows; g.A2 = A2; g.lda2 = lda2; g.a2_rows = a2_rows;
   if (ln) { g.ln_gamma = m->p(ln->gamma); g.ln_beta = m->p(ln->beta); }
   g.Wt = m->p(w.Wt); g.ldw = w.N; g.bias = m->p(w.bias);
-  g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.c_rows = c_rows; g.M = M; g.N = w.N; g.act = act;
+  g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.c_rows = c_rows; g.M = M; g.N = w.N; g.act = act; g.M_dev = M_dev;
   ProfScope ps(b, s, cat);
   if (b->use_tc) launch_gemm128_tc(g, m->p(w.Wtc), b->num_sms, s); else launch_gemm128(g, s);
   b->launches++;
@@ -691,7 +703,17 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     launch_knn_slot_meta(b->dst_sorted, b->n_slots_all, b->deg, b->nlig, b->is_lig, b->slot_meta_all, s);
     launch_knn_slot_meta(b->lig_idx, NL, b->deg, b->nlig, b->is_lig, b->slot_meta_lig, s);
     b->launches += 2;
+    if (b->prune) {
+      launch_receptive_field(b->nbr, b->deg, b->is_lig, b->node_ptr, b->n_protein_of, b->B, N, c.num_layers, b->lig_block, b->level, b->lvl_hist,
+                             b->lvl_counts, b->dst_lvl, s);
+      launch_knn_slot_meta(b->dst_lvl, b->lig_block + b->NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl, s);
+      b->launches += 11;
+    }
   }
+  // with pruning, per-node work of layer l runs on a prefix of dst_lvl whose length is a device-side counter
+  const int n_lvl = b->lig_block + b->NP, nl_layers = c.num_layers;
+  const bool prune_gemm = b->prune, prune_knn = b->prune;
+  const int* rows_lvl = prune_gemm ? b->dst_lvl : nullptr;
   float *h_in = b->h0, *x_in = b->x4_0, *hb_in = b->hbA;
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerOff& L = m->layers[l];
@@ -699,8 +721,12 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     float* x_out = (l % 2 == 0) ? b->x4_a : b->x4_b;
     float* hb_out = (l % 2 == 0) ? b->hbB : b->hbA;
     // --- projections of the layer input
-    gemm(b, s, PC_GEMM_NODE, h_in, H, nullptr, N, L.n1, b->PN, 5 * H);
-    gemm(b, s, PC_GEMM_NODE, b->PN + 4 * H, 5 * H, nullptr, N, L.q_ne, b->qN, H, &L.ln_q_ne);
+    const int* cnt_dst = prune_gemm ? b->lvl_counts + l : nullptr;                 // destinations of this layer's node update
+    const int* cnt_src = prune_gemm ? b->lvl_counts + nl_layers + l : nullptr;     // rows read as sources by it
+    const int* cnt_pos = prune_gemm ? b->lvl_counts + 2 * nl_layers : nullptr;     // sources of the position update (ligand + 1 hop)
+    const int n_node_rows = prune_gemm ? n_lvl : N;
+    gemm(b, s, PC_GEMM_NODE, h_in, H, rows_lvl, n_node_rows, L.n1, b->PN, 5 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_src);
+    gemm(b, s, PC_GEMM_NODE, b->PN + 4 * H, 5 * H, rows_lvl, n_node_rows, L.q_ne, b->qN, H, &L.ln_q_ne, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_dst);
     gemm(b, s, PC_GEMM_LIG, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
     gemm(b, s, PC_GEMM_LIG, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
     gemm(b, s, PC_GEMM_BOND, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
@@ -713,8 +739,11 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     if (b->tc_attn & 12) { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn_dist(x_in, b->nbr, b->deg, N, b->dist, s); b->launches += 1; }
     auto tc_dsts = [&](KnnAttnArgs& k, const KnnMlpOff& o, bool on) {      // the tensor-core kernels walk destinations by class
       k.dist = b->dist; k.B2tc[0] = m->p(o.B2tc[0]); k.B2tc[1] = m->p(o.B2tc[1]);
-      k.n_dst = on ? b->n_slots_all : N; k.dst_list = on ? b->dst_sorted : nullptr; k.n_slots_prot = on ? b->n_slots_prot : 0;
-      k.slot_meta = b->slot_meta_all;
+      k.n_dst = on ? b->n_slots_all : N; k.dst_list = on ? b->dst_sorted : nullptr; k.n_slots_first = on ? b->n_slots_prot : 0; k.first_class = 0;
+      k.slot_meta = b->slot_meta_all; k.n_dst_dev = nullptr;
+      if (on && prune_knn) {
+        k.n_dst = n_lvl; k.dst_list = b->dst_lvl; k.n_slots_first = b->lig_block; k.first_class = 1; k.slot_meta = b->slot_meta_lvl; k.n_dst_dev = b->lvl_counts + l;
+      }
     };
     tc_dsts(ka, L.ne_k, b->tc_attn & 4);
     { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, 0, sms, s); else launch_knn_attn_k(ka, sms, s); }
@@ -746,9 +775,9 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     { ProfScope ps(b, s, PC_TRIP_V); if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, s); else launch_trip_v(ta, sms, s); }
     b->launches += 6;
     // --- h_out = h_in + lin_node(h1)    (:277)
-    gemm(b, s, PC_GEMM_NODE, b->h1, H, nullptr, N, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H);
+    gemm(b, s, PC_GEMM_NODE, b->h1, H, rows_lvl, n_node_rows, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H, rows_lvl, 0, cnt_dst);
     // --- projections of the new h / new h_bond for the position update
-    gemm(b, s, PC_GEMM_NODE, h_out, H, nullptr, N, L.n2, b->PNx, 2 * H);
+    gemm(b, s, PC_GEMM_NODE, h_out, H, rows_lvl, n_node_rows, L.n2, b->PNx, 2 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_pos);
     gemm(b, s, PC_GEMM_LIG, h_out, H, b->lig_idx, NL, L.l2, b->PLx, 8 * H);
     gemm(b, s, PC_GEMM_LIG, b->PLx + 2 * H, 8 * H, nullptr, NL, L.q_pe, b->qXe, H, &L.ln_q_pe);
     gemm(b, s, PC_GEMM_LIG, b->PLx + 7 * H, 8 * H, nullptr, NL, L.q_pb, b->qXb, H, &L.ln_q_pb);
@@ -759,7 +788,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     kp.Hj = b->PNx; kp.ldhj = 2 * H; kp.q = b->qXe; kp.ldq = H; kp.q_by_slot = 1;
     kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
     kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k); kp.W2tc = m->p(L.pe_k.m.W2tc);
-    kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_prot = 0; kp.slot_meta = b->slot_meta_lig;      // ligand destinations only
+    kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_first = 0; kp.first_class = 0; kp.slot_meta = b->slot_meta_lig;      // ligand destinations only
     { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, 0, sms, s); else launch_knn_attn_k(kp, sms, s); }
     kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
     kp.W2tc = m->p(L.pe_v.m.W2tc); kp.B2tc[0] = m->p(L.pe_v.B2tc[0]); kp.B2tc[1] = m->p(L.pe_v.B2tc[1]);

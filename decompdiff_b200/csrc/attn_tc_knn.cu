@@ -107,14 +107,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const int n_tiles = (a.n_dst + 3) / 4;
-  const int tile_class1 = a.n_slots_prot / 4;          // tiles >= this hold ligand destinations
+  const int n_dst = a.n_dst_dev ? min(__ldg(a.n_dst_dev), a.n_dst) : a.n_dst;      // device-side count: receptive-field pruning
+  const int n_tiles = (n_dst + 3) / 4;
+  const int tile_first = a.n_slots_first / 4;          // tiles below this hold destinations of class a.first_class
+  auto class_of = [&](int tile) { return tile < tile_first ? a.first_class : 1 - a.first_class; };
   if (tid == 0) {
     const uint32_t bar = smem_u32(&sm.bars[0]);
     mbar_expect_tx(bar, W2_BYTES + 2 * KT_IMG);
     bulk_g2s(smem_u32(sm.W2), a.W2tc, W2_BYTES / 2, bar);
     bulk_g2s(smem_u32(sm.W2) + W2_BYTES / 2, a.W2tc + W2_BYTES / 8, W2_BYTES / 2, bar);
-    bulk_g2s(smem_u32(sm.B2), a.B2tc[(int)blockIdx.x >= tile_class1 ? 1 : 0], 2 * KT_IMG, bar);
+    bulk_g2s(smem_u32(sm.B2), a.B2tc[class_of(blockIdx.x)], 2 * KT_IMG, bar);
   }
   const uint32_t tmem_base = *sm.tmem_slot;
   cta_copy_f4(sm.gamma, a.w.gamma, H);
@@ -133,12 +135,12 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
 #endif
     if (warp == 16) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int cur_class = (int)blockIdx.x >= tile_class1 ? 1 : 0;
+      int cur_class = class_of(blockIdx.x);
       auto issue_d2 = [&](int tile) {
         knamed_sync(KBAR_A2_READY, KT_SYNC);          // every worker has written its A2 features and has read D2 of the tile before
         if (lane == 0) {
           tc_fence_after();
-          const int cls = tile >= tile_class1 ? 1 : 0;
+          const int cls = class_of(tile);
           if (cls != cur_class) {                     // class boundary: every distance MMA issued so far has retired (workers
             cur_class = cls;                          // waited on it), so B2 can be replaced
             const uint32_t bar = smem_u32(&sm.bars[3]);
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
           int any_lig = 0;
           for (int g4 = 0; g4 < 4; ++g4) {
             const int slot = tile * 4 + g4;
-            if (slot < a.n_dst) any_lig |= (__ldg(a.slot_meta + slot).y >> 8) & 0xff;
+            if (slot < n_dst) any_lig |= (__ldg(a.slot_meta + slot).y >> 8) & 0xff;
           }
           const int n_kb = any_lig ? KT_KB : 3;
 #pragma unroll 1
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
     auto load_group = [&](int tile) {
       Grp g; g.node = -1; g.pk = 0;
       const int slot = tile * 4 + q;
-      if (tile < n_tiles && slot < a.n_dst) { const int2 m = __ldg(a.slot_meta + slot); g.node = m.x; g.pk = m.y; }
+      if (tile < n_tiles && slot < n_dst) { const int2 m = __ldg(a.slot_meta + slot); g.node = m.x; g.pk = m.y; }
       return g;
     };
     // Gaussian features of this thread's row -> A2.  Slice-warp s owns the 4-column chunks {s} (and {4} for s == 0); a chunk goes

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm128_kernel(const GemmArgs
   float* Ws = smem + H * GEMM_BM;         // [2][GEMM_BK][GEMM_BN]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * GEMM_BM, col0 = blockIdx.y * GEMM_BN;
+  const int M = a.M_dev ? min(__ldg(a.M_dev), a.M) : a.M;
+  if (row0 >= M) return;
 
   auto load_w_stage = [&](int stage, int k0) {
     float* dst = Ws + stage * GEMM_BK * GEMM_BN;
@@ -47,8 +49,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm128_kernel(const GemmArgs
   for (int r = warp; r < GEMM_BM; r += GEMM_THREADS / 32) {
     int m = row0 + r;
     float4 z[1] = {make_float4(0, 0, 0, 0)};
-    if (m < a.M) {
-      int ar = a.a_rows ? a.a_rows[m] : m;
+    const int ar = m < M ? (a.a_rows ? a.a_rows[m] : m) : -1;
+    if (ar >= 0) {
       z[0] = ld4(a.A + (size_t)ar * a.lda + lane * 4);
       if (a.A2) {
         int r2 = a.a2_rows[m];
@@ -97,8 +99,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm128_kernel(const GemmArgs
   for (int i = 0; i < 8; ++i) {
     int r = (i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4));
     int m = row0 + r;
-    if (m >= a.M) continue;
+    if (m >= M) continue;
     int cr = a.c_rows ? a.c_rows[m] : m;
+    if (cr < 0) continue;
 #pragma unroll
     for (int jb = 0; jb < 2; ++jb) {
       int n = col0 + jb * 64 + tx * 4;

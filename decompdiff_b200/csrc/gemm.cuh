@@ -22,6 +22,8 @@ struct GemmArgs {
   float* C = nullptr; int ldc = 0;
   const int* c_rows = nullptr;                    // optional scatter of output (and residual) rows
   int M = 0, N = 0;                               // N multiple of 128
+  const int* M_dev = nullptr;                     // optional: the row count lives on the device (<= M, which sizes the grid);
+                                                  // rows whose a_rows / c_rows entry is negative are padding and are skipped
   int act = 0;                                    // 0 none, 1 shifted softplus
 };
 

@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * TC_BM;
+  const int M = a.M_dev ? min(__ldg(a.M_dev), a.M) : a.M;
+  if (row0 >= M) return;                            // device-side row count (exact receptive-field pruning): nothing to do
   const int tile0 = blockIdx.y * tiles_per_cta;
   const int n_tiles = min(tiles_per_cta, a.N / TC_BN - tile0);
   auto bar_full = [&](int i) { return smem_u32(&bars[i]); };                        // K-block landed in stage i
@@ -129,8 +131,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
       float z[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) z[i] = 0.f;
-      if (m < a.M) {
-        const float* src = a.A + (size_t)(a.a_rows ? a.a_rows[m] : m) * a.lda + s * 32;
+      const int ar = m < M ? (a.a_rows ? a.a_rows[m] : m) : -1;
+      if (ar >= 0) {
+        const float* src = a.A + (size_t)ar * a.lda + s * 32;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { float4 v = ld4(src + i * 4); z[4 * i] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w; }
         if (a.A2) {
@@ -199,8 +202,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
       for (int it = 0; it < 8; ++it) {
         const int rl = it * 4 + (lane >> 3);
         const int m = row0 + q * 32 + rl;
-        if (m < a.M) {
-          const int cr = a.c_rows ? a.c_rows[m] : m;
+        const int cr = m < M ? (a.c_rows ? a.c_rows[m] : m) : -1;
+        if (cr >= 0) {
           float4 o = add4(ld4(tile + rl * TC_EPI_LD + (lane & 7) * 4), bias4);
           if (a.R) o = add4(o, ld4(a.R + (size_t)cr * a.ldr + n0));
           if (a.act == 1) { o.x = ssp(o.x); o.y = ssp(o.y); o.z = ssp(o.z); o.w = ssp(o.w); }

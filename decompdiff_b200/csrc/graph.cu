@@ -8,6 +8,8 @@
 // keeps its strided share of candidate keys in registers, 32 rounds of warp-arg-min pick the k nearest.
 // Keys are (fp32 bits of d^2) << 32 | index, with d^2 = ((dx*dx)+(dy*dy))+(dz*dz) evaluated without
 // FMA contraction, so membership and order are bit-identical to the oracle (ties -> lower index).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace ddb {
@@ -157,6 +159,95 @@ void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, 
   if (n <= 0) return;
   const int wpb = 8;
   edge_weight_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, stream>>>(x4, nbr, deg, n, W1t, b1, gamma, beta, w2, b2, e_w, cache);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact receptive field of the outputs.  Only ligand positions / features / bond features leave the network, so the node
+// update of layer l (0-based, L layers) is needed only for nodes within L - l hops of a ligand atom along kNN edges
+// (destination -> its sources).  level[node] = that hop count (ligand 0, capped at LEVEL_CAP); protein nodes are then listed
+// by ascending level behind the (static) ligand block of `dst_list`, so every layer works on a PREFIX whose length is a
+// device-side counter - nothing is approximated, rows that cannot influence the outputs are simply not computed.
+constexpr int LEVEL_CAP = 7;
+__global__ void __launch_bounds__(256) level_init_kernel(const uint8_t* __restrict__ is_lig, int n, int* __restrict__ level) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) level[i] = is_lig[i] ? 0 : LEVEL_CAP;
+}
+__global__ void __launch_bounds__(256) level_relax_kernel(const int* __restrict__ nbr, const int* __restrict__ deg, int n, int round,
+                                                          int* __restrict__ level) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = idx >> 5, lane = idx & 31;
+  if (i >= n || level[i] != round || lane >= deg[i]) return;
+  atomicMin(level + nbr[idx], round + 1);
+}
+// Deterministic counting sort of the protein nodes by (level, graph, index): one warp per graph ranks its nodes with ballots, so
+// the destination list - and with it the tile composition of the attention kernels - is the same on every run.
+__global__ void __launch_bounds__(256) level_count_kernel(const int* __restrict__ level, const int* __restrict__ node_ptr,
+                                                          const int* __restrict__ n_protein, int num_graphs, int* __restrict__ cnt) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= num_graphs) return;
+  const int base = node_ptr[g], np = n_protein[g];
+  int c[LEVEL_CAP + 1];
+#pragma unroll
+  for (int v = 0; v <= LEVEL_CAP; ++v) c[v] = 0;
+  for (int i0 = 0; i0 < np; i0 += 32) {
+    const int lv = i0 + lane < np ? level[base + i0 + lane] : -1;
+#pragma unroll
+    for (int v = 0; v <= LEVEL_CAP; ++v) c[v] += __popc(__ballot_sync(FULL, lv == v));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int v = 0; v <= LEVEL_CAP; ++v) cnt[g * (LEVEL_CAP + 1) + v] = c[v];
+  }
+}
+// counts[0 .. n_layers): destinations of layer l (ligand block + protein nodes with level <= n_layers - l);
+// counts[n_layers .. 2 n_layers): source rows of layer l (level <= n_layers - l + 1); counts[2 n_layers]: level <= 1;
+// cnt[(g, v)] is replaced by the first list position of graph g's level-v nodes
+__global__ void level_offsets_kernel(int* __restrict__ cnt, int num_graphs, int lig_block, int n_layers, int* __restrict__ counts) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int start[LEVEL_CAP + 2];
+  start[0] = 0;
+  for (int v = 0; v <= LEVEL_CAP; ++v) {
+    int run = start[v];
+    for (int g = 0; g < num_graphs; ++g) { const int c = cnt[g * (LEVEL_CAP + 1) + v]; cnt[g * (LEVEL_CAP + 1) + v] = lig_block + run; run += c; }
+    start[v + 1] = run;
+  }
+  auto upto = [&](int lv) { return lig_block + start[min(max(lv, 0), LEVEL_CAP) + 1]; };
+  for (int l = 0; l < n_layers; ++l) {
+    counts[l] = upto(n_layers - l);
+    counts[n_layers + l] = upto(n_layers - l + 1);
+  }
+  counts[2 * n_layers] = upto(1);
+}
+__global__ void __launch_bounds__(256) level_scatter_kernel(const int* __restrict__ level, const int* __restrict__ node_ptr,
+                                                            const int* __restrict__ n_protein, int num_graphs, const int* __restrict__ first,
+                                                            int* __restrict__ dst_list) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= num_graphs) return;
+  const int base = node_ptr[g], np = n_protein[g];
+  int cur[LEVEL_CAP + 1];
+#pragma unroll
+  for (int v = 0; v <= LEVEL_CAP; ++v) cur[v] = first[g * (LEVEL_CAP + 1) + v];
+  for (int i0 = 0; i0 < np; i0 += 32) {
+    const int lv = i0 + lane < np ? level[base + i0 + lane] : -1;
+#pragma unroll
+    for (int v = 0; v <= LEVEL_CAP; ++v) {
+      const unsigned m = __ballot_sync(FULL, lv == v);
+      if (lv == v) dst_list[cur[v] + __popc(m & ((1u << lane) - 1u))] = base + i0 + lane;
+      cur[v] += __popc(m);
+    }
+  }
+}
+
+void launch_receptive_field(const int* nbr, const int* deg, const uint8_t* is_lig, const int* node_ptr, const int* n_protein, int num_graphs,
+                            int n, int n_layers, int lig_block, int* level, int* cnt /* 8 * num_graphs ints */,
+                            int* counts /* 2 * n_layers + 1 */, int* dst_list, cudaStream_t stream) {
+  if (n <= 0) return;
+  const int nb = (n + 255) / 256, gb = (num_graphs + 7) / 8;
+  level_init_kernel<<<nb, 256, 0, stream>>>(is_lig, n, level);
+  for (int r = 0; r < LEVEL_CAP - 1; ++r) level_relax_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(nbr, deg, n, r, level);
+  level_count_kernel<<<gb, 256, 0, stream>>>(level, node_ptr, n_protein, num_graphs, cnt);
+  level_offsets_kernel<<<1, 32, 0, stream>>>(cnt, num_graphs, lig_block, n_layers, counts);
+  level_scatter_kernel<<<gb, 256, 0, stream>>>(level, node_ptr, n_protein, num_graphs, cnt, dst_list);
 }
 
 }  // namespace ddb

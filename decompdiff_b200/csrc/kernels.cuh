@@ -20,6 +20,11 @@ void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, 
                         const float* gamma, const float* beta, const float* w2, float b2, float* e_w,
                         const EdgeWeightCache& cache, cudaStream_t stream);
 
+// exact receptive field of the outputs: hop level per node, protein destinations listed by level behind the ligand block of
+// `dst_list`, per-layer prefix lengths in `counts` (graph.cu)
+void launch_receptive_field(const int* nbr, const int* deg, const uint8_t* is_lig, const int* node_ptr, const int* n_protein, int num_graphs,
+                            int n, int n_layers, int lig_block, int* level, int* cnt, int* counts, int* dst_list, cudaStream_t stream);
+
 // Weights of one attention MLP whose first Linear acts on kNN-edge features (NodeUpdateLayer /
 // PosUpdateLayer with edge_feat = [type (x) gauss(d) | type]), re-packed by api.cu:
 struct KnnMlpW {
@@ -47,12 +52,12 @@ struct KnnAttnArgs {
   KnnMlpW w;
   const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 for the tensor-core kernels (attn_tc.cu)
   // tensor-core kernels only: distances at layer entry (N,32), the distance-term weights per destination class
-  // (0 = protein, 1 = ligand destinations; pack_wg_tc) and the number of leading slots of dst_list that are protein
-  // destinations (a multiple of 4; padding slots hold -1)
+  // (0 = protein, 1 = ligand destinations; pack_wg_tc); dst_list holds one class first, then the other (padding slots -1)
   const float* dist = nullptr;
   const int2* slot_meta = nullptr;    // (n_dst) {node or -1, deg | nlig << 8 | is_ligand << 16} per slot (launch_knn_slot_meta)
   const float* B2tc[2] = {nullptr, nullptr};
-  int n_slots_prot = 0;
+  int n_slots_first = 0, first_class = 0;   // the first n_slots_first slots (multiple of 4) are destinations of class first_class
+  const int* n_dst_dev = nullptr;     // optional device-side destination count (<= n_dst): exact receptive-field pruning
   // v pass outputs
   float* out_h = nullptr; int ldo = 0;          // node variant: (N,128) rows by node id
   float* out_dx = nullptr;                      // pos variant: (n_dst,4) by slot

@@ -30,3 +30,21 @@ def test_forward_matches_oracle_new_inputs(model_cpu, weights, oracle_cfg):
         ref = restate.forward(weights, oracle_cfg, **fk)
     for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
         assert tol_ratio(out[k], ref[k]) <= 1.0
+
+
+def test_receptive_field_pruning_is_exact(model_cpu, monkeypatch):
+    """Layers only compute the nodes that can still reach a ligand output (graph.cu: launch_receptive_field).  Nothing is
+    approximated: with the pruning switched off (every node in every layer) the outputs agree to the last couple of ulps -
+    the tile a destination lands in changes with the list, and the tensor-core feature GEMM is reproducible per tile order,
+    not across tile orders - and the pruned path itself is bit-reproducible (deterministic list construction).
+    DDB_NO_PRUNE / DDB_NO_EW_CACHE are read when a batch is created."""
+    kw = syn.make_batch(n_pockets=3, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, seed=91)     # deep enough for 6 hops to matter
+    fk = syn.forward_kwargs(kw, None)
+    pruned, again = model_cpu(**fk), model_cpu(**fk)
+    monkeypatch.setenv('DDB_NO_PRUNE', '1')
+    monkeypatch.setenv('DDB_NO_EW_CACHE', '1')
+    full = model_cpu(**fk)
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
+        assert torch.equal(pruned[k], again[k]), k
+        assert float((pruned[k] - full[k]).abs().max()) <= 5e-6, k
+        assert tol_ratio(pruned[k], full[k]) <= 0.1, k
