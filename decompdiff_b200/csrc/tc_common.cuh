@@ -23,14 +23,17 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  unsigned long long spins = 0;
-  while (!ok) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (!ok && ++spins > (1ull << 28)) __trap();     // turn a protocol bug into an error instead of a hang
-  }
+  if (mbar_try(bar, parity)) return;                  // fast path: already complete
+  uint32_t spins = 0;                                 // try_wait suspends in hardware; the counter only turns a protocol bug
+  while (!mbar_try(bar, parity))                      // into an error instead of a hang
+    if (++spins > (1u << 24)) __trap();
 }
 // 1-D bulk copy global -> shared through the TMA engine, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
