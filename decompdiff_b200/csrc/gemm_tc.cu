@@ -19,6 +19,7 @@
 //     alternate, so the epilogue of tile t overlaps the MMAs of tile t+1.  No CTA-wide barrier inside the tile loop.
 //   * epilogue: warp (s, q) drains rows 32q.. of columns 32s.. of the accumulator: tcgen05.ld, release, smem transpose, bias /
 //     residual / activation, coalesced global stores
+#include <algorithm>
 #include <cstring>
 
 #include "gemm.cuh"
@@ -55,9 +56,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStatB + 128 * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row0 = blockIdx.x * TC_BM;
-  const int M = a.M_dev ? min(__ldg(a.M_dev), a.M) : a.M;
-  if (row0 >= M) return;                            // device-side row count (exact receptive-field pruning): nothing to do
+  const int M = a.M_dev ? min(__ldg(a.M_dev), a.M) : a.M;      // device-side row count: exact receptive-field pruning
+  const int row_tiles = (M + TC_BM - 1) / TC_BM;
+  if ((int)blockIdx.x >= row_tiles) return;
+  // persistent over row tiles: blockIdx.x, blockIdx.x + gridDim.x, ...  (one TMEM allocation / barrier set-up per CTA; with a
+  // single output tile the whole weight stays resident in the ring and is streamed once)
+  const int my_rows = (row_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile0 = blockIdx.y * tiles_per_cta;
   const int n_tiles = min(tiles_per_cta, a.N / TC_BN - tile0);
   auto bar_full = [&](int i) { return smem_u32(&bars[i]); };                        // K-block landed in stage i
@@ -76,57 +80,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_blocks = n_tiles * 4;                 // K-blocks this CTA consumes
+  const int n_blocks = n_tiles * 4;                 // K-blocks per row tile
+  const bool resident = n_blocks <= TC_STAGES;      // the ring holds the whole weight: load once, never refill
 
   if (warp == 17) {
     // ------------------------------------------------------------------------------------ weight producer warp
     if (lane == 0) {
       const float* src = Wtc + (size_t)tile0 * 4 * (TC_B_STAGE / 4);
-      for (int i = 0; i < n_blocks; ++i) {
-        const int st = i % TC_STAGES, use = i / TC_STAGES;
-        if (use > 0) mbar_wait(bar_empty(st), (use - 1) & 1);
-        mbar_expect_tx(bar_full(st), TC_B_STAGE);
-        bulk_g2s(smem_u32(sB + st * TC_B_STAGE), src + (size_t)i * (TC_B_STAGE / 4), TC_B_STAGE, bar_full(st));
-      }
+      int gi = 0;                                   // running K-block index over all row tiles of this CTA
+      for (int rt = 0; rt < (resident ? 1 : my_rows); ++rt)
+        for (int i = 0; i < n_blocks; ++i, ++gi) {
+          const int st = gi % TC_STAGES, use = gi / TC_STAGES;
+          if (use > 0) mbar_wait(bar_empty(st), (use - 1) & 1);
+          mbar_expect_tx(bar_full(st), TC_B_STAGE);
+          bulk_g2s(smem_u32(sB + st * TC_B_STAGE), src + (size_t)i * (TC_B_STAGE / 4), TC_B_STAGE, bar_full(st));
+        }
     }
     __syncwarp();
   } else if (warp == 16) {
     // ------------------------------------------------------------------------------------ MMA issuer warp
-    asm volatile("bar.sync %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_WORKERS + 32) : "memory");   // A tile is in TMEM
-    if (lane == 0) {
-      tc_fence_after();
-      // instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint64_t desc0 = umma_desc_sw128(smem_u32(sB));     // descriptors of other addresses differ in the low field only
-      int i = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        const int db = t & 1;
-        if (t >= 2) mbar_wait(bar_dempty(db), ((t >> 1) - 1) & 1);      // the epilogue of tile t - 2 has drained this accumulator
-        const uint32_t d = tmem_base + TC_COL_D + db * TC_BN;
+    // instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint64_t desc0 = umma_desc_sw128(smem_u32(sB));     // descriptors of other addresses differ in the low field only
+    int gi = 0, tg = 0;                             // running K-block / output-tile counters over all row tiles
+    for (int rt = 0; rt < my_rows; ++rt) {
+      asm volatile("bar.sync %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_WORKERS + 32) : "memory");   // A tile of this row tile is in TMEM
+      if (lane == 0) {
+        tc_fence_after();
+        for (int t = 0; t < n_tiles; ++t, ++tg) {
+          const int db = tg & 1;
+          if (tg >= 2) mbar_wait(bar_dempty(db), ((tg >> 1) - 1) & 1);      // the epilogue two tiles back has drained this accumulator
+          const uint32_t d = tmem_base + TC_COL_D + db * TC_BN;
 #pragma unroll 1
-        for (int kb = 0; kb < 4; ++kb, ++i) {
-          const int st = i % TC_STAGES;
-          mbar_wait(bar_full(st), (i / TC_STAGES) & 1);
-          tc_fence_after();
-          const uint64_t d_hi = desc0 + (uint64_t)((st * TC_B_STAGE) >> 4), d_lo = d_hi + (uint64_t)(TC_B_PART >> 4);
+          for (int kb = 0; kb < 4; ++kb, ++gi) {
+            const int st = resident ? (t * 4 + kb) : gi % TC_STAGES;
+            mbar_wait(bar_full(st), resident ? 0u : (uint32_t)((gi / TC_STAGES) & 1));
+            tc_fence_after();
+            const uint64_t d_hi = desc0 + (uint64_t)((st * TC_B_STAGE) >> 4), d_lo = d_hi + (uint64_t)(TC_B_PART >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {   // UMMA K = 8 tf32: 8 TMEM columns of A, 32 bytes inside the 128-byte swizzle atom of B
-            const uint32_t acol = kb * 32 + kk * 8;
-            umma_tf32_ts(d, tmem_base + TC_COL_AHI + acol, d_hi + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
-            umma_tf32_ts(d, tmem_base + TC_COL_ALO + acol, d_hi + (uint64_t)(kk * 2), idesc, 1u);
-            umma_tf32_ts(d, tmem_base + TC_COL_AHI + acol, d_lo + (uint64_t)(kk * 2), idesc, 1u);
+            for (int kk = 0; kk < 4; ++kk) {   // UMMA K = 8 tf32: 8 TMEM columns of A, 32 bytes inside the 128-byte swizzle atom of B
+              const uint32_t acol = kb * 32 + kk * 8;
+              umma_tf32_ts(d, tmem_base + TC_COL_AHI + acol, d_hi + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+              umma_tf32_ts(d, tmem_base + TC_COL_ALO + acol, d_hi + (uint64_t)(kk * 2), idesc, 1u);
+              umma_tf32_ts(d, tmem_base + TC_COL_AHI + acol, d_lo + (uint64_t)(kk * 2), idesc, 1u);
+            }
+            if (!resident) umma_commit(bar_empty(st));           // stage st may be refilled once these MMAs retire
           }
-          umma_commit(bar_empty(st));           // stage st may be refilled once these MMAs retire
+          umma_commit(bar_dfull(db));             // accumulator complete (implies tcgen05.fence::before_thread_sync)
         }
-        umma_commit(bar_dfull(db));             // accumulator complete (implies tcgen05.fence::before_thread_sync)
       }
+      __syncwarp();
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------------------------------ worker warps
     const int q = warp & 3, s = warp >> 2;                  // TMEM lane quadrant, channel slice
+    float* tile = sEpi + warp * 32 * TC_EPI_LD;
+    int tg = 0;
+    for (int rt = 0; rt < my_rows; ++rt) {
+    const int row0 = ((int)blockIdx.x + rt * (int)gridDim.x) * TC_BM;
     {
-      // ---- stage A into TMEM: this thread owns channels [32s, 32s+32) of row 32q + lane
+      // ---- stage A into TMEM: this thread owns channels [32s, 32s+32) of row 32q + lane.  Every MMA that read the previous
+      // A tile has retired: this warp waited on the last accumulator's "full" barrier in its epilogue below
       const int r = q * 32 + lane, m = row0 + r;
       float z[32];
 #pragma unroll
@@ -180,10 +195,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
       asm volatile("bar.arrive %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_WORKERS + 32) : "memory");
     }
     // ---- epilogue: warp (s, q) drains rows 32q.., columns 32s.. of every output tile
-    float* tile = sEpi + warp * 32 * TC_EPI_LD;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int db = t & 1;
-      mbar_wait(bar_dfull(db), (t >> 1) & 1);
+    for (int t = 0; t < n_tiles; ++t, ++tg) {
+      const int db = tg & 1;
+      mbar_wait(bar_dfull(db), (tg >> 1) & 1);
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TC_COL_D + db * TC_BN + s * 32, v);
@@ -212,6 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
       }
       __syncwarp();
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -231,13 +246,14 @@ void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStr
   int best = 1; double best_cost = 1e30;
   for (int ns = 1; ns <= tiles; ++ns) {
     if (tiles % ns) continue;
-    long ctas = (long)row_tiles * ns;
-    double waves = (double)((ctas + num_sms - 1) / num_sms);
-    double cost = waves * (1.5 + (double)tiles / ns);
+    // CTAs are persistent over row tiles: num_sms / ns of them per column range, each walking ceil(row_tiles / that) row tiles
+    const int per_col = std::max(1, std::min(row_tiles, num_sms / ns));
+    const double rows_each = (double)((row_tiles + per_col - 1) / per_col);
+    const double cost = 1.0 + rows_each * (1.5 + (double)tiles / ns);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
   }
   const int per = tiles / best;
-  dim3 grid(row_tiles, (tiles + per - 1) / per);
+  dim3 grid(std::max(1, std::min(row_tiles, num_sms / best)), (tiles + per - 1) / per);
   gemm128_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(a, Wtc, per);
 }
 
