@@ -360,7 +360,7 @@ class SamplingRun:
 
     def enable_host_streaming(self):
         if self.keep_traj and self.host_traj is None and self.num_steps > 0:
-            self.host_traj = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.traj.items()}
+            self.host_traj = {k: [] for k in self.traj}          # per key: list of pinned chunks, allocated when they are needed
             self.copy_stream = torch.cuda.Stream(device=self.eb.device)
         return self
 
@@ -370,9 +370,14 @@ class SamplingRun:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.copy_stream.wait_event(ev)
+        # page-locking 1.7 GB up front costs ~1.1 s; chunk by chunk it happens while the GPU works through the steps that are
+        # already queued (the host runs far ahead of the device once the step is a CUDA graph)
         with torch.cuda.stream(self.copy_stream):
             for k, v in self.traj.items():
-                self.host_traj[k][self.copied:self.done].copy_(v[self.copied:self.done], non_blocking=True)
+                part = v[self.copied:self.done]
+                chunk = torch.empty(part.shape, dtype=part.dtype, pin_memory=True)
+                chunk.copy_(part, non_blocking=True)
+                self.host_traj[k].append(chunk)
         self.copied = self.done
 
     def _draw(self):
@@ -442,5 +447,5 @@ class SamplingRun:
             self._stream_out(force=True)
             self.copy_stream.synchronize()
             for key in self.traj:
-                result[key] = list(self.host_traj[key][:self.done].unbind(0))
+                result[key] = [row for chunk in self.host_traj[key] for row in chunk.unbind(0)]
         return result
