@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         const float mu = ((t01.x + t01.z) + (t23.x + t23.z)) * (1.0f / H);
         const float d0 = t01.x * (1.0f / 32.0f) - mu, d1 = t01.z * (1.0f / 32.0f) - mu, d2 = t23.x * (1.0f / 32.0f) - mu, d3 = t23.z * (1.0f / 32.0f) - mu;
         const float m2 = ((t01.y + t01.w) + (t23.y + t23.w)) + 32.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
-        const float rstd = 1.0f / sqrtf(m2 * (1.0f / H) + LN_EPS);
+        const float rstd = rsqrtf(m2 * (1.0f / H) + LN_EPS);
         const float2 rs2 = kf2(rstd, rstd), nm2 = kf2(-mu * rstd, -mu * rstd);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -417,13 +417,13 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
           for (int hh = 0; hh < 4; ++hh) {
             float m;
             asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(lg[hh]));
-            ex[hh] = prev_ok ? expf(lg[hh] - m) : 0.f;
+            ex[hh] = prev_ok ? __expf(lg[hh] - m) : 0.f;
           }
           float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
           warp_allreduce4(sum, lane);
           float w[4];
 #pragma unroll
-          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? ex[hh] * __frcp_rn(sum[hh]) * prev_ew : 0.f;
+          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? __fdividef(ex[hh], sum[hh]) * prev_ew : 0.f;
           if (prev_ok) st4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
         } else if (VPOS) {
           if (s == 0) {

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
       } else {
         const float n2 = cn * cn + dot * dot;
-        const float inv = n2 > 0.f ? 1.0f / sqrtf(n2) : 0.f;
+        const float inv = n2 > 0.f ? rsqrtf(n2) : 0.f;
         const float sn = cn * inv, cs = n2 > 0.f ? dot * inv : 1.f;
         if (s == 1) {
           a2_put(sm.A2, r, 1, sn); a2_put(sm.A2, r, 4, sn); a2_put(sm.A2, r, 7, cs); a2_put(sm.A2, r, 10, cs);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
         const float4 t01 = *reinterpret_cast<const float4*>(st), t23 = *reinterpret_cast<const float4*>(st + 2);
         const float mu = ((t01.x + t01.z) + (t23.x + t23.z)) * (1.0f / H);
         const float var = fmaxf(((t01.y + t01.w) + (t23.y + t23.w)) * (1.0f / H) - mu * mu, 0.f);
-        const float rstd = 1.0f / sqrtf(var + LN_EPS);
+        const float rstd = rsqrtf(var + LN_EPS);
         const float2 rs2 = f2(rstd, rstd), nm2 = f2(-mu * rstd, -mu * rstd);
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
@@ -362,13 +362,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
           for (int hh = 0; hh < 4; ++hh) {
             float m;
             asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(lg[hh]));
-            ex[hh] = prev_ok ? expf(lg[hh] - m) : 0.f;
+            ex[hh] = prev_ok ? __expf(lg[hh] - m) : 0.f;
           }
           float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
           warp_allreduce4(sum, lane);
           float w[4];
 #pragma unroll
-          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? ex[hh] * __frcp_rn(sum[hh]) : 0.f;
+          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? __fdividef(ex[hh], sum[hh]) : 0.f;
           if (prev_e >= 0) st4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
         } else {
           warp_reduce_scatter<32>(val, lane);
