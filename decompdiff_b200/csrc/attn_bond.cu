@@ -242,8 +242,8 @@ void launch_bond_attn_pos(const BondAttnArgs& a, int num_sms, cudaStream_t strea
 // prep: P[e] = Pe[e] + Hk[src(e)] + Hj[dst(e)] + Wd . gauss(d_e)   for the k and the v MLP.  One warp handles PREP_EDGES edges at
 // a time (lane = 4 channels) so that every weight row fetched from L1 feeds several edges - the kernel is bound by the L1
 // wavefronts of the Wd / Wc reads otherwise.
-constexpr int PREP_EDGES = 4;
-__global__ void __launch_bounds__(256) trip_prep_kernel(const TripArgs a) {
+constexpr int PREP_EDGES = 2;      // 2 edges x 64 registers -> 32 warps per SM: the kernel is latency / HBM bound, occupancy matters more than weight reuse
+__global__ void __launch_bounds__(256, 4) trip_prep_kernel(const TripArgs a) {
   const int lane = threadIdx.x & 31;
   const int e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PREP_EDGES;
   if (e0 >= a.n_bonds) return;
