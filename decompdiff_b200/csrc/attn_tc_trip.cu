@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     TL_DECL
     for (; it < per; ++it) {
       TL_MARK(0);
-      const bool gvalid = e >= 0;
       const bool rowok = rm.y >= 0;          // valid and k != i (:117-118)
       // requests for later: the Q slice of the next group, the query slice of this one, metadata two groups ahead
       const float q_next = __ldg(Qc + (size_t)max(e_n, 0) * H + s * 32 + lane);
