@@ -12,6 +12,6 @@ Public surface (mirrors the reference's Python API for the path, SURVEY.md secti
 from .batch import Batch, Data, FOLLOW_BATCH, ProteinLigandData  # noqa: F401
 from .decompdiff import AttrDict, DecompScorePosNet3D, get_refine_net  # noqa: F401
 from . import prior, transforms  # noqa: F401
-from .sampling import log_sample_categorical, sample_diffusion_ligand_decomp  # noqa: F401
+from .sampling import log_sample_categorical, sample_diffusion_ligand_decomp, save_results  # noqa: F401
 
 __version__ = '0.1.0'

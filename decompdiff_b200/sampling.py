@@ -284,3 +284,12 @@ class _OldCountPlan:
         pos.append(self.sca_center + torch.randn([n, 3]) * self.sca_std.unsqueeze(0))
         mask += [-1] * n
         return torch.cat(pos, dim=0), mask
+
+
+def save_results(raw_results, path: str, ligand_filename: Optional[str] = None, extra: Optional[Dict] = None) -> List[Dict]:
+    """Write the `result.pt` file of the reference driver (scripts/sample_diffusion_decomp.py:609-619): the list of per-sample
+    dicts with `ligand_filename` added to each, saved with torch.save - the format `scripts/evaluate_mol_from_meta_full.py:45-63`
+    reads (`pred_pos`, `pred_v`, `pred_bond_index`, `pred_bond_type`, `mol`, `smiles`, trajectories, `decomp_mask`)."""
+    results = [{**r, 'ligand_filename': ligand_filename, **(extra or {})} for r in raw_results]
+    torch.save(results, path)
+    return results

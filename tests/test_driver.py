@@ -84,6 +84,19 @@ def test_driver_result_schema_and_edges():
     assert len(run_driver(spec, StubModel(), num_samples=1, batch_size=4)) == 1
 
 
+def test_result_file_round_trip(tmp_path):
+    """result.pt hand-off (scripts/sample_diffusion_decomp.py:609-619): list of dicts + ligand_filename, loadable with torch.load."""
+    res = run_driver(DRIVER_CASES['ref_prior'], StubModel())
+    path = str(tmp_path / 'result.pt')
+    saved = sampling.save_results(res, path, ligand_filename='pocket/lig.sdf')
+    loaded = torch.load(path, weights_only=False)
+    assert len(loaded) == len(res) == NUM_SAMPLES and loaded[0]['ligand_filename'] == 'pocket/lig.sdf'
+    assert set(loaded[0]) == set(saved[0]) == set(res[0]) | {'ligand_filename'}
+    for a, b in zip(loaded, res):
+        assert np.array_equal(a['pred_pos'], b['pred_pos']) and a['pred_pos'].dtype == np.float64
+        assert np.array_equal(a['pred_bond_type'], b['pred_bond_type']) and a['pred_bond_index'] == b['pred_bond_index']
+
+
 def test_priors_and_transforms_match_reference():
     gold = load_golden('driver_transforms')
     d = syn.make_raw_pocket(seed=41, arm_sizes=(3, 1, 4), n_scaffold=4)

@@ -48,3 +48,23 @@ def test_receptive_field_pruning_is_exact(model_cpu, monkeypatch):
         assert torch.equal(pruned[k], again[k]), k
         assert float((pruned[k] - full[k]).abs().max()) <= 5e-6, k
         assert tol_ratio(pruned[k], full[k]) <= 0.1, k
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    # ligands with more than 33 atoms: bond groups / triplet groups exceed 32 rows -> the fp32 kernels take over for them
+    ('big_ligand', dict(n_pockets=2, n_protein=120, arm_sizes=(12, 11), n_scaffold=13, seed=501)),
+    # large complexes (cfg 5 end of the sweep): more than 512 / 1024 atoms per graph selects the wider kNN kernels
+    ('n700', dict(n_pockets=1, n_protein=670, arm_sizes=(8, 8), n_scaffold=14, seed=502)),
+    ('n1100', dict(n_pockets=1, n_protein=1070, arm_sizes=(8, 8), n_scaffold=14, seed=503)),
+    # a batch whose graphs differ a lot in size, one without ligand arms' scaffold and a 2-atom ligand
+    ('mixed', dict(n_pockets=4, n_protein=[40, 300, 90, 500], arm_sizes=(1,), n_scaffold=1, seed=504)),
+])
+def test_forward_edge_shapes_match_oracle(name, kwargs, model_cpu, weights, oracle_cfg):
+    kw = syn.make_batch(**kwargs)
+    fk = syn.forward_kwargs(kw, None)
+    out = model_cpu(**fk)
+    with torch.no_grad():
+        ref = restate.forward(weights, oracle_cfg, **fk)
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
+        assert out[k].shape == ref[k].shape
+        assert tol_ratio(out[k], ref[k]) <= 1.0, f'{name}:{k} {tol_ratio(out[k], ref[k]):.3f} x tol'
