@@ -277,6 +277,11 @@ def main():
         warmup += 4
         torch.cuda.synchronize()
     if world > 1:
+        # the first collective of a process group builds the NCCL communicator (hundreds of ms at 8 ranks): do one untimed
+        # gather so that the timed one costs what it costs at the end of a real T=1000 run
+        pos, v, bond = run.eb.get_state()
+        gather_molecules({'pos': pos, 'v': v, 'bond': bond}, atoms_per_mol, bonds_per_mol)
+        torch.cuda.synchronize()
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
