@@ -339,6 +339,10 @@ struct ddb_batch {
   // exact receptive-field pruning (launch_receptive_field): hop level per node, [ligand block | protein nodes by level], per-layer counts
   bool prune = false; int lig_block = 0;
   int *level = nullptr, *lvl_hist = nullptr, *lvl_counts = nullptr, *dst_lvl = nullptr;
+  // first-layer cache (launch_layer0_keys): layer 0 writes hC / reads PN0, both untouched by the other layers
+  bool l0cache = false, pn0_ready = false;
+  float *hC = nullptr, *PN0 = nullptr; uint8_t* valid0 = nullptr;
+  int *key0 = nullptr, *cnt0 = nullptr, *counts0 = nullptr, *dst_lvl0 = nullptr; int2* slot_meta_lvl0 = nullptr;
   float* ew_table = nullptr; long long* ew_table_base = nullptr; int* n_protein_of = nullptr;     // EdgeWeightCache   // destinations by class (protein first), padded to tiles of 4
   int *nbr = nullptr, *deg = nullptr, *nlig = nullptr;
   float *hid_v = nullptr, *v_logits = nullptr, *b_logits = nullptr, *x0 = nullptr, *grad = nullptr;
@@ -558,6 +562,13 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     lvl.resize(lvl.size() + (size_t)NP, -1);            // the protein part is rewritten every step
     DDB_TRY(b->upload(&b->dst_lvl, lvl)); DDB_TRY(b->dalloc(&b->slot_meta_lvl, lvl.size()));
     DDB_TRY(b->dalloc(&b->level, (size_t)N)); DDB_TRY(b->dalloc(&b->lvl_hist, (size_t)8 * B)); DDB_TRY(b->dalloc(&b->lvl_counts, (size_t)2 * m->cfg.num_layers + 1));
+    b->l0cache = b->prune && m->cfg.num_layers >= 2 && !getenv("DDB_NO_L0_CACHE");
+    if (b->l0cache) {
+      DDB_TRY(b->upload(&b->dst_lvl0, lvl)); DDB_TRY(b->dalloc(&b->slot_meta_lvl0, lvl.size()));
+      DDB_TRY(b->dalloc(&b->key0, (size_t)N)); DDB_TRY(b->dalloc(&b->cnt0, (size_t)8 * B)); DDB_TRY(b->dalloc(&b->counts0, (size_t)2 * m->cfg.num_layers + 1));
+      DDB_TRY(b->dalloc(&b->valid0, (size_t)N)); cudaMemset(b->valid0, 0, (size_t)N);
+      DDB_TRY(b->dalloc(&b->hC, (size_t)N * H)); DDB_TRY(b->dalloc(&b->PN0, (size_t)N * 5 * H));
+    }
   }
 
   DDB_TRY(b->upload(&b->node_ptr, node_ptr)); DDB_TRY(b->upload(&b->graph_of, graph_of));
@@ -708,6 +719,12 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
                              b->lvl_counts, b->dst_lvl, s);
       launch_knn_slot_meta(b->dst_lvl, b->lig_block + b->NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl, s);
       b->launches += 11;
+      if (b->l0cache) {
+        launch_layer0_keys(b->level, b->nlig, b->is_lig, N, c.num_layers, b->valid0, b->key0, s);
+        launch_level_sort(b->key0, b->node_ptr, b->n_protein_of, b->B, c.num_layers, b->lig_block, b->cnt0, b->counts0, b->dst_lvl0, s);
+        launch_knn_slot_meta(b->dst_lvl0, b->lig_block + b->NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl0, s);
+        b->launches += 5;
+      }
     }
   }
   // with pruning, per-node work of layer l runs on a prefix of dst_lvl whose length is a device-side counter
@@ -717,23 +734,31 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   float *h_in = b->h0, *x_in = b->x4_0, *hb_in = b->hbA;
   for (int l = 0; l < c.num_layers; ++l) {
     const LayerOff& L = m->layers[l];
-    float* h_out = (l % 2 == 0) ? b->hA : b->hB;
+    const bool l0c = b->l0cache && l == 0;           // layer 0 with the static-row cache: own output / projection buffers, own list
+    float* h_out = l0c ? b->hC : (l % 2 == 0) ? b->hA : b->hB;
+    float* PNl = l0c ? b->PN0 : b->PN;
     float* x_out = (l % 2 == 0) ? b->x4_a : b->x4_b;
     float* hb_out = (l % 2 == 0) ? b->hbB : b->hbA;
     // --- projections of the layer input
-    const int* cnt_dst = prune_gemm ? b->lvl_counts + l : nullptr;                 // destinations of this layer's node update
+    const int* rows_l = l0c ? b->dst_lvl0 : rows_lvl;
+    const int* cnt_dst = l0c ? b->counts0 + 2 * nl_layers : prune_gemm ? b->lvl_counts + l : nullptr;   // destinations of this layer's node update
     const int* cnt_src = prune_gemm ? b->lvl_counts + nl_layers + l : nullptr;     // rows read as sources by it
     const int* cnt_pos = prune_gemm ? b->lvl_counts + 2 * nl_layers : nullptr;     // sources of the position update (ligand + 1 hop)
     const int n_node_rows = prune_gemm ? n_lvl : N;
-    gemm(b, s, PC_GEMM_NODE, h_in, H, rows_lvl, n_node_rows, L.n1, b->PN, 5 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_src);
-    gemm(b, s, PC_GEMM_NODE, b->PN + 4 * H, 5 * H, rows_lvl, n_node_rows, L.q_ne, b->qN, H, &L.ln_q_ne, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_dst);
+    if (l0c) {      // projections of the (static) protein embeddings are computed once; afterwards only the ligand rows change
+      if (!b->pn0_ready) gemm(b, s, PC_GEMM_NODE, h_in, H, nullptr, N, L.n1, PNl, 5 * H);
+      else gemm(b, s, PC_GEMM_NODE, h_in, H, rows_l, b->lig_block, L.n1, PNl, 5 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_l);
+    } else {
+      gemm(b, s, PC_GEMM_NODE, h_in, H, rows_lvl, n_node_rows, L.n1, PNl, 5 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_src);
+    }
+    gemm(b, s, PC_GEMM_NODE, PNl + 4 * H, 5 * H, rows_l, n_node_rows, L.q_ne, b->qN, H, &L.ln_q_ne, nullptr, 0, nullptr, nullptr, 0, rows_l, 0, cnt_dst);
     gemm(b, s, PC_GEMM_LIG, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
     gemm(b, s, PC_GEMM_LIG, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
     gemm(b, s, PC_GEMM_BOND, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
     gemm(b, s, PC_GEMM_BOND, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
     // --- node update over kNN edges  -> h1
     KnnAttnArgs ka;
-    ka.n_dst = N; ka.Hi = b->PN; ka.ldhi = 5 * H; ka.Hj = b->PN + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
+    ka.n_dst = N; ka.Hi = PNl; ka.ldhi = 5 * H; ka.Hj = PNl + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
     ka.x4 = x_in; ka.nbr = b->nbr; ka.deg = b->deg; ka.nlig = b->nlig; ka.is_lig = b->is_lig; ka.e_w = b->e_w;
     ka.wbuf = b->wb_knn; ka.w = knn_w(m, L.ne_k); ka.W2tc = m->p(L.ne_k.m.W2tc);
     if (b->tc_attn & 12) { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn_dist(x_in, b->nbr, b->deg, N, b->dist, s); b->launches += 1; }
@@ -742,12 +767,13 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
       k.n_dst = on ? b->n_slots_all : N; k.dst_list = on ? b->dst_sorted : nullptr; k.n_slots_first = on ? b->n_slots_prot : 0; k.first_class = 0;
       k.slot_meta = b->slot_meta_all; k.n_dst_dev = nullptr;
       if (on && prune_knn) {
-        k.n_dst = n_lvl; k.dst_list = b->dst_lvl; k.n_slots_first = b->lig_block; k.first_class = 1; k.slot_meta = b->slot_meta_lvl; k.n_dst_dev = b->lvl_counts + l;
+        k.n_dst = n_lvl; k.dst_list = l0c ? b->dst_lvl0 : b->dst_lvl; k.n_slots_first = b->lig_block; k.first_class = 1;
+        k.slot_meta = l0c ? b->slot_meta_lvl0 : b->slot_meta_lvl; k.n_dst_dev = cnt_dst;
       }
     };
     tc_dsts(ka, L.ne_k, b->tc_attn & 4);
     { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, 0, sms, s); else launch_knn_attn_k(ka, sms, s); }
-    ka.Hi = b->PN + 2 * H; ka.Hj = b->PN + 3 * H; ka.w = knn_w(m, L.ne_v); ka.W2tc = m->p(L.ne_v.m.W2tc); ka.out_h = b->h1; ka.ldo = H;
+    ka.Hi = PNl + 2 * H; ka.Hj = PNl + 3 * H; ka.w = knn_w(m, L.ne_v); ka.W2tc = m->p(L.ne_v.m.W2tc); ka.out_h = b->h1; ka.ldo = H;
     tc_dsts(ka, L.ne_v, b->tc_attn & 8);
     { ProfScope ps(b, s, PC_KNN_ATTN_V); if (b->tc_attn & 8) launch_knn_tc(ka, 1, sms, s); else launch_knn_attn_v_node(ka, sms, s); }
     // --- node update over bond edges -> h1[ligand rows] +=
@@ -775,7 +801,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     { ProfScope ps(b, s, PC_TRIP_V); if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, s); else launch_trip_v(ta, sms, s); }
     b->launches += 6;
     // --- h_out = h_in + lin_node(h1)    (:277)
-    gemm(b, s, PC_GEMM_NODE, b->h1, H, rows_lvl, n_node_rows, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H, rows_lvl, 0, cnt_dst);
+    gemm(b, s, PC_GEMM_NODE, b->h1, H, rows_l, n_node_rows, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H, rows_l, 0, cnt_dst);
     // --- projections of the new h / new h_bond for the position update
     gemm(b, s, PC_GEMM_NODE, h_out, H, rows_lvl, n_node_rows, L.n2, b->PNx, 2 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_pos);
     gemm(b, s, PC_GEMM_LIG, h_out, H, b->lig_idx, NL, L.l2, b->PLx, 8 * H);
@@ -807,6 +833,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     h_in = h_out; x_in = x_out; hb_in = hb_out;
   }
   b->h_fin = h_in; b->x_fin = x_in; b->hb_fin = hb_in;
+  b->pn0_ready = true;
   // --- heads (decompdiff.py:315-338)
   gemm(b, s, PC_HEADS, b->h_fin, H, b->lig_idx, NL, m->v_head0, b->hid_v, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
   { ProfScope ps(b, s, PC_HEADS); launch_head_logits(b->hid_v, H, NL, m->p(m->v_W2), m->p(m->v_b2), c.num_classes, b->v_logits, s); }

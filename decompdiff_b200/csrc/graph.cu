@@ -238,16 +238,46 @@ __global__ void __launch_bounds__(256) level_scatter_kernel(const int* __restric
   }
 }
 
+// counting sort of the protein nodes by `level` behind the ligand block + the per-layer prefix lengths
+void launch_level_sort(const int* level, const int* node_ptr, const int* n_protein, int num_graphs, int n_layers, int lig_block,
+                       int* cnt /* 8 * num_graphs ints */, int* counts /* 2 * n_layers + 1 */, int* dst_list, cudaStream_t stream) {
+  if (num_graphs <= 0) return;
+  const int gb = (num_graphs + 7) / 8;
+  level_count_kernel<<<gb, 256, 0, stream>>>(level, node_ptr, n_protein, num_graphs, cnt);
+  level_offsets_kernel<<<1, 32, 0, stream>>>(cnt, num_graphs, lig_block, n_layers, counts);
+  level_scatter_kernel<<<gb, 256, 0, stream>>>(level, node_ptr, n_protein, num_graphs, cnt, dst_list);
+}
+
 void launch_receptive_field(const int* nbr, const int* deg, const uint8_t* is_lig, const int* node_ptr, const int* n_protein, int num_graphs,
                             int n, int n_layers, int lig_block, int* level, int* cnt /* 8 * num_graphs ints */,
                             int* counts /* 2 * n_layers + 1 */, int* dst_list, cudaStream_t stream) {
   if (n <= 0) return;
-  const int nb = (n + 255) / 256, gb = (num_graphs + 7) / 8;
+  const int nb = (n + 255) / 256;
   level_init_kernel<<<nb, 256, 0, stream>>>(is_lig, n, level);
   for (int r = 0; r < LEVEL_CAP - 1; ++r) level_relax_kernel<<<(n * 32 + 255) / 256, 256, 0, stream>>>(nbr, deg, n, r, level);
-  level_count_kernel<<<gb, 256, 0, stream>>>(level, node_ptr, n_protein, num_graphs, cnt);
-  level_offsets_kernel<<<1, 32, 0, stream>>>(cnt, num_graphs, lig_block, n_layers, counts);
-  level_scatter_kernel<<<gb, 256, 0, stream>>>(level, node_ptr, n_protein, num_graphs, cnt, dst_list);
+  launch_level_sort(level, node_ptr, n_protein, num_graphs, n_layers, lig_block, cnt, counts, dst_list, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// First-layer cache.  The layer-0 output of a protein node whose 32 sources are all protein atoms depends on nothing that
+// changes during a run (static positions, static embeddings, static neighbour set, static edge weights), so it is computed once
+// and kept in a buffer only layer 0 writes.  key0 = 1 for the protein nodes layer 0 still has to compute this step (inside the
+// receptive field AND (a ligand atom among the sources OR not cached yet)), LEVEL_CAP for the rest; the sort above turns it into
+// a destination list whose "level <= 1" prefix is exactly that set.  valid0 remembers which rows hold a static value.
+__global__ void __launch_bounds__(256) layer0_key_kernel(const int* __restrict__ level, const int* __restrict__ nlig,
+                                                         const uint8_t* __restrict__ is_lig, int n, int n_layers,
+                                                         uint8_t* __restrict__ valid0, int* __restrict__ key0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (is_lig[i]) { key0[i] = 0; return; }
+  const bool compute = level[i] <= n_layers && (nlig[i] > 0 || !valid0[i]);
+  key0[i] = compute ? 1 : LEVEL_CAP;
+  if (compute) valid0[i] = nlig[i] == 0;        // the row written this step is reusable iff it has no ligand source
+}
+void launch_layer0_keys(const int* level, const int* nlig, const uint8_t* is_lig, int n, int n_layers, uint8_t* valid0, int* key0,
+                        cudaStream_t stream) {
+  if (n <= 0) return;
+  layer0_key_kernel<<<(n + 255) / 256, 256, 0, stream>>>(level, nlig, is_lig, n, n_layers, valid0, key0);
 }
 
 }  // namespace ddb

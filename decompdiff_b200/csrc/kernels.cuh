@@ -25,6 +25,12 @@ void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, 
 void launch_receptive_field(const int* nbr, const int* deg, const uint8_t* is_lig, const int* node_ptr, const int* n_protein, int num_graphs,
                             int n, int n_layers, int lig_block, int* level, int* cnt, int* counts, int* dst_list, cudaStream_t stream);
 
+void launch_level_sort(const int* level, const int* node_ptr, const int* n_protein, int num_graphs, int n_layers, int lig_block, int* cnt,
+                       int* counts, int* dst_list, cudaStream_t stream);
+// first-layer cache of protein nodes without ligand sources (graph.cu): sort keys + validity flags
+void launch_layer0_keys(const int* level, const int* nlig, const uint8_t* is_lig, int n, int n_layers, uint8_t* valid0, int* key0,
+                        cudaStream_t stream);
+
 // Weights of one attention MLP whose first Linear acts on kNN-edge features (NodeUpdateLayer /
 // PosUpdateLayer with edge_feat = [type (x) gauss(d) | type]), re-packed by api.cu:
 struct KnnMlpW {
