@@ -149,3 +149,18 @@ def test_error_behaviour(model_cpu):
     bad['init_ligand_v'] = kw['init_ligand_v'] + 8
     with pytest.raises(AssertionError):           # index_to_log_onehot assert (transitions.py:66)
         model_cpu.sample_diffusion(**bad, num_steps=1, center_pos_mode='protein')
+
+
+def test_first_layer_cache_does_not_change_the_trajectory(model_cpu, monkeypatch):
+    """Rows of layer 0 that cannot change during a run are computed once.  With the cache switched off
+    every step recomputes them: same discrete samples, positions equal up to the tile-order effect of a few ulps per step."""
+    kw = syn.make_batch(n_pockets=2, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, seed=61)
+    n, Eb = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel()
+    noise = syn.step_noise(n, Eb, 8, seed=5)
+    cached = model_cpu.sample_diffusion(**kw, num_steps=8, center_pos_mode='protein', noise=noise)
+    monkeypatch.setenv('DDB_NO_L0_CACHE', '1')
+    plain = model_cpu.sample_diffusion(**kw, num_steps=8, center_pos_mode='protein', noise=noise)
+    assert torch.equal(cached['v'], plain['v']) and torch.equal(cached['bond'], plain['bond'])
+    assert float((cached['pos'] - plain['pos']).abs().max()) <= 2e-5
+    for a, b in zip(cached['pos_traj'], plain['pos_traj']):
+        assert float((a - b).abs().max()) <= 2e-5
