@@ -332,7 +332,9 @@ def main():
                 'alg_bytes_per_step': egnn['alg_bytes_per_step'],
                 'note': 'algorithmic bytes = gather-counted (E*528 + 2N*528 + 8E) B per layer (SURVEY.md 8d).  The gathered rows are L2 '
                         'hits (working set ~35 MB), so DRAM traffic is far below the algorithmic bytes and the kernels are bound by the '
-                        'SM-side data pipe / instruction issue, not by HBM (DESIGN.md section 4)',
+                        'SM-side data pipe / instruction issue, not by HBM (DESIGN.md section 4).  The bytes are those of the full layer (every node a '
+                        'destination); the exact receptive-field pruning and the first-layer cache (DESIGN.md section 3.1) skip rows that cannot '
+                        'change an output, which shows up here as a higher achieved rate, not as fewer algorithmic bytes',
                 'profiled_step_ms': round(prof_total, 3)}
     del run
 
@@ -387,7 +389,7 @@ def main():
                        'step': 'one reverse-diffusion step (network forward + posterior) over the batch; value = pockets / (1000 steps)',
                        'nodes': cnt['N'], 'knn_edges': cnt['E'], 'bond_edges': cnt['Eb'], 'triplets': cnt['E3'],
                        'l2': 'per-step working set ~1.4 GB of activations > 126 MB L2, no explicit flush (steady-state of the loop)',
-                       'cuda_graph': True, 'trajectories': 'kept on device, one D2H at the end'},
+                       'cuda_graph': True, 'trajectories': 'kept on device; e2e streams them to pinned host memory in 64-step chunks'},
             'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps), 'launches_per_step': launches_per_step,
             'clocks': clocks, 'roofline': roof, 'kernels': kernels, 'kernel_categories': prof_raw, 'cpu_baseline': cpu,
         }
