@@ -1,19 +1,23 @@
-// Tensor-core attention kernels (sm_100a): the same math as attn_knn.cu / attn_bond.cu, restructured so that the
-// second Linear of the key / value MLPs runs on tcgen05 as a true GEMM with shared weights.
+// Tensor-core attention kernels (sm_100a): the same math as attn_knn.cu / attn_bond.cu (fp32 cross-check kernels), restructured
+// so that the second Linear of the key / value MLPs - and the feature term of the first Linear - run on tcgen05 as true GEMMs
+// with shared weights.  Pieces shared by attn_tc_knn.cu (kNN edges), attn_tc_trip.cu (triplets) and attn_tc_bond.cu (bond edges).
 //
-//   rows   : one attention candidate each (a kNN edge of a destination node / a triplet k->j->i of a bond edge j->i);
-//            32 rows form one softmax group = one TMEM lane quadrant, 4 groups form a 128-row tile
-//   threads: 16 warps; warp w = 4*s + q owns rows 32q..32q+31 (thread = row) and hidden channels 32s..32s+31
-//   hidden : a = ReLU(LN(first-Linear pieces))  computed thread-per-row: no cross-lane reductions, row statistics are
-//            exchanged between the 4 slice-warps of a quadrant through shared memory
+//   rows   : one attention candidate each (a kNN edge of a destination node / a triplet k->j->i of a bond edge j->i / a bond edge
+//            entering a ligand atom); 32 rows form one softmax group = one TMEM lane quadrant, 4 groups form a 128-row tile
+//   threads: 640 = 16 worker warps + one warpgroup whose first warp issues every tcgen05.mma (the issuing thread is paced by the
+//            tensor pipe, so it carries no row work; setmaxnreg hands the group's registers to the workers: 112 / 32).
+//            Worker warp w = 4*s + q owns rows 32q..32q+31 (thread = row) and hidden channels 32s..32s+31
+//   hidden : a = ReLU(LN(first-Linear pieces))  computed thread-per-row with packed f32x2 math: no cross-lane reductions, row
+//            statistics are exchanged once between the 4 slice-warps of a quadrant through shared memory
 //   GEMM   : a (hi/lo TF32 split) is written to TMEM with tcgen05.st and used as the A operand of 48 tcgen05.mma
 //            (M128 N128 K8, 3xTF32) against W2 (hi/lo, K-major, 128B swizzle) resident in shared memory for the whole
 //            persistent kernel; D (128 x 128 fp32) lives in TMEM
-//   k pass : logits[row, head] = <q_group[head], D[row, head]>  (thread-local dot products), fused per-group softmax with
-//            warp max / sum over the 32 rows, times e_w -> wbuf
+//   k pass : logits[row, head] = <q_group[head], D[row, head]>  (thread-local dot products), fused per-group softmax (one REDUX
+//            per head for the max, a transposed all-reduce for the sums), times e_w -> wbuf
 //   v pass : out[group, c] = sum_rows w[row, head(c)] D[row, c] + b2[c] sum_rows w[row, head(c)]  via one 32-value
 //            butterfly reduce-scatter across the 32 rows
-//   The MMA of tile t overlaps the hidden computation of tile t+1; the epilogue of tile t runs right after it.
+//   The main MMA of tile t overlaps the first Linear / LayerNorm of tile t+1; D is drained into registers before the next A is
+//   written, so the tensor core restarts while the softmax / weighted sums of tile t are finished from registers.
 #pragma once
 #include "kernels.cuh"
 #include "tc_common.cuh"

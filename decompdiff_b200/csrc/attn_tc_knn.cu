@@ -1,16 +1,20 @@
-// Tensor-core attention over the kNN(32) edges: NodeUpdateLayer / PosUpdateLayer key pass and the node value pass
+// Tensor-core attention over the kNN(32) edges: NodeUpdateLayer / PosUpdateLayer key pass, the node value pass and the position
+// value pass
 // (uni_transformer_edge.py:42-74, 188-210).  Structure shared with the triplet kernel (attn_tc.cuh, attn_tc_trip.cu):
 //   rows   : one kNN edge each; 32 rows = the incoming edges of one destination node = one softmax group = one TMEM lane
 //            quadrant; 4 destinations form a 128-row tile; thread = (row, 32-channel slice)
 //   GEMM 1 : the distance term of the first Linear, sum_g gauss_g(d) Wg[type][g][:], on tcgen05: A2 = Gaussian features of the
 //            row placed in the column block of its source class (protein | ligand source, 2 x 20 columns, hi/lo TF32 split,
 //            SWIZZLE_32B K-major tile written by the workers), B2 = the two matching type blocks of Wg for the destination
-//            class of the tile (destinations are visited protein class first; B2 is swapped once at the class boundary)
+//            class of the tile (destinations are visited one class after the other; B2 is swapped once at the class boundary);
+//            tiles without a ligand source need only 3 of the 5 k-steps
 //   SIMT   : z = D2 + P_src[j] (row gather, LDG.256) + (P_dst[i] + Wt[type]) (staged per warp), LayerNorm, ReLU, TF32 split
 //   GEMM 2 : second Linear, A = hidden activations in TMEM, B = W2 hi/lo resident in shared memory (3xTF32)
 //   k pass : logits = <q_i[head], D[row, head]>, softmax over the 32 rows, times e_w -> wbuf
 //   v pass : out_h[i] = sum_rows w[row, head(c)] D[row, c] + b2[c] sum_rows w[row, head(c)]
-// A dedicated warp issues the MMAs (the angular... distance MMA one tile ahead); setmaxnreg moves its registers to the workers.
+//   pos v  : 16-column second Linear (one scalar per head); dx_i = mean_heads sum_rows w[row, h] (D[row, h] + b2[h]) (x_i - x_j)
+// A dedicated warp issues the MMAs (the distance MMA one tile ahead); setmaxnreg moves its registers to the workers.  The
+// destination list may be a device-counted prefix (exact receptive-field pruning / first-layer cache, graph.cu).
 #include "attn_tc.cuh"
 
 namespace ddb {

@@ -2,7 +2,8 @@
 // Two GEMMs per 128-row tile run on tcgen05:
 //   D2 = Ang[128 x 16] * Wa^T      the angular-feature term of the first Linear (A2 / B2 in 128B-swizzled smem, SS form)
 //   D  = a[128 x 128]  * W2^T      the second Linear on the hidden activations (A in TMEM, TS form)
-// so the SIMT side of a row is: gather P[kj] + Q[ji] + D2, LayerNorm, ReLU, TF32 split, and the thread-local epilogue.
+// so the SIMT side of a row is: P'[kj] (kept in registers while the source atom j is unchanged - groups are visited source-major)
+// + Q'[ji] (staged per warp) + D2, LayerNorm, ReLU, TF32 split, and the thread-local epilogue.
 #include "attn_tc.cuh"
 
 namespace ddb {
