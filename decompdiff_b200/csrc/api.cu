@@ -356,6 +356,10 @@ struct ddb_batch {
   bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
   int tc_attn = 31;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels (DDB_TC_ATTN=<mask>)
   int max_indeg = 0;
+  // the bond / triplet branch of a layer runs on a side stream (fork / join by events; becomes parallel branches of the step
+  // graph under capture); DDB_NO_FORK=1 keeps everything on the caller's stream
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_proj = nullptr, ev_trip = nullptr;
   // optional per-kernel timing (CUDA events on the launch stream; eager passes only, never under graph capture)
   bool profiling = false;
   struct ProfEv { int cat; cudaEvent_t a, b; };
@@ -387,6 +391,8 @@ struct ddb_batch {
 extern "C" void ddb_batch_destroy(ddb_batch* b) {
   if (!b) return;
   for (void* p : b->allocs) cudaFree(p);
+  for (cudaEvent_t e : {b->ev_fork, b->ev_proj, b->ev_trip}) if (e) cudaEventDestroy(e);
+  if (b->side) cudaStreamDestroy(b->side);
   delete b;
 }
 
@@ -418,6 +424,11 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   b->m = m; b->B = B; b->N = N; b->NL = NL; b->NP = NP; b->Eb = Eb;
   if (const char* e = getenv("DDB_GEMM")) b->use_tc = std::string(e) != "simt";
   if (const char* e = getenv("DDB_TC_ATTN")) b->tc_attn = atoi(e);
+  if (!getenv("DDB_NO_FORK")) {
+    if (cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking) != cudaSuccess) b->side = nullptr;
+    for (cudaEvent_t* e : {&b->ev_fork, &b->ev_proj, &b->ev_trip})
+      if (b->side && cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { cudaStreamDestroy(b->side); b->side = nullptr; }
+  }
   {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&b->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -703,6 +714,13 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   { ProfScope ps(b, s, PC_SETUP); launch_set_ligand_x(b->x_lig, NL, b->lig_idx, b->x4_0, s); }
   { ProfScope ps(b, s, PC_SETUP); launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s); }
   { ProfScope ps(b, s, PC_SETUP); launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s); }
+  // fork: the bond / triplet branch of a layer needs only the layer input, so it runs on the side stream next to the kNN branch
+  // (layer 0's also next to the graph build); timed eager passes stay on one stream so that the per-category events mean something
+  const bool fork = b->side != nullptr && !b->profiling;
+  cudaStream_t sb = fork ? b->side : s;
+  auto fork_side = [&]() { if (fork) { cudaEventRecord(b->ev_fork, s); cudaStreamWaitEvent(sb, b->ev_fork, 0); } };
+  auto join_side = [&](cudaEvent_t e) { if (fork) cudaStreamWaitEvent(s, e, 0); };
+  fork_side();
   { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s); }
   EdgeWeightCache ewc;
   ewc.table = b->ew_table; ewc.table_base = b->ew_table_base; ewc.n_protein = b->n_protein_of; ewc.node_ptr = b->node_ptr; ewc.graph_of = b->graph_of;
@@ -752,10 +770,12 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
       gemm(b, s, PC_GEMM_NODE, h_in, H, rows_lvl, n_node_rows, L.n1, PNl, 5 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_src);
     }
     gemm(b, s, PC_GEMM_NODE, PNl + 4 * H, 5 * H, rows_l, n_node_rows, L.q_ne, b->qN, H, &L.ln_q_ne, nullptr, 0, nullptr, nullptr, 0, rows_l, 0, cnt_dst);
-    gemm(b, s, PC_GEMM_LIG, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
-    gemm(b, s, PC_GEMM_LIG, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
-    gemm(b, s, PC_GEMM_BOND, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
-    gemm(b, s, PC_GEMM_BOND, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
+    if (l > 0) fork_side();      // the previous layer's position update is the last thing the side branch waits for
+    gemm(b, sb, PC_GEMM_LIG, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
+    gemm(b, sb, PC_GEMM_LIG, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
+    gemm(b, sb, PC_GEMM_BOND, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
+    gemm(b, sb, PC_GEMM_BOND, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
+    if (fork) cudaEventRecord(b->ev_proj, sb);      // PL, PB, qNB, qE are complete
     // --- node update over kNN edges  -> h1
     KnnAttnArgs ka;
     ka.n_dst = N; ka.Hi = PNl; ka.ldhi = 5 * H; ka.Hj = PNl + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
@@ -784,6 +804,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ba.v.Hi = b->PL + 2 * H; ba.v.Hj = b->PL + 3 * H; ba.v.Pe = b->PB + H; ba.v.w = bond_w(m, L.nb_v);
     ba.q = b->qNB; ba.ldq = H; ba.x4 = x_in; ba.wbuf = b->wb_bond; ba.out_h = b->h1; ba.ldo = H;
     ba.k.W2tc = m->p(L.nb_k.W2tc); ba.v.W2tc = m->p(L.nb_v.W2tc);
+    join_side(b->ev_proj);
     { ProfScope ps(b, s, PC_BOND_NODE); if (b->tc_attn & 16) { launch_bond_tc(ba, false, sms, s); b->launches += 1; } else launch_bond_attn_node(ba, sms, s); }
     // --- bond update over triplets -> hb_out
     TripArgs ta;
@@ -796,9 +817,11 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc); ta.v.Watc = m->p(L.bl_v.Watc);
     if (b->tc_attn & 2) { ta.v.Q = b->Qv; ta.v.Pm = b->Pmv; ta.v.Qm = b->Qmv; }
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
-    { ProfScope ps(b, s, PC_TRIP_PREP); launch_trip_prep(ta, s); }
-    { ProfScope ps(b, s, PC_TRIP_K); if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, s); else launch_trip_k(ta, sms, s); }
-    { ProfScope ps(b, s, PC_TRIP_V); if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, s); else launch_trip_v(ta, sms, s); }
+    { ProfScope ps(b, sb, PC_TRIP_PREP); launch_trip_prep(ta, sb); }
+    { ProfScope ps(b, sb, PC_TRIP_K); if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
+    { ProfScope ps(b, sb, PC_TRIP_V); if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
+    gemm(b, sb, PC_GEMM_BOND, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);      // projection of the new h_bond for the position update
+    if (fork) cudaEventRecord(b->ev_trip, sb);
     b->launches += 6;
     // --- h_out = h_in + lin_node(h1)    (:277)
     gemm(b, s, PC_GEMM_NODE, b->h1, H, rows_l, n_node_rows, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H, rows_l, 0, cnt_dst);
@@ -807,7 +830,6 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     gemm(b, s, PC_GEMM_LIG, h_out, H, b->lig_idx, NL, L.l2, b->PLx, 8 * H);
     gemm(b, s, PC_GEMM_LIG, b->PLx + 2 * H, 8 * H, nullptr, NL, L.q_pe, b->qXe, H, &L.ln_q_pe);
     gemm(b, s, PC_GEMM_LIG, b->PLx + 7 * H, 8 * H, nullptr, NL, L.q_pb, b->qXb, H, &L.ln_q_pb);
-    gemm(b, s, PC_GEMM_BOND, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);
     // --- position update over kNN edges (ligand destinations only) -> dx_edge
     KnnAttnArgs kp;
     kp.n_dst = NL; kp.dst_list = b->lig_idx; kp.Hi = b->PLx; kp.ldhi = 8 * H; kp.hi_by_slot = 1;
@@ -828,6 +850,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     bp.q = b->qXb; bp.ldq = H; bp.x4 = x_in; bp.wbuf = b->wb_bond; bp.dx_edge = b->dx_edge; bp.upd_mask = b->upd_mask;
     bp.x4_out = x_out;
     bp.k.W2tc = m->p(L.pb_k.W2tc); bp.v.W2tc = m->p(L.pb_v.W2tc);
+    join_side(b->ev_trip);      // h_bond_out and its projection: the side branch of this layer is complete
     { ProfScope ps(b, s, PC_BOND_POS); if (b->tc_attn & 16) { launch_bond_tc(bp, true, sms, s); b->launches += 1; } else launch_bond_attn_pos(bp, sms, s); }
     b->launches += 3;
     h_in = h_out; x_in = x_out; hb_in = hb_out;
