@@ -164,3 +164,29 @@ def test_first_layer_cache_does_not_change_the_trajectory(model_cpu, monkeypatch
     assert float((cached['pos'] - plain['pos']).abs().max()) <= 2e-5
     for a, b in zip(cached['pos_traj'], plain['pos_traj']):
         assert float((a - b).abs().max()) <= 2e-5
+
+
+def test_two_branch_step_is_bit_identical_to_the_single_stream_step(model_cpu, monkeypatch):
+    """The bond / triplet branch of every layer runs on a side stream.  Same kernels, same tile
+    order: eager steps and graph replays must reproduce the single-stream (`DDB_NO_FORK=1`) trajectory bit for bit."""
+    kw = syn.make_batch(n_pockets=3, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, seed=67)
+    n, Eb = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel()
+    noise = syn.step_noise(n, Eb, 6, seed=9)
+
+    def both():
+        eager = model_cpu.sample_diffusion(**kw, num_steps=6, center_pos_mode='protein', noise=noise)
+        torch.manual_seed(1234)
+        torch.cuda.manual_seed_all(1234)
+        graph = model_cpu.sample_diffusion(**kw, num_steps=12, center_pos_mode='protein')
+        return eager, graph
+
+    forked = both()
+    monkeypatch.setenv('DDB_NO_FORK', '1')
+    single = both()
+    for f, s in zip(forked, single):
+        for key in ('pos', 'v', 'bond'):
+            assert torch.equal(f[key], s[key]), key
+        for a, b in zip(f['pos_traj'], s['pos_traj']):
+            assert torch.equal(a, b)
+        for a, b in zip(f['bt_traj'], s['bt_traj']):
+            assert torch.equal(a, b)
