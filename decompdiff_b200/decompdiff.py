@@ -416,7 +416,9 @@ class SamplingRun:
             k -= 1
             torch.cuda.current_stream().synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # captured on a high-priority stream: the kernel nodes of the main (kNN) branch inherit it, so their short grids are
+            # placed ahead of the side branch's long triplet grids whenever SMs free up (the side stream has default priority)
+            with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=-1)):
                 self._draw()
                 self.eb.reverse_step(self.io)
         for _ in range(k):
