@@ -16,6 +16,10 @@
  *   - "device" pointers are CUDA device memory on the current device; kernels are
  *     launched on the `stream` argument (a cudaStream_t passed as void*), nothing
  *     synchronises unless stated, so every per-step call is CUDA-graph capturable.
+ *     ddb_forward / ddb_reverse_step fork part of each layer onto a stream the batch
+ *     owns and join it back with events before they return: all of their work is
+ *     ordered before whatever the caller enqueues on `stream` next, and under stream
+ *     capture the fork becomes parallel branches of the caller's graph.
  *   - fp32 everywhere the reference is fp32; indices are int64 at the boundary
  *     exactly as the reference passes them (torch.long).
  */
