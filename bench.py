@@ -31,7 +31,24 @@ WORKLOADS = {   # BASELINE.json configs; cfg2 is the headline (64 pockets fit on
     'cfg2': dict(n_pockets=64, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, guided=False),
     'cfg3': dict(n_pockets=64, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, guided=True),
     'cfg1': dict(n_pockets=1, n_protein=300, arm_sizes=(8, 8), n_scaffold=14, guided=False),
+    # ligand-size sweep: 64 pockets x 400 atoms with 40 / 50 / 64 ligand atoms
+    'lig40': dict(n_pockets=64, n_protein=360, arm_sizes=(10, 10), n_scaffold=20, guided=False),
+    'lig50': dict(n_pockets=64, n_protein=350, arm_sizes=(13, 12), n_scaffold=25, guided=False),
+    'lig64': dict(n_pockets=64, n_protein=336, arm_sizes=(16, 16), n_scaffold=32, guided=False),
 }
+
+
+def workload_config(name):
+    """The `config` object of the JSON line - the same for both arms (`--impl ours` / `--impl reference`)."""
+    wl = WORKLOADS[name]
+    n_lig = sum(wl['arm_sizes']) + wl['n_scaffold']
+    B, N = wl['n_pockets'], wl['n_protein'] + n_lig
+    return {'workload': f'{name}: {B} synthetic pockets per GPU x ({wl["n_protein"]} protein + {n_lig} ligand atoms), T=1000, '
+                        'ref_prior' + (', armsca_prox + clash drift guidance' if wl['guided'] else ''),
+            'step': 'one reverse-diffusion step (network forward + posterior) over the batch; value = pockets / (1000 steps)',
+            'nodes': B * N, 'knn_edges': B * N * 32, 'bond_edges': B * n_lig * (n_lig - 1),
+            'triplets': B * n_lig * (n_lig - 1) * (n_lig - 2),
+            'l2': 'per-step working set ~1.4 GB of activations > 126 MB L2, no explicit flush (steady-state of the loop)'}
 DRIFT = [{'type': 'armsca_prox', 'min_d': 1.2, 'max_d': 1.9}, {'type': 'clash', 'sigma': 2, 'gamma': 4}]
 
 
@@ -161,28 +178,28 @@ def cpu_reference_step_time(n_pockets, wl, steps, warmup, guided):
 def run_reference_arm(args, rank, world):
     """`--impl reference`: the reference's own algorithm on the host cores.  The reference is pure Python + PyG wheels
     that are absent here, so the timed code is the oracle port (bit-identical to the reference on CPU, see
-    tests/test_oracle_golden.py); rank 0 only."""
+    tests/test_oracle_golden.py); rank 0 only.  A step = one reverse step over a bounded number of the workload's pockets:
+    all of them when (steps + warmup) x their cost fits the time budget, else as many as fit (the cost per pocket does not
+    depend on the batch size on the CPU; a one-pocket probe step calibrates it)."""
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    # bounded sample: a few pockets of the workload's shape so that (steps + warmup) stay within minutes
-    budget_s = 150.0
-    est_per_pocket = 1.0 * (8.0 / max(cores, 1)) ** 0.7
-    n_s = int(max(1, min(wl['n_pockets'], 8, budget_s / ((args.steps + args.warmup) * est_per_pocket))))
+    budget_s = float(os.environ.get('DDB_REF_BUDGET_S', '240'))
+    probe = cpu_reference_step_time(min(2, wl['n_pockets']), wl, 1, 1, wl['guided']) / min(2, wl['n_pockets'])
+    n_s = int(max(1, min(wl['n_pockets'], budget_s / (max(args.steps + args.warmup, 1) * probe))))
     sec = cpu_reference_step_time(n_s, wl, args.steps, args.warmup, wl['guided'])
     value = n_s / (T_FULL * sec)
-    sample = (f'{n_s} of {wl["n_pockets"]} pockets ({wl["n_protein"]}+{sum(wl["arm_sizes"]) + wl["n_scaffold"]} atoms each), '
-              f'{args.warmup} warm-up + {args.steps} timed reverse steps, extrapolated x{T_FULL} steps (network is '
-              f't-independent); per-pocket cost is batch-size independent on CPU')
+    n_lig = sum(wl['arm_sizes']) + wl['n_scaffold']
+    sample = (f'{n_s} of {wl["n_pockets"]} pockets ({wl["n_protein"]}+{n_lig} atoms each) per step, '
+              f'{args.warmup} warm-up + {args.steps} timed reverse steps ({sec:.2f} s/step), extrapolated x{T_FULL} steps (network is '
+              f't-independent); probe {probe:.2f} s per pocket-step, budget {budget_s:.0f} s')
     line = {
         'impl': 'reference', 'metric': 'molecules/sec (T=1000)', 'value': value, 'unit': 'molecules/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {wl["n_pockets"]} synthetic pockets x ({wl["n_protein"]} protein + 30 ligand '
-                               f'atoms), T=1000, ref_prior' + (', drift guidance' if wl['guided'] else ''),
-                   'step': 'one reverse-diffusion step over the bounded sample'},
+        'config': workload_config(args.workload),
         'cpu_baseline': {'value': value, 'unit': 'molecules/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'molecules/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -245,9 +262,9 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     dev = torch.device('cuda', local_rank)
     wl = WORKLOADS[args.workload]
-    warmup = max(args.warmup, 3)
-    if warmup + args.steps + 64 > T_FULL:
-        raise SystemExit('warmup + steps must stay below T=1000')
+    warmup = args.warmup
+    if warmup + args.steps + 200 > T_FULL:
+        raise SystemExit('warmup + steps must stay below T=800')
 
     model = ddb.DecompScorePosNet3D(syn.DEFAULT_MODEL_CONFIG, syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
     model.load_state_dict(syn.synthetic_state_dict(model, seed=0))
@@ -267,15 +284,18 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_first(5.0)
-    run.advance(warmup)
-    # W warm-up steps are the contract's minimum; keep stepping (untimed) until the GPU has been busy for ~0.5 s so that the
-    # timed steps run at steady-state clocks with an instantiated graph
+    # clock settling BEFORE t = 0 of the contract (reported as `settle_steps`, not as warm-up): step (untimed) until the GPU has
+    # been busy for ~0.5 s so that the graph is instantiated and the clocks are at their steady state; then exactly W warm-up steps
+    settle = 4
+    run.advance(settle)
     torch.cuda.synchronize()
     t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 0.5 and warmup + args.steps + 16 < T_FULL:
+    while time.perf_counter() - t_w < 0.5 and settle + warmup + args.steps + 16 < T_FULL - 100:
         run.advance(4)
-        warmup += 4
+        settle += 4
         torch.cuda.synchronize()
+    run.advance(warmup)
+    torch.cuda.synchronize()
     if world > 1:
         # the first collective of a process group builds the NCCL communicator (hundreds of ms at 8 ranks): do one untimed
         # gather so that the timed one costs what it costs at the end of a real T=1000 run
@@ -313,23 +333,28 @@ def main():
             run.step_eager()
         run.eb.profile(False)
         prof_raw = run.eb.profile_read()
+        rows_exec, rows_full = run.eb.executed_rows()
         kernels, prof_total = kernel_report(prof_raw, cnt, model.config.num_layers, peak_gbs, prof_steps)
         prof_raw = {k: {'ms_per_step': round(v['ms'] / prof_steps, 4), 'launches_per_step': v['count'] / prof_steps} for k, v in prof_raw.items()}
         egnn = next(k for k in kernels if k['kernel'] == 'knn_edge_attention')
         layers = model.config.num_layers
-        traffic, traffic_src = None, None
+        traffic, traffic_src, tensor_pct, tensor_src = None, None, None, None
         tpath = os.path.join(REPO, 'profiles', 'ncu_traffic.json')      # dram__bytes_read + write of the same kernels from one
         if os.path.exists(tpath):                                       # `ncu --set full` capture (committed summary, cfg2 shape)
             with open(tpath) as f:
                 t = json.load(f).get('knn_edge_attention')
             if t and args.workload == 'cfg2':
                 traffic, traffic_src = t['dram_bytes_per_layer'], t['source']
+                tensor_pct, tensor_src = t.get('tensor_pipe_pct'), t.get('tensor_pipe_source', t['source'])
         roof = {'kernel': 'knn_edge_attention: the fused EGNN layer over kNN edges = 4 launches per layer (tcgen05 key / node-value / '
                           'position-key / position-value passes); one "launch" below = one layer',
                 'bound': 'hbm', 'achieved': egnn['achieved_gbs'], 'peak': peak_gbs, 'unit': 'GB/s', 'frac': egnn['hbm_frac'],
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'time_share_of_step': egnn['share'],
                 'alg_bytes_per_launch': egnn['alg_bytes_per_step'] / layers, 'ms_per_launch': egnn['ms_per_step'] / layers,
                 'alg_bytes_per_step': egnn['alg_bytes_per_step'],
+                'executed_rows_frac': round(rows_exec / max(rows_full, 1), 4),
+                'frac_on_executed_rows': round(egnn['hbm_frac'] * rows_exec / max(rows_full, 1), 4),
+                'tensor_pipe_pct': tensor_pct, 'tensor_pipe_source': tensor_src,
                 'note': 'algorithmic bytes = gather-counted (E*528 + 2N*528 + 8E) B per layer (SURVEY.md 8d).  The gathered rows are L2 '
                         'hits (working set ~35 MB), so DRAM traffic is far below the algorithmic bytes and the kernels are bound by the '
                         'SM-side data pipe / instruction issue, not by HBM (DESIGN.md section 4).  The bytes are those of the full layer (every node a '
@@ -346,6 +371,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        model.step_event_interval = max(e2e_steps // 10, 1)
         t0 = time.perf_counter()
         r = model.sample_diffusion(**host_kw, num_steps=e2e_steps, center_pos_mode='protein', energy_drift_opt=drift)
         if world > 1:
@@ -363,7 +389,11 @@ def main():
         h2d = eb_probe.h2d_bytes() + sum(kw[k].numel() * kw[k].element_size() for k in
                                          ('init_ligand_pos', 'init_ligand_v', 'init_ligand_fc_bond_type', 'prior_stds', 'ligand_decomp_batch'))
         del eb_probe
-        e2e = {'value': wl['n_pockets'] * world / (el * T_FULL / e2e_steps), 'unit': 'molecules/s',
+        marks = model.last_step_events
+        model.step_event_interval = 0
+        by_t = [{'t_from': T_FULL - 1 - a[0], 't_to': T_FULL - b[0], 'ms_per_step': round(a[1].elapsed_time(b[1]) / max(b[0] - a[0], 1), 4)}
+                for a, b in zip(marks, marks[1:]) if b[0] > a[0]]
+        e2e = {'value': wl['n_pockets'] * world / (el * T_FULL / e2e_steps), 'unit': 'molecules/s', 'step_ms_by_t': by_t,
                'h2d_bytes_per_step': h2d / e2e_steps, 'd2h_bytes_per_step': d2h / e2e_steps,
                'h2d_bytes_per_call': h2d, 'd2h_bytes_per_call': d2h, 'steps_run': e2e_steps, 'seconds': el,
                'call': 'DecompScorePosNet3D.sample_diffusion(pinned host tensors) -> molecules + 6 trajectories on the host'}
@@ -384,12 +414,11 @@ def main():
             'metric': 'molecules/sec (T=1000)', 'value': value, 'unit': 'molecules/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{args.workload}: {wl["n_pockets"]} synthetic pockets per GPU x ({wl["n_protein"]} protein + 30 '
-                                   f'ligand atoms), T=1000, ref_prior' + (', beta-prior style drift guidance' if wl['guided'] else ''),
-                       'step': 'one reverse-diffusion step (network forward + posterior) over the batch; value = pockets / (1000 steps)',
-                       'nodes': cnt['N'], 'knn_edges': cnt['E'], 'bond_edges': cnt['Eb'], 'triplets': cnt['E3'],
-                       'l2': 'per-step working set ~1.4 GB of activations > 126 MB L2, no explicit flush (steady-state of the loop)',
-                       'cuda_graph': True, 'trajectories': 'kept on device; e2e streams them to pinned host memory in 64-step chunks'},
+            'config': workload_config(args.workload),
+            'run': {'cuda_graph': True, 'settle_steps_before_warmup': settle, 'time_index_of_first_timed_step': T_FULL - 1 - settle - warmup,
+                    'trajectories': 'kept on device; e2e streams them to pinned host memory in 64-step chunks',
+                    'value_note': 'step cost depends mildly on t (receptive-field pruning and the first-layer cache follow the ligand spread); '
+                                  'e2e runs the whole T=1000 trajectory and is the primary figure, step_ms_by_t its per-window device time'},
             'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps), 'launches_per_step': launches_per_step,
             'clocks': clocks, 'roofline': roof, 'kernels': kernels, 'kernel_categories': prof_raw, 'cpu_baseline': cpu,
         }

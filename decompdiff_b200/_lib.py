@@ -19,6 +19,7 @@ SYMBOLS = [
     'ddb_forward', 'ddb_batch_set_time', 'ddb_reverse_step', 'ddb_batch_set_guidance',
     'ddb_knn_graph', 'ddb_gemm128', 'ddb_batch_debug_buffer', 'ddb_copy_device', 'ddb_batch_last_launch_count', 'ddb_batch_h2d_bytes',
     'ddb_batch_profile', 'ddb_profile_num_categories', 'ddb_profile_category_name', 'ddb_batch_profile_read',
+    'ddb_batch_executed_rows',
 ]
 
 
@@ -75,6 +76,7 @@ def lib():
     L.ddb_profile_category_name.argtypes = [i32]
     L.ddb_profile_category_name.restype = C.c_char_p
     L.ddb_batch_profile_read.argtypes = [vp, vp, vp]
+    L.ddb_batch_executed_rows.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.ddb_batch_last_launch_count.argtypes = [vp]
     L.ddb_batch_last_launch_count.restype = i64
     L.ddb_batch_h2d_bytes.argtypes = [vp]

@@ -610,6 +610,9 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   DDB_TRY(b->dalloc(&b->b_logits, eb * c.num_bond_classes)); DDB_TRY(b->dalloc(&b->x0, nl * 3));
   DDB_TRY(b->dalloc(&b->grad, nl * 3));
   cudaMemset(b->nbr, 0, n * KNN * sizeof(int));
+  // the fills above ran on the legacy default stream; the kernels of this batch run on the caller's (possibly non-blocking)
+  // stream, so order them once here
+  { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { ddb_batch_destroy(b); return fail(DDB_ERR_CUDA, std::string("batch create: ") + cudaGetErrorString(e)); } }
   *out = b;
   return DDB_OK;
 }
@@ -1065,6 +1068,23 @@ extern "C" int ddb_batch_profile_read(const ddb_batch* b, double* ms_out, int64_
 extern "C" int ddb_copy_device(void* dst, const void* src, int64_t bytes, void* stream) {
   if (!dst || !src || bytes < 0) return fail(DDB_ERR_INVALID, "bad copy argument");
   DDB_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_executed_rows(const ddb_batch* b, int64_t* executed, int64_t* full) {
+  if (!b || !executed || !full) return fail(DDB_ERR_INVALID, "null argument");
+  const int L = b->m->cfg.num_layers;
+  *full = (int64_t)L * b->N;
+  *executed = *full;
+  if (b->prune) {      // per-layer destination counts of the last forward (device-side counters of the level sort)
+    std::vector<int> c(2 * L + 1), c0(2 * L + 1);
+    DDB_CUDA(cudaMemcpy(c.data(), b->lvl_counts, c.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (b->l0cache) DDB_CUDA(cudaMemcpy(c0.data(), b->counts0, c0.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    int64_t e = 0;
+    const int pad = b->lig_block - b->NL;      // padding slots of the ligand block are not rows
+    for (int l = 0; l < L; ++l) e += ((b->l0cache && l == 0) ? c0[2 * L] : c[l]) - pad;
+    *executed = e;
+  }
   return DDB_OK;
 }
 

@@ -225,16 +225,16 @@ static int bnd_grid(int groups, int num_sms) {
 
 void launch_bond_attn_node(const BondAttnArgs& a, int num_sms, cudaStream_t stream) {
   if (a.n_lig <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   int bytes = BondSmem::bytes(true);
-  if (!once) { cudaFuncSetAttribute(bond_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(bond_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   bond_attn_kernel<false><<<bnd_grid(a.n_lig, num_sms), BND_THREADS, bytes, stream>>>(a);
 }
 void launch_bond_attn_pos(const BondAttnArgs& a, int num_sms, cudaStream_t stream) {
   if (a.n_lig <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   int bytes = BondSmem::bytes(false);
-  if (!once) { cudaFuncSetAttribute(bond_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(bond_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   bond_attn_kernel<true><<<bnd_grid(a.n_lig, num_sms), BND_THREADS, bytes, stream>>>(a);
 }
 
@@ -470,16 +470,16 @@ __global__ void __launch_bounds__(BND_THREADS, 1) trip_kernel(const TripArgs a) 
 
 void launch_trip_k(const TripArgs& a, int num_sms, cudaStream_t stream) {
   if (a.n_bonds <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   int bytes = TripSmem::bytes();
-  if (!once) { cudaFuncSetAttribute(trip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(trip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   trip_kernel<false><<<bnd_grid(a.n_bonds, num_sms), BND_THREADS, bytes, stream>>>(a);
 }
 void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream) {
   if (a.n_bonds <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   int bytes = TripSmem::bytes();
-  if (!once) { cudaFuncSetAttribute(trip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(trip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   trip_kernel<true><<<bnd_grid(a.n_bonds, num_sms), BND_THREADS, bytes, stream>>>(a);
 }
 

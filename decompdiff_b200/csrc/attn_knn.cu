@@ -282,23 +282,23 @@ static int knn_grid(const KnnAttnArgs& a, int num_sms) {
 
 void launch_knn_attn_k(const KnnAttnArgs& a, int num_sms, cudaStream_t stream) {
   if (a.n_dst <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   int bytes = KnnSmem::bytes(true);
-  if (!once) { cudaFuncSetAttribute(knn_attn_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(knn_attn_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   knn_attn_k_kernel<<<knn_grid(a, num_sms), ATT_THREADS, bytes, stream>>>(a);
 }
 void launch_knn_attn_v_node(const KnnAttnArgs& a, int num_sms, cudaStream_t stream) {
   if (a.n_dst <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   int bytes = KnnSmem::bytes(true);
-  if (!once) { cudaFuncSetAttribute(knn_attn_v_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(knn_attn_v_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   knn_attn_v_node_kernel<<<knn_grid(a, num_sms), ATT_THREADS, bytes, stream>>>(a);
 }
 void launch_knn_attn_v_pos(const KnnAttnArgs& a, int num_sms, cudaStream_t stream) {
   if (a.n_dst <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   int bytes = KnnSmem::bytes(false);
-  if (!once) { cudaFuncSetAttribute(knn_attn_v_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(knn_attn_v_pos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   knn_attn_v_pos_kernel<<<knn_grid(a, num_sms), ATT_THREADS, bytes, stream>>>(a);
 }
 

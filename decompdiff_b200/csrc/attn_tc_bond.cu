@@ -355,9 +355,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
 
 template <int PASS>
 static void launch_bond_tc_pass(const BondAttnArgs& a, int num_sms, cudaStream_t stream) {
-  static bool once = false;
+  static DeviceOnce once;
   const int bytes = BondTcSmem::bytes();
-  if (!once) { cudaFuncSetAttribute(bond_tc_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once = true; }
+  if (!once.done()) { cudaFuncSetAttribute(bond_tc_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   const int grid = atc_grid((a.n_lig + 3) / 4, num_sms);
   bond_tc_kernel<PASS><<<grid, BT_THREADS, bytes, stream>>>(a);
 }

@@ -489,13 +489,13 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
 
 void launch_knn_tc(const KnnAttnArgs& a, int pass, int num_sms, cudaStream_t stream) {      // pass: 0 key, 1 node value, 2 position value
   if (a.n_dst <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   const int bytes = KnnTcSmem::bytes();
-  if (!once) {
+  if (!once.done()) {
     cudaFuncSetAttribute(knn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(knn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(knn_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    once = true;
+    once.mark();
   }
   const int grid = atc_grid((a.n_dst + 3) / 4, num_sms);
   if (pass == 2) knn_tc_kernel<2><<<grid, KT_THREADS, bytes, stream>>>(a);

@@ -410,12 +410,12 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
 
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream) {
   if (a.n_bonds <= 0) return;
-  static bool once = false;
+  static DeviceOnce once;
   const int bytes = TripTcSmem::bytes();
-  if (!once) {
+  if (!once.done()) {
     cudaFuncSetAttribute(trip_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(trip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    once = true;
+    once.mark();
   }
   const int grid = atc_grid((a.n_bonds + 3) / 4, num_sms);
   if (vpass) trip_tc_kernel<true><<<grid, TT_THREADS, bytes, stream>>>(a);

@@ -115,6 +115,15 @@ __device__ __forceinline__ void ln_relu_rows(float4 (&z)[BLK], float4 gamma, flo
   }
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: one flag per (call site, device).  A thread that
+// races the first caller at worst sets the attribute a second time; it never launches before the attribute is set.
+struct DeviceOnce {
+  volatile bool flag[64] = {};
+  static int dev() { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool done() const { return flag[dev()]; }
+  void mark() { flag[dev()] = true; }
+};
+
 // cooperative copy of `n_floats` (multiple of 4) from global to shared by the whole CTA
 __device__ __forceinline__ void cta_copy_f4(float* dst, const float* __restrict__ src, int n_floats) {
   for (int i = threadIdx.x * 4; i < n_floats; i += blockDim.x * 4) st4(dst + i, ldg4(src + i));

@@ -119,10 +119,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm128_kernel(const GemmArgs
 
 void launch_gemm128(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     cudaFuncSetAttribute(gemm128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    attr_set = true;
+    attr_set.mark();
   }
   dim3 grid((a.M + GEMM_BM - 1) / GEMM_BM, a.N / GEMM_BN);
   gemm128_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(a);

@@ -254,10 +254,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
 
 void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     cudaFuncSetAttribute(gemm128_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    attr_set = true;
+    attr_set.mark();
   }
   const int row_tiles = (a.M + TC_BM - 1) / TC_BM, tiles = a.N / TC_BN;
   // Split the output tiles over `nsplit` CTAs per row tile.  Cost model in units of one output tile of MMA work: every CTA

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, schedules
-from .engine import EngineBatch, EngineModel, require_cuda
+from .engine import EngineBatch, EngineModel, _on_device, require_cuda
 
 GAUSS_OFFSETS = [0, 1, 1.25, 1.5, 1.75, 2, 2.25, 2.5, 2.75, 3, 3.5, 4, 4.5, 5, 5.5, 6, 7, 8, 9, 10]
 
@@ -191,6 +191,10 @@ class DecompScorePosNet3D(nn.Module):
                                             nn.Linear(self.hidden_dim, self.num_bond_classes))
         self._engine: Optional[EngineModel] = None
         self.use_cuda_graph = True
+        # profiling aid: record a CUDA event every `step_event_interval` steps of a sampling run (0 = off); the (step, event)
+        # pairs of the last run are kept in `last_step_events` (bench.py turns them into device ms/step per window of t)
+        self.step_event_interval = 0
+        self.last_step_events = []
 
     # -- engine handling ---------------------------------------------------------------------------
     def engine_config(self) -> Dict[str, int]:
@@ -200,10 +204,13 @@ class DecompScorePosNet3D(nn.Module):
                     protein_feature_dim=self.protein_atom_feature_dim, ligand_feature_dim=self.ligand_atom_feature_dim,
                     num_timesteps=self.num_timesteps)
 
-    def engine(self) -> EngineModel:
-        """Hand the current parameters to the CUDA library (once; call `refresh_engine` after editing them)."""
-        if self._engine is None:
-            self._engine = EngineModel(self.engine_config(), self.state_dict())
+    def engine(self, device=None) -> EngineModel:
+        """Hand the current parameters to the CUDA library (once per device; call `refresh_engine` after editing them)."""
+        if device is None:
+            device = self._engine.device if self._engine is not None else torch.device('cuda', torch.cuda.current_device())
+        device = torch.device(device)
+        if self._engine is None or self._engine.device != device:
+            self._engine = EngineModel(self.engine_config(), self.state_dict(), device)
         return self._engine
 
     def refresh_engine(self):
@@ -217,7 +224,11 @@ class DecompScorePosNet3D(nn.Module):
     def _new_batch(self, protein_pos, protein_v, batch_protein, batch_ligand, ligand_v_aux, bond_index,
                    ligand_atom_mask, center_mode) -> EngineBatch:
         num_graphs = int(batch_protein.max().item()) + 1
-        return EngineBatch(self.engine(), num_graphs, protein_pos, protein_v, batch_protein, batch_ligand,
+        # the run lives where the caller's tensors live (the reference computes on its inputs' device); host tensors -> current device
+        from .engine import _device_of
+        dev = _device_of(protein_pos, batch_protein, batch_ligand, ligand_v_aux,
+                         default=torch.device('cuda', torch.cuda.current_device()))
+        return EngineBatch(self.engine(dev), num_graphs, protein_pos, protein_v, batch_protein, batch_ligand,
                            ligand_v_aux, bond_index, ligand_atom_mask, center_mode)
 
     # -- forward -----------------------------------------------------------------------------------
@@ -332,7 +343,7 @@ class SamplingRun:
 
     def __init__(self, model: DecompScorePosNet3D, eb: EngineBatch, prior_std_atom, num_steps, keep_traj, out_device):
         self.model, self.eb, self.num_steps, self.keep_traj, self.out_device = model, eb, num_steps, keep_traj, out_device
-        dev = eb.device
+        dev = self.device = eb.device
         n, Eb, Cn, Cb = eb.n_ligand, eb.n_bonds, model.num_classes, model.num_bond_classes
         self.prior_std_atom = prior_std_atom
         self.u_atom = torch.empty(n, Cn, device=dev)
@@ -352,6 +363,9 @@ class SamplingRun:
                ('pos_traj', 'v_traj', 'v0_traj', 'vt_traj', 'bond_traj', 'bt_traj')})
         self.done = 0
         self.graph = None
+        self.event_interval = int(getattr(model, 'step_event_interval', 0) or 0)
+        if self.event_interval:
+            model.last_step_events = []
         # trajectories stream to pinned host memory while later steps run (side stream, every STREAM_CHUNK steps), so the end
         # of a run only waits for the last chunk instead of a 1.7 GB device->host copy (cfg 2)
         self.host_traj, self.copied, self.copy_stream = None, 0, None
@@ -387,6 +401,7 @@ class SamplingRun:
         self.u_bond.uniform_()
         self.eps.normal_()
 
+    @_on_device
     def step_eager(self, noise=None):
         if noise is None:
             self._draw()
@@ -395,6 +410,7 @@ class SamplingRun:
         self.eb.reverse_step(self.io)
         self.done += 1
 
+    @_on_device
     def advance(self, k: int, noise=None):
         """Run `k` more reverse steps."""
         if self.done + k > self.num_steps:
@@ -422,16 +438,26 @@ class SamplingRun:
                 self._draw()
                 self.eb.reverse_step(self.io)
         for _ in range(k):
+            if self.event_interval and self.done % self.event_interval == 0:
+                self._mark()
             self.graph.replay()
             self.done += 1
             self._stream_out()
+        if self.event_interval and self.done == self.num_steps:
+            self._mark()
         return self
+
+    def _mark(self):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream())
+        self.model.last_step_events.append((self.done, ev))
 
     @property
     def launches_per_step(self) -> int:
         """library kernels + the three torch RNG kernels of one step"""
         return self.eb.launch_count() + 3
 
+    @_on_device
     def finish(self, traj_on_device: bool = False):
         pos, v, bond = self.eb.get_state()
         dev = self.out_device

@@ -15,8 +15,19 @@ import torch
 from . import _lib
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _on_device(fn):
+    """Run a method with the object's CUDA device current (kernel launches go to the thread's current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 def _host(t: torch.Tensor, dtype) -> torch.Tensor:
@@ -32,10 +43,26 @@ def require_cuda():
         raise RuntimeError('decompdiff_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
 
 
+def _device_of(*tensors, default=None) -> torch.device:
+    """The CUDA device the call runs on: the first CUDA tensor among the inputs (as the reference, which computes where its
+    tensors live), else `default`, else the current device."""
+    for t in tensors:
+        if torch.is_tensor(t) and t.is_cuda:
+            return t.device
+    if default is not None:
+        return torch.device(default)
+    return torch.device('cuda', torch.cuda.current_device())
+
+
 class EngineModel:
-    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor]):
+    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor], device=None):
         require_cuda()
         L = _lib.lib()
+        self.device = _device_of(default=device)
+        with torch.cuda.device(self.device):
+            self._init(L, cfg, state_dict)
+
+    def _init(self, L, cfg, state_dict):
         c = _lib.Config(**cfg)
         self._h = C.c_void_p()
         _lib.check(L.ddb_model_create(C.byref(self._h), C.byref(c)))
@@ -65,6 +92,7 @@ class EngineBatch:
         require_cuda()
         L = _lib.lib()
         self.model = model
+        self.device = model.device      # the weight blob lives there; every call of this batch runs under that device
         pp, pv = _host(protein_pos, torch.float32), _host(protein_v, torch.float32)
         bp, bl = _host(batch_protein, torch.int64), _host(batch_ligand, torch.int64)
         aux = _host(ligand_v_aux, torch.float32)
@@ -80,10 +108,10 @@ class EngineBatch:
         self.num_graphs = num_graphs
         self.C, self.Cb = model.cfg['num_classes'], model.cfg['num_bond_classes']
         self._h = C.c_void_p()
-        _lib.check(L.ddb_batch_create(
-            C.byref(self._h), model._h, num_graphs, self.n_protein, _ptr(pp), _ptr(pv), _ptr(bp),
-            self.n_ligand, _ptr(bl), _ptr(aux), self.n_bonds, _ptr(bi), _ptr(mask), center_mode))
-        self.device = torch.device('cuda', torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            _lib.check(L.ddb_batch_create(
+                C.byref(self._h), model._h, num_graphs, self.n_protein, _ptr(pp), _ptr(pv), _ptr(bp),
+                self.n_ligand, _ptr(bl), _ptr(aux), self.n_bonds, _ptr(bi), _ptr(mask), center_mode))
 
     def __del__(self):
         h = getattr(self, '_h', None)
@@ -100,6 +128,7 @@ class EngineBatch:
         _lib.check(_lib.lib().ddb_batch_get_offset(self._h, _ptr(out)))
         return out
 
+    @_on_device
     def set_state(self, ligand_pos, ligand_v, bond_type):
         dev = self.device
         if bond_type is None:
@@ -113,28 +142,32 @@ class EngineBatch:
             raise AssertionError(f'Error: {int(self._v.max())} >= {self.C}')      # transitions.py:66
         if self._b.numel() and (int(self._b.max()) >= self.Cb or int(self._b.min()) < 0):
             raise AssertionError(f'Error: {int(self._b.max())} >= {self.Cb}')
-        _lib.check(_lib.lib().ddb_batch_set_state(self._h, _ptr(self._pos), _ptr(self._v), _ptr(self._b), _stream_ptr()))
+        _lib.check(_lib.lib().ddb_batch_set_state(self._h, _ptr(self._pos), _ptr(self._v), _ptr(self._b), _stream_ptr(self.device)))
 
+    @_on_device
     def get_state(self):
         dev = self.device
         pos = torch.empty(self.n_ligand, 3, device=dev, dtype=torch.float32)
         v = torch.empty(self.n_ligand, device=dev, dtype=torch.int64)
         b = torch.empty(self.n_bonds, device=dev, dtype=torch.int64)
-        _lib.check(_lib.lib().ddb_batch_get_state(self._h, _ptr(pos), _ptr(v), _ptr(b), _stream_ptr()))
+        _lib.check(_lib.lib().ddb_batch_get_state(self._h, _ptr(pos), _ptr(v), _ptr(b), _stream_ptr(self.device)))
         return pos, v, b
 
     # -- compute -------------------------------------------------------------------------------
+    @_on_device
     def forward(self):
         dev = self.device
         pos = torch.empty(self.n_ligand, 3, device=dev, dtype=torch.float32)
         vl = torch.empty(self.n_ligand, self.C, device=dev, dtype=torch.float32)
         bl = torch.empty(self.n_bonds, self.Cb, device=dev, dtype=torch.float32)
-        _lib.check(_lib.lib().ddb_forward(self._h, _ptr(pos), _ptr(vl), _ptr(bl), _stream_ptr()))
+        _lib.check(_lib.lib().ddb_forward(self._h, _ptr(pos), _ptr(vl), _ptr(bl), _stream_ptr(self.device)))
         return pos, vl, bl
 
+    @_on_device
     def set_time(self, t_start: int):
-        _lib.check(_lib.lib().ddb_batch_set_time(self._h, int(t_start), _stream_ptr()))
+        _lib.check(_lib.lib().ddb_batch_set_time(self._h, int(t_start), _stream_ptr(self.device)))
 
+    @_on_device
     def set_guidance(self, armsca=None, clash=None):
         """armsca = (ligand_decomp_index, min_d, max_d) | None;  clash = (full_pos, full_batch, sigma, gamma) | None"""
         L = _lib.lib()
@@ -146,11 +179,19 @@ class EngineBatch:
             1 if clash else 0, fp.size(0) if clash else 0, _ptr(fp), _ptr(fb),
             float(clash[2]) if clash else 0.0, float(clash[3]) if clash else 0.0))
 
+    @_on_device
     def reverse_step(self, io):
-        _lib.check(_lib.lib().ddb_reverse_step(self._h, C.byref(io), _stream_ptr()))
+        _lib.check(_lib.lib().ddb_reverse_step(self._h, C.byref(io), _stream_ptr(self.device)))
 
     def launch_count(self) -> int:
         return int(_lib.lib().ddb_batch_last_launch_count(self._h))
+
+    @_on_device
+    def executed_rows(self):
+        """(executed, full) kNN-attention destination rows of the last forward (pruning + first-layer cache)."""
+        e, f = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().ddb_batch_executed_rows(self._h, C.byref(e), C.byref(f)))
+        return int(e.value), int(f.value)
 
     def h2d_bytes(self) -> int:
         return int(_lib.lib().ddb_batch_h2d_bytes(self._h))
@@ -166,11 +207,12 @@ class EngineBatch:
         _lib.check(L.ddb_batch_profile_read(self._h, ms, cnt))
         return {L.ddb_profile_category_name(i).decode(): {'ms': ms[i], 'count': int(cnt[i])} for i in range(n) if cnt[i]}
 
+    @_on_device
     def debug_buffer(self, name: str) -> torch.Tensor:
         """Copy of an internal buffer of the last forward (tests / profiling)."""
         p, r, c = C.c_void_p(), C.c_int64(), C.c_int64()
         _lib.check(_lib.lib().ddb_batch_debug_buffer(self._h, name.encode(), C.byref(p), C.byref(r), C.byref(c)))
         dtype = torch.int32 if name in ('nbr', 'deg', 'nlig') else torch.float32
         out = torch.empty(r.value, c.value, device=self.device, dtype=dtype)
-        _lib.check(_lib.lib().ddb_copy_device(_ptr(out), p, out.numel() * out.element_size(), _stream_ptr()))
+        _lib.check(_lib.lib().ddb_copy_device(_ptr(out), p, out.numel() * out.element_size(), _stream_ptr(self.device)))
         return out

@@ -52,14 +52,29 @@ def get_space_size(pocket_pos: np.ndarray) -> float:
     return float(np.median(d[:10]))
 
 
-def sample_atom_num(space_size: float, config_dict: Dict) -> int:
-    """Atom count from the binned empirical distribution (utils/evaluation/atom_num.py:20-35); the bin bounds have to
-    come with the dictionary (`{'bounds': [...], 'bins': [(counts, probs), ...]}`)."""
-    if config_dict is None or 'bounds' not in config_dict:
-        raise ValueError("num_atoms_mode='prior' needs a config dict with 'bounds' and 'bins'")
-    bounds = config_dict['bounds']
+_ATOM_NUM_CONFIG = None
+
+
+def atom_num_config() -> Dict:
+    """The reference's built-in table `atom_num_config.CONFIG` (bin bounds + per-bin atom-count distribution), exported to
+    `data/atom_num_config.json` by `oracle/make_atom_num_config.py`."""
+    global _ATOM_NUM_CONFIG
+    if _ATOM_NUM_CONFIG is None:
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'atom_num_config.json')) as f:
+            raw = json.load(f)
+        _ATOM_NUM_CONFIG = {'bounds': raw['bounds'], 'bins': [(c, p) for c, p in raw['bins']]}
+    return _ATOM_NUM_CONFIG
+
+
+def sample_atom_num(space_size: float, config_dict: Optional[Dict] = None) -> int:
+    """Atom count from the binned empirical distribution (utils/evaluation/atom_num.py:20-35).  As in the reference the bin
+    index ALWAYS comes from the built-in bounds (`_get_bin_idx` reads CONFIG['bounds'], :20-25); a passed dictionary (the
+    arm / scaffold pickles) only replaces the per-bin distributions, and `None` falls back to the built-in ones."""
+    bounds = atom_num_config()['bounds']
     idx = next((i for i, b in enumerate(bounds) if b > space_size), len(bounds))
-    counts, probs = config_dict['bins'][idx]
+    counts, probs = (atom_num_config() if config_dict is None else config_dict)['bins'][idx]
     return int(np.random.choice(counts, p=probs))
 
 

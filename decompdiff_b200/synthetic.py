@@ -122,6 +122,13 @@ def make_batch(n_pockets: int, n_protein=370, arm_sizes: Sequence[int] = (8, 8),
             npi = n_protein[p] if isinstance(n_protein, (list, tuple)) else n_protein
             arms, nsc = arm_sizes, n_scaffold
         pockets.append(make_pocket(gen, npi, arms, nsc, dense))
+    return collate_pockets(pockets, n_full_extra, gen)
+
+
+def collate_pockets(pockets: Sequence[ProteinLigandData], n_full_extra: int = 0,
+                    gen: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+    """Collate complexes (`make_pocket`) into the keyword arguments of `DecompScorePosNet3D.sample_diffusion`."""
+    n_pockets = len(pockets)
     batch = Batch.from_data_list(pockets, follow_batch=FOLLOW_BATCH)
     n_lig = [p.ligand_atom_mask.numel() for p in pockets]
     batch_ligand = torch.repeat_interleave(torch.arange(n_pockets), torch.tensor(n_lig))
@@ -268,3 +275,41 @@ def beta_prior_dict(seed: int, arm_sizes: Sequence[int] = (3, 4), n_scaffold: in
         var = float(rng.uniform(0.2, 2.0))
         sca.append((int(n_scaffold), rng.randn(3) * 3.0, var if scalar_scaffold_cov else np.eye(3) * var, None, None))
     return {'arms_prior': arms, 'scaffold_prior': sca, 'num_arms': len(arms), 'num_scaffold': len(sca)}
+
+
+def select_pockets(kw: Dict[str, torch.Tensor], ids: Sequence[int]):
+    """(sub_kw, rows): the `sample_diffusion` keyword arguments of a sub-batch holding pockets `ids` (ascending) of `kw`, re-numbered
+    0..len(ids)-1 with the collate offsets of utils/data.py:439-444 re-applied.  Complexes never interact, so running a
+    sub-batch gives the rows of the full batch that belong to those pockets (used for sharding and by the parity tests,
+    which run the CPU oracle on a few pockets of a 64-pocket batch).  `rows['ligand']` / `rows['bond']` are the rows of the
+    full batch's per-atom / per-bond tensors that the sub-batch holds."""
+    ids = [int(i) for i in ids]
+    if sorted(ids) != ids or len(set(ids)) != len(ids):
+        raise ValueError('ids must be ascending and unique')
+    B = int(kw['batch_protein'].max()) + 1
+    new_id = torch.full((B,), -1, dtype=torch.long)
+    new_id[torch.tensor(ids)] = torch.arange(len(ids))
+    bp, bl, bb, bpr = kw['batch_protein'], kw['batch_ligand'], kw['batch_ligand_bond'], kw['batch_prior']
+    mp, ml, mb, mpr = new_id[bp] >= 0, new_id[bl] >= 0, new_id[bb] >= 0, new_id[bpr] >= 0
+    # old -> new row numbers of ligand atoms and prior rows (for the index-valued tensors)
+    lig_new = torch.cumsum(ml.long(), 0) - 1
+    prior_new = torch.cumsum(mpr.long(), 0) - 1
+    out = dict(kw)
+    out.update(
+        protein_pos=kw['protein_pos'][mp], protein_v=kw['protein_v'][mp], batch_protein=new_id[bp[mp]],
+        protein_group_idx=kw['protein_group_idx'][mp],
+        init_ligand_pos=kw['init_ligand_pos'][ml], init_ligand_v=kw['init_ligand_v'][ml], ligand_v_aux=kw['ligand_v_aux'][ml],
+        batch_ligand=new_id[bl[ml]], ligand_group_idx=kw['ligand_group_idx'][ml],
+        ligand_atom_mask=None if kw.get('ligand_atom_mask') is None else kw['ligand_atom_mask'][ml],
+        prior_centers=kw['prior_centers'][mpr], prior_stds=kw['prior_stds'][mpr], prior_num_atoms=kw['prior_num_atoms'][mpr],
+        batch_prior=new_id[bpr[mpr]], prior_group_idx=kw['prior_group_idx'][mpr],
+        ligand_fc_bond_index=lig_new[kw['ligand_fc_bond_index'][:, mb]],
+        init_ligand_fc_bond_type=kw['init_ligand_fc_bond_type'][mb], batch_ligand_bond=new_id[bb[mb]],
+        ligand_decomp_batch=prior_new[kw['ligand_decomp_batch'][ml]], ligand_decomp_index=kw['ligand_decomp_index'][ml],
+    )
+    if 'full_protein_pos' in kw:
+        mf = new_id[kw['full_batch_protein']] >= 0
+        out['full_protein_pos'] = kw['full_protein_pos'][mf]
+        out['full_batch_protein'] = new_id[kw['full_batch_protein'][mf]]
+    rows = {'ligand': ml.nonzero().squeeze(1), 'bond': mb.nonzero().squeeze(1)}
+    return out, rows

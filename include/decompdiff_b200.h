@@ -166,6 +166,10 @@ int ddb_batch_profile_read(const ddb_batch* b, double* ms_out, int64_t* count_ou
 int ddb_copy_device(void* dst, const void* src, int64_t bytes, void* stream);
 /* number of kernel launches issued by the last ddb_forward / ddb_reverse_step on this batch    */
 int64_t ddb_batch_last_launch_count(const ddb_batch* b);
+/* kNN-attention destination rows of the last forward: `full` = num_layers * nodes (what the reference computes,
+ * uni_transformer_edge.py:259-287 on every node), `executed` = what ran after the exact receptive-field pruning and the
+ * first-layer cache.  Synchronous (reads device counters). */
+int ddb_batch_executed_rows(const ddb_batch* b, int64_t* executed, int64_t* full);
 /* bytes copied host->device by ddb_batch_create / ddb_batch_set_guidance for this batch */
 int64_t ddb_batch_h2d_bytes(const ddb_batch* b);
 

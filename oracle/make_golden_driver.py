@@ -42,8 +42,25 @@ DRIVER_CASES = {
                            beta_matrix_cov=True),
     'subpocket_ref': dict(pocket=dict(seed=36), prior_mode='subpocket', num_atoms_mode='ref', type_priors=False),
     'subpocket_ref_large': dict(pocket=dict(seed=37), prior_mode='subpocket', num_atoms_mode='ref_large', type_priors=False),
+    # atom counts drawn from binned distributions: the bin comes from the reference's BUILT-IN bounds whatever the passed
+    # dictionaries say (utils/evaluation/atom_num.py:20-35); one dictionary, one None (built-in distributions)
+    'subpocket_prior': dict(pocket=dict(seed=38), prior_mode='subpocket', num_atoms_mode='prior', type_priors=False, natoms_seed=3),
 }
 NUM_SAMPLES, BATCH_SIZE, NUM_STEPS, SEED = 5, 2, 3, 2021
+
+
+def natoms_configs(spec):
+    """(arms_natoms_config, scaffold_natoms_config) of a case: a synthetic stand-in for the shipped arm_num_config.pkl (its own
+    'bounds' differ from the built-in ones and must be ignored) and None for the scaffold."""
+    if 'natoms_seed' not in spec:
+        return None, None
+    rng = np.random.RandomState(spec['natoms_seed'])
+    bins = []
+    for _ in range(10):
+        counts = list(rng.choice(np.arange(2, 9), size=4, replace=False))
+        p = rng.rand(4) + 0.1
+        bins.append(([int(c) for c in counts], list(p / p.sum())))
+    return {'bounds': list(np.linspace(5.0, 9.0, 9)), 'bins': bins}, None
 
 
 class StubModel:
@@ -118,7 +135,10 @@ def main():
     import utils.transforms as ref_trans
     from torch_geometric.transforms import Compose
 
+    only = set(sys.argv[1:])
     for name, spec in DRIVER_CASES.items():
+        if only and name not in only:
+            continue
         data, init_transform, full_pos = build_case(spec, ref_trans, ref_prior, Compose)
         drv.full_protein_pos = full_pos
         model = StubModel()
@@ -128,11 +148,14 @@ def main():
             model, data, init_transform=init_transform, num_samples=NUM_SAMPLES, batch_size=BATCH_SIZE, device='cpu',
             prior_mode=spec['prior_mode'], num_steps=NUM_STEPS, center_pos_mode='protein', num_atoms_mode=spec['num_atoms_mode'],
             atom_prior_probs=ATOM_PRIOR if spec['type_priors'] else None, bond_prior_probs=BOND_PRIOR if spec['type_priors'] else None,
-            atom_enc_mode='basic', bond_fc_mode='fc',
+            atom_enc_mode='basic', bond_fc_mode='fc', arms_natoms_config=natoms_configs(spec)[0],
+            scaffold_natoms_config=natoms_configs(spec)[1],
             energy_drift_opt=[{'type': 'armsca_prox', 'min_d': 1.2, 'max_d': 1.9}, {'type': 'clash', 'sigma': 2, 'gamma': 4}])
         torch.save(pack_results(model, res), os.path.join(GOLDEN_DIR, f'driver_{name}.pt'))
         print(name, len(model.calls), 'calls,', len(res), 'results, atoms', [len(r['decomp_mask']) for r in res])
 
+    if only:
+        return
     # transforms / priors not reached by the driver cases
     extra = {}
     d = syn.make_raw_pocket(seed=41, arm_sizes=(3, 1, 4), n_scaffold=4)

@@ -327,7 +327,8 @@ def gumbel_argmax(logits, uniform):
 # ----------------------------------------------------------------------------
 # drift guidance (utils/guidance_funcs.py:24-78, models/decompdiff.py:638-677)
 # ----------------------------------------------------------------------------
-def armsca_prox_energy(pos, batch_ligand, decomp_index, min_d, max_d):
+def armsca_prox_energy(pos, batch_ligand, decomp_index, min_d, max_d, num_graphs_div=None):
+    """`num_graphs_div`: the batch size the energy is divided by (:78) when `pos` holds only some pockets of a larger batch."""
     total = torch.tensor(0.)
     num_graphs = int(batch_ligand.max()) + 1
     n_valid = 0
@@ -342,7 +343,7 @@ def armsca_prox_energy(pos, batch_ligand, decomp_index, min_d, max_d):
             md, _ = min_all.min(-1)
             total = total + torch.mean(torch.clamp(min_d - md, min=0) + torch.clamp(md - max_d, min=0))
             n_valid += 1
-    return total / num_graphs, n_valid  # the 1/num_graphs quirk of :78
+    return total / (num_graphs_div or num_graphs), n_valid  # the 1/num_graphs quirk of :78
 
 
 def clash_energy(full_protein_pos, lig_pos, full_batch_protein, batch_ligand, sigma, surface_ct):
@@ -356,13 +357,13 @@ def clash_energy(full_protein_pos, lig_pos, full_batch_protein, batch_ligand, si
 
 
 def guidance_grad(xt, offset_l, energy_drift_opt, batch_ligand, decomp_index,
-                  full_protein_pos=None, full_batch_protein=None):
+                  full_protein_pos=None, full_batch_protein=None, num_graphs_div=None):
     """Sum of energy gradients w.r.t. x_t (centred frame), shipped drift types only."""
     total = torch.zeros_like(xt)
     for drift in energy_drift_opt:
         x = xt.detach().clone().requires_grad_(True)
         if drift['type'] == 'armsca_prox':
-            e, n_valid = armsca_prox_energy(x, batch_ligand, decomp_index, drift['min_d'], drift['max_d'])
+            e, n_valid = armsca_prox_energy(x, batch_ligand, decomp_index, drift['min_d'], drift['max_d'], num_graphs_div)
             if n_valid > 0:
                 total = total + torch.autograd.grad(e, x)[0]
         elif drift['type'] == 'clash':
@@ -411,10 +412,12 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
                      ligand_fc_bond_index, init_ligand_fc_bond_type, batch_ligand_bond,
                      num_steps=None, center_pos_mode='protein', energy_drift_opt=None,
                      full_protein_pos=None, full_batch_protein=None, ligand_atom_mask=None,
-                     noise=None, generator=None, keep_traj=True, **_unused):
+                     noise=None, generator=None, keep_traj=True, first_t=None, num_graphs_div=None, **_unused):
     """DecompScorePosNet3D.sample_diffusion.  `noise` = optional list (one per step, first step
     first) of dicts {'u_atom','u_bond','eps_pos'}; otherwise drawn with torch in the reference's
-    order rand(n,8) -> rand(Eb,5) -> randn(n,3) from `generator` (or the global CPU generator)."""
+    order rand(n,8) -> rand(Eb,5) -> randn(n,3) from `generator` (or the global CPU generator).
+    Test hooks beyond the reference: `first_t` starts the loop at that time index instead of T-1 (teacher-forced single steps),
+    `num_graphs_div` is the batch size of the armsca quirk when the inputs are a slice of a larger batch."""
     tab = sd        # the schedule tables are part of the state_dict (models/common.py:280-283)
     T = cfg['num_diffusion_timesteps']
     num_steps = T if num_steps is None else num_steps
@@ -431,7 +434,8 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
     ligand_v, ligand_bond = init_ligand_v, init_ligand_fc_bond_type
     traj = dict(pos_traj=[], v_traj=[], bond_traj=[], v0_traj=[], vt_traj=[], bt_traj=[])
     n, Eb = ligand_pos.size(0), ligand_bond.numel()
-    for s, i in enumerate(reversed(range(T - num_steps, T))):
+    t_hi = T if first_t is None else first_t + 1
+    for s, i in enumerate(reversed(range(t_hi - num_steps, t_hi))):
         t = torch.full((B,), i, dtype=torch.long)
         preds = forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, ligand_v_aux,
                         batch_ligand, ligand_fc_bond_index, ligand_bond, ligand_atom_mask=ligand_atom_mask)
@@ -445,7 +449,7 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
         if energy_drift_opt is not None:
             with torch.enable_grad():
                 grad = guidance_grad(ligand_pos, offset_l, energy_drift_opt, batch_ligand, ligand_decomp_index,
-                                     full_protein_pos, full_batch_protein)
+                                     full_protein_pos, full_batch_protein, num_graphs_div)
         st = reverse_step(tab, cfg, preds, ligand_pos, ligand_v, ligand_bond, t, batch_ligand,
                           batch_ligand_bond, prior_stds[ligand_decomp_batch], u_a, u_b, eps, grad,
                           ligand_atom_mask)

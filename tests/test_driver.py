@@ -13,7 +13,7 @@ import torch
 from conftest import load_golden
 from decompdiff_b200 import prior, sampling, synthetic as syn, transforms as trans
 from oracle.make_golden_driver import (ATOM_PRIOR, BATCH_SIZE, BOND_PRIOR, DRIVER_CASES, NUM_SAMPLES, NUM_STEPS, SEED, StubModel,
-                                       build_case, pack_results)
+                                       build_case, natoms_configs, pack_results)
 
 DRIFT = [{'type': 'armsca_prox', 'min_d': 1.2, 'max_d': 1.9}, {'type': 'clash', 'sigma': 2, 'gamma': 4}]
 
@@ -25,7 +25,8 @@ def run_driver(spec, model, device='cpu', **over):
     kw = dict(init_transform=init_transform, num_samples=NUM_SAMPLES, batch_size=BATCH_SIZE, device=device,
               prior_mode=spec['prior_mode'], num_steps=NUM_STEPS, center_pos_mode='protein', num_atoms_mode=spec['num_atoms_mode'],
               atom_prior_probs=ATOM_PRIOR if spec['type_priors'] else None, bond_prior_probs=BOND_PRIOR if spec['type_priors'] else None,
-              atom_enc_mode='basic', bond_fc_mode='fc', energy_drift_opt=DRIFT, full_protein_pos=full_pos)
+              atom_enc_mode='basic', bond_fc_mode='fc', energy_drift_opt=DRIFT, full_protein_pos=full_pos,
+              arms_natoms_config=natoms_configs(spec)[0], scaffold_natoms_config=natoms_configs(spec)[1])
     kw.update(over)
     return sampling.sample_diffusion_ligand_decomp(model, data, **kw)
 

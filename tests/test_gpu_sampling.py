@@ -97,7 +97,8 @@ def test_free_running_trajectory(case, model_cpu):
           f'bond agreement {(r["bond"] == gold["bond"]).float().mean():.4f}, '
           f'final pos rms diff {(r["pos"] - gold["pos"]).pow(2).mean().sqrt():.2e}')
     assert tol_ratio(r['v0_traj'][0], gold['v0_first']) <= 1.0 and tol_ratio(r['bt_traj'][0], gold['bt_first']) <= 1.0
-    assert first_flip >= 1 and worst <= 1.0
+    # the reference's discrete samples are reproduced for (nearly) the whole run: a Gumbel near-tie may flip one late
+    assert first_flip >= int(0.9 * S) and worst <= 1.0, (first_flip, worst)
 
 
 def test_guidance_gradients_match_reference(model_cpu):
@@ -190,3 +191,32 @@ def test_two_branch_step_is_bit_identical_to_the_single_stream_step(model_cpu, m
             assert torch.equal(a, b)
         for a, b in zip(f['bt_traj'], s['bt_traj']):
             assert torch.equal(a, b)
+
+
+def test_full_T1000_run_against_the_reference(model_cpu):
+    """The whole T=1000 reverse diffusion of cfg 1 against the reference's own run (tests/golden/traj_cfg1_T1000.pt, produced by
+    `oracle/make_golden_T1000.py`) with the reference's noise stream.  Trajectory-level equality is ill-posed once a discrete
+    sample flips (module docstring), so: bit-equal discrete samples and in-tolerance positions up to the first flip, which must
+    come late, and the same final type / bond statistics (the histograms can differ by the few atoms / bonds a flip touches)."""
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, 'traj_cfg1_T1000.pt')):
+        pytest.skip('T=1000 golden not generated')
+    gold = load_golden('traj_cfg1_T1000')
+    kw = syn.make_batch(n_pockets=1, n_protein=300, arm_sizes=(8, 8), n_scaffold=14, seed=21)
+    n, Eb, S = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel(), 1000
+    noise = syn.step_noise(n, Eb, S, 2021)
+    r = model_cpu.sample_diffusion(**kw, num_steps=S, center_pos_mode='protein', noise=noise)
+    vtr, btr = torch.stack(r['v_traj']), torch.stack(r['bond_traj'])
+    same = ((vtr == gold['v_traj'].long()).all(1) & (btr == gold['bond_traj'].long()).all(1)).long()
+    first_flip = int(same.cumprod(0).sum())
+    worst = max([tol_ratio(r['pos_traj'][s], gold['pos_traj'][s]) for s in range(first_flip)] or [0.0])
+    hv = torch.bincount(r['v'], minlength=8), torch.bincount(gold['v'], minlength=8)
+    hb = torch.bincount(r['bond'], minlength=5), torch.bincount(gold['bond'], minlength=5)
+    print(f'T=1000 cfg1: first discrete flip at step {first_flip}/{S}; pos err/tol before it {worst:.3f}; final atom-type agreement '
+          f'{(r["v"] == gold["v"]).float().mean():.3f}, bond agreement {(r["bond"] == gold["bond"]).float().mean():.4f}, '
+          f'final pos rms diff {(r["pos"] - gold["pos"]).pow(2).mean().sqrt():.2e}; type hist {hv[0].tolist()} vs {hv[1].tolist()}; '
+          f'bond hist {hb[0].tolist()} vs {hb[1].tolist()}')
+    assert worst <= 1.0
+    assert first_flip >= 100, first_flip
+    assert int((hv[0] - hv[1]).abs().sum()) <= 8 and int((hb[0] - hb[1]).abs().sum()) <= 0.1 * Eb
