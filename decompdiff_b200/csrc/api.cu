@@ -39,7 +39,7 @@ struct Blob {
 
 struct Mlp2 { size_t gamma, beta, W2, b2, W2tc; };   // offsets: LayerNorm affine + second Linear (natural layout) + tensor-core image
 struct KnnMlpOff { size_t Wg, Wt, B2tc[2]; Mlp2 m; };
-struct TripOff { size_t Wd, Wc, Wa, Watc; Mlp2 m; };
+struct TripOff { size_t Wd, Wc, Wa, Watc, Wa32, W2c; Mlp2 m; };
 struct GemmW { size_t Wt, bias, Wtc; int N; };     // K-major weight (128 x N) + bias (N) + tensor-core image (2*128*N)
 
 struct LayerOff {
@@ -150,7 +150,7 @@ struct Packer {
     r.m = mlp2(pre, out_dim, scale);
     return r;
   }
-  TripOff trip(const std::string& pre, float scale) {
+  TripOff trip(const std::string& pre, float scale, bool key) {
     TripOff r;
     r.Wd = cols_t(pre + ".net.0.weight", 437, 128, NG);
     r.Wc = cols_t(pre + ".net.0.weight", 437, 148, NG);
@@ -161,6 +161,19 @@ struct Packer {
       pack_wa_tc(wa.data(), m.blob.data.data() + r.Watc);
     }
     r.m = mlp2(pre, H, scale);
+    // commuted-W2 kernels (attn_trip2.cu): compact image of Wa^T; the key W2 in pair layout, the value W2 as it is
+    r.Wa32 = m.blob.alloc(4096);
+    {
+      std::vector<float> wa(m.blob.data.begin() + r.Wa, m.blob.data.begin() + r.Wa + (size_t)NANG * H);
+      pack_wa_sw32(wa.data(), m.blob.data.data() + r.Wa32);
+    }
+    if (key) {
+      r.W2c = m.blob.alloc((size_t)H * H);
+      std::vector<float> w2(m.blob.data.begin() + r.m.W2, m.blob.data.begin() + r.m.W2 + (size_t)H * H);
+      pack_w2k_pairs(w2.data(), m.blob.data.data() + r.W2c);
+    } else {
+      r.W2c = r.m.W2;
+    }
     return r;
   }
   GemmW second(const std::string& pre) {   // second Linear of a query MLP as a GEMM weight
@@ -260,8 +273,8 @@ extern "C" int ddb_model_finalize(ddb_model* m) {
     L.nb_v = P.mlp2(nb + "hv_func", H, 1.f);
     L.pb_k = P.mlp2(pb + "xk_func", H, kInvSqrtDh);
     L.pb_v = P.mlp2(pb + "xv_func", NH, 1.f);
-    L.bl_k = P.trip(bl + "hk_func", kInvSqrtDh);
-    L.bl_v = P.trip(bl + "hv_func", 1.f);
+    L.bl_k = P.trip(bl + "hk_func", kInvSqrtDh, true);
+    L.bl_v = P.trip(bl + "hv_func", 1.f, false);
     m->layers.push_back(L);
   }
   // global edge weight MLP (20 -> 128 -> 1)
@@ -324,6 +337,7 @@ struct ddb_batch {
   uint8_t *is_lig = nullptr, *upd_mask = nullptr;
   int *bsrc = nullptr, *bdst = nullptr, *in_ptr = nullptr, *in_eid = nullptr, *in_src = nullptr, *trip_base = nullptr;
   int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr; int* trip_grp_order = nullptr;
+  int4* trip_grp4 = nullptr; int *trip_grp_pk = nullptr, *csr_slot = nullptr; float *PcsrK = nullptr, *PcsrV = nullptr, *xcsr = nullptr;
   float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
   // evolving state
   float* x_lig = nullptr; int64_t* v = nullptr; int64_t* bond = nullptr; bool has_state = false;
@@ -354,7 +368,8 @@ struct ddb_batch {
   long long launches = 0;
   long long h2d_bytes = 0;
   bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
-  int tc_attn = 31;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels (DDB_TC_ATTN=<mask>)
+  int tc_attn = 31;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels; bit 5 (off by default, measured
+                             // slower - DESIGN.md section 4.1): commuted-W2 fp32 triplet kernels of attn_trip2.cu (DDB_TC_ATTN=<mask>)
   int max_indeg = 0;
   // the bond / triplet branch of a layer runs on a side stream (fork / join by events; becomes parallel branches of the step
   // graph under capture); DDB_NO_FORK=1 keeps everything on the caller's stream
@@ -542,6 +557,20 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     }
     DDB_TRY(b->upload(&b->trip_row_meta, row_meta)); DDB_TRY(b->upload(&b->trip_grp_meta, grp_meta));
     DDB_TRY(b->upload(&b->trip_grp_order, order));
+    // commuted-W2 kernels: per group {edge id, node of i, node of j, first CSR row of j}, deg(j) | excluded slot << 8; CSR row per edge
+    std::vector<int4> grp4(Eb); std::vector<int> grp_pk(Eb), csr_slot(Eb);
+    for (int p = 0; p < Eb; ++p) csr_slot[in_eid[p]] = p;
+    for (int pos = 0; pos < Eb; ++pos) {
+      const int e = order[pos], j = bsrc[e], i = bdst[e];
+      int excl = 32;
+      for (int p = in_ptr[j]; p < in_ptr[j + 1]; ++p) if (in_src[p] == i) excl = p - in_ptr[j];
+      grp4[pos] = make_int4(e, lig_idx[i], lig_idx[j], in_ptr[j]);
+      grp_pk[pos] = (in_ptr[j + 1] - in_ptr[j]) | (excl << 8);
+    }
+    DDB_TRY(b->upload(&b->trip_grp4, grp4)); DDB_TRY(b->upload(&b->trip_grp_pk, grp_pk)); DDB_TRY(b->upload(&b->csr_slot, csr_slot));
+    const size_t prow = ((size_t)Eb + 32) * H;
+    DDB_TRY(b->dalloc(&b->PcsrK, prow)); DDB_TRY(b->dalloc(&b->PcsrV, prow)); DDB_TRY(b->dalloc(&b->xcsr, ((size_t)Eb + 32) * 4));
+    cudaMemset(b->PcsrK, 0, prow * 4); cudaMemset(b->PcsrV, 0, prow * 4); cudaMemset(b->xcsr, 0, ((size_t)Eb + 32) * 16);
   }
   std::vector<uint8_t> upd(NL, 1);
   if (ligand_atom_mask) for (int i = 0; i < NL; ++i) upd[i] = ligand_atom_mask[i] ? 1 : 0;
@@ -815,14 +844,20 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.row_meta = b->trip_row_meta; ta.grp_meta = b->trip_grp_meta; ta.grp_order = b->trip_grp_order; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
     ta.k.Pe = b->PB + 2 * H; ta.k.Hk = b->PL + 5 * H; ta.k.Hj = b->PL + 6 * H; ta.k.Wd = m->p(L.bl_k.Wd);
     ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m); ta.k.W2tc = m->p(L.bl_k.m.W2tc); ta.k.Watc = m->p(L.bl_k.Watc);
+    const bool trip2 = (b->tc_attn & 35) == 35 && b->max_indeg <= 32;      // commuted-W2 kernels for both passes
     if (b->tc_attn & 1) { ta.k.Q = b->Qk; ta.k.Pm = b->Pmk; ta.k.Qm = b->Qmk; }
     ta.v.Pe = b->PB + 3 * H; ta.v.Hk = b->PL + 7 * H; ta.v.Hj = b->PL + 8 * H; ta.v.Wd = m->p(L.bl_v.Wd);
     ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc); ta.v.Watc = m->p(L.bl_v.Watc);
     if (b->tc_attn & 2) { ta.v.Q = b->Qv; ta.v.Pm = b->Pmv; ta.v.Qm = b->Qmv; }
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
+    if (trip2) {
+      ta.k.Pcsr = b->PcsrK; ta.v.Pcsr = b->PcsrV; ta.k.W2c = m->p(L.bl_k.W2c); ta.v.W2c = m->p(L.bl_v.W2c);
+      ta.k.Wa32 = m->p(L.bl_k.Wa32); ta.v.Wa32 = m->p(L.bl_v.Wa32);
+      ta.grp4 = b->trip_grp4; ta.grp_pk = b->trip_grp_pk; ta.csr_slot = b->csr_slot; ta.xcsr = b->xcsr;
+    }
     { ProfScope ps(b, sb, PC_TRIP_PREP); launch_trip_prep(ta, sb); }
-    { ProfScope ps(b, sb, PC_TRIP_K); if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
-    { ProfScope ps(b, sb, PC_TRIP_V); if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
+    { ProfScope ps(b, sb, PC_TRIP_K); if (trip2) launch_trip2(ta, false, sms, sb); else if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
+    { ProfScope ps(b, sb, PC_TRIP_V); if (trip2) launch_trip2(ta, true, sms, sb); else if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
     gemm(b, sb, PC_GEMM_BOND, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);      // projection of the new h_bond for the position update
     if (fork) cudaEventRecord(b->ev_trip, sb);
     b->launches += 6;

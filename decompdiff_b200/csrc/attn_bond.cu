@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(256, 4) trip_prep_kernel(const TripArgs a) {
     float dx = xj.x - xk.x, dy = xj.y - xk.y, dz = xj.z - xk.z;
     float d = sqrtf(dx * dx + dy * dy + dz * dz);       // (pos[i]-pos[j]).pow(2).sum(-1).sqrt()  (:130)
     gl[u] = lane < NG ? gauss_feat(d, lane) : 0.f;
+    if (a.xcsr && lane == 0 && e0 + u < a.n_bonds) st4(a.xcsr + (size_t)a.csr_slot[es[u]] * 4, xk);
   }
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
@@ -287,7 +288,8 @@ __global__ void __launch_bounds__(256, 4) trip_prep_kernel(const TripArgs a) {
         const float pm = warp_sum((z[u].x + z[u].y) + (z[u].z + z[u].w)) * (1.0f / H);
         const float qm = warp_sum((qv[u].x + qv[u].y) + (qv[u].z + qv[u].w)) * (1.0f / H);
         if (e0 + u < a.n_bonds) {
-          st4(t.P + (size_t)es[u] * H + lane * 4, make_float4(z[u].x - pm, z[u].y - pm, z[u].z - pm, z[u].w - pm));
+          float* prow = t.Pcsr ? t.Pcsr + (size_t)a.csr_slot[es[u]] * H : t.P + (size_t)es[u] * H;
+          st4(prow + lane * 4, make_float4(z[u].x - pm, z[u].y - pm, z[u].z - pm, z[u].w - pm));
           st4(t.Q + (size_t)es[u] * H + lane * 4, make_float4(qv[u].x - qm, qv[u].y - qm, qv[u].z - qm, qv[u].w - qm));
         }
       } else if (e0 + u < a.n_bonds) {

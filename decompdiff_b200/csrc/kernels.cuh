@@ -122,6 +122,10 @@ struct TripSide {
   BondMlpW w;
   const float* W2tc = nullptr;        // hi | lo swizzled image of w.W2 (tensor-core kernels)
   const float* Watc = nullptr;        // hi | lo swizzled image of Wa^T: B operand of the angular-feature MMA
+  // commuted-W2 kernels (attn_trip2.cu)
+  float* Pcsr = nullptr;              // (Eb + 32, 128) centred P rows in CSR order (rows of the edges entering one atom contiguous)
+  const float* W2c = nullptr;         // k: W2 in the pair layout of pack_w2k_pairs; v: W2 natural [out][in]
+  const float* Wa32 = nullptr;        // hi | lo SWIZZLE_32B image of Wa^T (pack_wa_sw32)
 };
 struct TripArgs {
   int n_bonds = 0;
@@ -140,6 +144,10 @@ struct TripArgs {
   const float* q = nullptr; int ldq = 0;        // (Eb,128) per-edge query
   float* wbuf = nullptr;                        // (sum of slots,16)
   const float* h_bond_in = nullptr; float* h_bond_out = nullptr;   // (Eb,128) residual update
+  // commuted-W2 kernels (attn_trip2.cu): per group in visiting order {edge id, node id of i, node id of j, first CSR row of j} and
+  // deg(j) | excluded row slot << 8 (32: none); csr_slot[e] = CSR row of edge e; xcsr = position of the source atom of every CSR
+  // row (written by trip_prep every layer)
+  const int4* grp4 = nullptr; const int* grp_pk = nullptr; const int* csr_slot = nullptr; float* xcsr = nullptr;
 };
 void launch_trip_prep(const TripArgs& a, cudaStream_t stream);
 void launch_trip_k(const TripArgs& a, int num_sms, cudaStream_t stream);
@@ -148,6 +156,9 @@ void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
 // ---- tensor-core variants (attn_tc.cu): same arguments, wbuf rows of a group are 32 apart; groups of <= 32 rows only
 void launch_knn_tc(const KnnAttnArgs& a, int pass /* 0 key, 1 node value, 2 position value */, int num_sms, cudaStream_t stream);
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
+void launch_trip2(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);      // attn_trip2.cu (groups of <= 32 rows)
+void pack_wa_sw32(const float* Wa, float* out /* 4096 floats */);
+void pack_w2k_pairs(const float* W2, float* out /* 128*128 floats */);
 void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, const int* nlig, const uint8_t* is_lig, int2* out,
                           cudaStream_t stream);
 void launch_knn_dist(const float* x4, const int* nbr, const int* deg, int n, float* dist, cudaStream_t stream);
