@@ -275,6 +275,7 @@ def main():
     cnt = shape_counts(kw)
     atoms_per_mol = torch.bincount(kw['batch_ligand']).tolist()
     bonds_per_mol = torch.bincount(kw['batch_ligand_bond']).tolist()
+    gather_cap = (wl['n_pockets'], cnt['NL'], cnt['Eb'])      # every rank holds a shard of the same shape: one all_gather, no size exchange
     torch.manual_seed(2021 + rank)
 
     # ---------------------------------------------------------------- device-resident steps (value)
@@ -300,7 +301,7 @@ def main():
         # the first collective of a process group builds the NCCL communicator (hundreds of ms at 8 ranks): do one untimed
         # gather so that the timed one costs what it costs at the end of a real T=1000 run
         pos, v, bond = run.eb.get_state()
-        gather_molecules({'pos': pos, 'v': v, 'bond': bond}, atoms_per_mol, bonds_per_mol)
+        gather_molecules({'pos': pos, 'v': v, 'bond': bond}, atoms_per_mol, bonds_per_mol, capacity=gather_cap)
         torch.cuda.synchronize()
         dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -309,7 +310,7 @@ def main():
     run.advance(args.steps)
     if world > 1:   # the one exchange of the path: gather the sampled molecules (here after K steps)
         pos, v, bond = run.eb.get_state()
-        gather_molecules({'pos': pos, 'v': v, 'bond': bond}, atoms_per_mol, bonds_per_mol)
+        gather_molecules({'pos': pos, 'v': v, 'bond': bond}, atoms_per_mol, bonds_per_mol, capacity=gather_cap)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -375,7 +376,7 @@ def main():
         t0 = time.perf_counter()
         r = model.sample_diffusion(**host_kw, num_steps=e2e_steps, center_pos_mode='protein', energy_drift_opt=drift)
         if world > 1:
-            gather_molecules({k: r[k].to(dev) for k in ('pos', 'v', 'bond')}, atoms_per_mol, bonds_per_mol)
+            gather_molecules({k: r[k].to(dev) for k in ('pos', 'v', 'bond')}, atoms_per_mol, bonds_per_mol, capacity=gather_cap)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         if world > 1:

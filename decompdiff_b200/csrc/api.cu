@@ -57,6 +57,7 @@ struct ddb_model {
   ddb_config cfg{};
   std::map<std::string, std::vector<float>> host;
   bool finalized = false;
+  bool refine_only = false;      // only the refine_net.* tensors are required (stand-alone refine-net seam)
   Blob blob;
   float* dev = nullptr;
   std::vector<LayerOff> layers;
@@ -64,7 +65,7 @@ struct ddb_model {
   size_t lig_Wv = 0, bond_table = 0;
   GemmW v_head0{}, b_head0{};
   size_t v_W2 = 0, v_b2 = 0, b_W2 = 0, b_b2 = 0;
-  size_t tab_c0 = 0, tab_ct = 0, tab_logvar = 0;
+  size_t tab_c0 = 0, tab_ct = 0, tab_logvar = 0, tab_score = 0;
   size_t tab_a[5] = {0, 0, 0, 0, 0}, tab_b[5] = {0, 0, 0, 0, 0};   // log_alpha, log_1m_alpha, log_cumprod, log_1m_cumprod, prior
   const float* p(size_t off) const { return dev + off; }
 };
@@ -76,6 +77,7 @@ struct Packer {
   std::string missing;
   explicit Packer(ddb_model& mm) : m(mm) {}
   const std::vector<float>* get(const std::string& name, size_t numel) {
+    if (m.refine_only && name.compare(0, 11, "refine_net.") != 0) return nullptr;      // embeddings / heads / tables: not needed
     auto it = m.host.find(name);
     if (it == m.host.end() || it->second.size() != numel) {
       if (missing.empty()) missing = name + (it == m.host.end() ? " (absent)" : " (wrong size)");
@@ -216,6 +218,13 @@ extern "C" int ddb_model_set_tensor(ddb_model* m, const char* name, const float*
   return DDB_OK;
 }
 
+extern "C" int ddb_model_set_refine_only(ddb_model* m, int32_t on) {
+  if (!m) return fail(DDB_ERR_INVALID, "null model");
+  m->refine_only = on != 0;
+  m->finalized = false;
+  return DDB_OK;
+}
+
 extern "C" void ddb_model_destroy(ddb_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
@@ -310,6 +319,7 @@ extern "C" int ddb_model_finalize(ddb_model* m) {
   m->tab_c0 = P.vec("posterior_mean_c0_coef", T);
   m->tab_ct = P.vec("posterior_mean_ct_coef", T);
   m->tab_logvar = P.vec("posterior_logvar", T);
+  m->tab_score = P.vec("pos_score_coef", T);
   const char* tn[4] = {"log_alphas_v", "log_one_minus_alphas_v", "log_alphas_cumprod_v", "log_one_minus_alphas_cumprod_v"};
   for (int i = 0; i < 4; ++i) {
     m->tab_a[i] = P.vec(std::string("atom_type_trans.") + tn[i], T);
@@ -363,10 +373,13 @@ struct ddb_batch {
   // results of the last forward
   float *h_fin = nullptr, *x_fin = nullptr, *hb_fin = nullptr;
   // guidance
-  int enable_armsca = 0, enable_clash = 0; float min_d = 0, max_d = 0, sigma = 0, gamma = 0;
+  int enable_armsca = 0, enable_clash = 0, scale_armsca = 0, scale_clash = 0; float min_d = 0, max_d = 0, sigma = 0, gamma = 0;
   int* decomp_index = nullptr; float* full_pos4 = nullptr; int* full_ptr = nullptr;
   long long launches = 0;
   long long h2d_bytes = 0;
+  bool refine = false;       // refine-net seam: h / x / h_bond come from the caller (ddb_refine_forward), every node row is an output
+  float *tap_h = nullptr, *tap_x = nullptr, *tap_hb = nullptr;      // optional per-layer copies of h / x / h_bond (ddb_batch_set_layer_tap)
+  float* v_logits0 = nullptr;   // return_all: v_inference of the input embedding (decompdiff.py:345-346)
   bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
   int tc_attn = 31;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels; bit 5 (off by default, measured
                              // slower - DESIGN.md section 4.1): commuted-W2 fp32 triplet kernels of attn_trip2.cu (DDB_TC_ATTN=<mask>)
@@ -413,12 +426,13 @@ extern "C" void ddb_batch_destroy(ddb_batch* b) {
 
 #define DDB_TRY(expr) do { int _r = (expr); if (_r) { ddb_batch_destroy(b); return _r; } } while (0)
 
-extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num_graphs, int64_t n_protein,
-                                const float* protein_pos, const float* protein_v, const int64_t* batch_protein,
-                                int64_t n_ligand, const int64_t* batch_ligand, const float* ligand_v_aux,
-                                int64_t n_bonds, const int64_t* bond_index, const uint8_t* ligand_atom_mask,
-                                int32_t center_mode) {
+static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_graphs, int64_t n_protein,
+                             const float* protein_pos, const float* protein_v, const int64_t* batch_protein,
+                             int64_t n_ligand, const int64_t* batch_ligand, const float* ligand_v_aux,
+                             int64_t n_bonds, const int64_t* bond_index, const uint8_t* ligand_atom_mask,
+                             int32_t center_mode, bool refine) {
   if (!out || !m) return fail(DDB_ERR_INVALID, "null argument");
+  if (m->refine_only && !refine) return fail(DDB_ERR_STATE, "a refine-only model serves ddb_refine_batch_create only");
   if (!m->finalized) return fail(DDB_ERR_STATE, "model not finalized");
   if (num_graphs < 1 || n_protein < 0 || n_ligand < 0 || n_bonds < 0) return fail(DDB_ERR_INVALID, "negative size");
   if (center_mode != 0 && center_mode != 1) return fail(DDB_ERR_INVALID, "center_pos_mode must be 'none' or 'protein'");
@@ -436,7 +450,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     if (bond_index[e] < 0 || bond_index[e] >= n_ligand) return fail(DDB_ERR_INVALID, "ligand_fc_bond_index out of range");
 
   auto* b = new ddb_batch();
-  b->m = m; b->B = B; b->N = N; b->NL = NL; b->NP = NP; b->Eb = Eb;
+  b->m = m; b->B = B; b->N = N; b->NL = NL; b->NP = NP; b->Eb = Eb; b->refine = refine;
   if (const char* e = getenv("DDB_GEMM")) b->use_tc = std::string(e) != "simt";
   if (const char* e = getenv("DDB_TC_ATTN")) b->tc_attn = atoi(e);
   if (!getenv("DDB_NO_FORK")) {
@@ -471,7 +485,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   }
   // ---- centring offset = per-graph mean of protein positions (scatter_mean, decompdiff.py:25)
   b->offset_host.assign((size_t)B * 3, 0.f);
-  if (center_mode == 1) {
+  if (center_mode == 1 && protein_pos) {
     for (int g = 0; g < B; ++g) {
       float s[3] = {0.f, 0.f, 0.f};
       for (int i = prot_ptr[g]; i < prot_ptr[g + 1]; ++i)
@@ -481,7 +495,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     }
   }
   std::vector<float> x4((size_t)N * 4, 0.f), offset_lig((size_t)NL * 3, 0.f);
-  for (int i = 0; i < NP; ++i) {
+  for (int i = 0; i < NP && protein_pos; ++i) {
     int g = (int)batch_protein[i];
     for (int d = 0; d < 3; ++d) x4[(size_t)prot_idx[i] * 4 + d] = protein_pos[(size_t)i * 3 + d] - b->offset_host[(size_t)g * 3 + d];
   }
@@ -489,7 +503,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     for (int d = 0; d < 3; ++d) offset_lig[(size_t)i * 3 + d] = b->offset_host[(size_t)batch_ligand[i] * 3 + d];
   // ---- protein embedding (decompdiff.py:238,252-255): Linear(F_p -> 127) | indicator 0
   std::vector<float> h0((size_t)N * H, 0.f);
-  {
+  if (!refine) {
     const auto& W = m->host.at("protein_atom_emb.weight");
     const auto& bias = m->host.at("protein_atom_emb.bias");
     const int F = c.protein_feature_dim;
@@ -506,7 +520,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   }
   // ---- ligand embedding base: b + W[:, C:C+2] aux | indicator 1 (decompdiff.py:219-222,239,253-256)
   std::vector<float> lig_base((size_t)NL * H, 0.f);
-  {
+  if (!refine) {
     const auto& W = m->host.at("ligand_atom_emb.weight");
     const auto& bias = m->host.at("ligand_atom_emb.bias");
     const int F = c.ligand_feature_dim, C = c.num_classes, A = F - C;
@@ -579,7 +593,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     long long total = 0;
     for (int g = 0; g < B; ++g) { base[g] = total; npg[g] = cnt_p[g]; total += (long long)cnt_p[g] * cnt_p[g]; }
     DDB_TRY(b->upload(&b->n_protein_of, npg));
-    if (total > 0 && total <= (1ll << 28) && !getenv("DDB_NO_EW_CACHE")) {
+    if (total > 0 && total <= (1ll << 28) && !getenv("DDB_NO_EW_CACHE") && !refine) {      // refine: protein positions are per call
       DDB_TRY(b->dalloc(&b->ew_table, (size_t)total));
       cudaMemset(b->ew_table, 0xff, (size_t)total * sizeof(float));      // all-ones bit pattern = NaN = empty
       DDB_TRY(b->upload(&b->ew_table_base, base));
@@ -594,7 +608,7 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
     b->n_slots_all = (int)sorted.size();
     DDB_TRY(b->upload(&b->dst_sorted, sorted));
     DDB_TRY(b->dalloc(&b->slot_meta_all, sorted.size())); DDB_TRY(b->dalloc(&b->slot_meta_lig, (size_t)NL));
-    b->prune = b->use_tc && (b->tc_attn & 12) == 12 && !getenv("DDB_NO_PRUNE");
+    b->prune = b->use_tc && (b->tc_attn & 12) == 12 && !getenv("DDB_NO_PRUNE") && !refine;      // the refine net returns every node's h
     std::vector<int> lvl;
     for (int i = 0; i < N; ++i) if (is_lig[i]) lvl.push_back(i);
     while (lvl.size() % 4) lvl.push_back(-1);
@@ -637,13 +651,54 @@ extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num
   DDB_TRY(b->dalloc(&b->nbr, n * KNN)); DDB_TRY(b->dalloc(&b->deg, n)); DDB_TRY(b->dalloc(&b->nlig, n));
   DDB_TRY(b->dalloc(&b->hid_v, nl * H)); DDB_TRY(b->dalloc(&b->v_logits, nl * c.num_classes));
   DDB_TRY(b->dalloc(&b->b_logits, eb * c.num_bond_classes)); DDB_TRY(b->dalloc(&b->x0, nl * 3));
-  DDB_TRY(b->dalloc(&b->grad, nl * 3));
+  DDB_TRY(b->dalloc(&b->grad, nl * 3)); DDB_TRY(b->dalloc(&b->v_logits0, nl * c.num_classes));
   cudaMemset(b->nbr, 0, n * KNN * sizeof(int));
   // the fills above ran on the legacy default stream; the kernels of this batch run on the caller's (possibly non-blocking)
   // stream, so order them once here
   { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { ddb_batch_destroy(b); return fail(DDB_ERR_CUDA, std::string("batch create: ") + cudaGetErrorString(e)); } }
   *out = b;
   return DDB_OK;
+}
+
+extern "C" int ddb_batch_create(ddb_batch** out, const ddb_model* m, int32_t num_graphs, int64_t n_protein,
+                                const float* protein_pos, const float* protein_v, const int64_t* batch_protein,
+                                int64_t n_ligand, const int64_t* batch_ligand, const float* ligand_v_aux,
+                                int64_t n_bonds, const int64_t* bond_index, const uint8_t* ligand_atom_mask,
+                                int32_t center_mode) {
+  if (!protein_pos && n_protein > 0) return fail(DDB_ERR_INVALID, "null protein_pos");
+  if ((!protein_v && n_protein > 0) || (!ligand_v_aux && n_ligand > 0)) return fail(DDB_ERR_INVALID, "null feature pointer");
+  return batch_create_impl(out, m, num_graphs, n_protein, protein_pos, protein_v, batch_protein, n_ligand, batch_ligand, ligand_v_aux,
+                           n_bonds, bond_index, ligand_atom_mask, center_mode, false);
+}
+
+// The refine-net seam (uni_transformer_edge.py:394): nodes arrive already merged (sorted by graph id) with their features.
+extern "C" int ddb_refine_batch_create(ddb_batch** out, const ddb_model* m, int32_t num_graphs, int64_t n_nodes, const int64_t* batch,
+                                       const uint8_t* mask_ligand, const uint8_t* mask_ligand_atom, int64_t n_bonds,
+                                       const int64_t* bond_index) {
+  if (!out || !m || (n_nodes > 0 && (!batch || !mask_ligand))) return fail(DDB_ERR_INVALID, "null argument");
+  if (n_nodes < 0 || n_bonds < 0 || (n_bonds > 0 && !bond_index)) return fail(DDB_ERR_INVALID, "bad size");
+  // split the merged order back into the (protein, ligand) lists of ddb_batch_create; the kernels index a graph's protein atoms
+  // before its ligand atoms (the order compose_context produces, common.py:172-191), so that order is required here
+  std::vector<int64_t> bp, bl, lig_rank((size_t)n_nodes, -1);
+  std::vector<uint8_t> upd;
+  for (int64_t i = 0; i < n_nodes; ++i) {
+    if (i && batch[i] < batch[i - 1]) return fail(DDB_ERR_INVALID, "batch must be ascending");
+    if (mask_ligand[i]) {
+      lig_rank[i] = (int64_t)bl.size(); bl.push_back(batch[i]); upd.push_back(mask_ligand_atom ? mask_ligand_atom[i] : 1);
+    } else {
+      if (!bl.empty() && bl.back() == batch[i]) return fail(DDB_ERR_INVALID, "within a graph protein nodes must precede ligand nodes (compose_context order)");
+      if (mask_ligand_atom && mask_ligand_atom[i]) return fail(DDB_ERR_INVALID, "mask_ligand_atom set on a protein node");
+      bp.push_back(batch[i]);
+    }
+  }
+  std::vector<int64_t> bi((size_t)2 * n_bonds);
+  for (int64_t e = 0; e < 2 * n_bonds; ++e) {
+    const int64_t v = bond_index[e];
+    if (v < 0 || v >= n_nodes || lig_rank[v] < 0) return fail(DDB_ERR_INVALID, "bond_index must address ligand nodes of the merged order");
+    bi[e] = lig_rank[v];
+  }
+  return batch_create_impl(out, m, num_graphs, (int64_t)bp.size(), nullptr, nullptr, bp.data(), (int64_t)bl.size(), bl.data(), nullptr,
+                           n_bonds, bi.data(), upd.data(), 0, true);
 }
 
 extern "C" int ddb_batch_get_offset(const ddb_batch* b, float* offset_out) {
@@ -659,6 +714,14 @@ __global__ void shift_kernel(const float* __restrict__ in, const float* __restri
   if (i < n3) out[i] = in[i] + sign * off[i];
 }
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
+__global__ void xyz_to_x4_kernel(const float* __restrict__ x, int n, float* __restrict__ x4) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) *reinterpret_cast<float4*>(x4 + (size_t)i * 4) = make_float4(x[(size_t)i * 3], x[(size_t)i * 3 + 1], x[(size_t)i * 3 + 2], 0.f);
+}
+__global__ void x4_to_xyz_kernel(const float* __restrict__ x4, int n, float* __restrict__ x) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float4 v = *reinterpret_cast<const float4*>(x4 + (size_t)i * 4); x[(size_t)i * 3] = v.x; x[(size_t)i * 3 + 1] = v.y; x[(size_t)i * 3 + 2] = v.z; }
+}
 }  // namespace
 
 extern "C" int ddb_batch_set_state(ddb_batch* b, const float* ligand_pos, const int64_t* ligand_v, const int64_t* bond_type,
@@ -743,9 +806,11 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   const ddb_config& c = m->cfg;
   const int N = b->N, NL = b->NL, Eb = b->Eb, sms = b->num_sms;
   b->launches = 0;
-  { ProfScope ps(b, s, PC_SETUP); launch_set_ligand_x(b->x_lig, NL, b->lig_idx, b->x4_0, s); }
-  { ProfScope ps(b, s, PC_SETUP); launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s); }
-  { ProfScope ps(b, s, PC_SETUP); launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s); }
+  if (!b->refine) {      // refine seam: x4_0 / h0 / hbA were filled from the caller's tensors
+    { ProfScope ps(b, s, PC_SETUP); launch_set_ligand_x(b->x_lig, NL, b->lig_idx, b->x4_0, s); }
+    { ProfScope ps(b, s, PC_SETUP); launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s); }
+    { ProfScope ps(b, s, PC_SETUP); launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s); }
+  }
   // fork: the bond / triplet branch of a layer needs only the layer input, so it runs on the side stream next to the kNN branch
   // (layer 0's also next to the graph build); timed eager passes stay on one stream so that the per-category events mean something
   const bool fork = b->side != nullptr && !b->profiling;
@@ -892,9 +957,18 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     { ProfScope ps(b, s, PC_BOND_POS); if (b->tc_attn & 16) { launch_bond_tc(bp, true, sms, s); b->launches += 1; } else launch_bond_attn_pos(bp, sms, s); }
     b->launches += 3;
     h_in = h_out; x_in = x_out; hb_in = hb_out;
+    if (b->tap_h) cudaMemcpyAsync(b->tap_h + (size_t)l * N * H, h_out, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (b->tap_x) cudaMemcpyAsync(b->tap_x + (size_t)l * N * 4, x_out, (size_t)N * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (b->tap_hb && Eb > 0) cudaMemcpyAsync(b->tap_hb + (size_t)l * Eb * H, hb_out, (size_t)Eb * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
   }
   b->h_fin = h_in; b->x_fin = x_in; b->hb_fin = hb_in;
   b->pn0_ready = true;
+  if (b->refine) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("refine forward launch: ") + cudaGetErrorString(e));
+    prof_collect(b, s);
+    return DDB_OK;
+  }
   // --- heads (decompdiff.py:315-338)
   gemm(b, s, PC_HEADS, b->h_fin, H, b->lig_idx, NL, m->v_head0, b->hid_v, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
   { ProfScope ps(b, s, PC_HEADS); launch_head_logits(b->hid_v, H, NL, m->p(m->v_W2), m->p(m->v_b2), c.num_classes, b->v_logits, s); }
@@ -912,6 +986,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
 
 extern "C" int ddb_forward(ddb_batch* b, float* out_pos, float* out_v_logits, float* out_bond_logits, void* stream) {
   if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  if (b->refine) return fail(DDB_ERR_STATE, "refine batches are driven by ddb_refine_forward");
   if (!b->has_state) return fail(DDB_ERR_STATE, "ddb_batch_set_state must precede ddb_forward");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int r = run_forward(b, s);
@@ -923,6 +998,44 @@ extern "C" int ddb_forward(ddb_batch* b, float* out_pos, float* out_v_logits, fl
   if (out_bond_logits && b->Eb > 0)
     DDB_CUDA(cudaMemcpyAsync(out_bond_logits, b->b_logits, (size_t)b->Eb * c.num_bond_classes * sizeof(float),
                              cudaMemcpyDeviceToDevice, s));
+  return DDB_OK;
+}
+
+extern "C" int ddb_forward_ex(ddb_batch* b, float* out_pos, float* out_v_logits, float* out_bond_logits, float* out_v_logits_input,
+                              void* stream) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  if (b->refine) return fail(DDB_ERR_STATE, "refine batches are driven by ddb_refine_forward");
+  int r = ddb_forward(b, out_pos, out_v_logits, out_bond_logits, stream);
+  if (r || !out_v_logits_input) return r;
+  // return_all (decompdiff.py:343-350): the head applied to the INPUT embedding of the ligand atoms (h0 still holds it)
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const ddb_model* m = b->m;
+  gemm(b, s, PC_HEADS, b->h0, H, b->lig_idx, b->NL, m->v_head0, b->hid_v, H, nullptr, nullptr, 0, nullptr, nullptr, 0, nullptr, 1);
+  launch_head_logits(b->hid_v, H, b->NL, m->p(m->v_W2), m->p(m->v_b2), m->cfg.num_classes, b->v_logits0, s);
+  DDB_CUDA(cudaMemcpyAsync(out_v_logits_input, b->v_logits0, (size_t)b->NL * m->cfg.num_classes * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  DDB_CUDA(cudaGetLastError());
+  return DDB_OK;
+}
+
+extern "C" int ddb_refine_forward(ddb_batch* b, const float* h, const float* x, const float* h_bond, float* h_out, float* x_out,
+                                  float* h_bond_out, void* stream) {
+  if (!b || !h || !x || (b->Eb > 0 && !h_bond)) return fail(DDB_ERR_INVALID, "null argument");
+  if (!b->refine) return fail(DDB_ERR_STATE, "not a refine batch (ddb_refine_batch_create)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = (size_t)b->N;
+  DDB_CUDA(cudaMemcpyAsync(b->h0, h, n * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (b->Eb > 0) DDB_CUDA(cudaMemcpyAsync(b->hbA, h_bond, (size_t)b->Eb * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (n > 0) xyz_to_x4_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(x, (int)n, b->x4_0);
+  // protein rows of the ping / pong position buffers are read by later layers: keep them in step with this call's x
+  DDB_CUDA(cudaMemcpyAsync(b->x4_a, b->x4_0, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  DDB_CUDA(cudaMemcpyAsync(b->x4_b, b->x4_0, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  b->has_state = true;
+  int r = run_forward(b, s);
+  if (r) return r;
+  if (h_out) DDB_CUDA(cudaMemcpyAsync(h_out, b->h_fin, n * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (x_out && n > 0) x4_to_xyz_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(b->x_fin, (int)n, x_out);
+  if (h_bond_out && b->Eb > 0) DDB_CUDA(cudaMemcpyAsync(h_bond_out, b->hb_fin, (size_t)b->Eb * H * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  DDB_CUDA(cudaGetLastError());
   return DDB_OK;
 }
 
@@ -974,8 +1087,15 @@ extern "C" int ddb_batch_set_guidance(ddb_batch* b, int32_t enable_armsca, const
   return DDB_OK;
 }
 
+extern "C" int ddb_batch_set_guidance_scale(ddb_batch* b, int32_t scale_armsca, int32_t scale_clash) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  b->scale_armsca = scale_armsca != 0; b->scale_clash = scale_clash != 0;
+  return DDB_OK;
+}
+
 extern "C" int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* stream) {
   if (!b || !io) return fail(DDB_ERR_INVALID, "null argument");
+  if (b->refine) return fail(DDB_ERR_STATE, "refine batches are driven by ddb_refine_forward");
   if (!b->has_state) return fail(DDB_ERR_STATE, "ddb_batch_set_state must precede ddb_reverse_step");
   if (!io->prior_std_atom || !io->u_atom || !io->eps_pos || (b->Eb > 0 && !io->u_bond))
     return fail(DDB_ERR_INVALID, "noise / prior_std pointers are required");
@@ -990,6 +1110,7 @@ extern "C" int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* strea
     g.num_graphs = b->B; g.n_lig = b->NL; g.lig_ptr = b->lig_ptr; g.x = b->x_lig; g.offset_lig = b->offset_lig; g.grad = b->grad;
     g.enable_armsca = b->enable_armsca; g.decomp_index = b->decomp_index; g.min_d = b->min_d; g.max_d = b->max_d;
     g.enable_clash = b->enable_clash; g.full_pos4 = b->full_pos4; g.full_ptr = b->full_ptr; g.sigma = b->sigma; g.gamma = b->gamma;
+    g.scale_armsca = b->scale_armsca; g.scale_clash = b->scale_clash; g.score_coef = m->p(m->tab_score); g.t_dev = b->t_dev;
     { ProfScope ps(b, s, PC_GUIDANCE); launch_guidance(g, s); }
     b->launches++;
   }
@@ -1083,6 +1204,12 @@ extern "C" int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, cons
   else if (n == "grad") { *ptr = b->grad; *rows = b->NL; *cols = 3; }
   else return fail(DDB_ERR_INVALID, "unknown buffer " + n);
   if (*ptr == nullptr) return fail(DDB_ERR_STATE, "no forward has run yet");
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_set_layer_tap(ddb_batch* b, float* h_layers, float* x_layers, float* h_bond_layers) {
+  if (!b) return fail(DDB_ERR_INVALID, "null batch");
+  b->tap_h = h_layers; b->tap_x = x_layers; b->tap_hb = h_bond_layers;
   return DDB_OK;
 }
 

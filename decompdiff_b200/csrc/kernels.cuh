@@ -216,6 +216,8 @@ struct GuidanceArgs {
   float* grad = nullptr;               // (n,3) out (overwritten)
   int enable_armsca = 0; const int* decomp_index = nullptr; float min_d = 0.f, max_d = 0.f;
   int enable_clash = 0; const float* full_pos4 = nullptr; const int* full_ptr = nullptr; float sigma = 0.f, gamma = 0.f;
+  // drift option `scale: True` (decompdiff.py:657-658,668-669): the gradient is multiplied by pos_score_coef[t]
+  int scale_armsca = 0, scale_clash = 0; const float* score_coef = nullptr; const int* t_dev = nullptr;
 };
 void launch_guidance(const GuidanceArgs& a, cudaStream_t stream);
 

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(256) guidance_kernel(const GuidanceArgs a) {
   for (int i = threadIdx.x; i < n * 3; i += blockDim.x) a.grad[(size_t)l0 * 3 + i] = 0.f;
   __syncthreads();
   if (n == 0) return;
+  const float coef_t = (a.scale_armsca || a.scale_clash) ? a.score_coef[*a.t_dev] : 1.f;
   if (a.enable_clash) {
     // compute_batch_clash_loss: per complex mean_i relu(gamma + sigma log(1e-3 + sum_j exp(-|p_j - x_i|^2 / sigma)))
     const int p0 = a.full_ptr[g], p1 = a.full_ptr[g + 1];
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(256) guidance_kernel(const GuidanceArgs a) {
       if (lane == 0) {
         float G = -a.sigma * logf(1e-3f + S);
         if (a.gamma - G > 0.f) {
-          float c = 2.0f / ((1e-3f + S) * (float)n);
+          float c = 2.0f / ((1e-3f + S) * (float)n) * (a.scale_clash ? coef_t : 1.f);
           a.grad[r * 3] += c * vx; a.grad[r * 3 + 1] += c * vy; a.grad[r * 3 + 2] += c * vz;
         }
       }
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(256) guidance_kernel(const GuidanceArgs a) {
         if (lane == 0 && bp >= 0) {
           float dm = (a.min_d - best > 0.f ? -1.f : 0.f) + (best - a.max_d > 0.f ? 1.f : 0.f);
           if (dm != 0.f && best > 0.f) {
-            float c = dm / (best * (float)narm * (float)a.num_graphs);
+            float c = dm / (best * (float)narm * (float)a.num_graphs) * (a.scale_armsca ? coef_t : 1.f);
             int rp = l0 + bp, rs = l0 + bs;
             float dx = a.x[rp * 3] - a.x[rs * 3], dy = a.x[rp * 3 + 1] - a.x[rs * 3 + 1], dz = a.x[rp * 3 + 2] - a.x[rs * 3 + 2];
             atomicAdd(a.grad + rp * 3, c * dx); atomicAdd(a.grad + rp * 3 + 1, c * dy); atomicAdd(a.grad + rp * 3 + 2, c * dz);

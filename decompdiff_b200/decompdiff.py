@@ -114,6 +114,35 @@ class UniTransformerO2TwoUpdateGeneralBond(nn.Module):
         self.base_block = nn.ModuleList([
             AttentionLayerO2TwoUpdateNodeGeneral(hidden_dim, n_heads, num_r_gaussian, edge_feat_dim, h_node_in_bond_net)
             for _ in range(num_layers)])
+        self._engine = None
+
+    def _refine_engine(self, device):
+        """The refine net's own weights handed to the CUDA library under their full-model names (refine-only model)."""
+        from .engine import EngineModel
+        if self._engine is None or self._engine.device != device:
+            cfg = dict(hidden_dim=self.hidden_dim, n_heads=self.n_heads, knn=self.k, num_layers=self.num_layers, num_blocks=self.num_blocks,
+                       num_classes=1, num_bond_classes=1, protein_feature_dim=1, ligand_feature_dim=2, num_timesteps=1)
+            sd = {'refine_net.' + k: v for k, v in self.state_dict().items()}
+            self._engine = EngineModel(cfg, sd, device, refine_only=True)
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, h, x, group_idx=None, bond_index=None, h_bond=None, mask_ligand=None, mask_ligand_atom=None, batch=None,
+                return_all=False):
+        """uni_transformer_edge.py:394-443 on the CUDA kernels: `{'x', 'h', 'h_bond'}` (+ `all_x / all_h / all_h_bond`, one entry per
+        block boundary, with return_all).  Nodes in compose_context order (batch ascending, protein before ligand per graph)."""
+        from .engine import RefineBatch, _device_of, require_cuda
+        require_cuda()
+        if bond_index is None or h_bond is None or mask_ligand is None or batch is None:
+            raise ValueError('uni_o2_bond needs bond_index, h_bond, mask_ligand and batch')
+        dev = _device_of(h, x, default=torch.device('cuda', torch.cuda.current_device()))
+        rb = RefineBatch(self._refine_engine(dev), batch, mask_ligand, mask_ligand_atom, bond_index)
+        ho, xo, hbo = rb.forward(h, x, h_bond)
+        out_dev = h.device
+        out = {'x': xo.to(out_dev), 'h': ho.to(out_dev), 'h_bond': hbo.to(out_dev)}
+        if return_all:
+            out.update({'all_x': [x, out['x']], 'all_h': [h, out['h']], 'all_h_bond': [h_bond, out['h_bond']]})
+        return out
 
 
 def get_refine_net(refine_net_type, config):
@@ -238,8 +267,6 @@ class DecompScorePosNet3D(nn.Module):
                 prior_centers, prior_stds, batch_prior, prior_group_idx,
                 ligand_fc_bond_index, init_ligand_fc_bond_type,
                 ligand_atom_mask=None, time_step=None, return_all=False):
-        if return_all:
-            raise NotImplementedError('return_all (per-layer predictions) is a training-time diagnostic')
         if ligand_fc_bond_index is None:
             raise NotImplementedError('uni_o2_bond needs ligand_fc_bond_index')
         require_cuda()
@@ -247,11 +274,21 @@ class DecompScorePosNet3D(nn.Module):
         eb = self._new_batch(protein_pos, protein_v, batch_protein, batch_ligand, init_ligand_v_aux,
                              ligand_fc_bond_index, ligand_atom_mask, center_mode=0)
         eb.set_state(init_ligand_pos, init_ligand_v, init_ligand_fc_bond_type)
-        pos, v_logits, b_logits = eb.forward()
+        v0 = None
+        if return_all:
+            pos, v_logits, b_logits, v0 = eb.forward_all()
+        else:
+            pos, v_logits, b_logits = eb.forward()
+        pos_in = init_ligand_pos.detach().to(pos.device, torch.float32)
         if ligand_atom_mask is not None:      # final_pos[mask_ligand_atom] (:316)
             keep = ligand_atom_mask.to(pos.device).bool()
-            pos, v_logits = pos[keep], v_logits[keep]
-        return {'pred_ligand_pos': pos.to(out_dev), 'pred_ligand_v': v_logits.to(out_dev), 'pred_bond': b_logits.to(out_dev)}
+            pos, v_logits, pos_in = pos[keep], v_logits[keep], pos_in[keep]
+            v0 = None if v0 is None else v0[keep]
+        preds = {'pred_ligand_pos': pos.to(out_dev), 'pred_ligand_v': v_logits.to(out_dev), 'pred_bond': b_logits.to(out_dev)}
+        if return_all:      # one entry per block boundary (:343-350; num_blocks = 1): the inputs and the final predictions
+            preds['layer_pred_ligand_pos'] = [pos_in.to(out_dev), preds['pred_ligand_pos']]
+            preds['layer_pred_ligand_v'] = [v0.to(out_dev), preds['pred_ligand_v']]
+        return preds
 
     def get_diffusion_loss(self, *a, **k):
         raise NotImplementedError('training is out of scope of the sampling hot path (SURVEY.md section 8f, N4)')
@@ -288,19 +325,27 @@ class DecompScorePosNet3D(nn.Module):
         eb = self._new_batch(protein_pos, protein_v, batch_protein, batch_ligand, ligand_v_aux,
                              ligand_fc_bond_index, ligand_atom_mask, center_mode)
         armsca = clash = None
+        scale = {'armsca_prox': False, 'clash': False}
         for drift in (energy_drift_opt or []):
             if drift['type'] == 'armsca_prox':
+                if armsca is not None:
+                    raise NotImplementedError('one armsca_prox drift per run')
                 armsca = (ligand_decomp_index, drift['min_d'], drift['max_d'])
             elif drift['type'] == 'clash':
+                if clash is not None:
+                    raise NotImplementedError('one clash drift per run')
                 clash = (full_protein_pos, full_batch_protein, drift['sigma'], drift['gamma'])
-            elif drift['type'] in ('center_prox', 'mmff_min'):
-                raise NotImplementedError(f"drift {drift['type']} is not part of the shipped sampling config")
+            elif drift['type'] == 'center_prox':
+                # the reference differentiates a per-atom (non-scalar) energy without grad_outputs (decompdiff.py:646-649,
+                # guidance_funcs.py:45-47) and torch raises exactly this
+                raise RuntimeError('grad can be implicitly created only for scalar outputs')
+            elif drift['type'] == 'mmff_min':
+                raise NotImplementedError('mmff_min drift needs RDKit force fields (utils/guidance_funcs.py compute_conf_drift)')
             else:
                 raise ValueError(drift['type'])
-            if drift.get('scale', False):
-                raise NotImplementedError('drift scale=True is not part of the shipped sampling config')
+            scale[drift['type']] = bool(drift.get('scale', False))
         if armsca or clash:
-            eb.set_guidance(armsca, clash)
+            eb.set_guidance(armsca, clash, scale['armsca_prox'], scale['clash'])
         eb.set_state(init_ligand_pos, init_ligand_v, init_ligand_fc_bond_type)
         eb.set_time(T - 1)
         prior_std_atom = prior_stds.to(eb.device, torch.float32)[ligand_decomp_batch.to(eb.device)].contiguous()

@@ -55,10 +55,11 @@ def _device_of(*tensors, default=None) -> torch.device:
 
 
 class EngineModel:
-    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor], device=None):
+    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor], device=None, refine_only: bool = False):
         require_cuda()
         L = _lib.lib()
         self.device = _device_of(default=device)
+        self.refine_only = refine_only
         with torch.cuda.device(self.device):
             self._init(L, cfg, state_dict)
 
@@ -72,6 +73,8 @@ class EngineModel:
                 continue
             ht = _host(t, torch.float32)
             _lib.check(L.ddb_model_set_tensor(self._h, name.encode(), C.c_void_p(ht.data_ptr()), ht.numel()))
+        if self.refine_only:
+            _lib.check(L.ddb_model_set_refine_only(self._h, 1))
         _lib.check(L.ddb_model_finalize(self._h))
 
     def __del__(self):
@@ -164,12 +167,24 @@ class EngineBatch:
         return pos, vl, bl
 
     @_on_device
+    @_on_device
+    def forward_all(self):
+        """forward + the head on the input ligand embedding (return_all=True, decompdiff.py:343-350)."""
+        dev = self.device
+        pos = torch.empty(self.n_ligand, 3, device=dev, dtype=torch.float32)
+        vl = torch.empty(self.n_ligand, self.C, device=dev, dtype=torch.float32)
+        v0 = torch.empty(self.n_ligand, self.C, device=dev, dtype=torch.float32)
+        bl = torch.empty(self.n_bonds, self.Cb, device=dev, dtype=torch.float32)
+        _lib.check(_lib.lib().ddb_forward_ex(self._h, _ptr(pos), _ptr(vl), _ptr(bl), _ptr(v0), _stream_ptr(self.device)))
+        return pos, vl, bl, v0
+
     def set_time(self, t_start: int):
         _lib.check(_lib.lib().ddb_batch_set_time(self._h, int(t_start), _stream_ptr(self.device)))
 
     @_on_device
-    def set_guidance(self, armsca=None, clash=None):
-        """armsca = (ligand_decomp_index, min_d, max_d) | None;  clash = (full_pos, full_batch, sigma, gamma) | None"""
+    def set_guidance(self, armsca=None, clash=None, scale_armsca=False, scale_clash=False):
+        """armsca = (ligand_decomp_index, min_d, max_d) | None;  clash = (full_pos, full_batch, sigma, gamma) | None;
+        scale_* = the drift's `scale: True` option (gradient x pos_score_coef[t])"""
         L = _lib.lib()
         di = _host(armsca[0], torch.int64) if armsca else None
         fp = _host(clash[0], torch.float32) if clash else None
@@ -178,6 +193,7 @@ class EngineBatch:
             self._h, 1 if armsca else 0, _ptr(di), float(armsca[1]) if armsca else 0.0, float(armsca[2]) if armsca else 0.0,
             1 if clash else 0, fp.size(0) if clash else 0, _ptr(fp), _ptr(fb),
             float(clash[2]) if clash else 0.0, float(clash[3]) if clash else 0.0))
+        _lib.check(L.ddb_batch_set_guidance_scale(self._h, int(bool(scale_armsca)), int(bool(scale_clash))))
 
     @_on_device
     def reverse_step(self, io):
@@ -216,3 +232,53 @@ class EngineBatch:
         out = torch.empty(r.value, c.value, device=self.device, dtype=dtype)
         _lib.check(_lib.lib().ddb_copy_device(_ptr(out), p, out.numel() * out.element_size(), _stream_ptr(self.device)))
         return out
+
+
+class RefineBatch:
+    """One merged-order graph batch for the refine-net seam (ddb_refine_batch_create / ddb_refine_forward)."""
+
+    def __init__(self, model: EngineModel, batch, mask_ligand, mask_ligand_atom, bond_index):
+        require_cuda()
+        L = _lib.lib()
+        self.model, self.device = model, model.device
+        bt, ml = _host(batch, torch.int64), _host(mask_ligand, torch.uint8)
+        mla = None if mask_ligand_atom is None else _host(mask_ligand_atom, torch.uint8)
+        if bond_index is None:
+            bond_index = torch.zeros(2, 0, dtype=torch.int64)
+        bi = _host(bond_index, torch.int64)
+        self.n_nodes, self.n_bonds = bt.numel(), bi.size(1)
+        num_graphs = int(bt.max()) + 1 if bt.numel() else 1
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(L.ddb_refine_batch_create(C.byref(self._h), model._h, num_graphs, self.n_nodes, _ptr(bt), _ptr(ml), _ptr(mla),
+                                                 self.n_bonds, _ptr(bi)))
+
+    def __del__(self):
+        h = getattr(self, '_h', None)
+        if h:
+            try:
+                _lib.lib().ddb_batch_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    @_on_device
+    def forward(self, h, x, h_bond, tap_layers: int = 0):
+        """-> (h, x, h_bond) after the last layer; with `tap_layers` = num_layers also the per-layer stacks (test seam)."""
+        dev = self.device
+        h = h.detach().to(dev, torch.float32).contiguous()
+        x = x.detach().to(dev, torch.float32).contiguous()
+        hb = h_bond.detach().to(dev, torch.float32).contiguous()
+        if h.shape != (self.n_nodes, 128) or x.shape != (self.n_nodes, 3) or hb.shape != (self.n_bonds, 128):
+            raise ValueError('h / x / h_bond do not match the batch')
+        ho, xo, hbo = torch.empty_like(h), torch.empty_like(x), torch.empty_like(hb)
+        taps = None
+        if tap_layers:
+            taps = (torch.empty(tap_layers, self.n_nodes, 128, device=dev), torch.empty(tap_layers, self.n_nodes, 4, device=dev),
+                    torch.empty(tap_layers, self.n_bonds, 128, device=dev))
+            _lib.check(_lib.lib().ddb_batch_set_layer_tap(self._h, _ptr(taps[0]), _ptr(taps[1]), _ptr(taps[2])))
+        _lib.check(_lib.lib().ddb_refine_forward(self._h, _ptr(h), _ptr(x), _ptr(hb), _ptr(ho), _ptr(xo), _ptr(hbo), _stream_ptr(dev)))
+        if tap_layers:
+            _lib.check(_lib.lib().ddb_batch_set_layer_tap(self._h, None, None, None))
+            return ho, xo, hbo, taps
+        return ho, xo, hbo

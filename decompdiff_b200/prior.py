@@ -125,3 +125,46 @@ def apply_num_atoms_change(data, num_atoms_change):
     data.arms_prior = [_rescaled(e, num_atoms_change=num_atoms_change) for e in data.arms_prior]
     assert len(data.scaffold_prior) <= 1
     data.scaffold_prior = [_rescaled(e, num_atoms_change=num_atoms_change) for e in data.scaffold_prior]
+
+
+class NumAtomsSampler:
+    """Atom counts / prior stds predicted from pocket statistics (utils/prior.py:162-208, `num_atoms_mode='stat'`).
+    `pred_models_dict` = {'arm_model', 'armstd_model', 'sca_model', 'scastd_model'}: any regressors with a scikit-learn style
+    `.predict(X)` (the reference unpickles sklearn models).  Draws use `np.random` in the reference's order."""
+
+    RADII = np.linspace(1, 10, 50)
+
+    def __init__(self, pred_models_dict):
+        self.arm_model = pred_models_dict['arm_model']
+        self.armstd_model = pred_models_dict['armstd_model']
+        self.sca_model = pred_models_dict['sca_model']
+        self.scastd_model = pred_models_dict['scastd_model']
+
+    @classmethod
+    def _shell_counts(cls, centers, protein_pos):
+        """(n_centers, 50) number of protein atoms within r of each centre, r = 1..10 A (:171-172)."""
+        d = torch.norm(centers.view(-1, 1, 3) - protein_pos.view(1, -1, 3), p=2, dim=-1)
+        return torch.stack([(d < r).sum(1) for r in cls.RADII], dim=1).numpy()
+
+    def sample_arm_natoms(self, arm_centers, protein_pos):
+        y = self.arm_model.predict(self._shell_counts(arm_centers, protein_pos))
+        arm_natoms = self.sample_natoms_from_prediction(y, std=0.2)
+        arm_stds = self.armstd_model.predict(arm_natoms[:, None])
+        arm_stds = torch.from_numpy(np.asarray(arm_stds).astype(np.float32)).reshape(-1, 1).expand(-1, 3)
+        return arm_natoms.tolist(), arm_stds
+
+    def sample_sca_natoms(self, sca_center, arm_centers, arm_stds, protein_pos):
+        feat = self._shell_counts(sca_center, protein_pos)
+        dist = torch.norm(sca_center.view(-1, 1, 3) - arm_centers.view(1, -1, 3), p=2, dim=-1).numpy()
+        res = [d - r for d, r in zip(dist, arm_stds.numpy())]            # zip over the single scaffold row, as the reference (:188)
+        x = np.concatenate([feat, np.array([d.sum() for d in res])[:, None]], axis=-1)
+        y = self.sca_model.predict(x)
+        sca_natoms = self.sample_natoms_from_prediction(y, std=0.)
+        sca_stds = self.scastd_model.predict(sca_natoms[:, None])
+        assert len(sca_natoms) == len(sca_stds) == 1
+        return sca_natoms.tolist()[0], torch.from_numpy(np.asarray(sca_stds).astype(np.float32)).expand(3)
+
+    @staticmethod
+    def sample_natoms_from_prediction(n, std, min_natoms=2):
+        natoms = np.ceil(n + std * n * np.random.randn(len(n))).astype(int)
+        return np.maximum(natoms, min_natoms)

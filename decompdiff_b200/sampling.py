@@ -14,7 +14,8 @@ Differences, all at the edges of the hot path:
   arguments `full_protein_pos`, `logger`, `reconstruct_fn`;
 * RDKit reconstruction (:416-455) is out of scope: `mol` is None and `smiles` '' unless a
   `reconstruct_fn(pred_pos, atomic_numbers, aromatic, bond_index, bond_type)` is supplied;
-* `num_atoms_mode='stat'` (sklearn regressors from a pickle, utils/prior.py:162-208) raises NotImplementedError.
+* `num_atoms_mode='stat'`: `natoms_config` may be the path of the pickle (as in the reference) or the already loaded dictionary
+  of regressors (`prior.NumAtomsSampler`).
 """
 from __future__ import annotations
 
@@ -25,6 +26,7 @@ import numpy as np
 import torch
 
 from . import transforms as trans
+from .prior import NumAtomsSampler
 from .batch import FOLLOW_BATCH, Batch
 
 COLLATE_EXCLUDE_KEYS = ('scaffold_prior', 'arms_prior')      # sample_diffusion_decomp.py:314
@@ -119,8 +121,13 @@ def sample_diffusion_ligand_decomp(
     `pred_bond_type`, `mol`, `smiles`)."""
     if prior_mode not in ('subpocket', 'ref_prior', 'beta_prior'):
         raise ValueError(prior_mode)
-    if num_atoms_mode == 'stat':
-        raise NotImplementedError("num_atoms_mode='stat' needs the sklearn regressors of utils/prior.py:162-208")
+    natoms_sampler = None
+    if num_atoms_mode == 'stat':      # :72-75
+        if isinstance(natoms_config, (str, bytes)):
+            import pickle
+            with open(natoms_config, 'rb') as f:
+                natoms_config = pickle.load(f)
+        natoms_sampler = NumAtomsSampler(natoms_config)
     if full_protein_pos is None:
         full_protein_pos = data.protein_pos
     num_batch = int(np.ceil(num_samples / batch_size))
@@ -162,10 +169,18 @@ def sample_diffusion_ligand_decomp(
             elif num_atoms_mode == 'v2':
                 arm_counts = [int(data.arms_prior[a][0]) for a in range(data.num_arms)]
                 sca_count = int(data.scaffold_prior[0][0]) if len(data.scaffold_prior) > 0 else 0
-            elif num_atoms_mode != 'old':
+            elif num_atoms_mode not in ('old', 'stat'):
                 raise ValueError(num_atoms_mode)
 
             def plan_for_sample():
+                if num_atoms_mode == 'stat':      # counts and stds predicted from the pocket, drawn per sample (:221-231)
+                    natoms, stds = natoms_sampler.sample_arm_natoms(arm_centers, data.protein_pos)
+                    if len(data.scaffold_prior) > 0:
+                        center = [p[1] for p in data.scaffold_prior][0]
+                        sca_n, sca_s = natoms_sampler.sample_sca_natoms(center, arm_centers, stds, data.protein_pos)
+                    else:
+                        center, sca_n, sca_s = data.protein_pos.mean(0), 0, torch.tensor([0.])
+                    return _Plan(arm_centers, stds, [int(n) for n in natoms], center, sca_s, int(sca_n))
                 if prior_mode == 'beta_prior' and num_atoms_mode == 'old':
                     # atom count ~ U{lower..upper} from a linear fit on the prior std (:238-246, :257-263)
                     m, b = 12.41, -4.98
@@ -173,10 +188,13 @@ def sample_diffusion_ligand_decomp(
                 return _Plan(arm_centers, arm_stds, arm_counts, sca_center, sca_std, sca_count)
 
         # ---- per sample: x_T, decomposition mask, transforms, initial bond types (draw order = the reference's)
-        samples, init_pos, ligand_num_atoms, decomp_ind = [], [], [], []
+        samples, init_pos, ligand_num_atoms, decomp_ind, noise_stds = [], [], [], [], []
         for _ in range(n_data):
             plan = plan_for_sample()
             pos, mask = plan.draw() if isinstance(plan, _OldCountPlan) else _draw_sample(plan)
+            if num_atoms_mode == 'stat':      # the predicted stds replace the collated prior stds (:249-250, :264-265, :322-323)
+                noise_stds += [plan.arm_stds[a, :].unsqueeze(0).expand(1, 3) for a in range(len(plan.arm_counts))]
+                noise_stds.append(plan.sca_std.unsqueeze(0).expand(1, 3))
             new_data = data.clone()
             new_data.ligand_atom_mask = torch.tensor(mask, dtype=torch.long)
             new_data = init_transform(new_data)
@@ -198,6 +216,8 @@ def sample_diffusion_ligand_decomp(
         batch = Batch.from_data_list(samples, exclude_keys=COLLATE_EXCLUDE_KEYS, follow_batch=FOLLOW_BATCH).to(device)
         batch_full_protein_pos = full_protein_pos.repeat(n_data, 1).to(device)
         full_batch_protein = torch.arange(n_data).repeat_interleave(len(full_protein_pos)).to(device)
+        if num_atoms_mode == 'stat':
+            batch.ligand_decomp_stds = torch.cat(noise_stds, dim=0).to(device)
 
         r = model.sample_diffusion(
             protein_pos=batch.protein_pos,

@@ -71,6 +71,10 @@ int ddb_model_set_tensor(ddb_model* m, const char* name, const float* host_data,
  * DDB_ERR_MISSING naming the first absent key (strict=True behaviour). */
 int ddb_model_finalize(ddb_model* m);
 void ddb_model_destroy(ddb_model* m);
+/* Stand-alone refine net (get_refine_net('uni_o2_bond', config), models/encoders/__init__.py:27-43): call before
+ * ddb_model_finalize; only the "refine_net.*" tensors are then required and the model serves ddb_refine_batch_create /
+ * ddb_refine_forward only. */
+int ddb_model_set_refine_only(ddb_model* m, int32_t on);
 
 /* ---------------------------------------------------------------- batch ------------------
  * Replaces the per-call set-up of sample_diffusion / forward that does not depend on t:
@@ -105,6 +109,26 @@ int ddb_batch_get_state(const ddb_batch* b, float* ligand_pos, int64_t* ligand_v
 int ddb_forward(ddb_batch* b, float* out_pos, float* out_v_logits, float* out_bond_logits,
                 void* stream);
 
+/* Same with return_all=True (decompdiff.py:343-350): out_v_logits_input (n_ligand,num_classes) receives v_inference of the
+ * INPUT ligand embedding - the reference's 'layer_pred_ligand_v'[0]; its [1] is out_v_logits ('layer_pred_ligand_pos' is
+ * [input positions, out_pos]; the lists have one entry per BLOCK boundary, uni_transformer_edge.py:436-438, num_blocks = 1). */
+int ddb_forward_ex(ddb_batch* b, float* out_pos, float* out_v_logits, float* out_bond_logits,
+                   float* out_v_logits_input, void* stream);
+
+/* ---------------------------------------------------------------- refine-net seam ---------
+ * Replaces UniTransformerO2TwoUpdateGeneralBond.forward(h, x, group_idx, bond_index, h_bond, mask_ligand, mask_ligand_atom,
+ * batch) (uni_transformer_edge.py:394-443) - the narrowest swap point of the reference (contract 2).
+ * ddb_refine_batch_create: HOST pointers; nodes in merged order (batch ascending, within a graph protein nodes before ligand
+ * nodes - what compose_context produces, common.py:172-191); mask_ligand / mask_ligand_atom (n_nodes) uint8 (the latter may be
+ * NULL = mask_ligand); bond_index (2, n_bonds) in MERGED node numbering as the reference passes it (decompdiff.py:291).
+ * ddb_refine_forward: DEVICE pointers; h (n_nodes,128), x (n_nodes,3), h_bond (n_bonds,128) in, the same shapes out
+ * ({'h','x','h_bond'} of the reference; every node row is computed - no receptive-field pruning on this path). */
+int ddb_refine_batch_create(ddb_batch** out, const ddb_model* m, int32_t num_graphs, int64_t n_nodes,
+                            const int64_t* batch, const uint8_t* mask_ligand, const uint8_t* mask_ligand_atom,
+                            int64_t n_bonds, const int64_t* bond_index);
+int ddb_refine_forward(ddb_batch* b, const float* h, const float* x, const float* h_bond,
+                       float* h_out, float* x_out, float* h_bond_out, void* stream);
+
 /* ---------------------------------------------------------------- reverse step -----------
  * Replaces one iteration of the loop in sample_diffusion (decompdiff.py:576-689): forward,
  * Gaussian posterior, categorical posteriors + Gumbel-argmax, optional drift, x_{t-1}.
@@ -137,6 +161,9 @@ int ddb_batch_set_guidance(ddb_batch* b,
                            float min_d, float max_d,
                            int32_t enable_clash, int64_t n_full, const float* full_protein_pos,
                            const int64_t* full_batch_protein, float sigma, float gamma);
+/* drift option `scale: True` (decompdiff.py:657-658, :668-669): multiply the armsca_prox / clash gradient by
+ * pos_score_coef[t] (the coefficient goes to 0 as t -> 0).  Off by default (the shipped sampling_drift.yml has no `scale`). */
+int ddb_batch_set_guidance_scale(ddb_batch* b, int32_t scale_armsca, int32_t scale_clash);
 
 /* ---------------------------------------------------------------- building blocks --------
  * Stand-alone entry points for the kernels (unit-testable seams; DEVICE pointers).            */
@@ -156,6 +183,10 @@ int ddb_gemm128(const float* A, int32_t lda, const float* Wt, int32_t ldw, const
  * name in {"h","x","h_bond","nbr","deg","nlig","e_w","grad"}; rows/cols describe the layout.          */
 int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, const void** ptr,
                            int64_t* rows, int64_t* cols);
+/* Per-layer intermediates (test seam): DEVICE buffers (num_layers, n_nodes, 128), (num_layers, n_nodes, 4) [xyz + pad]
+ * and (num_layers, n_bonds, 128) that receive h / x / h_bond after every layer of the following forwards; NULL disables a tap.
+ * With receptive-field pruning (sampling batches) protein rows outside a layer's receptive field hold stale values. */
+int ddb_batch_set_layer_tap(ddb_batch* b, float* h_layers, float* x_layers, float* h_bond_layers);
 /* Per-kernel device timing of eager (non-captured) forward / reverse-step calls: CUDA events recorded on the launch
  * stream around every kernel, accumulated per category.  enable=1 makes each call end with a stream synchronise. */
 int ddb_batch_profile(ddb_batch* b, int32_t enable, int32_t reset);

@@ -44,6 +44,10 @@ DRIVER_CASES = {
     'subpocket_ref_large': dict(pocket=dict(seed=37), prior_mode='subpocket', num_atoms_mode='ref_large', type_priors=False),
     # atom counts drawn from binned distributions: the bin comes from the reference's BUILT-IN bounds whatever the passed
     # dictionaries say (utils/evaluation/atom_num.py:20-35); one dictionary, one None (built-in distributions)
+    # atom counts / stds from regressors (utils/prior.py:162-208); 3 arms: the reference's zip over (distances, stds) only
+    # broadcasts for 1 or 3 arms
+    'beta_prior_stat': dict(pocket=dict(seed=39, arm_sizes=(2, 3, 2), n_scaffold=4), prior_mode='beta_prior', num_atoms_mode='stat',
+                            type_priors=False, beta_seed=8, stat_seed=4),
     'subpocket_prior': dict(pocket=dict(seed=38), prior_mode='subpocket', num_atoms_mode='prior', type_priors=False, natoms_seed=3),
 }
 NUM_SAMPLES, BATCH_SIZE, NUM_STEPS, SEED = 5, 2, 3, 2021
@@ -61,6 +65,24 @@ def natoms_configs(spec):
         p = rng.rand(4) + 0.1
         bins.append(([int(c) for c in counts], list(p / p.sum())))
     return {'bounds': list(np.linspace(5.0, 9.0, 9)), 'bins': bins}, None
+
+
+class LinearRegressor:
+    """scikit-learn style stand-in for the pickled regressors of `num_atoms_mode='stat'`: predict(X) = X w + b."""
+
+    def __init__(self, w, b):
+        self.w, self.b = np.asarray(w, dtype=np.float64), float(b)
+
+    def predict(self, X):
+        return np.asarray(X, dtype=np.float64) @ self.w + self.b
+
+
+def stat_models(spec):
+    if 'stat_seed' not in spec:
+        return None
+    rng = np.random.RandomState(spec['stat_seed'])
+    return {'arm_model': LinearRegressor(rng.rand(50) * 0.004, 3.0), 'armstd_model': LinearRegressor([0.08], 0.5),
+            'sca_model': LinearRegressor(np.append(rng.rand(50) * 0.004, 0.05), 3.5), 'scastd_model': LinearRegressor([0.06], 0.7)}
 
 
 class StubModel:
@@ -128,6 +150,18 @@ def load_reference_driver():
     return mod
 
 
+def stat_path(spec):
+    """The reference opens `natoms_config` as a pickle file (:72-74)."""
+    if 'stat_seed' not in spec:
+        return None
+    import pickle
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), f'ddb_stat_models_{spec["stat_seed"]}.pkl')
+    with open(path, 'wb') as f:
+        pickle.dump(stat_models(spec), f)
+    return path
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     drv = load_reference_driver()
@@ -149,7 +183,7 @@ def main():
             prior_mode=spec['prior_mode'], num_steps=NUM_STEPS, center_pos_mode='protein', num_atoms_mode=spec['num_atoms_mode'],
             atom_prior_probs=ATOM_PRIOR if spec['type_priors'] else None, bond_prior_probs=BOND_PRIOR if spec['type_priors'] else None,
             atom_enc_mode='basic', bond_fc_mode='fc', arms_natoms_config=natoms_configs(spec)[0],
-            scaffold_natoms_config=natoms_configs(spec)[1],
+            scaffold_natoms_config=natoms_configs(spec)[1], natoms_config=stat_path(spec),
             energy_drift_opt=[{'type': 'armsca_prox', 'min_d': 1.2, 'max_d': 1.9}, {'type': 'clash', 'sigma': 2, 'gamma': 4}])
         torch.save(pack_results(model, res), os.path.join(GOLDEN_DIR, f'driver_{name}.pt'))
         print(name, len(model.calls), 'calls,', len(res), 'results, atoms', [len(r['decomp_mask']) for r in res])

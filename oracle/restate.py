@@ -357,7 +357,7 @@ def clash_energy(full_protein_pos, lig_pos, full_batch_protein, batch_ligand, si
 
 
 def guidance_grad(xt, offset_l, energy_drift_opt, batch_ligand, decomp_index,
-                  full_protein_pos=None, full_batch_protein=None, num_graphs_div=None):
+                  full_protein_pos=None, full_batch_protein=None, num_graphs_div=None, score_coef_t=None):
     """Sum of energy gradients w.r.t. x_t (centred frame), shipped drift types only."""
     total = torch.zeros_like(xt)
     for drift in energy_drift_opt:
@@ -365,11 +365,13 @@ def guidance_grad(xt, offset_l, energy_drift_opt, batch_ligand, decomp_index,
         if drift['type'] == 'armsca_prox':
             e, n_valid = armsca_prox_energy(x, batch_ligand, decomp_index, drift['min_d'], drift['max_d'], num_graphs_div)
             if n_valid > 0:
-                total = total + torch.autograd.grad(e, x)[0]
+                g = torch.autograd.grad(e, x)[0]
+                total = total + (g * score_coef_t if drift.get('scale', False) else g)      # :657-658
         elif drift['type'] == 'clash':
             e = clash_energy(full_protein_pos, x + offset_l, full_batch_protein, batch_ligand,
                              drift['sigma'], drift['gamma'])
-            total = total + torch.autograd.grad(e, x)[0]
+            g = torch.autograd.grad(e, x)[0]
+            total = total + (g * score_coef_t if drift.get('scale', False) else g)          # :668-669
         else:
             raise ValueError(drift['type'])
     return total
@@ -449,7 +451,8 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
         if energy_drift_opt is not None:
             with torch.enable_grad():
                 grad = guidance_grad(ligand_pos, offset_l, energy_drift_opt, batch_ligand, ligand_decomp_index,
-                                     full_protein_pos, full_batch_protein, num_graphs_div)
+                                     full_protein_pos, full_batch_protein, num_graphs_div,
+                                     tab['pos_score_coef'][t][batch_ligand].unsqueeze(-1))
         st = reverse_step(tab, cfg, preds, ligand_pos, ligand_v, ligand_bond, t, batch_ligand,
                           batch_ligand_bond, prior_stds[ligand_decomp_batch], u_a, u_b, eps, grad,
                           ligand_atom_mask)

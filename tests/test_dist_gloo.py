@@ -35,6 +35,9 @@ def _worker(rank, world, port, out_dir):
     res, atoms, bonds = _fake_result(rank)
     out = gather_molecules(res, atoms, bonds)
     torch.save(out, os.path.join(out_dir, f'gathered_{rank}.pt'))
+    # capacities known a priori: the single packed all_gather alone
+    out2 = gather_molecules(res, atoms, bonds, capacity=(3, 40, 400))
+    assert all(torch.equal(a, b) for k in out for a, b in zip(out[k], out2[k]))
     dist.destroy_process_group()
 
 

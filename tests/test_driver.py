@@ -13,7 +13,7 @@ import torch
 from conftest import load_golden
 from decompdiff_b200 import prior, sampling, synthetic as syn, transforms as trans
 from oracle.make_golden_driver import (ATOM_PRIOR, BATCH_SIZE, BOND_PRIOR, DRIVER_CASES, NUM_SAMPLES, NUM_STEPS, SEED, StubModel,
-                                       build_case, natoms_configs, pack_results)
+                                       build_case, natoms_configs, pack_results, stat_models)
 
 DRIFT = [{'type': 'armsca_prox', 'min_d': 1.2, 'max_d': 1.9}, {'type': 'clash', 'sigma': 2, 'gamma': 4}]
 
@@ -26,7 +26,8 @@ def run_driver(spec, model, device='cpu', **over):
               prior_mode=spec['prior_mode'], num_steps=NUM_STEPS, center_pos_mode='protein', num_atoms_mode=spec['num_atoms_mode'],
               atom_prior_probs=ATOM_PRIOR if spec['type_priors'] else None, bond_prior_probs=BOND_PRIOR if spec['type_priors'] else None,
               atom_enc_mode='basic', bond_fc_mode='fc', energy_drift_opt=DRIFT, full_protein_pos=full_pos,
-              arms_natoms_config=natoms_configs(spec)[0], scaffold_natoms_config=natoms_configs(spec)[1])
+              arms_natoms_config=natoms_configs(spec)[0], scaffold_natoms_config=natoms_configs(spec)[1],
+              natoms_config=stat_models(spec))
     kw.update(over)
     return sampling.sample_diffusion_ligand_decomp(model, data, **kw)
 
@@ -74,13 +75,11 @@ def test_driver_result_schema_and_edges():
     res = run_driver(spec, StubModel(), reconstruct_fn=lambda pos, z, arom, bi, bt: (seen.append((z, arom)) or ('MOL', 'CC')))
     assert res[0]['mol'] == 'MOL' and res[0]['smiles'] == 'CC' and seen[0][1] is None
     assert set(seen[0][0]) <= {1, 6, 7, 8, 9, 15, 16, 17}
-    # errors: unknown prior mode / atom-count mode (ValueError as the reference), 'stat' is declared out of scope
+    # errors: unknown prior mode / atom-count mode (ValueError as the reference)
     with pytest.raises(ValueError):
         run_driver(spec, StubModel(), prior_mode='nope')
     with pytest.raises(ValueError):
         run_driver(DRIVER_CASES['subpocket_ref'], StubModel(), num_atoms_mode='nope')
-    with pytest.raises(NotImplementedError):
-        run_driver(DRIVER_CASES['beta_prior_v2'], StubModel(), num_atoms_mode='stat')
     # one sample, batch larger than the request
     assert len(run_driver(spec, StubModel(), num_samples=1, batch_size=4)) == 1
 

@@ -220,3 +220,21 @@ def test_full_T1000_run_against_the_reference(model_cpu):
     assert worst <= 1.0
     assert first_flip >= 100, first_flip
     assert int((hv[0] - hv[1]).abs().sum()) <= 8 and int((hb[0] - hb[1]).abs().sum()) <= 0.1 * Eb
+
+
+def test_scaled_drift_matches_oracle_and_center_prox_fails_like_the_reference(model_cpu, weights, oracle_cfg):
+    """`scale: True` multiplies a drift's gradient by pos_score_coef[t] (decompdiff.py:657-658, :668-669; the oracle with this option
+    is bit-identical to the reference on CPU).  `center_prox` differentiates a non-scalar energy upstream, which torch refuses."""
+    from oracle import restate
+    spec = make_golden.TRAJ_CASES['traj_b3_T8_guided']
+    kw = syn.make_batch(**spec['batch'])
+    n, Eb = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel()
+    noise = syn.step_noise(n, Eb, 2, seed=11)
+    drift = [dict(spec['drift'][0], scale=True), dict(spec['drift'][1], scale=True)]
+    got = model_cpu.sample_diffusion(**kw, num_steps=2, center_pos_mode='protein', energy_drift_opt=drift, noise=noise)
+    want = restate.sample_diffusion(weights, oracle_cfg, **kw, num_steps=2, center_pos_mode='protein', energy_drift_opt=drift, noise=noise)
+    plain = restate.sample_diffusion(weights, oracle_cfg, **kw, num_steps=2, center_pos_mode='protein', energy_drift_opt=spec['drift'], noise=noise)
+    assert tol_ratio(got['pos'], want['pos']) <= 1.0 and torch.equal(got['v'].cpu(), want['v'])
+    assert float((want['pos'] - plain['pos']).abs().max()) > 1e-4          # the option changes the result
+    with pytest.raises(RuntimeError, match='scalar outputs'):
+        model_cpu.sample_diffusion(**kw, num_steps=1, center_pos_mode='protein', energy_drift_opt=[{'type': 'center_prox'}])
