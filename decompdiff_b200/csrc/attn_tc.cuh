@@ -38,16 +38,6 @@ static __device__ unsigned long long g_timeline[2][2][16];      // one copy per 
 #endif
 
 constexpr int ATC_THREADS = 512;
-// the MMA-issuing warp rides along as a 17th warp: 544 threads leave 120 registers per thread at compile time, more than the
-// setmaxnreg hand-over of a whole idle warpgroup gave the workers (112) - round 1 spilled ~15 registers in the key pass and the
-// spill traffic (local memory behind a few KB of L1) accounted for ~30 % of its stall samples (profiles/r2_trip_old_vs_trip2.md)
-#ifdef DDB_SETMAXNREG
-constexpr int ATC_ISSUER_THREADS = 128;
-#define ATC_MAXNREG 96
-#else
-constexpr int ATC_ISSUER_THREADS = 32;
-#define ATC_MAXNREG 112      // 17 warps x 112 registers = 60 928 (120 would be rounded up to 128 per thread by the allocator and no longer fit)
-#endif
 constexpr int ATC_W2_BYTES = 2 * 128 * 128 * 4;                       // hi | lo image of W2
 constexpr int ANG_LD = 20;              // padded row of the per-tile angular features (bank-conflict-free float4 reads)
 constexpr int ATC_COL_AHI = 0, ATC_COL_ALO = 128, ATC_COL_D = 256;    // TMEM column map (512 allocated)

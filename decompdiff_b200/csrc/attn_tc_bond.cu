@@ -13,7 +13,7 @@
 
 namespace ddb {
 
-constexpr int BT_THREADS = ATC_THREADS + ATC_ISSUER_THREADS;     // 16 worker warps + the issuing warpgroup
+constexpr int BT_THREADS = ATC_THREADS + 128;     // 16 worker warps + the issuing warpgroup
 constexpr int BT_SYNC = ATC_THREADS + 32;
 constexpr int BBAR_A_READY = 6;
 enum { BT_K = 0, BT_V_NODE = 1, BT_V_POS = 2 };
@@ -56,7 +56,7 @@ __device__ __forceinline__ void bt_issue_mma(uint32_t tmem_base, uint32_t w2_sme
 }
 
 template <int PASS>
-__global__ void __maxnreg__(ATC_MAXNREG) bond_tc_kernel(const BondAttnArgs a) {
+__global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnArgs a) {
   constexpr int NOUT = PASS == BT_V_POS ? 16 : 128;
   constexpr int W2_BYTES = 2 * NOUT * 128 * 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -89,7 +89,7 @@ __global__ void __maxnreg__(ATC_MAXNREG) bond_tc_kernel(const BondAttnArgs a) {
   const int n_tiles = (a.n_lig + 3) / 4;
 
   if (warp >= 16) {
-#ifdef DDB_SETMAXNREG
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
 #endif
     if (warp == 16) {
@@ -100,7 +100,7 @@ __global__ void __maxnreg__(ATC_MAXNREG) bond_tc_kernel(const BondAttnArgs a) {
       }
     }
   } else {
-#ifdef DDB_SETMAXNREG
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
 #endif
     float* const whit = sm.hit + warp * 32;

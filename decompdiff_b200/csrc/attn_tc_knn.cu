@@ -19,7 +19,7 @@
 
 namespace ddb {
 
-constexpr int KT_THREADS = ATC_THREADS + ATC_ISSUER_THREADS;     // 16 worker warps + the issuing warpgroup
+constexpr int KT_THREADS = ATC_THREADS + 128;     // 16 worker warps + the issuing warpgroup
 constexpr int KT_SYNC = ATC_THREADS + 32;         // participants of the hand-over barriers
 constexpr int KT_KB = 5;                          // 40 feature columns = 5 k-steps of 8
 constexpr int KT_IMG = KT_KB * 128 * 32;          // one TF32 image of a [128 rows][40 cols] SWIZZLE_32B operand: 20480 bytes
@@ -95,7 +95,7 @@ void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, cons
 
 // PASS: 0 = key pass, 1 = node value pass, 2 = position value pass (16-output second Linear, dx per destination slot)
 template <int PASS>
-__global__ void __maxnreg__(ATC_MAXNREG) knn_tc_kernel(const KnnAttnArgs a) {
+__global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) {
   constexpr bool VPASS = PASS != 0, VPOS = PASS == 2;
   constexpr int W2_BYTES = VPOS ? 2 * NH * 128 * 4 : ATC_W2_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -134,7 +134,7 @@ __global__ void __maxnreg__(ATC_MAXNREG) knn_tc_kernel(const KnnAttnArgs a) {
 
   if (warp >= 16) {
     // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
-#ifdef DDB_SETMAXNREG
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
 #endif
     if (warp == 16) {
@@ -182,7 +182,7 @@ __global__ void __maxnreg__(ATC_MAXNREG) knn_tc_kernel(const KnnAttnArgs a) {
       }
     }
   } else {
-#ifdef DDB_SETMAXNREG
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
 #endif
     // ---------------------------------------------------------------- 16 worker warps: thread = (row r, channel slice s)

@@ -48,7 +48,7 @@ __device__ __forceinline__ float2 u2f(uint32_t a, uint32_t b) { return make_floa
 
 // 16 worker warps + one warpgroup whose first warp issues the MMAs (tcgen05.mma blocks its issuing thread while the tensor
 // queue is full, so the issuer must not be a worker).  setmaxnreg moves the registers of the idle warps to the workers.
-constexpr int TT_THREADS = ATC_THREADS + ATC_ISSUER_THREADS;
+constexpr int TT_THREADS = ATC_THREADS + 128;
 constexpr int TT_ISSUER = 16;
 #ifndef TT_EARLY_PREFETCH
 #define TT_EARLY_PREFETCH 0
@@ -59,7 +59,7 @@ __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sy
 constexpr int BAR_A2_READY = 5, BAR_A_READY = 6;  // named barriers: every warp arrives, the issuing warp waits on them
 
 template <bool VPASS>
-__global__ void __maxnreg__(ATC_MAXNREG) trip_tc_kernel(const TripArgs a) {
+__global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TripTcSmem sm(smem_raw);
   const TripSide& side = VPASS ? a.v : a.k;
@@ -98,7 +98,7 @@ __global__ void __maxnreg__(ATC_MAXNREG) trip_tc_kernel(const TripArgs a) {
 
   if (warp >= 16) {
     // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
-#ifdef DDB_SETMAXNREG
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
 #endif
     if (warp == TT_ISSUER) {
@@ -127,7 +127,7 @@ __global__ void __maxnreg__(ATC_MAXNREG) trip_tc_kernel(const TripArgs a) {
       }
     }
   } else {
-#ifdef DDB_SETMAXNREG
+#ifndef DDB_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
 #endif
     auto hand_over_a2 = [&]() { named_arrive(BAR_A2_READY, TT_SYNC); };
