@@ -347,6 +347,8 @@ struct ddb_batch {
   uint8_t *is_lig = nullptr, *upd_mask = nullptr;
   int *bsrc = nullptr, *bdst = nullptr, *in_ptr = nullptr, *in_eid = nullptr, *in_src = nullptr, *trip_base = nullptr;
   int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr; int* trip_grp_order = nullptr;
+  int4* bond_vg = nullptr; int n_bvg = 0, n_tvg = 0; float2 *bond_stats = nullptr, *trip_stats = nullptr;
+  float *bond_factor = nullptr, *bond_part_h = nullptr, *bond_part_dx = nullptr, *trip_factor = nullptr, *trip_part = nullptr; int* trip_vg_pair = nullptr;
   int4* trip_grp4 = nullptr; int *trip_grp_pk = nullptr, *csr_slot = nullptr; float *PcsrK = nullptr, *PcsrV = nullptr, *xcsr = nullptr;
   float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
   // evolving state
@@ -547,30 +549,69 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
     for (int s = 0; s < Eb; ++s) { in_eid[s] = order[s]; in_src[s] = bsrc[order[s]]; }
   }
   for (int a = 0; a < NL; ++a) b->max_indeg = std::max(b->max_indeg, in_ptr[a + 1] - in_ptr[a]);
-  if (b->max_indeg > 32) b->tc_attn &= ~(3 | 16);     // triplet groups of more than 32 rows: fp32 FMA kernels
+  // softmax groups of up to 64 rows run on the tensor-core kernels as two chunks of <= 32 rows (kernels.cuh: BondAttnArgs);
+  // beyond that (ligands of more than 65 atoms) the fp32 FMA kernels take over
+  const bool tc_groups = b->max_indeg <= 64;
+  if (!tc_groups) b->tc_attn &= ~(3 | 16);
+  if ((b->tc_attn & 3) != 3) b->tc_attn &= ~3;      // the two triplet passes share the layout of the weight buffer: both or none
+  auto chunks_of = [](int deg) { return deg > 32 ? 2 : 1; };
   long long slots = 0;
   for (int e = 0; e < Eb; ++e) {
     if (slots > 2000000000LL) { ddb_batch_destroy(b); return fail(DDB_ERR_INVALID, "too many bond triplets"); }
     trip_base[e] = (int)slots;
-    // rows of a softmax group are 32 apart when the tensor-core kernels may run (they write whole 32-row groups)
-    slots += (b->max_indeg <= 32) ? 32 : (in_ptr[bsrc[e] + 1] - in_ptr[bsrc[e]]);
+    const int deg = in_ptr[bsrc[e] + 1] - in_ptr[bsrc[e]];
+    // the tensor-core kernels write whole 32-row chunks; the fp32 kernels one slot per triplet
+    slots += tc_groups ? 32 * chunks_of(deg) : deg;
   }
   b->trip_slots = slots;
-  if (b->max_indeg <= 32) {      // static per-row metadata of the tensor-core triplet kernels
-    std::vector<int> order(Eb);      // groups are visited source-major: consecutive groups read the same rows P[k->j]
-    for (int e = 0; e < Eb; ++e) order[e] = e;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bsrc[x] != bsrc[y] ? bsrc[x] < bsrc[y] : bdst[x] < bdst[y]; });
-    std::vector<int2> row_meta((size_t)Eb * 32, make_int2(-1, -1)), grp_meta(Eb);
-    for (int pos = 0; pos < Eb; ++pos) {
-      const int e = order[pos], j = bsrc[e], i = bdst[e];
+  if (tc_groups) {
+    // ---- bond-edge attention: (chunk of) the edges entering a ligand atom
+    std::vector<int4> bvg;
+    for (int at = 0; at < NL; ++at) {
+      const int deg = in_ptr[at + 1] - in_ptr[at];
+      if (deg <= 32) { bvg.push_back(make_int4(at, in_ptr[at], deg, -1)); continue; }
+      const int idx = (int)bvg.size();
+      bvg.push_back(make_int4(at, in_ptr[at], 32, idx + 1));
+      bvg.push_back(make_int4(at, in_ptr[at] + 32, deg - 32, idx));
+    }
+    b->n_bvg = (int)bvg.size();
+    DDB_TRY(b->upload(&b->bond_vg, bvg));
+    DDB_TRY(b->dalloc(&b->bond_stats, bvg.size() * NH)); DDB_TRY(b->dalloc(&b->bond_factor, bvg.size() * NH));
+    DDB_TRY(b->dalloc(&b->bond_part_h, bvg.size() * H)); DDB_TRY(b->dalloc(&b->bond_part_dx, bvg.size() * 4));
+    // ---- triplets: static per-row metadata, (edge j->i, chunk of the edges entering j) visited source-major, chunk-major:
+    // consecutive groups read the same rows P[k->j]
+    struct VG { int e, c; };
+    std::vector<VG> order;
+    for (int e = 0; e < Eb; ++e)
+      for (int ch = 0; ch < chunks_of(in_ptr[bsrc[e] + 1] - in_ptr[bsrc[e]]); ++ch) order.push_back({e, ch});
+    std::stable_sort(order.begin(), order.end(), [&](const VG& x, const VG& y) {
+      if (bsrc[x.e] != bsrc[y.e]) return bsrc[x.e] < bsrc[y.e];
+      if (x.c != y.c) return x.c < y.c;
+      return bdst[x.e] < bdst[y.e];
+    });
+    const int nvg = (int)order.size();
+    b->n_tvg = nvg;
+    std::vector<int2> row_meta((size_t)nvg * 32, make_int2(-1, -1)), grp_meta(nvg);
+    std::vector<int> grp_order(nvg), vg_pair(nvg, -1), first_pos(Eb, -1);
+    for (int pos = 0; pos < nvg; ++pos) {
+      const int e = order[pos].e, ch = order[pos].c, j = bsrc[e], i = bdst[e];
+      grp_order[pos] = e;
       grp_meta[pos] = make_int2(lig_idx[i], lig_idx[j]);
-      for (int p = in_ptr[j]; p < in_ptr[j + 1]; ++p) {
+      for (int p = in_ptr[j] + 32 * ch; p < std::min(in_ptr[j + 1], in_ptr[j] + 32 * (ch + 1)); ++p) {
         const int k = in_src[p];
-        row_meta[(size_t)pos * 32 + (p - in_ptr[j])] = make_int2(in_eid[p], k == i ? -1 : lig_idx[k]);
+        row_meta[(size_t)pos * 32 + (p - in_ptr[j] - 32 * ch)] = make_int2(in_eid[p], k == i ? -1 : lig_idx[k]);
       }
+      if (first_pos[e] < 0) first_pos[e] = pos; else { vg_pair[pos] = first_pos[e]; vg_pair[first_pos[e]] = pos; }
     }
     DDB_TRY(b->upload(&b->trip_row_meta, row_meta)); DDB_TRY(b->upload(&b->trip_grp_meta, grp_meta));
-    DDB_TRY(b->upload(&b->trip_grp_order, order));
+    DDB_TRY(b->upload(&b->trip_grp_order, grp_order)); DDB_TRY(b->upload(&b->trip_vg_pair, vg_pair));
+    DDB_TRY(b->dalloc(&b->trip_stats, (size_t)nvg * NH)); DDB_TRY(b->dalloc(&b->trip_factor, (size_t)nvg * NH));
+    DDB_TRY(b->dalloc(&b->trip_part, (size_t)(nvg > Eb ? nvg : 1) * H));
+  }
+  if (b->max_indeg <= 32) {
+    std::vector<int> order(Eb);      // the visiting order above (one chunk per group)
+    for (int e = 0; e < Eb; ++e) order[e] = e;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bsrc[x] != bsrc[y] ? bsrc[x] < bsrc[y] : bdst[x] < bdst[y]; });
     // commuted-W2 kernels: per group {edge id, node of i, node of j, first CSR row of j}, deg(j) | excluded slot << 8; CSR row per edge
     std::vector<int4> grp4(Eb); std::vector<int> grp_pk(Eb), csr_slot(Eb);
     for (int p = 0; p < Eb; ++p) csr_slot[in_eid[p]] = p;
@@ -901,6 +942,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ba.v.Hi = b->PL + 2 * H; ba.v.Hj = b->PL + 3 * H; ba.v.Pe = b->PB + H; ba.v.w = bond_w(m, L.nb_v);
     ba.q = b->qNB; ba.ldq = H; ba.x4 = x_in; ba.wbuf = b->wb_bond; ba.out_h = b->h1; ba.ldo = H;
     ba.k.W2tc = m->p(L.nb_k.W2tc); ba.v.W2tc = m->p(L.nb_v.W2tc);
+    ba.vg = b->bond_vg; ba.n_vg = b->n_bvg; ba.stats = b->bond_stats; ba.factor = b->bond_factor; ba.part_h = b->bond_part_h; ba.part_dx = b->bond_part_dx;
     join_side(b->ev_proj);
     { ProfScope ps(b, s, PC_BOND_NODE); if (b->tc_attn & 16) { launch_bond_tc(ba, false, sms, s); b->launches += 1; } else launch_bond_attn_node(ba, sms, s); }
     // --- bond update over triplets -> hb_out
@@ -915,6 +957,8 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc); ta.v.Watc = m->p(L.bl_v.Watc);
     if (b->tc_attn & 2) { ta.v.Q = b->Qv; ta.v.Pm = b->Pmv; ta.v.Qm = b->Qmv; }
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
+    ta.n_groups = b->n_tvg; ta.vg_pair = b->trip_vg_pair; ta.stats = b->trip_stats; ta.factor = b->trip_factor; ta.part = b->trip_part;
+    const bool trip_chunked = b->n_tvg > Eb;
     if (trip2) {
       ta.k.Pcsr = b->PcsrK; ta.v.Pcsr = b->PcsrV; ta.k.W2c = m->p(L.bl_k.W2c); ta.v.W2c = m->p(L.bl_v.W2c);
       ta.k.Wa32 = m->p(L.bl_k.Wa32); ta.v.Wa32 = m->p(L.bl_v.Wa32);
@@ -922,7 +966,9 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     }
     { ProfScope ps(b, sb, PC_TRIP_PREP); launch_trip_prep(ta, sb); }
     { ProfScope ps(b, sb, PC_TRIP_K); if (trip2) launch_trip2(ta, false, sms, sb); else if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
+    if (trip_chunked && (b->tc_attn & 3) == 3) { launch_chunk_factors(ta.stats, ta.vg_pair, 1, ta.n_groups, b->trip_factor, sb); b->launches++; }
     { ProfScope ps(b, sb, PC_TRIP_V); if (trip2) launch_trip2(ta, true, sms, sb); else if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
+    if (trip_chunked && (b->tc_attn & 3) == 3) { launch_trip_combine(ta, m->p(L.bl_v.m.b2), sb); b->launches++; }
     gemm(b, sb, PC_GEMM_BOND, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);      // projection of the new h_bond for the position update
     if (fork) cudaEventRecord(b->ev_trip, sb);
     b->launches += 6;
@@ -953,6 +999,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     bp.q = b->qXb; bp.ldq = H; bp.x4 = x_in; bp.wbuf = b->wb_bond; bp.dx_edge = b->dx_edge; bp.upd_mask = b->upd_mask;
     bp.x4_out = x_out;
     bp.k.W2tc = m->p(L.pb_k.W2tc); bp.v.W2tc = m->p(L.pb_v.W2tc);
+    bp.vg = b->bond_vg; bp.n_vg = b->n_bvg; bp.stats = b->bond_stats; bp.factor = b->bond_factor; bp.part_h = b->bond_part_h; bp.part_dx = b->bond_part_dx;
     join_side(b->ev_trip);      // h_bond_out and its projection: the side branch of this layer is complete
     { ProfScope ps(b, s, PC_BOND_POS); if (b->tc_attn & 16) { launch_bond_tc(bp, true, sms, s); b->launches += 1; } else launch_bond_attn_pos(bp, sms, s); }
     b->launches += 3;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), w2_smem = smem_u32(sm.W2);
-  const int n_tiles = (a.n_lig + 3) / 4;
+  const int n_tiles = (a.n_vg + 3) / 4;
 
   if (warp >= 16) {
 #ifndef DDB_NO_SETMAXNREG
@@ -107,26 +107,46 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
     float* const wqry = sm.qry + warp * 64;
     const int step = gridDim.x;
     int it = 0;
-    // group = ligand atom: {first CSR slot, number of incoming edges}; row = {source atom, edge id}
+    // group = (chunk of) the edges entering a ligand atom: {atom (-1: none), first CSR slot, rows, partner chunk or -1};
+    // row = {source atom, edge id}
     auto load_group = [&](int tile) {
-      const int at = tile * 4 + q;
-      int2 g = make_int2(0, 0);
-      if (tile < n_tiles && at < a.n_lig) { const int s0 = __ldg(a.in_ptr + at); g = make_int2(s0, __ldg(a.in_ptr + at + 1) - s0); }
+      const int v = tile * 4 + q;
+      int4 g = make_int4(-1, 0, 0, -1);
+      if (tile < n_tiles && v < a.n_vg) g = __ldg(a.vg + v);
       return g;
     };
-    auto load_row = [&](int2 g) {
+    auto load_row = [&](int4 g) {
       int2 rw = make_int2(0, 0);
-      if (lane < g.y) rw = make_int2(__ldg(a.in_src + g.x + lane), __ldg(a.in_eid + g.x + lane));
+      if (lane < g.z) rw = make_int2(__ldg(a.in_src + g.y + lane), __ldg(a.in_eid + g.y + lane));
       return rw;
     };
-    int2 g = load_group(blockIdx.x), rw = load_row(g);
-    int2 g_n = load_group(blockIdx.x + step);
-    int prev_at = -1, prev_slot0 = 0; bool prev_ok = false;
+    // softmax over the rows of the previous group for heads 4s..4s+3 -> wbuf; chunked groups also record {max, sum of exp}
+    auto finish_k = [&](const float (&lg)[4], bool ok, int slot0, int vgi, int pair) {
+      float ex[4], mx[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx[hh]) : "f"(lg[hh]));
+        ex[hh] = ok ? __expf(lg[hh] - mx[hh]) : 0.f;
+      }
+      float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
+      warp_allreduce4(sum, lane);
+      float w[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? __fdividef(ex[hh], sum[hh]) : 0.f;
+      if (ok) st4(a.wbuf + ((size_t)slot0 + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
+      if (pair >= 0 && lane < 4)
+        a.stats[(size_t)vgi * NH + s * 4 + lane] = make_float2(lane == 0 ? mx[0] : lane == 1 ? mx[1] : lane == 2 ? mx[2] : mx[3],
+                                                               lane == 0 ? sum[0] : lane == 1 ? sum[1] : lane == 2 ? sum[2] : sum[3]);
+    };
+    int4 g = load_group(blockIdx.x);
+    int2 rw = load_row(g);
+    int4 g_n = load_group(blockIdx.x + step);
+    int prev_at = -1, prev_slot0 = 0, prev_vg = 0, prev_pair = -1; bool prev_ok = false;
     float4 prev_rel = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tile = blockIdx.x; tile < n_tiles; tile += step, ++it) {
-      const int at = tile * 4 + q;
-      const bool gvalid = at < a.n_lig;
-      const bool rowok = lane < g.y;
+      const int at = g.x;
+      const bool gvalid = at >= 0;
+      const bool rowok = lane < g.z;
       const int atc = gvalid ? at : 0;
       // ---- gathers of this tile (small launch: no cross-tile prefetch of rows), metadata of the next one
       float4 pj[8], pe[8];
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
         rel = make_float4(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z, 0.f);
       }
       const int2 rw_n = load_row(g_n);
-      const int2 g_nn = load_group(tile + 2 * step);
+      const int4 g_nn = load_group(tile + 2 * step);
       whit[lane] = hi;
       if (PASS == BT_K) wqry[(it & 1) * 32 + lane] = qry_v;
       __syncwarp();
@@ -193,10 +213,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
       float val[32];
       float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
       float4 wpos[4];
-      if (PASS == BT_V_NODE && it > 0 && prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + s * 4);
+      if (PASS == BT_V_NODE && it > 0 && prev_ok) {
+        w4 = ld4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + s * 4);
+        if (prev_pair >= 0) w4 = mul4(w4, ld4(a.factor + (size_t)prev_vg * NH + s * 4));      // chunk -> whole-group softmax
+      }
       if (PASS == BT_V_POS && it > 0 && s == 0) {
 #pragma unroll
-        for (int h4 = 0; h4 < 4; ++h4) wpos[h4] = prev_ok ? ld4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + h4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int h4 = 0; h4 < 4; ++h4) {
+          wpos[h4] = prev_ok ? ld4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + h4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (prev_pair >= 0) wpos[h4] = mul4(wpos[h4], ld4(a.factor + (size_t)prev_vg * NH + h4 * 4));
+        }
       }
       float cpos = 0.f;
       if (it > 0) {
@@ -266,31 +292,26 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
       // ---- finish the epilogue of the previous tile
       if (it > 0) {
         if (PASS == BT_K) {
-          float ex[4];
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
-            float m;
-            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(lg[hh]));
-            ex[hh] = prev_ok ? __expf(lg[hh] - m) : 0.f;
-          }
-          float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
-          warp_allreduce4(sum, lane);
-          float w[4];
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? __fdividef(ex[hh], sum[hh]) : 0.f;
-          if (prev_ok) st4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
+          finish_k(lg, prev_ok, prev_slot0, prev_vg, prev_pair);
         } else if (PASS == BT_V_NODE) {
           float ws[4] = {w4.x, w4.y, w4.z, w4.w};
           warp_allreduce4(ws, lane);
           warp_reduce_scatter<32>(val, lane);
           if (prev_at >= 0) {
             const int c = s * 32 + lane;
-            float* dst = a.out_h + (size_t)__ldg(a.lig_idx + prev_at) * a.ldo + c;
-            *dst = *dst + (val[0] + sm.b2[c] * ws[lane >> 3]);
+            const float res = val[0] + sm.b2[c] * ws[lane >> 3];
+            if (prev_pair >= 0) {
+              a.part_h[(size_t)prev_vg * H + c] = res;           // chunked atom: launch_bond_combine adds the two chunks
+            } else {
+              float* dst = a.out_h + (size_t)__ldg(a.lig_idx + prev_at) * a.ldo + c;
+              *dst = *dst + res;
+            }
           }
         } else if (s == 0) {
           float ax = warp_sum(cpos * prev_rel.x), ay = warp_sum(cpos * prev_rel.y), az = warp_sum(cpos * prev_rel.z);
-          if (lane == 0 && prev_at >= 0) {
+          if (lane == 0 && prev_at >= 0 && prev_pair >= 0) {
+            st4(a.part_dx + (size_t)prev_vg * 4, make_float4(ax * (1.f / NH), ay * (1.f / NH), az * (1.f / NH), 0.f));
+          } else if (lane == 0 && prev_at >= 0) {
             const int node = __ldg(a.lig_idx + prev_at);
             float4 xi = ldg4(a.x4 + (size_t)node * 4);
             const float4 de = a.dx_edge ? ld4(a.dx_edge + (size_t)prev_at * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -302,7 +323,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
           }
         }
       }
-      prev_at = gvalid ? at : -1; prev_slot0 = g.x; prev_ok = rowok; prev_rel = rel;
+      prev_at = gvalid ? at : -1; prev_slot0 = g.y; prev_ok = rowok; prev_rel = rel; prev_vg = tile * 4 + q; prev_pair = g.w;
       g = g_n; g_n = g_nn; rw = rw_n;
     }
     // ---- epilogue of the last tile (same code path: one more drain without a new A)
@@ -310,17 +331,36 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
       mbar_wait(bar_mma, (it - 1) & 1);
       tc_fence_after();
       if (PASS == BT_K) {
-        float4 w4 = atc_logits_softmax(tmem_base, q, s, wqry + ((it - 1) & 1) * 32 - s * 32, prev_ok);
-        if (prev_ok) st4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + s * 4, w4);
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float* qr = wqry + ((it - 1) & 1) * 32;
+        float lg[4];
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          float acc = 0.f;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) acc = fmaf(qr[hh * 8 + d], __uint_as_float(v[hh * 8 + d]), acc);
+          lg[hh] = prev_ok ? acc : -INFINITY;
+        }
+        finish_k(lg, prev_ok, prev_slot0, prev_vg, prev_pair);
       } else if (PASS == BT_V_NODE) {
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + s * 4);
+        if (prev_ok) {
+          w4 = ld4(a.wbuf + ((size_t)prev_slot0 + lane) * NH + s * 4);
+          if (prev_pair >= 0) w4 = mul4(w4, ld4(a.factor + (size_t)prev_vg * NH + s * 4));
+        }
         float tot = atc_weighted_colsum(tmem_base, q, s, lane, w4);
         float4 ws = make_float4(warp_sum(w4.x), warp_sum(w4.y), warp_sum(w4.z), warp_sum(w4.w));
         if (prev_at >= 0) {
           const int c = s * 32 + lane;
-          float* dst = a.out_h + (size_t)__ldg(a.lig_idx + prev_at) * a.ldo + c;
-          *dst = *dst + (tot + sm.b2[c] * sel4(ws, lane >> 3));
+          const float res = tot + sm.b2[c] * sel4(ws, lane >> 3);
+          if (prev_pair >= 0) {
+            a.part_h[(size_t)prev_vg * H + c] = res;
+          } else {
+            float* dst = a.out_h + (size_t)__ldg(a.lig_idx + prev_at) * a.ldo + c;
+            *dst = *dst + res;
+          }
         }
       } else if (s == 0) {
         uint32_t v[16];
@@ -332,10 +372,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
         float cpos = 0.f;
         if (prev_ok) {
 #pragma unroll
-          for (int h = 0; h < 16; ++h) cpos = fmaf(__ldg(a.wbuf + ((size_t)prev_slot0 + lane) * NH + h), __uint_as_float(v[h]) + sm.b2[h], cpos);
+          for (int h = 0; h < 16; ++h) {
+            float wv = __ldg(a.wbuf + ((size_t)prev_slot0 + lane) * NH + h);
+            if (prev_pair >= 0) wv *= __ldg(a.factor + (size_t)prev_vg * NH + h);
+            cpos = fmaf(wv, __uint_as_float(v[h]) + sm.b2[h], cpos);
+          }
         }
         float ax = warp_sum(cpos * prev_rel.x), ay = warp_sum(cpos * prev_rel.y), az = warp_sum(cpos * prev_rel.z);
-        if (lane == 0 && prev_at >= 0) {
+        if (lane == 0 && prev_at >= 0 && prev_pair >= 0) {
+          st4(a.part_dx + (size_t)prev_vg * 4, make_float4(ax * (1.f / NH), ay * (1.f / NH), az * (1.f / NH), 0.f));
+        } else if (lane == 0 && prev_at >= 0) {
           const int node = __ldg(a.lig_idx + prev_at);
           float4 xi = ldg4(a.x4 + (size_t)node * 4);
           const float4 de = a.dx_edge ? ld4(a.dx_edge + (size_t)prev_at * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -358,16 +404,19 @@ static void launch_bond_tc_pass(const BondAttnArgs& a, int num_sms, cudaStream_t
   static DeviceOnce once;
   const int bytes = BondTcSmem::bytes();
   if (!once.done()) { cudaFuncSetAttribute(bond_tc_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
-  const int grid = atc_grid((a.n_lig + 3) / 4, num_sms);
+  const int grid = atc_grid((a.n_vg + 3) / 4, num_sms);
   bond_tc_kernel<PASS><<<grid, BT_THREADS, bytes, stream>>>(a);
 }
 
 // node variant: key pass then value pass; position variant: key pass then the 16-output value pass + x update
 void launch_bond_tc(const BondAttnArgs& a, bool pos, int num_sms, cudaStream_t stream) {
-  if (a.n_lig <= 0) return;
+  if (a.n_lig <= 0 || a.n_vg <= 0) return;
   launch_bond_tc_pass<BT_K>(a, num_sms, stream);
+  const bool chunked = a.n_vg > a.n_lig;      // some atom has more than 32 incoming edges
+  if (chunked) launch_chunk_factors(a.stats, reinterpret_cast<const int*>(a.vg) + 3, 4, a.n_vg, const_cast<float*>(a.factor), stream);
   if (pos) launch_bond_tc_pass<BT_V_POS>(a, num_sms, stream);
   else launch_bond_tc_pass<BT_V_NODE>(a, num_sms, stream);
+  if (chunked) launch_bond_combine(a, pos, stream);
 }
 
 // host-side packing of the position value MLP's second Linear W2[16 out][128 in] into the hi | lo swizzled image (N = 16)

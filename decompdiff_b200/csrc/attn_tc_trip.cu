@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
   // Work distribution: the groups (bond edges j->i) are visited in SOURCE-major order (a.grp_order) and every (CTA, quadrant)
   // pair walks one contiguous chunk of that order.  All groups with the same source j read the same rows P'[k->j], so a thread
   // keeps its row slice in registers and gathers again only when j changes (once per ~n_lig groups).
-  const int per = (a.n_bonds + 4 * (int)gridDim.x - 1) / (4 * (int)gridDim.x);      // iterations of every CTA
+  const int per = (a.n_groups + 4 * (int)gridDim.x - 1) / (4 * (int)gridDim.x);      // iterations of every CTA
 
   if (warp >= 16) {
     // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     };
     // metadata of a tile: clamped so that every load below is unconditional (padding rows read edge 0 / node 0; their
     // results are never stored and they get zero attention weight)
-    const int g_begin = ((int)blockIdx.x * 4 + q) * per, g_end = min(a.n_bonds, g_begin + per);
+    const int g_begin = ((int)blockIdx.x * 4 + q) * per, g_end = min(a.n_groups, g_begin + per);
     auto load_meta = [&](int i, int& e, int2& gm, int2& rm) {      // metadata is stored in visiting order: three independent loads
       e = -1; gm = make_int2(0, 0); rm = make_int2(-1, -1);
       const int pos = g_begin + i;
@@ -199,8 +199,26 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     const float* __restrict__ Pc = side.P;          // centred rows (trip_prep): LayerNorm is shift invariant
     const float* __restrict__ Qc = side.Q;
 
+    // softmax over the 32 rows of the previous group for heads 4s..4s+3 -> wbuf; chunked groups also record {max, sum of exp}
+    auto finish_k = [&](const float (&lg)[4], bool ok, int pe, int tb, int pair) {
+      float ex[4], mx[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx[hh]) : "f"(lg[hh]));
+        ex[hh] = ok ? __expf(lg[hh] - mx[hh]) : 0.f;
+      }
+      float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
+      warp_allreduce4(sum, lane);
+      float w[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? __fdividef(ex[hh], sum[hh]) : 0.f;
+      if (pe >= 0) st4(a.wbuf + ((size_t)tb + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
+      if (pe >= 0 && pair >= 0 && lane < 4)
+        a.stats[(size_t)(tb >> 5) * NH + s * 4 + lane] = make_float2(lane == 0 ? mx[0] : lane == 1 ? mx[1] : lane == 2 ? mx[2] : mx[3],
+                                                                     lane == 0 ? sum[0] : lane == 1 ? sum[1] : lane == 2 ? sum[2] : sum[3]);
+    };
     int it = 0;
-    int prev_e = -1, prev_tb = 0; bool prev_ok = false; int prev_nvalid = 0;
+    int prev_e = -1, prev_tb = 0, prev_pair = -1; bool prev_ok = false; int prev_nvalid = 0;
     int2 gm, rm, gm_n, rm_n;
     int e, e_n;
     load_meta(0, e, gm, rm);
@@ -228,7 +246,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       int e_nn;
       load_meta(it + 2, e_nn, gm_nn, rm_nn);
       request_xyz(gm_n, rm_n);
-      const int tb = __ldg(a.trip_base + max(e, 0));
+      const int tb = (g_begin + it) * 32;      // wbuf rows of a (group, chunk) are its 32 slots in visiting order
+      const int pair = e >= 0 ? __ldg(a.vg_pair + g_begin + it) : -1;
       // ---- first Linear: z = P'[kj] (in registers) + Q'[ji] (staged) + D2 (angular MMA, issued one iteration ago)
       float2 z[16];
       {
@@ -299,7 +318,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
       float hb_in = 0.f;
       if (VPASS && it > 0) {      // requested before the wait on the tensor core: attention weights of this thread's row, residual input
-        if (prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
+        if (prev_ok) {
+          w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
+          if (prev_pair >= 0) w4 = mul4(w4, ld4(a.factor + (size_t)(prev_tb >> 5) * NH + s * 4));      // chunk -> whole-group softmax
+        }
         if (prev_e >= 0) hb_in = __ldg(a.h_bond_in + (size_t)prev_e * H + s * 32 + lane);
       }
       TL_MARK(6);
@@ -357,29 +379,21 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       if (it > 0) {
         if (!VPASS) {
           // softmax over the 32 rows of the group, 4 heads at once: max by one REDUX each, sums by a transposed all-reduce
-          float ex[4];
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
-            float m;
-            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(lg[hh]));
-            ex[hh] = prev_ok ? __expf(lg[hh] - m) : 0.f;
-          }
-          float sum[4] = {ex[0], ex[1], ex[2], ex[3]};
-          warp_allreduce4(sum, lane);
-          float w[4];
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? __fdividef(ex[hh], sum[hh]) : 0.f;
-          if (prev_e >= 0) st4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
+          finish_k(lg, prev_ok, prev_e, prev_tb, prev_pair);
         } else {
           warp_reduce_scatter<32>(val, lane);
           if (prev_e >= 0) {
             const int c = s * 32 + lane;
-            const float upd = prev_nvalid > 0 ? val[0] + sm.b2[c] : 0.f;
-            a.h_bond_out[(size_t)prev_e * H + c] = hb_in + upd;      // :274
+            if (prev_pair >= 0) {
+              a.part[(size_t)(prev_tb >> 5) * H + c] = val[0];      // chunked group: launch_trip_combine finishes the edge
+            } else {
+              const float upd = prev_nvalid > 0 ? val[0] + sm.b2[c] : 0.f;
+              a.h_bond_out[(size_t)prev_e * H + c] = hb_in + upd;      // :274
+            }
           }
         }
       }
-      prev_e = e; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok)); prev_tb = tb;
+      prev_e = e; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok)); prev_tb = tb; prev_pair = pair;
       e = e_n; gm = gm_n; rm = rm_n; e_n = e_nn; gm_n = gm_nn; rm_n = rm_nn;
       TL_MARK(10);
     }
@@ -389,16 +403,34 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
       mbar_wait(bar_mma, (it - 1) & 1);
       tc_fence_after();
       if (!VPASS) {
-        float4 w4 = atc_logits_softmax(tmem_base, q, s, wqry + ((it - 1) & 3) * 32 - s * 32, prev_ok);
-        if (prev_e >= 0) st4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4, w4);
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float* qr = wqry + ((it - 1) & 3) * 32;
+        float lg[4];
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          float acc = 0.f;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) acc = fmaf(qr[hh * 8 + d], __uint_as_float(v[hh * 8 + d]), acc);
+          lg[hh] = prev_ok ? acc : -INFINITY;
+        }
+        finish_k(lg, prev_ok, prev_e, prev_tb, prev_pair);
       } else {
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
+        if (prev_ok) {
+          w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
+          if (prev_pair >= 0) w4 = mul4(w4, ld4(a.factor + (size_t)(prev_tb >> 5) * NH + s * 4));
+        }
         float tot = atc_weighted_colsum(tmem_base, q, s, lane, w4);
         if (prev_e >= 0) {
           const int c = s * 32 + lane;
-          float upd = prev_nvalid > 0 ? tot + sm.b2[c] : 0.f;
-          a.h_bond_out[(size_t)prev_e * H + c] = a.h_bond_in[(size_t)prev_e * H + c] + upd;
+          if (prev_pair >= 0) {
+            a.part[(size_t)(prev_tb >> 5) * H + c] = tot;
+          } else {
+            float upd = prev_nvalid > 0 ? tot + sm.b2[c] : 0.f;
+            a.h_bond_out[(size_t)prev_e * H + c] = a.h_bond_in[(size_t)prev_e * H + c] + upd;
+          }
         }
       }
     }
@@ -409,7 +441,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
 }
 
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream) {
-  if (a.n_bonds <= 0) return;
+  if (a.n_bonds <= 0 || a.n_groups <= 0) return;
   static DeviceOnce once;
   const int bytes = TripTcSmem::bytes();
   if (!once.done()) {
@@ -417,7 +449,7 @@ void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t str
     cudaFuncSetAttribute(trip_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     once.mark();
   }
-  const int grid = atc_grid((a.n_bonds + 3) / 4, num_sms);
+  const int grid = atc_grid((a.n_groups + 3) / 4, num_sms);
   if (vpass) trip_tc_kernel<true><<<grid, TT_THREADS, bytes, stream>>>(a);
   else trip_tc_kernel<false><<<grid, TT_THREADS, bytes, stream>>>(a);
 }

@@ -103,7 +103,20 @@ struct BondAttnArgs {
   const float* dx_edge = nullptr;               // (n_lig,4) contribution of the kNN pos layer
   const uint8_t* upd_mask = nullptr;            // (n_lig) 1 = position is updated
   float* x4_out = nullptr;                      // (N,4) next-layer positions (ligand rows written)
+  // Softmax groups of more than 32 rows (ligands of 34..65 atoms) are split into two CHUNKS of <= 32 rows, each handled like a
+  // group of its own (tensor-core kernels only).  vg[i] = {ligand atom, first CSR slot, rows, partner chunk or -1}; the key pass
+  // also writes the chunk's softmax statistics {max logit, sum of exp} per head, launch_chunk_factors turns the two chunks'
+  // statistics into the factor that rescales a chunk's weights to the softmax over the whole group, the value passes apply it and
+  // write per-chunk partial results which launch_bond_combine adds up in a fixed order (deterministic).
+  const int4* vg = nullptr; int n_vg = 0;
+  float2* stats = nullptr;                      // (n_vg,16)
+  const float* factor = nullptr;                // (n_vg,16)
+  float* part_h = nullptr;                      // (n_vg,128) node variant partial sums (chunked atoms only)
+  float* part_dx = nullptr;                     // (n_vg,4)   position variant partial sums
 };
+void launch_chunk_factors(const float2* stats, const int* pair /* stride in ints between entries */, int pair_stride, int n_vg, float* factor,
+                          cudaStream_t stream);
+void launch_bond_combine(const BondAttnArgs& a, bool pos, cudaStream_t stream);
 void launch_bond_attn_node(const BondAttnArgs& a, int num_sms, cudaStream_t stream);
 void launch_bond_attn_pos(const BondAttnArgs& a, int num_sms, cudaStream_t stream);
 
@@ -148,7 +161,11 @@ struct TripArgs {
   // deg(j) | excluded row slot << 8 (32: none); csr_slot[e] = CSR row of edge e; xcsr = position of the source atom of every CSR
   // row (written by trip_prep every layer)
   const int4* grp4 = nullptr; const int* grp_pk = nullptr; const int* csr_slot = nullptr; float* xcsr = nullptr;
+  // chunked groups (see BondAttnArgs): n_groups = number of (edge, chunk) pairs in visiting order (= n_bonds when every atom has
+  // <= 32 incoming edges); vg_pair[pos] = position of the partner chunk or -1
+  int n_groups = 0; const int* vg_pair = nullptr; float2* stats = nullptr; const float* factor = nullptr; float* part = nullptr;
 };
+void launch_trip_combine(const TripArgs& a, const float* b2, cudaStream_t stream);
 void launch_trip_prep(const TripArgs& a, cudaStream_t stream);
 void launch_trip_k(const TripArgs& a, int num_sms, cudaStream_t stream);
 void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
