@@ -58,6 +58,7 @@ struct ddb_model {
   std::map<std::string, std::vector<float>> host;
   bool finalized = false;
   bool refine_only = false;      // only the refine_net.* tensors are required (stand-alone refine-net seam)
+  float r_max = 0.f;             // > 0: cutoff_mode 'radius' (ddb_model_set_cutoff)
   Blob blob;
   float* dev = nullptr;
   std::vector<LayerOff> layers;
@@ -225,6 +226,13 @@ extern "C" int ddb_model_set_refine_only(ddb_model* m, int32_t on) {
   return DDB_OK;
 }
 
+extern "C" int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max) {
+  if (!m) return fail(DDB_ERR_INVALID, "null model");
+  if (mode == 0) { m->r_max = 0.f; return DDB_OK; }
+  if (mode == 1 && r_max > 0.f) { m->r_max = r_max; return DDB_OK; }
+  return fail(DDB_ERR_INVALID, "Not supported cutoff mode");      // uni_transformer_edge.py:358
+}
+
 extern "C" void ddb_model_destroy(ddb_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
@@ -367,6 +375,8 @@ struct ddb_batch {
   int *level = nullptr, *lvl_hist = nullptr, *lvl_counts = nullptr, *dst_lvl = nullptr;
   // first-layer cache (launch_layer0_keys): layer 0 writes hC / reads PN0, both untouched by the other layers
   bool l0cache = false, pn0_ready = false;
+  // static protein neighbour cache (graph.cu: knn_merge_kernel): sorted keys of every protein node's k nearest protein atoms
+  bool knn_cache = false, knn_static_ready = false; unsigned long long* skeys = nullptr; int* sdeg = nullptr;
   float *hC = nullptr, *PN0 = nullptr; uint8_t* valid0 = nullptr;
   int *key0 = nullptr, *cnt0 = nullptr, *counts0 = nullptr, *dst_lvl0 = nullptr; int2* slot_meta_lvl0 = nullptr;
   float* ew_table = nullptr; long long* ew_table_base = nullptr; int* n_protein_of = nullptr;     // EdgeWeightCache   // destinations by class (protein first), padded to tiles of 4
@@ -690,10 +700,20 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
   DDB_TRY(b->dalloc(&b->wb_trip, (size_t)slots * NH));
   DDB_TRY(b->dalloc(&b->e_w, n * KNN)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4)); DDB_TRY(b->dalloc(&b->dist, n * KNN));
   DDB_TRY(b->dalloc(&b->nbr, n * KNN)); DDB_TRY(b->dalloc(&b->deg, n)); DDB_TRY(b->dalloc(&b->nlig, n));
+  {
+    int max_lig = 0;
+    for (int g = 0; g < B; ++g) max_lig = std::max(max_lig, cnt_l[g]);
+    b->knn_cache = !refine && max_lig <= 64 && NP > 0 && !getenv("DDB_NO_KNN_CACHE");
+    if (b->knn_cache) { DDB_TRY(b->dalloc(&b->skeys, n * KNN)); DDB_TRY(b->dalloc(&b->sdeg, n)); }
+  }
   DDB_TRY(b->dalloc(&b->hid_v, nl * H)); DDB_TRY(b->dalloc(&b->v_logits, nl * c.num_classes));
   DDB_TRY(b->dalloc(&b->b_logits, eb * c.num_bond_classes)); DDB_TRY(b->dalloc(&b->x0, nl * 3));
   DDB_TRY(b->dalloc(&b->grad, nl * 3)); DDB_TRY(b->dalloc(&b->v_logits0, nl * c.num_classes));
   cudaMemset(b->nbr, 0, n * KNN * sizeof(int));
+  cudaMemset(b->deg, 0, n * sizeof(int)); cudaMemset(b->nlig, 0, n * sizeof(int));
+  // padding slots of the destination lists keep {-1, 0} for good (launch_graph_lists rewrites the live entries every step)
+  launch_knn_slot_meta(b->dst_lvl, b->lig_block + NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl, 0);
+  if (b->l0cache) launch_knn_slot_meta(b->dst_lvl0, b->lig_block + NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl0, 0);
   // the fills above ran on the legacy default stream; the kernels of this batch run on the caller's (possibly non-blocking)
   // stream, so order them once here
   { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) { ddb_batch_destroy(b); return fail(DDB_ERR_CUDA, std::string("batch create: ") + cudaGetErrorString(e)); } }
@@ -859,27 +879,52 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   auto fork_side = [&]() { if (fork) { cudaEventRecord(b->ev_fork, s); cudaStreamWaitEvent(sb, b->ev_fork, 0); } };
   auto join_side = [&](cudaEvent_t e) { if (fork) cudaStreamWaitEvent(s, e, 0); };
   fork_side();
-  { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s); }
+  if (b->knn_cache) {
+    // protein atoms never move during a run: their k nearest PROTEIN neighbours are computed once (sorted keys); per step the ligand
+    // nodes are searched brute force and every protein node only ranks the graph's ligand atoms against its cached list
+    ProfScope ps(b, s, PC_KNN_GRAPH);
+    if (!b->knn_static_ready) {
+      launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->sdeg, b->nlig, s, m->r_max, nullptr,
+                 b->n_protein_of, b->skeys);
+      b->launches++;
+    }
+    launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, NL, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s, m->r_max, b->lig_idx);
+    launch_knn_merge(b->x4_0, b->node_ptr, b->graph_of, b->n_protein_of, b->is_lig, N, c.knn, m->r_max, b->skeys, b->sdeg, b->nbr, b->deg, b->nlig, s);
+    b->launches += 2;
+  } else {
+    ProfScope ps(b, s, PC_KNN_GRAPH);
+    launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s, m->r_max);
+    b->launches++;
+  }
   EdgeWeightCache ewc;
   ewc.table = b->ew_table; ewc.table_base = b->ew_table_base; ewc.n_protein = b->n_protein_of; ewc.node_ptr = b->node_ptr; ewc.graph_of = b->graph_of;
   { ProfScope ps(b, s, PC_EDGE_WEIGHT); launch_edge_weight(b->x4_0, b->nbr, b->deg, N, m->p(m->ew_W1t), m->p(m->ew_b1), m->p(m->ew_gamma), m->p(m->ew_beta),
                      m->p(m->ew_w2), m->ew_b2, b->e_w, ewc, s); }
-  b->launches += 5;
+  b->launches++;
   if (b->tc_attn & 12) {
     ProfScope ps(b, s, PC_KNN_GRAPH);
-    launch_knn_slot_meta(b->dst_sorted, b->n_slots_all, b->deg, b->nlig, b->is_lig, b->slot_meta_all, s);
-    launch_knn_slot_meta(b->lig_idx, NL, b->deg, b->nlig, b->is_lig, b->slot_meta_lig, s);
-    b->launches += 2;
-    if (b->prune) {
-      launch_receptive_field(b->nbr, b->deg, b->is_lig, b->node_ptr, b->n_protein_of, b->B, N, c.num_layers, b->lig_block, b->level, b->lvl_hist,
-                             b->lvl_counts, b->dst_lvl, s);
-      launch_knn_slot_meta(b->dst_lvl, b->lig_block + b->NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl, s);
-      b->launches += 11;
-      if (b->l0cache) {
-        launch_layer0_keys(b->level, b->nlig, b->is_lig, N, c.num_layers, b->valid0, b->key0, s);
-        launch_level_sort(b->key0, b->node_ptr, b->n_protein_of, b->B, c.num_layers, b->lig_block, b->cnt0, b->counts0, b->dst_lvl0, s);
-        launch_knn_slot_meta(b->dst_lvl0, b->lig_block + b->NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl0, s);
-        b->launches += 5;
+    bool merged = false;
+    if (b->prune && !getenv("DDB_OLD_LISTS")) {
+      merged = launch_graph_lists(b->nbr, b->deg, b->nlig, b->is_lig, b->node_ptr, b->n_protein_of, b->lig_ptr, b->lig_idx, b->B, b->max_graph_nodes,
+                                  c.num_layers, b->lig_block, b->l0cache, b->valid0, b->level, b->key0, b->lvl_hist, b->cnt0, b->lvl_counts,
+                                  b->counts0, b->dst_lvl, b->dst_lvl0, b->slot_meta_lvl, b->slot_meta_lvl0, b->slot_meta_lig, s);
+      if (merged) b->launches += 2;
+    }
+    if (!merged) {
+      launch_knn_slot_meta(b->dst_sorted, b->n_slots_all, b->deg, b->nlig, b->is_lig, b->slot_meta_all, s);
+      launch_knn_slot_meta(b->lig_idx, NL, b->deg, b->nlig, b->is_lig, b->slot_meta_lig, s);
+      b->launches += 2;
+      if (b->prune) {
+        launch_receptive_field(b->nbr, b->deg, b->is_lig, b->node_ptr, b->n_protein_of, b->B, N, c.num_layers, b->lig_block, b->level, b->lvl_hist,
+                               b->lvl_counts, b->dst_lvl, s);
+        launch_knn_slot_meta(b->dst_lvl, b->lig_block + b->NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl, s);
+        b->launches += 11;
+        if (b->l0cache) {
+          launch_layer0_keys(b->level, b->nlig, b->is_lig, N, c.num_layers, b->valid0, b->key0, s);
+          launch_level_sort(b->key0, b->node_ptr, b->n_protein_of, b->B, c.num_layers, b->lig_block, b->cnt0, b->counts0, b->dst_lvl0, s);
+          launch_knn_slot_meta(b->dst_lvl0, b->lig_block + b->NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl0, s);
+          b->launches += 5;
+        }
       }
     }
   }
@@ -1009,7 +1054,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     if (b->tap_hb && Eb > 0) cudaMemcpyAsync(b->tap_hb + (size_t)l * Eb * H, hb_out, (size_t)Eb * H * sizeof(float), cudaMemcpyDeviceToDevice, s);
   }
   b->h_fin = h_in; b->x_fin = x_in; b->hb_fin = hb_in;
-  b->pn0_ready = true;
+  b->pn0_ready = true; b->knn_static_ready = true;
   if (b->refine) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(DDB_ERR_CUDA, std::string("refine forward launch: ") + cudaGetErrorString(e));

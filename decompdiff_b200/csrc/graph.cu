@@ -35,15 +35,20 @@ __device__ __forceinline__ unsigned long long knn_key(float4 xi, const float* __
 template <int MAXT>
 __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, const int* __restrict__ node_ptr,
                                                   const int* __restrict__ graph_of, const uint8_t* __restrict__ is_lig,
-                                                  int n, int k, int* __restrict__ nbr, int* __restrict__ deg_out,
-                                                  int* __restrict__ nlig_out) {
+                                                  int n, int k, float r2max, int* __restrict__ nbr, int* __restrict__ deg_out,
+                                                  int* __restrict__ nlig_out, const int* __restrict__ node_list,
+                                                  const int* __restrict__ n_protein, unsigned long long* __restrict__ skeys) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n) return;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= n) return;
+  const int i = node_list ? node_list[w] : w;      // optional list of query nodes (ligand atoms when the protein part is cached)
   const int g = graph_of[i];
-  const int s = node_ptr[g], e = node_ptr[g + 1];
+  const int s = node_ptr[g];
+  // static mode (skeys != null): candidates are the graph's PROTEIN atoms only, the sorted keys are the output
+  const int e = skeys ? s + n_protein[g] : node_ptr[g + 1];
+  if (skeys && i >= e) return;                     // ligand node: no static list
   const float4 xi = ldg4(x4 + (size_t)i * 4);
-  const int deg = min(k, e - s - 1);
+  int deg = min(k, e - s - 1);
 
   unsigned long long keys[MAXT > 0 ? MAXT : 1];
   if (MAXT > 0) {
@@ -72,10 +77,14 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, 
       }
     }
     best = warp_min_u64(best);
+    // 'radius' cut-off: neighbours come nearest first, so the first one beyond r_max ends the list (warp-uniform)
+    if (__uint_as_float((unsigned)(best >> 32)) > r2max) { deg = r; break; }
     last = best;
     first = false;
     if (lane == r) mine = (int)(best & 0xffffffffu);
+    if (skeys && lane == r) skeys[(size_t)i * KNN + r] = best;
   }
+  if (skeys) { if (lane == 0) deg_out[i] = deg; return; }
   // stable partition: ligand sources first (so the attention kernels see type-uniform runs)
   const bool has = lane < deg;
   const bool lig = has && is_lig[mine];
@@ -90,14 +99,74 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, 
 }
 
 void launch_knn(const float* x4, const int* node_ptr, const int* graph_of, const uint8_t* is_lig, int n, int k,
-                int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream) {
+                int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream, float r_max, const int* node_list,
+                const int* n_protein, unsigned long long* skeys) {
+  const float r2max = r_max > 0.f ? r_max * r_max : INFINITY;
   if (n <= 0) return;
   const int wpb = 8;
   dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
-  if (max_graph_nodes <= 32 * 16) knn_kernel<16><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
-  else if (max_graph_nodes <= 32 * 32) knn_kernel<32><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
-  else if (max_graph_nodes <= 32 * 64) knn_kernel<64><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
-  else knn_kernel<0><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, nbr, deg, nlig);
+  if (max_graph_nodes <= 32 * 16) knn_kernel<16><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
+  else if (max_graph_nodes <= 32 * 32) knn_kernel<32><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
+  else if (max_graph_nodes <= 32 * 64) knn_kernel<64><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
+  else knn_kernel<0><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
+}
+
+// Protein destinations with the cached static part (launch_knn with skeys, once per run: protein atoms never move): the k nearest
+// PROTEIN neighbours are known and sorted, so per step only the graph's <= 64 ligand atoms have to be ranked against them.  Ranks
+// are counted, not sorted: a key's rank in the union is the number of smaller keys; keys are unique ((d^2 bits, index) as in
+// knn_kernel), so the selected set, its order and the tie rule are exactly those of the brute-force kernel.
+__global__ void __launch_bounds__(256) knn_merge_kernel(const float* __restrict__ x4, const int* __restrict__ node_ptr,
+                                                        const int* __restrict__ graph_of, const int* __restrict__ n_protein,
+                                                        const uint8_t* __restrict__ is_lig, int n, int k, float r2max,
+                                                        const unsigned long long* __restrict__ skeys, const int* __restrict__ sdeg,
+                                                        int* __restrict__ nbr, int* __restrict__ deg_out, int* __restrict__ nlig_out) {
+  __shared__ unsigned long long sh[8][96];                 // per warp: 32 static keys | up to 64 ligand keys
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int i = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (i >= n || is_lig[i]) return;
+  const int g = graph_of[i];
+  const int s = node_ptr[g], e = node_ptr[g + 1], l0 = s + n_protein[g], nl = e - l0;
+  const float4 xi = ldg4(x4 + (size_t)i * 4);
+  unsigned long long* my = sh[wib];
+  const unsigned long long sk = lane < sdeg[i] ? skeys[(size_t)i * KNN + lane] : ~0ull;
+  unsigned long long lk[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int j = l0 + c * 32 + lane;
+    lk[c] = j < e ? knn_key(xi, x4, j, i) : ~0ull;
+    if (__uint_as_float((unsigned)(lk[c] >> 32)) > r2max) lk[c] = ~0ull;
+    my[32 + c * 32 + lane] = lk[c];
+  }
+  my[lane] = sk;
+  __syncwarp();
+  const int nlk = nl > 32 ? 64 : 32;
+  int below_s = 0;                                         // ligand keys smaller than this lane's static key
+  for (int j = 0; j < nlk; ++j) below_s += my[32 + j] < sk;
+  int rank[2], lrank[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    int rs = 0, rl = 0;
+    if (c * 32 < nlk) {
+      for (int j = 0; j < 32; ++j) rs += my[j] < lk[c];
+      for (int j = 0; j < nlk; ++j) rl += my[32 + j] < lk[c];
+    }
+    lrank[c] = rl; rank[c] = rs + rl;
+  }
+  const bool sel_s = sk != ~0ull && lane + below_s < k;
+  const bool sel0 = lk[0] != ~0ull && rank[0] < k, sel1 = lk[1] != ~0ull && rank[1] < k;
+  const int nlig = __popc(__ballot_sync(FULL, sel0)) + __popc(__ballot_sync(FULL, sel1));
+  const int nsta = __popc(__ballot_sync(FULL, sel_s));
+  if (sel0) nbr[(size_t)i * KNN + lrank[0]] = (int)(lk[0] & 0xffffffffu);          // ligand sources first, nearest first
+  if (sel1) nbr[(size_t)i * KNN + lrank[1]] = (int)(lk[1] & 0xffffffffu);
+  if (sel_s) nbr[(size_t)i * KNN + nlig + lane] = (int)(sk & 0xffffffffu);          // then the protein sources, nearest first
+  if (lane == 0) { deg_out[i] = nlig + nsta; nlig_out[i] = nlig; }
+}
+
+void launch_knn_merge(const float* x4, const int* node_ptr, const int* graph_of, const int* n_protein, const uint8_t* is_lig, int n, int k,
+                      float r_max, const unsigned long long* skeys, const int* sdeg, int* nbr, int* deg, int* nlig, cudaStream_t stream) {
+  if (n <= 0) return;
+  const float r2max = r_max > 0.f ? r_max * r_max : INFINITY;
+  knn_merge_kernel<<<(n + 7) / 8, 256, 0, stream>>>(x4, node_ptr, graph_of, n_protein, is_lig, n, k, r2max, skeys, sdeg, nbr, deg, nlig);
 }
 
 // e_w = sigmoid(MLP_{20->128->1}(gauss(d)))  (uni_transformer_edge.py:422-427), one warp per destination node,
@@ -278,6 +347,126 @@ void launch_layer0_keys(const int* level, const int* nlig, const uint8_t* is_lig
                         cudaStream_t stream) {
   if (n <= 0) return;
   layer0_key_kernel<<<(n + 255) / 256, 256, 0, stream>>>(level, nlig, is_lig, n, n_layers, valid0, key0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same lists in two launches (graphs of up to GL_MAX_NODES nodes): one CTA per graph does the hop levels in shared memory, the
+// first-layer keys and both histograms; a second CTA per graph turns the histograms of all graphs into list positions and scatters
+// its nodes (same deterministic order: level, graph, index) together with the per-slot metadata of the attention kernels.
+constexpr int GL_MAX_NODES = 6144;
+__global__ void __launch_bounds__(256) graph_levels_kernel(const int* __restrict__ nbr, const int* __restrict__ deg, const int* __restrict__ nlig,
+                                                           const uint8_t* __restrict__ is_lig, const int* __restrict__ node_ptr,
+                                                           const int* __restrict__ n_protein, int n_layers, int use_l0,
+                                                           uint8_t* __restrict__ valid0, int* __restrict__ level, int* __restrict__ key0,
+                                                           int* __restrict__ cnt, int* __restrict__ cnt0) {
+  __shared__ int lv[GL_MAX_NODES];
+  __shared__ int hist[2][LEVEL_CAP + 1];
+  const int g = blockIdx.x, base = node_ptr[g], ng = node_ptr[g + 1] - base, np = n_protein[g];
+  if (threadIdx.x < 2 * (LEVEL_CAP + 1)) (&hist[0][0])[threadIdx.x] = 0;
+  for (int t = threadIdx.x; t < ng; t += blockDim.x) lv[t] = is_lig[base + t] ? 0 : LEVEL_CAP;
+  __syncthreads();
+  for (int round = 0; round < LEVEL_CAP - 1; ++round) {
+    for (int idx = threadIdx.x; idx < ng * 32; idx += blockDim.x) {
+      const int t = idx >> 5, j = idx & 31;
+      if (lv[t] == round && j < deg[base + t]) atomicMin(&lv[nbr[(size_t)(base + t) * KNN + j] - base], round + 1);
+    }
+    __syncthreads();
+  }
+  for (int t = threadIdx.x; t < ng; t += blockDim.x) {
+    const int i = base + t, l = lv[t];
+    level[i] = l;
+    if (t < np) {
+      atomicAdd(&hist[0][l], 1);
+      if (use_l0) {
+        const bool compute = l <= n_layers && (nlig[i] > 0 || !valid0[i]);
+        const int k0 = compute ? 1 : LEVEL_CAP;
+        key0[i] = k0;
+        if (compute) valid0[i] = nlig[i] == 0;
+        atomicAdd(&hist[1][k0], 1);
+      }
+    } else if (use_l0) {
+      key0[i] = 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x <= LEVEL_CAP) {
+    cnt[g * (LEVEL_CAP + 1) + threadIdx.x] = hist[0][threadIdx.x];
+    if (use_l0) cnt0[g * (LEVEL_CAP + 1) + threadIdx.x] = hist[1][threadIdx.x];
+  }
+}
+
+struct GraphListArgs {
+  const int *level, *key0, *cnt, *cnt0, *node_ptr, *n_protein, *lig_ptr, *lig_idx, *deg, *nlig;
+  int num_graphs, n_layers, lig_block, use_l0;
+  int *counts, *counts0, *dst_lvl, *dst_lvl0;
+  int2 *meta_lvl, *meta_lvl0, *meta_lig;
+};
+__global__ void __launch_bounds__(64) graph_lists_kernel(const GraphListArgs a) {
+  __shared__ int first[2][LEVEL_CAP + 1];       // list position of this graph's first node of every level / key
+  __shared__ int total[2][LEVEL_CAP + 2];       // exclusive prefix over levels of the totals
+  const int g = blockIdx.x, lane = threadIdx.x & 31, which = threadIdx.x >> 5;      // warp 0: level list, warp 1: first-layer list
+  if (which == 1 && !a.use_l0) return;
+  const int* c = which ? a.cnt0 : a.cnt;
+  if (lane <= LEVEL_CAP) {
+    int before = 0, all = 0;
+    for (int gg = 0; gg < a.num_graphs; ++gg) { const int v = c[gg * (LEVEL_CAP + 1) + lane]; all += v; before += gg < g ? v : 0; }
+    first[which][lane] = before; total[which][lane + 1] = all;
+  }
+  __syncwarp();
+  if (lane == 0) { total[which][0] = 0; for (int v = 0; v <= LEVEL_CAP; ++v) total[which][v + 1] += total[which][v]; }
+  __syncwarp();
+  if (lane <= LEVEL_CAP) first[which][lane] += a.lig_block + total[which][lane];
+  __syncwarp();
+  if (g == 0 && lane == 0) {      // per-layer prefix lengths (see level_offsets_kernel)
+    int* counts = which ? a.counts0 : a.counts;
+    auto upto = [&](int lv) { return a.lig_block + total[which][min(max(lv, 0), LEVEL_CAP) + 1]; };
+    for (int l = 0; l < a.n_layers; ++l) { counts[l] = upto(a.n_layers - l); counts[a.n_layers + l] = upto(a.n_layers - l + 1); }
+    counts[2 * a.n_layers] = upto(1);
+  }
+  const int* key = which ? a.key0 : a.level;
+  int* dst = which ? a.dst_lvl0 : a.dst_lvl;
+  int2* meta = which ? a.meta_lvl0 : a.meta_lvl;
+  const int base = a.node_ptr[g], np = a.n_protein[g];
+  int cur[LEVEL_CAP + 1];
+#pragma unroll
+  for (int v = 0; v <= LEVEL_CAP; ++v) cur[v] = first[which][v];
+  for (int i0 = 0; i0 < np; i0 += 32) {
+    const int node = base + i0 + lane;
+    const int lv = i0 + lane < np ? key[node] : -1;
+#pragma unroll
+    for (int v = 0; v <= LEVEL_CAP; ++v) {
+      const unsigned m = __ballot_sync(FULL, lv == v);
+      if (lv == v) {
+        const int pos = cur[v] + __popc(m & ((1u << lane) - 1u));
+        dst[pos] = node;
+        meta[pos] = make_int2(node, a.deg[node] | (a.nlig[node] << 8));
+      }
+      cur[v] += __popc(m);
+    }
+  }
+  // the ligand block of the list (static node order) and the ligand-only list of the position layers
+  for (int r = a.lig_ptr[g] + lane; r < a.lig_ptr[g + 1]; r += 32) {
+    const int node = a.lig_idx[r];
+    const int2 mm = make_int2(node, a.deg[node] | (a.nlig[node] << 8) | (1 << 16));
+    meta[r] = mm;
+    if (which == 0) a.meta_lig[r] = mm;
+  }
+}
+
+bool launch_graph_lists(const int* nbr, const int* deg, const int* nlig, const uint8_t* is_lig, const int* node_ptr, const int* n_protein,
+                        const int* lig_ptr, const int* lig_idx, int num_graphs, int max_graph_nodes, int n_layers, int lig_block, bool use_l0,
+                        uint8_t* valid0, int* level, int* key0, int* cnt, int* cnt0, int* counts, int* counts0, int* dst_lvl, int* dst_lvl0,
+                        int2* meta_lvl, int2* meta_lvl0, int2* meta_lig, cudaStream_t stream) {
+  if (num_graphs <= 0 || max_graph_nodes > GL_MAX_NODES) return false;
+  graph_levels_kernel<<<num_graphs, 256, 0, stream>>>(nbr, deg, nlig, is_lig, node_ptr, n_protein, n_layers, use_l0 ? 1 : 0, valid0, level, key0,
+                                                      cnt, cnt0);
+  GraphListArgs a;
+  a.level = level; a.key0 = key0; a.cnt = cnt; a.cnt0 = cnt0; a.node_ptr = node_ptr; a.n_protein = n_protein; a.lig_ptr = lig_ptr;
+  a.lig_idx = lig_idx; a.deg = deg; a.nlig = nlig; a.num_graphs = num_graphs; a.n_layers = n_layers; a.lig_block = lig_block;
+  a.use_l0 = use_l0 ? 1 : 0; a.counts = counts; a.counts0 = counts0; a.dst_lvl = dst_lvl; a.dst_lvl0 = dst_lvl0;
+  a.meta_lvl = meta_lvl; a.meta_lvl0 = meta_lvl0; a.meta_lig = meta_lig;
+  graph_lists_kernel<<<num_graphs, 64, 0, stream>>>(a);
+  return true;
 }
 
 }  // namespace ddb

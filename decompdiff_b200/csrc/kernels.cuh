@@ -6,8 +6,15 @@
 namespace ddb {
 
 // ---- K1 graph build ---------------------------------------------------------------------------
+// r_max > 0: 'radius' cut-off - the k nearest neighbours within r_max (|x_i - x_j| <= r_max) only
 void launch_knn(const float* x4, const int* node_ptr, const int* graph_of, const uint8_t* is_lig, int n, int k,
-                int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream);
+                int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream, float r_max = 0.f,
+                const int* node_list = nullptr, const int* n_protein = nullptr, unsigned long long* skeys = nullptr);
+// static protein neighbour cache: launch_knn(..., n_protein, skeys) once per run writes every protein node's sorted keys of its k
+// nearest PROTEIN atoms (and their number into `deg`); per step launch_knn over the ligand nodes (node_list) + launch_knn_merge
+// over the protein nodes reproduce launch_knn over all nodes bit for bit
+void launch_knn_merge(const float* x4, const int* node_ptr, const int* graph_of, const int* n_protein, const uint8_t* is_lig, int n, int k,
+                      float r_max, const unsigned long long* skeys, const int* sdeg, int* nbr, int* deg, int* nlig, cudaStream_t stream);
 // memo table of the global edge weight for protein-protein pairs (positions of protein atoms are constant over a run)
 struct EdgeWeightCache {
   float* table = nullptr;               // sum_g n_protein[g]^2 entries, NaN = empty; null disables the cache
@@ -27,6 +34,12 @@ void launch_receptive_field(const int* nbr, const int* deg, const uint8_t* is_li
 
 void launch_level_sort(const int* level, const int* node_ptr, const int* n_protein, int num_graphs, int n_layers, int lig_block, int* cnt,
                        int* counts, int* dst_list, cudaStream_t stream);
+// hop levels + first-layer keys + both level-sorted destination lists + the per-slot metadata of the attention kernels in two
+// launches (one CTA per graph); returns false (nothing launched) when a graph is too large for the shared-memory BFS
+bool launch_graph_lists(const int* nbr, const int* deg, const int* nlig, const uint8_t* is_lig, const int* node_ptr, const int* n_protein,
+                        const int* lig_ptr, const int* lig_idx, int num_graphs, int max_graph_nodes, int n_layers, int lig_block, bool use_l0,
+                        uint8_t* valid0, int* level, int* key0, int* cnt, int* cnt0, int* counts, int* counts0, int* dst_lvl, int* dst_lvl0,
+                        int2* meta_lvl, int2* meta_lvl0, int2* meta_lig, cudaStream_t stream);
 // first-layer cache of protein nodes without ligand sources (graph.cu): sort keys + validity flags
 void launch_layer0_keys(const int* level, const int* nlig, const uint8_t* is_lig, int n, int n_layers, uint8_t* valid0, int* key0,
                         cudaStream_t stream);

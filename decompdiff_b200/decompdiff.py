@@ -104,8 +104,11 @@ class UniTransformerO2TwoUpdateGeneralBond(nn.Module):
                  act_fn='relu', norm=True, cutoff_mode='radius', r_max=10., x2h_out_fc=True, sync_twoup=False,
                  h_node_in_bond_net=False):
         super().__init__()
-        if cutoff_mode != 'knn':
-            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')   # radius is broken upstream (:351), hybrid: N3
+        if cutoff_mode not in ('knn', 'radius'):      # 'hybrid' (common.py:250-277): not implemented
+            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')
+        # 'radius' raises upstream (`self.r` is never set, :351); here it is radius_graph(r = r_max, max_num_neighbors = k) with
+        # nearest-first truncation (include/decompdiff_b200.h: ddb_model_set_cutoff)
+        self.cutoff_mode, self.r_max = cutoff_mode, float(r_max)
         if act_fn != 'relu' or not norm or x2h_out_fc or not h_node_in_bond_net or num_blocks != 1:
             raise NotImplementedError('only the shipped uni_o2_bond configuration (configs/training.yml) is implemented')
         self.num_blocks, self.num_layers, self.hidden_dim, self.n_heads, self.k = num_blocks, num_layers, hidden_dim, n_heads, k
@@ -123,7 +126,7 @@ class UniTransformerO2TwoUpdateGeneralBond(nn.Module):
             cfg = dict(hidden_dim=self.hidden_dim, n_heads=self.n_heads, knn=self.k, num_layers=self.num_layers, num_blocks=self.num_blocks,
                        num_classes=1, num_bond_classes=1, protein_feature_dim=1, ligand_feature_dim=2, num_timesteps=1)
             sd = {'refine_net.' + k: v for k, v in self.state_dict().items()}
-            self._engine = EngineModel(cfg, sd, device, refine_only=True)
+            self._engine = EngineModel(cfg, sd, device, refine_only=True, cutoff_mode=self.cutoff_mode, r_max=self.r_max)
         return self._engine
 
     @torch.no_grad()
@@ -239,7 +242,8 @@ class DecompScorePosNet3D(nn.Module):
             device = self._engine.device if self._engine is not None else torch.device('cuda', torch.cuda.current_device())
         device = torch.device(device)
         if self._engine is None or self._engine.device != device:
-            self._engine = EngineModel(self.engine_config(), self.state_dict(), device)
+            self._engine = EngineModel(self.engine_config(), self.state_dict(), device, cutoff_mode=self.refine_net.cutoff_mode,
+                                       r_max=self.refine_net.r_max)
         return self._engine
 
     def refresh_engine(self):

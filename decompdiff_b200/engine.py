@@ -55,11 +55,15 @@ def _device_of(*tensors, default=None) -> torch.device:
 
 
 class EngineModel:
-    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor], device=None, refine_only: bool = False):
+    def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor], device=None, refine_only: bool = False,
+                 cutoff_mode: str = 'knn', r_max: float = 0.0):
         require_cuda()
         L = _lib.lib()
         self.device = _device_of(default=device)
         self.refine_only = refine_only
+        if cutoff_mode not in ('knn', 'radius'):
+            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')
+        self.cutoff = (1 if cutoff_mode == 'radius' else 0, float(r_max))
         with torch.cuda.device(self.device):
             self._init(L, cfg, state_dict)
 
@@ -75,6 +79,7 @@ class EngineModel:
             _lib.check(L.ddb_model_set_tensor(self._h, name.encode(), C.c_void_p(ht.data_ptr()), ht.numel()))
         if self.refine_only:
             _lib.check(L.ddb_model_set_refine_only(self._h, 1))
+        _lib.check(L.ddb_model_set_cutoff(self._h, self.cutoff[0], self.cutoff[1]))
         _lib.check(L.ddb_model_finalize(self._h))
 
     def __del__(self):

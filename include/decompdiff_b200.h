@@ -71,6 +71,11 @@ int ddb_model_set_tensor(ddb_model* m, const char* name, const float* host_data,
  * DDB_ERR_MISSING naming the first absent key (strict=True behaviour). */
 int ddb_model_finalize(ddb_model* m);
 void ddb_model_destroy(ddb_model* m);
+/* Graph construction of the refine net (uni_transformer_edge.py:349-359): mode 0 = 'knn' (k nearest neighbours per node within
+ * its graph, the shipped configuration), mode 1 = 'radius': the k nearest neighbours within r_max.  Upstream 'radius' raises
+ * (it reads an attribute `self.r` that is never set, :351), so mode 1 is DEFINED here as radius_graph(r = r_max,
+ * max_num_neighbors = k) with nearest-first truncation; 'hybrid' is not implemented.  Call before any batch is created. */
+int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max);
 /* Stand-alone refine net (get_refine_net('uni_o2_bond', config), models/encoders/__init__.py:27-43): call before
  * ddb_model_finalize; only the "refine_net.*" tensors are then required and the model serves ddb_refine_batch_create /
  * ddb_refine_forward only. */

@@ -247,6 +247,14 @@ def refine_net(sd, cfg, h, x, bond_index, h_bond, mask_ligand, mask_ligand_atom,
     edge_index = None
     for _ in range(cfg['num_blocks']):
         edge_index = knn_graph(x, k=cfg['knn'], batch=batch) if knn_edge_index is None else knn_edge_index
+        if cfg.get('cutoff_mode', 'knn') == 'radius':
+            # upstream raises here (`self.r` undefined, :351); the product DEFINES the mode as the k nearest neighbours within r_max
+            # (include/decompdiff_b200.h: ddb_model_set_cutoff) and this restates that definition
+            s_, d_ = edge_index
+            dd = x[d_] - x[s_]
+            d2 = (dd[:, 0] * dd[:, 0] + dd[:, 1] * dd[:, 1]) + dd[:, 2] * dd[:, 2]
+            keep = d2 <= torch.tensor(cfg['r_max'], dtype=torch.float32) ** 2
+            edge_index = torch.stack([s_[keep], d_[keep]])
         src, dst = edge_index
         et = F.one_hot(edge_types(src, dst, mask_ligand), num_classes=4).to(h.dtype)
         dist = torch.norm(x[dst] - x[src], p=2, dim=-1, keepdim=True)

@@ -68,3 +68,26 @@ def test_forward_edge_shapes_match_oracle(name, kwargs, model_cpu, weights, orac
     for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
         assert out[k].shape == ref[k].shape
         assert tol_ratio(out[k], ref[k]) <= 1.0, f'{name}:{k} {tol_ratio(out[k], ref[k]):.3f} x tol'
+
+
+def test_radius_cutoff_mode_matches_its_restatement(weights, oracle_cfg):
+    """cutoff_mode='radius' raises upstream (`self.r` is never set, uni_transformer_edge.py:351); the product defines it as the k
+    nearest neighbours within r_max (nearest-first truncation) and the oracle restates that definition.  r_max = 6 A on the
+    N(0, 8^2) synthetic pockets leaves many nodes with fewer than 32 (some with no) neighbours."""
+    import decompdiff_b200 as ddb
+    cfg = dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='radius', r_max=6.0)
+    m = ddb.DecompScorePosNet3D(cfg, syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
+    m.load_state_dict(weights)
+    kw = syn.make_batch(n_pockets=3, n_protein=150, arm_sizes=(4, 5), n_scaffold=7, seed=93)
+    fk = syn.forward_kwargs(kw, None)
+    out = m.eval()(**fk)
+    ocfg = dict(oracle_cfg, cutoff_mode='radius', r_max=6.0)
+    with torch.no_grad():
+        ref = restate.forward(weights, ocfg, **fk)
+        knn = restate.forward(weights, oracle_cfg, **fk)
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
+        assert tol_ratio(out[k], ref[k]) <= 1.0, k
+    assert float((ref['pred_ligand_v'] - knn['pred_ligand_v']).abs().max()) > 1e-3      # the cut-off changes the graph
+    with pytest.raises(ValueError):
+        ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='hybrid'), syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM,
+                                syn.NUM_CLASSES)

@@ -81,3 +81,30 @@ def test_knn_graph_bit_exact(sizes, k):
         lig_first = torch.cat([want[is_lig[want]], want[~is_lig[want]]])      # stable partition, ligand sources first
         assert torch.equal(got, lig_first), (i, got.tolist(), lig_first.tolist())
         assert int(nlig[i]) == int(is_lig[want].sum())
+
+
+def test_cached_graph_build_equals_brute_force(model_cpu, monkeypatch):
+    """The static protein-neighbour cache + rank-merge (graph.cu: knn_merge_kernel) and the two-launch level lists must reproduce
+    the brute-force kNN / multi-launch lists bit for bit: same neighbour lists, same trajectory."""
+    from decompdiff_b200 import synthetic as syn
+    kw = syn.make_batch(n_pockets=5, n_protein=[370, 40, 25, 600, 90], arm_sizes=(8, 8), n_scaffold=14, seed=71)
+    n, Eb = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel()
+    noise = syn.step_noise(n, Eb, 4, seed=3)
+
+    def run():
+        r = model_cpu.begin_sampling(**kw, num_steps=4, center_pos_mode='protein')
+        r.advance(4, noise=noise)
+        out = r.finish(traj_on_device=True)
+        return out, r.eb.debug_buffer('nbr').cpu(), r.eb.debug_buffer('deg').cpu(), r.eb.debug_buffer('nlig').cpu()
+
+    fast = run()
+    monkeypatch.setenv('DDB_NO_KNN_CACHE', '1')
+    monkeypatch.setenv('DDB_OLD_LISTS', '1')
+    slow = run()
+    assert torch.equal(fast[2], slow[2]) and torch.equal(fast[3], slow[3])
+    deg = fast[2].view(-1)
+    mask = torch.arange(32)[None, :] < deg[:, None]
+    assert torch.equal(fast[1][mask], slow[1][mask])
+    for k in ('pos', 'v', 'bond'):
+        assert torch.equal(fast[0][k], slow[0][k]), k
+    assert torch.equal(fast[0]['pos_traj'], slow[0]['pos_traj'])
