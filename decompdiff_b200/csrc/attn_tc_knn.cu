@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
             const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;
             val[i] = wh * __uint_as_float(v[i]);
           }
+          warp_reduce_scatter<32>(val, lane);      // 32 live values -> 1 before the TF32 split needs the registers
         }
       }
       // ---- hidden activations -> TMEM, 16 columns at a time (hi = z truncated to TF32, lo = z - hi, exact)
@@ -437,7 +438,6 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
         } else {
           float ws[4] = {w4.x, w4.y, w4.z, w4.w};
           warp_allreduce4(ws, lane);
-          warp_reduce_scatter<32>(val, lane);
           if (prev_node >= 0) {
             const int c = s * 32 + lane;
             a.out_h[(size_t)prev_node * a.ldo + c] = val[0] + sm.b2[c] * ws[lane >> 3];

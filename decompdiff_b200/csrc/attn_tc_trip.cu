@@ -349,6 +349,9 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
             const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;
             val[i] = wh * __uint_as_float(v[i]);
           }
+          // reduce over the group's rows right away: 32 live values become one before the TF32 split below needs its registers
+          // (holding them across the split cost ~50 spill stores per thread and tile; the tensor pipe has the slack)
+          warp_reduce_scatter<32>(val, lane);
         }
       }
       // ---- hidden activations -> TMEM (D is in registers, so the issuer may start the main MMA right away)
@@ -381,7 +384,6 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
           // softmax over the 32 rows of the group, 4 heads at once: max by one REDUX each, sums by a transposed all-reduce
           finish_k(lg, prev_ok, prev_e, prev_tb, prev_pair);
         } else {
-          warp_reduce_scatter<32>(val, lane);
           if (prev_e >= 0) {
             const int c = s * 32 + lane;
             if (prev_pair >= 0) {
