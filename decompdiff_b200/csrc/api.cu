@@ -389,6 +389,7 @@ struct ddb_batch {
   int* decomp_index = nullptr; float* full_pos4 = nullptr; int* full_ptr = nullptr;
   long long launches = 0;
   long long h2d_bytes = 0;
+  bool gq_open = false, gq_overflow = false; int gq_n = 0, gq_cat = 0; GemmArgs gq_a[GEMM_MAX_BATCH]; const float* gq_w[GEMM_MAX_BATCH];   // batched GEMM launch
   bool refine = false;       // refine-net seam: h / x / h_bond come from the caller (ddb_refine_forward), every node row is an output
   float *tap_h = nullptr, *tap_x = nullptr, *tap_hb = nullptr;      // optional per-layer copies of h / x / h_bond (ddb_batch_set_layer_tap)
   float* v_logits0 = nullptr;   // return_all: v_inference of the input embedding (decompdiff.py:345-346)
@@ -852,9 +853,28 @@ void gemm(ddb_batch* b, cudaStream_t s, int cat, const float* A, int lda, const 
   if (ln) { g.ln_gamma = m->p(ln->gamma); g.ln_beta = m->p(ln->beta); }
   g.Wt = m->p(w.Wt); g.ldw = w.N; g.bias = m->p(w.bias);
   g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.c_rows = c_rows; g.M = M; g.N = w.N; g.act = act; g.M_dev = M_dev;
+  if (b->gq_open) {      // collect: the problems between gemm_begin() and gemm_flush() are independent and share one launch
+    if (b->gq_n == GEMM_MAX_BATCH) { b->gq_overflow = true; return; }
+    b->gq_a[b->gq_n] = g; b->gq_w[b->gq_n] = m->p(w.Wtc); b->gq_cat = b->gq_n ? b->gq_cat : cat; ++b->gq_n;
+    return;
+  }
   ProfScope ps(b, s, cat);
   if (b->use_tc) launch_gemm128_tc(g, m->p(w.Wtc), b->num_sms, s); else launch_gemm128(g, s);
   b->launches++;
+}
+void gemm_begin(ddb_batch* b) { b->gq_open = true; b->gq_n = 0; }
+void gemm_flush(ddb_batch* b, cudaStream_t s) {
+  b->gq_open = false;
+  if (b->gq_n == 0) return;
+  ProfScope ps(b, s, b->gq_cat);
+  if (b->use_tc) {
+    launch_gemm128_tc_batch(b->gq_a, b->gq_w, b->gq_n, b->num_sms, s);
+    b->launches++;
+  } else {
+    for (int i = 0; i < b->gq_n; ++i) launch_gemm128(b->gq_a[i], s);
+    b->launches += b->gq_n;
+  }
+  b->gq_n = 0;
 }
 
 KnnMlpW knn_w(const ddb_model* m, const KnnMlpOff& o) {
@@ -878,7 +898,6 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   cudaStream_t sb = fork ? b->side : s;
   auto fork_side = [&]() { if (fork) { cudaEventRecord(b->ev_fork, s); cudaStreamWaitEvent(sb, b->ev_fork, 0); } };
   auto join_side = [&](cudaEvent_t e) { if (fork) cudaStreamWaitEvent(s, e, 0); };
-  fork_side();
   if (b->knn_cache) {
     // protein atoms never move during a run: their k nearest PROTEIN neighbours are computed once (sorted keys); per step the ligand
     // nodes are searched brute force and every protein node only ranks the graph's ligand atoms against its cached list
@@ -946,19 +965,24 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     const int* cnt_src = prune_gemm ? b->lvl_counts + nl_layers + l : nullptr;     // rows read as sources by it
     const int* cnt_pos = prune_gemm ? b->lvl_counts + 2 * nl_layers : nullptr;     // sources of the position update (ligand + 1 hop)
     const int n_node_rows = prune_gemm ? n_lvl : N;
+    // the three projections of the layer input (node / ligand-atom / bond-edge rows) are independent: one launch; then the second
+    // Linear of the three query MLPs: one launch
+    gemm_begin(b);
+    gemm(b, s, PC_GEMM_BOND, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
     if (l0c) {      // projections of the (static) protein embeddings are computed once; afterwards only the ligand rows change
       if (!b->pn0_ready) gemm(b, s, PC_GEMM_NODE, h_in, H, nullptr, N, L.n1, PNl, 5 * H);
       else gemm(b, s, PC_GEMM_NODE, h_in, H, rows_l, b->lig_block, L.n1, PNl, 5 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_l);
     } else {
       gemm(b, s, PC_GEMM_NODE, h_in, H, rows_lvl, n_node_rows, L.n1, PNl, 5 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_src);
     }
+    gemm(b, s, PC_GEMM_LIG, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
+    gemm_flush(b, s);
+    gemm_begin(b);
+    gemm(b, s, PC_GEMM_BOND, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
     gemm(b, s, PC_GEMM_NODE, PNl + 4 * H, 5 * H, rows_l, n_node_rows, L.q_ne, b->qN, H, &L.ln_q_ne, nullptr, 0, nullptr, nullptr, 0, rows_l, 0, cnt_dst);
-    if (l > 0) fork_side();      // the previous layer's position update is the last thing the side branch waits for
-    gemm(b, sb, PC_GEMM_LIG, h_in, H, b->lig_idx, NL, L.l1, b->PL, 10 * H);
-    gemm(b, sb, PC_GEMM_LIG, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
-    gemm(b, sb, PC_GEMM_BOND, hb_in, H, nullptr, Eb, L.b1, b->PB, 5 * H);
-    gemm(b, sb, PC_GEMM_BOND, b->PB + 4 * H, 5 * H, nullptr, Eb, L.q_bl, b->qE, H, &L.ln_q_bl, b->PL + 9 * H, 10 * H, b->bdst);
-    if (fork) cudaEventRecord(b->ev_proj, sb);      // PL, PB, qNB, qE are complete
+    gemm(b, s, PC_GEMM_LIG, b->PL + 4 * H, 10 * H, nullptr, NL, L.q_nb, b->qNB, H, &L.ln_q_nb);
+    gemm_flush(b, s);
+    fork_side();      // the bond / triplet branch needs the projections above and the layer input only
     // --- node update over kNN edges  -> h1
     KnnAttnArgs ka;
     ka.n_dst = N; ka.Hi = PNl; ka.ldhi = 5 * H; ka.Hj = PNl + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
@@ -988,7 +1012,6 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ba.q = b->qNB; ba.ldq = H; ba.x4 = x_in; ba.wbuf = b->wb_bond; ba.out_h = b->h1; ba.ldo = H;
     ba.k.W2tc = m->p(L.nb_k.W2tc); ba.v.W2tc = m->p(L.nb_v.W2tc);
     ba.vg = b->bond_vg; ba.n_vg = b->n_bvg; ba.stats = b->bond_stats; ba.factor = b->bond_factor; ba.part_h = b->bond_part_h; ba.part_dx = b->bond_part_dx;
-    join_side(b->ev_proj);
     { ProfScope ps(b, s, PC_BOND_NODE); if (b->tc_attn & 16) { launch_bond_tc(ba, false, sms, s); b->launches += 1; } else launch_bond_attn_node(ba, sms, s); }
     // --- bond update over triplets -> hb_out
     TripArgs ta;
@@ -1020,10 +1043,14 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     // --- h_out = h_in + lin_node(h1)    (:277)
     gemm(b, s, PC_GEMM_NODE, b->h1, H, rows_l, n_node_rows, L.lin, h_out, H, nullptr, nullptr, 0, nullptr, h_in, H, rows_l, 0, cnt_dst);
     // --- projections of the new h / new h_bond for the position update
+    gemm_begin(b);
     gemm(b, s, PC_GEMM_NODE, h_out, H, rows_lvl, n_node_rows, L.n2, b->PNx, 2 * H, nullptr, nullptr, 0, nullptr, nullptr, 0, rows_lvl, 0, cnt_pos);
     gemm(b, s, PC_GEMM_LIG, h_out, H, b->lig_idx, NL, L.l2, b->PLx, 8 * H);
+    gemm_flush(b, s);
+    gemm_begin(b);
     gemm(b, s, PC_GEMM_LIG, b->PLx + 2 * H, 8 * H, nullptr, NL, L.q_pe, b->qXe, H, &L.ln_q_pe);
     gemm(b, s, PC_GEMM_LIG, b->PLx + 7 * H, 8 * H, nullptr, NL, L.q_pb, b->qXb, H, &L.ln_q_pb);
+    gemm_flush(b, s);
     // --- position update over kNN edges (ligand destinations only) -> dx_edge
     KnnAttnArgs kp;
     kp.n_dst = NL; kp.dst_list = b->lig_idx; kp.Hi = b->PLx; kp.ldhi = 8 * H; kp.hi_by_slot = 1;

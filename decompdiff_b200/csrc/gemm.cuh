@@ -30,7 +30,14 @@ struct GemmArgs {
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 32, GEMM_THREADS = 256;
 constexpr int GEMM_SMEM = (H * GEMM_BM + 2 * GEMM_BK * GEMM_BN) * 4;   // 64 KB A + 32 KB W stages
 
+constexpr int GEMM_MAX_BATCH = 4;
+struct GemmBatch {       // kernel argument of the batched tensor-core launch (gemm_tc.cu)
+  GemmArgs p[GEMM_MAX_BATCH]; const float* Wtc[GEMM_MAX_BATCH]; int per[GEMM_MAX_BATCH], gx[GEMM_MAX_BATCH], gy[GEMM_MAX_BATCH];
+};
+
 void launch_gemm128(const GemmArgs& a, cudaStream_t stream);
+// up to GEMM_MAX_BATCH independent problems in one launch
+void launch_gemm128_tc_batch(const GemmArgs* args, const float* const* Wtc, int n, int num_sms, cudaStream_t stream);
 // tcgen05 / TMEM 3xTF32 version (gemm_tc.cu); Wtc = weight packed by pack_gemm_tc (2*128*N floats)
 void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream);
 void pack_gemm_tc(const float* Wt, int N, float* out);

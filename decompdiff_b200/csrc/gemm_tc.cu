@@ -47,13 +47,14 @@ __device__ __forceinline__ float ssp(float x) { return (x > 20.f ? x : log1pf(ex
 __device__ __forceinline__ void tc_quad_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-// CS = cluster size along the row tiles (1 or 2).  With CS = 2 the two CTAs of a cluster walk their row tiles in lockstep and share
-// every weight K-block: rank 0 multicasts the hi half, rank 1 the lo half, into the same ring stage of both CTAs (the weight image
-// is otherwise re-read from L2 for every 128-row tile, which is what bounds the wide projections); a stage is refilled once the
-// MMAs of BOTH CTAs that read it have retired (multicast commit onto both "empty" barriers).
-template <int CS>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArgs a, const float* __restrict__ Wtc,
-                                                                   int tiles_per_cta) {
+// One launch serves up to GEMM_MAX_BATCH independent problems (blockIdx.z selects one): the projections of a layer phase share a
+// launch, so the 15-CTA ligand problems run next to the wide ones instead of paying a launch of their own.
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBatch gb) {
+  const int pz = blockIdx.z;
+  if ((int)blockIdx.x >= gb.gx[pz] || (int)blockIdx.y >= gb.gy[pz]) return;
+  const GemmArgs& a = gb.p[pz];
+  const float* __restrict__ Wtc = gb.Wtc[pz];
+  const int tiles_per_cta = gb.per[pz], grid_x = gb.gx[pz];
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sB = smem_raw;                                                // TC_STAGES x (hi | lo)
   float* sEpi = reinterpret_cast<float*>(sB + TC_STAGES * TC_B_STAGE);   // per-warp 32 x 36 transpose tiles
@@ -64,14 +65,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = a.M_dev ? min(__ldg(a.M_dev), a.M) : a.M;      // device-side row count: exact receptive-field pruning
   const int row_tiles = (M + TC_BM - 1) / TC_BM;
-  const int first_of_cluster = (int)blockIdx.x - (int)blockIdx.x % CS;
-  if (first_of_cluster >= row_tiles) return;          // uniform over the cluster
+  if ((int)blockIdx.x >= row_tiles) return;
   // persistent over row tiles: blockIdx.x, blockIdx.x + gridDim.x, ...  (one TMEM allocation / barrier set-up per CTA; with a
-  // single output tile the whole weight stays resident in the ring and is streamed once).  The CTAs of a cluster run the same
-  // number of passes (a CTA without a row tile left computes a masked, store-free pass).
-  const int my_rows = (row_tiles - first_of_cluster + (int)gridDim.x - 1) / (int)gridDim.x;
-  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
-  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+  // single output tile the whole weight stays resident in the ring and is streamed once).
+  const int my_rows = (row_tiles - (int)blockIdx.x + grid_x - 1) / grid_x;
   const int tile0 = blockIdx.y * tiles_per_cta;
   const int n_tiles = min(tiles_per_cta, a.N / TC_BN - tile0);
   auto bar_full = [&](int i) { return smem_u32(&bars[i]); };                        // K-block landed in stage i
@@ -82,14 +79,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   if ((smem_u32(sB) & 1023u) != 0u) __trap();      // SWIZZLE_128B operands need a 1024-byte aligned base
   if (tid == 0) {
     for (int i = 0; i < 2 * TC_STAGES + 2; ++i) mbar_init(smem_u32(&bars[i]), 1);
-    for (int i = 0; i < TC_STAGES; ++i) mbar_init(bar_empty(i), CS);      // one MMA-completion arrival per CTA of the cluster
     for (int i = 0; i < 2; ++i) mbar_init(bar_dempty(i), 16);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(tmem_slot), 512); }
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();                     // peers may arrive on / copy into this CTA from here on
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_blocks = n_tiles * 4;                 // K-blocks per row tile
@@ -105,13 +100,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
           const int st = gi % TC_STAGES, use = gi / TC_STAGES;
           if (use > 0) mbar_wait(bar_empty(st), (use - 1) & 1);
           mbar_expect_tx(bar_full(st), TC_B_STAGE);
-          if (CS == 1 || resident) {
-            bulk_g2s(smem_u32(sB + st * TC_B_STAGE), src + (size_t)i * (TC_B_STAGE / 4), TC_B_STAGE, bar_full(st));
-          } else {          // this CTA's half of the K-block (rank 0: hi, rank 1: lo) goes to every CTA of the cluster
-            const uint32_t part = crank * (TC_B_STAGE / CS);
-            bulk_g2s_multicast(smem_u32(sB + st * TC_B_STAGE) + part, src + (size_t)i * (TC_B_STAGE / 4) + part / 4, TC_B_STAGE / CS,
-                               bar_full(st), kMask);
-          }
+          bulk_g2s(smem_u32(sB + st * TC_B_STAGE), src + (size_t)i * (TC_B_STAGE / 4), TC_B_STAGE, bar_full(st));
         }
     }
     __syncwarp();
@@ -142,7 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
               umma_tf32_ts(d, tmem_base + TC_COL_ALO + acol, d_hi + (uint64_t)(kk * 2), idesc, 1u);
               umma_tf32_ts(d, tmem_base + TC_COL_AHI + acol, d_lo + (uint64_t)(kk * 2), idesc, 1u);
             }
-            if (!resident) { if (CS > 1) umma_commit_multicast(bar_empty(st), kMask); else umma_commit(bar_empty(st)); }      // stage may be refilled
+            if (!resident) umma_commit(bar_empty(st));      // stage may be refilled
           }
           umma_commit(bar_dfull(db));             // accumulator complete (implies tcgen05.fence::before_thread_sync)
         }
@@ -156,7 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
     float* tile = sEpi + warp * 32 * TC_EPI_LD;
     int tg = 0;
     for (int rt = 0; rt < my_rows; ++rt) {
-    const int row0 = ((int)blockIdx.x + rt * (int)gridDim.x) * TC_BM;
+    const int row0 = ((int)blockIdx.x + rt * grid_x) * TC_BM;
     {
       // ---- stage A into TMEM: this thread owns channels [32s, 32s+32) of row 32q + lane.  Every MMA that read the previous
       // A tile has retired: this warp waited on the last accumulator's "full" barrier in its epilogue below
@@ -248,48 +237,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmArg
   }
   tc_fence_before();
   __syncthreads();
-  if (CS > 1) cluster_sync_all();                     // no CTA leaves while a peer may still multicast into it
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream) {
-  if (a.M <= 0 || a.N <= 0) return;
+void launch_gemm128_tc_batch(const GemmArgs* args, const float* const* Wtc, int n, int num_sms, cudaStream_t stream) {
   static DeviceOnce attr_set;
   if (!attr_set.done()) {
-    cudaFuncSetAttribute(gemm128_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaFuncSetAttribute(gemm128_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     attr_set.mark();
   }
-  const int row_tiles = (a.M + TC_BM - 1) / TC_BM, tiles = a.N / TC_BN;
-  // Split the output tiles over `nsplit` CTAs per row tile.  Cost model in units of one output tile of MMA work: every CTA
-  // pays ~1.5 units to stage its A tile, then tiles/nsplit units; CTAs run in waves of num_sms (1 CTA per SM).
-  int best = 1; double best_cost = 1e30;
-  for (int ns = 1; ns <= tiles; ++ns) {
-    if (tiles % ns) continue;
-    // CTAs are persistent over row tiles: num_sms / ns of them per column range, each walking ceil(row_tiles / that) row tiles
-    const int per_col = std::max(1, std::min(row_tiles, num_sms / ns));
-    const double rows_each = (double)((row_tiles + per_col - 1) / per_col);
-    const double cost = 1.0 + rows_each * (1.5 + (double)tiles / ns);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+  GemmBatch gb;
+  int np = 0, gx = 1, gy = 1;
+  for (int i = 0; i < n && np < GEMM_MAX_BATCH; ++i) {
+    const GemmArgs& a = args[i];
+    if (a.M <= 0 || a.N <= 0) continue;
+    const int row_tiles = (a.M + TC_BM - 1) / TC_BM, tiles = a.N / TC_BN;
+    // Split the output tiles over `nsplit` CTAs per row tile.  Cost model in units of one output tile of MMA work: every CTA
+    // pays ~1.5 units to stage its A tile, then tiles/nsplit units; CTAs run in waves of num_sms (1 CTA per SM).
+    int best = 1; double best_cost = 1e30;
+    for (int ns = 1; ns <= tiles; ++ns) {
+      if (tiles % ns) continue;
+      // CTAs are persistent over row tiles: num_sms / ns of them per column range, each walking ceil(row_tiles / that) row tiles
+      const int per_col = std::max(1, std::min(row_tiles, num_sms / ns));
+      const double rows_each = (double)((row_tiles + per_col - 1) / per_col);
+      const double cost = 1.0 + rows_each * (1.5 + (double)tiles / ns);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
+    }
+    const int per = tiles / best;
+    gb.p[np] = a; gb.Wtc[np] = Wtc[i]; gb.per[np] = per;
+    gb.gx[np] = std::max(1, std::min(row_tiles, num_sms / best)); gb.gy[np] = (tiles + per - 1) / per;
+    gx = std::max(gx, gb.gx[np]); gy = std::max(gy, gb.gy[np]);
+    ++np;
   }
-  const int per = tiles / best;
-  dim3 grid(std::max(1, std::min(row_tiles, num_sms / best)), (tiles + per - 1) / per);
-  // measured on cfg 2: no gain (the wide projections are bound by writing their 60-140 MB outputs, not by re-reading the
-  // weights), so the cluster variant is opt-in: DDB_GEMM_CLUSTER=1
-  static const bool use_cluster = getenv("DDB_GEMM_CLUSTER") != nullptr && atoi(getenv("DDB_GEMM_CLUSTER")) != 0;
-  if (use_cluster && per >= 2 && grid.x >= 2) {       // streamed weights and at least one pair of row tiles: share the stream
-    static bool attr2 = false;
-    if (!attr2) { cudaFuncSetAttribute(gemm128_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); attr2 = true; }
-    grid.x &= ~1u;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, gemm128_tc_kernel<2>, a, Wtc, per);
-    return;
-  }
-  gemm128_tc_kernel<1><<<grid, TC_THREADS, TC_SMEM, stream>>>(a, Wtc, per);
+  if (np == 0) return;
+  for (int i = np; i < GEMM_MAX_BATCH; ++i) { gb.gx[i] = 0; gb.gy[i] = 0; gb.per[i] = 0; gb.Wtc[i] = nullptr; }
+  gemm128_tc_kernel<<<dim3(gx, gy, np), TC_THREADS, TC_SMEM, stream>>>(gb);
+}
+
+void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream) {
+  launch_gemm128_tc_batch(&a, &Wtc, 1, num_sms, stream);
 }
 
 // host-side packing of a K-major weight Wt[128][N] into the image the kernel streams: for every 128-column output tile, 4
