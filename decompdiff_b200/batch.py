@@ -131,3 +131,53 @@ class Batch(Data):
             else:
                 out[key] = values
         return out
+
+    @classmethod
+    def from_replicas(cls, proto: Data, n: int, follow_batch: Iterable[str] = (), exclude_keys: Iterable[str] = (),
+                      overrides=None, device=None):
+        """`from_data_list([proto_0 .. proto_{n-1}])` for n samples that share every attribute of `proto` except the keys in
+        `overrides` ({key: list of n tensors}) - the mini-batches of the sampling driver when the atom counts are fixed (same
+        ligand_atom_mask for every sample, so the transforms give the same result).  Built with a handful of tensor ops on
+        `device` instead of a per-sample python loop: only ONE copy of the shared tensors crosses to the device.  The result is
+        bit-identical to `from_data_list` (tests/test_host_logic.py)."""
+        follow_batch, exclude, overrides = set(follow_batch or ()), set(exclude_keys or ()), dict(overrides or {})
+        out = cls()
+        out.num_graphs = n
+        dev = device
+        for key in [k for k in proto.keys if k not in exclude]:
+            first = proto[key]
+            if torch.is_tensor(first) and first.dim() > 0:
+                cat_dim = proto.__cat_dim__(key, first)
+                step = proto.__inc__(key, first)
+                step = int(step.item()) if isinstance(step, torch.Tensor) else int(step)
+                if key in overrides:
+                    vals = [v.to(dev) if dev is not None else v for v in overrides[key]]
+                    if step != 0:
+                        vals = [v + step * k if v.dtype != torch.bool else v for k, v in enumerate(vals)]
+                    value = torch.cat(vals, dim=cat_dim)
+                    size = vals[0].size(cat_dim)
+                else:
+                    v = first.to(dev) if dev is not None else first
+                    size = v.size(cat_dim)
+                    reps = [1] * v.dim()
+                    reps[cat_dim] = n
+                    value = v.repeat(*reps)
+                    if step != 0 and v.dtype != torch.bool:
+                        offs = (torch.arange(n, device=value.device, dtype=value.dtype) * step).repeat_interleave(size)
+                        shape = [1] * v.dim()
+                        shape[cat_dim] = n * size
+                        value = value + offs.view(*shape)
+                out[key] = value
+                if key in follow_batch:
+                    counts = torch.full((n,), size, dtype=torch.long, device=value.device)
+                    out[f'{key}_batch'] = torch.repeat_interleave(torch.arange(n, device=value.device), counts)
+                    out[f'{key}_ptr'] = torch.cat([counts.new_zeros(1), counts.cumsum(0)])
+            elif torch.is_tensor(first):
+                v = first.to(dev) if dev is not None else first
+                out[key] = torch.stack([v] * n)
+            elif isinstance(first, (int, float)) and not isinstance(first, bool):
+                t = torch.tensor([first] * n)
+                out[key] = t.to(dev) if dev is not None else t
+            else:
+                out[key] = [first] * n
+        return out

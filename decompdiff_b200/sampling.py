@@ -188,20 +188,36 @@ def sample_diffusion_ligand_decomp(
                 return _Plan(arm_centers, arm_stds, arm_counts, sca_center, sca_std, sca_count)
 
         # ---- per sample: x_T, decomposition mask, transforms, initial bond types (draw order = the reference's)
-        samples, init_pos, ligand_num_atoms, decomp_ind, noise_stds = [], [], [], [], []
+        # With fixed atom counts every sample of the mini-batch has the same decomposition mask, so the (RNG-free) transforms
+        # give the same result: they run ONCE, the per-sample loop only makes the reference's draws in the reference's order, and
+        # the batch is assembled on the device from one copy of the shared tensors (`Batch.from_replicas`, bit-identical to the
+        # per-sample collate).  Drawn counts ('prior', 'old', 'stat') keep the per-sample path.
+        fixed_counts = (prior_mode == 'subpocket' and num_atoms_mode in ('ref', 'ref_large')) or \
+                       (prior_mode == 'ref_prior') or (prior_mode == 'beta_prior' and num_atoms_mode == 'v2')
+        samples, init_pos, ligand_num_atoms, decomp_ind, noise_stds, bond_types = [], [], [], [], [], []
+        proto = None
         for _ in range(n_data):
             plan = plan_for_sample()
             pos, mask = plan.draw() if isinstance(plan, _OldCountPlan) else _draw_sample(plan)
             if num_atoms_mode == 'stat':      # the predicted stds replace the collated prior stds (:249-250, :264-265, :322-323)
                 noise_stds += [plan.arm_stds[a, :].unsqueeze(0).expand(1, 3) for a in range(len(plan.arm_counts))]
                 noise_stds.append(plan.sca_std.unsqueeze(0).expand(1, 3))
-            new_data = data.clone()
-            new_data.ligand_atom_mask = torch.tensor(mask, dtype=torch.long)
-            new_data = init_transform(new_data)
+            if fixed_counts and proto is not None:
+                new_data = proto
+            else:
+                new_data = data.clone()
+                new_data.ligand_atom_mask = torch.tensor(mask, dtype=torch.long)
+                new_data = init_transform(new_data)
+                if fixed_counts:
+                    proto = new_data
             if getattr(new_data, 'ligand_fc_bond_index', None) is not None:
-                new_data.ligand_fc_bond_type = _draw_types(new_data.ligand_fc_bond_index.size(1), model.num_bond_classes,
-                                                           bond_prior_probs, 'cpu')
-            samples.append(new_data)
+                bt = _draw_types(new_data.ligand_fc_bond_index.size(1), model.num_bond_classes, bond_prior_probs, 'cpu')
+                if fixed_counts:
+                    bond_types.append(bt)
+                else:
+                    new_data.ligand_fc_bond_type = bt
+            if not fixed_counts:
+                samples.append(new_data)
             init_pos.append(pos)
             ligand_num_atoms.append(len(mask))
             decomp_ind.append(new_data.ligand_atom_mask.tolist())
@@ -213,7 +229,13 @@ def sample_diffusion_ligand_decomp(
         batch_ligand = torch.repeat_interleave(torch.arange(n_data), torch.tensor(ligand_num_atoms)).to(device)
         assert len(init_ligand_pos) == len(batch_ligand)
         init_ligand_v = _draw_types(len(batch_ligand), model.num_classes, atom_prior_probs, device)
-        batch = Batch.from_data_list(samples, exclude_keys=COLLATE_EXCLUDE_KEYS, follow_batch=FOLLOW_BATCH).to(device)
+        if fixed_counts:
+            if bond_types:
+                proto.ligand_fc_bond_type = bond_types[0]      # the key (and its follow_batch vector) exists as in the per-sample path
+            batch = Batch.from_replicas(proto, n_data, exclude_keys=COLLATE_EXCLUDE_KEYS, follow_batch=FOLLOW_BATCH, device=device,
+                                        overrides={'ligand_fc_bond_type': bond_types} if bond_types else None)
+        else:
+            batch = Batch.from_data_list(samples, exclude_keys=COLLATE_EXCLUDE_KEYS, follow_batch=FOLLOW_BATCH).to(device)
         batch_full_protein_pos = full_protein_pos.repeat(n_data, 1).to(device)
         full_batch_protein = torch.arange(n_data).repeat_interleave(len(full_protein_pos)).to(device)
         if num_atoms_mode == 'stat':

@@ -113,3 +113,24 @@ def test_product_path_fails_loudly_without_cuda(model_cpu):
         model_cpu.sample_diffusion(**kw, num_steps=1, center_pos_mode='protein')
     with pytest.raises(NotImplementedError):
         model_cpu.get_diffusion_loss()
+
+
+def test_replicated_collate_equals_per_sample_collate():
+    """`Batch.from_replicas` (one shared sample + per-sample overrides, assembled with tensor ops) == `Batch.from_data_list`."""
+    gen = torch.Generator().manual_seed(7)
+    proto = syn.make_pocket(gen, 40, (3, 4), 5)
+    n = 4
+    bt = [torch.randint(0, 5, (proto.ligand_fc_bond_index.size(1),), generator=gen) for _ in range(n)]
+    samples = []
+    for k in range(n):
+        d = proto.clone()
+        d.ligand_fc_bond_type = bt[k]
+        samples.append(d)
+    a = ddb.Batch.from_data_list(samples, follow_batch=ddb.FOLLOW_BATCH)
+    b = ddb.Batch.from_replicas(proto, n, follow_batch=ddb.FOLLOW_BATCH, overrides={'ligand_fc_bond_type': bt})
+    assert set(a.keys) == set(b.keys)
+    for k in a.keys:
+        if torch.is_tensor(a[k]):
+            assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+        else:
+            assert a[k] == b[k], k
