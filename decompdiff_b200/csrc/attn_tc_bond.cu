@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
   cta_copy_f4(sm.beta, side.w.beta, H);
   if (PASS == BT_V_NODE) cta_copy_f4(sm.b2, side.w.b2, H);
   if (PASS == BT_V_POS && tid < 16) sm.b2[tid] = side.w.b2[tid];
+  pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), w2_smem = smem_u32(sm.W2);
@@ -405,7 +406,7 @@ static void launch_bond_tc_pass(const BondAttnArgs& a, int num_sms, cudaStream_t
   const int bytes = BondTcSmem::bytes();
   if (!once.done()) { cudaFuncSetAttribute(bond_tc_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
   const int grid = atc_grid((a.n_vg + 3) / 4, num_sms);
-  bond_tc_kernel<PASS><<<grid, BT_THREADS, bytes, stream>>>(a);
+  launch_pdl(bond_tc_kernel<PASS>, dim3(grid), dim3(BT_THREADS), bytes, stream, a);
 }
 
 // node variant: key pass then value pass; position variant: key pass then the 16-output value pass + x update

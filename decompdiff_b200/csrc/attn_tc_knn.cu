@@ -111,8 +111,6 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const int n_dst = a.n_dst_dev ? min(__ldg(a.n_dst_dev), a.n_dst) : a.n_dst;      // device-side count: receptive-field pruning
-  const int n_tiles = (n_dst + 3) / 4;
   const int tile_first = a.n_slots_first / 4;          // tiles below this hold destinations of class a.first_class
   auto class_of = [&](int tile) { return tile < tile_first ? a.first_class : 1 - a.first_class; };
   if (tid == 0) {
@@ -127,6 +125,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   cta_copy_f4(sm.beta, a.w.beta, H);
   if (VPASS && !VPOS) cta_copy_f4(sm.b2, a.w.b2, H);
   if (VPOS && tid < NH) sm.b2[tid] = a.w.b2[tid];
+  pdl_wait();      // everything above is set-up on static data; below this line the previous kernels' results are visible
+  const int n_dst = a.n_dst_dev ? min(__ldg(a.n_dst_dev), a.n_dst) : a.n_dst;      // device-side count: receptive-field pruning
+  const int n_tiles = (n_dst + 3) / 4;
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_d2 = smem_u32(&sm.bars[2]);
@@ -498,9 +499,9 @@ void launch_knn_tc(const KnnAttnArgs& a, int pass, int num_sms, cudaStream_t str
     once.mark();
   }
   const int grid = atc_grid((a.n_dst + 3) / 4, num_sms);
-  if (pass == 2) knn_tc_kernel<2><<<grid, KT_THREADS, bytes, stream>>>(a);
-  else if (pass == 1) knn_tc_kernel<1><<<grid, KT_THREADS, bytes, stream>>>(a);
-  else knn_tc_kernel<0><<<grid, KT_THREADS, bytes, stream>>>(a);
+  if (pass == 2) launch_pdl(knn_tc_kernel<2>, dim3(grid), dim3(KT_THREADS), bytes, stream, a);
+  else if (pass == 1) launch_pdl(knn_tc_kernel<1>, dim3(grid), dim3(KT_THREADS), bytes, stream, a);
+  else launch_pdl(knn_tc_kernel<0>, dim3(grid), dim3(KT_THREADS), bytes, stream, a);
 }
 
 #ifdef DDB_TIMELINE

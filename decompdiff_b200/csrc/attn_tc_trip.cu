@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
   cta_copy_f4(sm.b2, side.w.b2, H);
   // rows of A2 are 128 bytes but only 16 features are used: clear both images once (features 13..31 stay zero)
   for (int i = tid * 16; i < TT_A2_BYTES; i += TT_THREADS * 16) *reinterpret_cast<float4*>(sm.A2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]);
@@ -452,8 +453,8 @@ void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t str
     once.mark();
   }
   const int grid = atc_grid((a.n_groups + 3) / 4, num_sms);
-  if (vpass) trip_tc_kernel<true><<<grid, TT_THREADS, bytes, stream>>>(a);
-  else trip_tc_kernel<false><<<grid, TT_THREADS, bytes, stream>>>(a);
+  if (vpass) launch_pdl(trip_tc_kernel<true>, dim3(grid), dim3(TT_THREADS), bytes, stream, a);
+  else launch_pdl(trip_tc_kernel<false>, dim3(grid), dim3(TT_THREADS), bytes, stream, a);
 }
 
 #ifdef DDB_TIMELINE

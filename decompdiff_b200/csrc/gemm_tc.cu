@@ -51,7 +51,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarri
 // launch, so the 15-CTA ligand problems run next to the wide ones instead of paying a launch of their own.
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBatch gb) {
   const int pz = blockIdx.z;
-  if ((int)blockIdx.x >= gb.gx[pz] || (int)blockIdx.y >= gb.gy[pz]) return;
+  if ((int)blockIdx.x >= gb.gx[pz] || (int)blockIdx.y >= gb.gy[pz]) { pdl_wait(); return; }
   const GemmArgs& a = gb.p[pz];
   const float* __restrict__ Wtc = gb.Wtc[pz];
   const int tiles_per_cta = gb.per[pz], grid_x = gb.gx[pz];
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStatB + 128 * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();      // the row count below may be a device-side counter of the previous kernels
   const int M = a.M_dev ? min(__ldg(a.M_dev), a.M) : a.M;      // device-side row count: exact receptive-field pruning
   const int row_tiles = (M + TC_BM - 1) / TC_BM;
   if ((int)blockIdx.x >= row_tiles) return;
@@ -271,7 +272,7 @@ void launch_gemm128_tc_batch(const GemmArgs* args, const float* const* Wtc, int 
   }
   if (np == 0) return;
   for (int i = np; i < GEMM_MAX_BATCH; ++i) { gb.gx[i] = 0; gb.gy[i] = 0; gb.per[i] = 0; gb.Wtc[i] = nullptr; }
-  gemm128_tc_kernel<<<dim3(gx, gy, np), TC_THREADS, TC_SMEM, stream>>>(gb);
+  launch_pdl(gemm128_tc_kernel, dim3(gx, gy, np), dim3(TC_THREADS), TC_SMEM, stream, gb);
 }
 
 void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream) {

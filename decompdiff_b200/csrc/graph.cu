@@ -354,7 +354,7 @@ void launch_layer0_keys(const int* level, const int* nlig, const uint8_t* is_lig
 // first-layer keys and both histograms; a second CTA per graph turns the histograms of all graphs into list positions and scatters
 // its nodes (same deterministic order: level, graph, index) together with the per-slot metadata of the attention kernels.
 constexpr int GL_MAX_NODES = 6144;
-__global__ void __launch_bounds__(256) graph_levels_kernel(const int* __restrict__ nbr, const int* __restrict__ deg, const int* __restrict__ nlig,
+__global__ void __launch_bounds__(1024) graph_levels_kernel(const int* __restrict__ nbr, const int* __restrict__ deg, const int* __restrict__ nlig,
                                                            const uint8_t* __restrict__ is_lig, const int* __restrict__ node_ptr,
                                                            const int* __restrict__ n_protein, int n_layers, int use_l0,
                                                            uint8_t* __restrict__ valid0, int* __restrict__ level, int* __restrict__ key0,
@@ -458,7 +458,7 @@ bool launch_graph_lists(const int* nbr, const int* deg, const int* nlig, const u
                         uint8_t* valid0, int* level, int* key0, int* cnt, int* cnt0, int* counts, int* counts0, int* dst_lvl, int* dst_lvl0,
                         int2* meta_lvl, int2* meta_lvl0, int2* meta_lig, cudaStream_t stream) {
   if (num_graphs <= 0 || max_graph_nodes > GL_MAX_NODES) return false;
-  graph_levels_kernel<<<num_graphs, 256, 0, stream>>>(nbr, deg, nlig, is_lig, node_ptr, n_protein, n_layers, use_l0 ? 1 : 0, valid0, level, key0,
+  graph_levels_kernel<<<num_graphs, 1024, 0, stream>>>(nbr, deg, nlig, is_lig, node_ptr, n_protein, n_layers, use_l0 ? 1 : 0, valid0, level, key0,
                                                       cnt, cnt0);
   GraphListArgs a;
   a.level = level; a.key0 = key0; a.cnt = cnt; a.cnt0 = cnt0; a.node_ptr = node_ptr; a.n_protein = n_protein; a.lig_ptr = lig_ptr;

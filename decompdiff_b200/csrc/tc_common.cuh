@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy primitives shared by the tensor-core kernels (inline PTX for sm_100a).
 // Descriptor encodings follow cute::UMMA::SmemDescriptor / InstrDescriptor (cute/arch/mma_sm100_desc.hpp).
 #pragma once
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -104,6 +105,30 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------
+// The persistent tensor-core kernels start with a few microseconds of set-up that touches nothing a predecessor writes (barrier
+// init, TMEM allocation, the 128 KB weight image through the bulk-copy engine).  Launched with programmatic stream serialisation
+// their CTAs may start that set-up as soon as SM resources free up under the previous kernel's tail; pdl_wait() then blocks until
+// the previous grid has completed and flushed.  Rules kept by every kernel launched this way: (1) EVERY thread executes
+// pdl_wait() before its first read of anything a predecessor may have written - device-side counts included - and before any
+// exit path (a CTA that left early would let the grid complete while the predecessor still runs); (2) the trigger for the NEXT
+// kernel comes right after the wait, so a kernel can never overtake its grand-predecessor.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  static const bool off = getenv("DDB_NO_PDL") != nullptr;
+  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // ---- host-side helpers for pre-packed B operands --------------------------------------------------
