@@ -9,6 +9,10 @@ re-associations of the reference arithmetic:
    U_i[head] = sum_{c in head} q_i[c] W2k[c, :]   (the constant cancels in the softmax),
 3. value contraction sum_e w_e (W2v a_e + b2v) = W2v (sum_e w_e a_e) + b2v sum_e w_e.
 
+Re-associations 2 and 3 are what `csrc/attn_trip2.cu` executes (the commuted-W2 triplet kernels; measured slower than the
+tensor-core W2 GEMM and kept selectable); the default kernels keep W2 as a shared-weight GEMM, which is
+re-association 1 only plus the per-group bias handling of 3.
+
 This file evaluates the network that way on the CPU so that `tests/test_fused_algebra.py` can show
 the re-association stays inside the stated tolerance (rtol 1e-4 / atol 1e-5) against
 `oracle/restate.py`, and so kernel unit tests have per-stage intermediates to compare with.
