@@ -999,10 +999,19 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
       }
     };
     tc_dsts(ka, L.ne_k, b->tc_attn & 4);
-    { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, 0, sms, s); else launch_knn_attn_k(ka, sms, s); }
+    // Key + value phase of an edge family in ONE launch pays when the launch is latency bound (grids that do not fill the GPU:
+    // cfg 1 1.02 -> 1.00 ms/step, 123 -> 93 launches); on full grids it is neutral (kNN, bond) or loses (triplets, cfg 2:
+    // 11.22 -> 11.43 ms/step - one long kernel per branch shares the SMs worse than two), so full grids keep two launches.
+    // DDB_PAIR=0 / 1 forces never / always.
+    static const int pair_mode = getenv("DDB_PAIR") ? atoi(getenv("DDB_PAIR")) : -1;
+    auto want_pair = [&](int tiles) { return pair_mode >= 0 ? pair_mode != 0 : tiles < sms; };
+    const bool knn_pair = (b->tc_attn & 12) == 12 && !b->profiling && want_pair((n_node_rows + 3) / 4);      // key + value phase in one launch (timed passes stay apart)
+    const KnnAttnArgs ka_key = ka;
+    if (!knn_pair) { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, 0, sms, s); else launch_knn_attn_k(ka, sms, s); }
     ka.Hi = PNl + 2 * H; ka.Hj = PNl + 3 * H; ka.w = knn_w(m, L.ne_v); ka.W2tc = m->p(L.ne_v.m.W2tc); ka.out_h = b->h1; ka.ldo = H;
     tc_dsts(ka, L.ne_v, b->tc_attn & 8);
-    { ProfScope ps(b, s, PC_KNN_ATTN_V); if (b->tc_attn & 8) launch_knn_tc(ka, 1, sms, s); else launch_knn_attn_v_node(ka, sms, s); }
+    if (knn_pair) { launch_knn_tc_pair(ka_key, ka, false, sms, s); b->launches -= 1; }
+    else { ProfScope ps(b, s, PC_KNN_ATTN_V); if (b->tc_attn & 8) launch_knn_tc(ka, 1, sms, s); else launch_knn_attn_v_node(ka, sms, s); }
     // --- node update over bond edges -> h1[ligand rows] +=
     BondAttnArgs ba;
     ba.n_lig = NL; ba.lig_idx = b->lig_idx; ba.in_ptr = b->in_ptr; ba.in_eid = b->in_eid; ba.in_src = b->in_src;
@@ -1012,7 +1021,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ba.q = b->qNB; ba.ldq = H; ba.x4 = x_in; ba.wbuf = b->wb_bond; ba.out_h = b->h1; ba.ldo = H;
     ba.k.W2tc = m->p(L.nb_k.W2tc); ba.v.W2tc = m->p(L.nb_v.W2tc);
     ba.vg = b->bond_vg; ba.n_vg = b->n_bvg; ba.stats = b->bond_stats; ba.factor = b->bond_factor; ba.part_h = b->bond_part_h; ba.part_dx = b->bond_part_dx;
-    { ProfScope ps(b, s, PC_BOND_NODE); if (b->tc_attn & 16) { launch_bond_tc(ba, false, sms, s); b->launches += 1; } else launch_bond_attn_node(ba, sms, s); }
+    { ProfScope ps(b, s, PC_BOND_NODE); if (b->tc_attn & 16) b->launches += launch_bond_tc(ba, false, sms, s) - 1; else launch_bond_attn_node(ba, sms, s); }
     // --- bond update over triplets -> hb_out
     TripArgs ta;
     ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
@@ -1033,9 +1042,11 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
       ta.grp4 = b->trip_grp4; ta.grp_pk = b->trip_grp_pk; ta.csr_slot = b->csr_slot; ta.xcsr = b->xcsr;
     }
     { ProfScope ps(b, sb, PC_TRIP_PREP); launch_trip_prep(ta, sb); }
-    { ProfScope ps(b, sb, PC_TRIP_K); if (trip2) launch_trip2(ta, false, sms, sb); else if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
+    const bool trip_pair = !trip2 && (b->tc_attn & 3) == 3 && !trip_chunked && !b->profiling && want_pair((b->n_tvg + 3) / 4);
+    if (trip_pair) { launch_trip_tc_pair(ta, sms, sb); b->launches -= 1; }
+    if (!trip_pair) { ProfScope ps(b, sb, PC_TRIP_K); if (trip2) launch_trip2(ta, false, sms, sb); else if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
     if (trip_chunked && (b->tc_attn & 3) == 3) { launch_chunk_factors(ta.stats, ta.vg_pair, 1, ta.n_groups, b->trip_factor, sb); b->launches++; }
-    { ProfScope ps(b, sb, PC_TRIP_V); if (trip2) launch_trip2(ta, true, sms, sb); else if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
+    if (!trip_pair) { ProfScope ps(b, sb, PC_TRIP_V); if (trip2) launch_trip2(ta, true, sms, sb); else if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
     if (trip_chunked && (b->tc_attn & 3) == 3) { launch_trip_combine(ta, m->p(L.bl_v.m.b2), sb); b->launches++; }
     gemm(b, sb, PC_GEMM_BOND, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);      // projection of the new h_bond for the position update
     if (fork) cudaEventRecord(b->ev_trip, sb);
@@ -1058,10 +1069,13 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
     kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k); kp.W2tc = m->p(L.pe_k.m.W2tc);
     kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_first = 0; kp.first_class = 0; kp.slot_meta = b->slot_meta_lig;      // ligand destinations only
-    { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, 0, sms, s); else launch_knn_attn_k(kp, sms, s); }
+    const KnnAttnArgs kp_key = kp;
+    if (!((b->tc_attn & 12) == 12 && !b->profiling && want_pair((NL + 3) / 4))) { ProfScope ps(b, s, PC_KNN_POS_K); if (b->tc_attn & 4) launch_knn_tc(kp, 0, sms, s); else launch_knn_attn_k(kp, sms, s); }
     kp.Hi = b->PLx + H; kp.Hj = b->PNx + H; kp.w = knn_w(m, L.pe_v); kp.out_dx = b->dx_edge;
     kp.W2tc = m->p(L.pe_v.m.W2tc); kp.B2tc[0] = m->p(L.pe_v.B2tc[0]); kp.B2tc[1] = m->p(L.pe_v.B2tc[1]);
-    { ProfScope ps(b, s, PC_KNN_POS_V); if (b->tc_attn & 8) launch_knn_tc(kp, 2, sms, s); else launch_knn_attn_v_pos(kp, sms, s); }
+    const bool pos_pair = (b->tc_attn & 12) == 12 && !b->profiling && want_pair((NL + 3) / 4);
+    if (pos_pair) { launch_knn_tc_pair(kp_key, kp, true, sms, s); b->launches -= 1; }
+    else { ProfScope ps(b, s, PC_KNN_POS_V); if (b->tc_attn & 8) launch_knn_tc(kp, 2, sms, s); else launch_knn_attn_v_pos(kp, sms, s); }
     // --- position update over bond edges + x_out = x_in + (dx_edge + dx_bond) * mask   (:280-285)
     BondAttnArgs bp;
     bp.n_lig = NL; bp.lig_idx = b->lig_idx; bp.in_ptr = b->in_ptr; bp.in_eid = b->in_eid; bp.in_src = b->in_src;
@@ -1073,7 +1087,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     bp.k.W2tc = m->p(L.pb_k.W2tc); bp.v.W2tc = m->p(L.pb_v.W2tc);
     bp.vg = b->bond_vg; bp.n_vg = b->n_bvg; bp.stats = b->bond_stats; bp.factor = b->bond_factor; bp.part_h = b->bond_part_h; bp.part_dx = b->bond_part_dx;
     join_side(b->ev_trip);      // h_bond_out and its projection: the side branch of this layer is complete
-    { ProfScope ps(b, s, PC_BOND_POS); if (b->tc_attn & 16) { launch_bond_tc(bp, true, sms, s); b->launches += 1; } else launch_bond_attn_pos(bp, sms, s); }
+    { ProfScope ps(b, s, PC_BOND_POS); if (b->tc_attn & 16) b->launches += launch_bond_tc(bp, true, sms, s) - 1; else launch_bond_attn_pos(bp, sms, s); }
     b->launches += 3;
     h_in = h_out; x_in = x_out; hb_in = hb_out;
     if (b->tap_h) cudaMemcpyAsync(b->tap_h + (size_t)l * N * H, h_out, (size_t)N * H * sizeof(float), cudaMemcpyDeviceToDevice, s);

@@ -9,6 +9,8 @@
 //                 dx_i = mean_heads sum_rows w[row, h] (D[row, h] + b2[h]) (x_i - x_j);  x_i += (dx_edge + dx) * mask   (:284-285)
 // The launch is small (n_lig / 4 tiles, ~3 per SM), so rows are gathered at the top of each iteration without cross-tile
 // prefetch; the fixed cost is the 128 KB W2 image per CTA.
+#include <cstdlib>
+
 #include "attn_tc.cuh"
 
 namespace ddb {
@@ -55,8 +57,9 @@ __device__ __forceinline__ void bt_issue_mma(uint32_t tmem_base, uint32_t w2_sme
   umma_commit(bar);
 }
 
+// `first` / `last`: key pass and value pass may run back to back inside one launch (bond_tc_pair_kernel, see attn_tc_knn.cu)
 template <int PASS>
-__global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnArgs a) {
+__device__ __forceinline__ void bond_tc_body(const BondAttnArgs& a, const bool first, const bool last) {
   constexpr int NOUT = PASS == BT_V_POS ? 16 : 128;
   constexpr int W2_BYTES = 2 * NOUT * 128 * 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -65,10 +68,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
+    if (!first) { mbar_inval(smem_u32(&sm.bars[0])); mbar_inval(smem_u32(&sm.bars[1])); }
     mbar_init(smem_u32(&sm.bars[0]), 1); mbar_init(smem_u32(&sm.bars[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
+  if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
   cta_copy_f4(sm.beta, side.w.beta, H);
   if (PASS == BT_V_NODE) cta_copy_f4(sm.b2, side.w.b2, H);
   if (PASS == BT_V_POS && tid < 16) sm.b2[tid] = side.w.b2[tid];
-  pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
+  if (first) pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), w2_smem = smem_u32(sm.W2);
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
         if (prev_ok) {
 #pragma unroll
           for (int h = 0; h < 16; ++h) {
-            float wv = __ldg(a.wbuf + ((size_t)prev_slot0 + lane) * NH + h);
+            float wv = a.wbuf[((size_t)prev_slot0 + lane) * NH + h];
             if (prev_pair >= 0) wv *= __ldg(a.factor + (size_t)prev_vg * NH + h);
             cpos = fmaf(wv, __uint_as_float(v[h]) + sm.b2[h], cpos);
           }
@@ -396,8 +400,24 @@ __global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnAr
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  __syncthreads();      // also orders this phase's attention weights before the next phase's reads within the CTA
+  if (last && warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_kernel(const BondAttnArgs a) { bond_tc_body<PASS>(a, true, true); }
+template <int P2>
+__global__ void __launch_bounds__(BT_THREADS, 1) bond_tc_pair_kernel(const BondAttnArgs a) {
+  bond_tc_body<BT_K>(a, true, false);
+  bond_tc_body<P2>(a, false, true);
+}
+template <int P2>
+static void launch_bond_tc_pair(const BondAttnArgs& a, int num_sms, cudaStream_t stream) {
+  static DeviceOnce once;
+  const int bytes = BondTcSmem::bytes();
+  if (!once.done()) { cudaFuncSetAttribute(bond_tc_pair_kernel<P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
+  const int grid = atc_grid((a.n_vg + 3) / 4, num_sms);
+  launch_pdl(bond_tc_pair_kernel<P2>, dim3(grid), dim3(BT_THREADS), bytes, stream, a);
 }
 
 template <int PASS>
@@ -410,14 +430,21 @@ static void launch_bond_tc_pass(const BondAttnArgs& a, int num_sms, cudaStream_t
 }
 
 // node variant: key pass then value pass; position variant: key pass then the 16-output value pass + x update
-void launch_bond_tc(const BondAttnArgs& a, bool pos, int num_sms, cudaStream_t stream) {
-  if (a.n_lig <= 0 || a.n_vg <= 0) return;
-  launch_bond_tc_pass<BT_K>(a, num_sms, stream);
+int launch_bond_tc(const BondAttnArgs& a, bool pos, int num_sms, cudaStream_t stream) {      // returns the number of launches
+  if (a.n_lig <= 0 || a.n_vg <= 0) return 0;
   const bool chunked = a.n_vg > a.n_lig;      // some atom has more than 32 incoming edges
+  static const int pair_mode = getenv("DDB_PAIR") ? atoi(getenv("DDB_PAIR")) : -1;      // see api.cu: pairs pay on small grids only
+  const bool pair = pair_mode >= 0 ? pair_mode != 0 : (a.n_vg + 3) / 4 < num_sms;
+  if (!chunked && pair) {      // key + value phase in one launch (a chunked group needs the factors of all CTAs in between)
+    if (pos) launch_bond_tc_pair<BT_V_POS>(a, num_sms, stream); else launch_bond_tc_pair<BT_V_NODE>(a, num_sms, stream);
+    return 1;
+  }
+  launch_bond_tc_pass<BT_K>(a, num_sms, stream);
   if (chunked) launch_chunk_factors(a.stats, reinterpret_cast<const int*>(a.vg) + 3, 4, a.n_vg, const_cast<float*>(a.factor), stream);
   if (pos) launch_bond_tc_pass<BT_V_POS>(a, num_sms, stream);
   else launch_bond_tc_pass<BT_V_NODE>(a, num_sms, stream);
   if (chunked) launch_bond_combine(a, pos, stream);
+  return chunked ? 4 : 2;
 }
 
 // host-side packing of the position value MLP's second Linear W2[16 out][128 in] into the hi | lo swizzled image (N = 16)

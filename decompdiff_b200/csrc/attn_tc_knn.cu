@@ -94,8 +94,11 @@ void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, cons
 }
 
 // PASS: 0 = key pass, 1 = node value pass, 2 = position value pass (16-output second Linear, dx per destination slot)
+// `first` / `last`: the key pass and a value pass may run back to back inside ONE launch (knn_tc_pair_kernel): same tiles per CTA in
+// both phases, so a phase only reads attention weights its own CTA wrote; barriers are re-initialised and the weight images
+// swapped in between, TMEM and the register hand-over are set up once
 template <int PASS>
-__global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) {
+__device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool first, const bool last) {
   constexpr bool VPASS = PASS != 0, VPOS = PASS == 2;
   constexpr int W2_BYTES = VPOS ? 2 * NH * 128 * 4 : ATC_W2_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -104,10 +107,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   // barriers: [0] W2 (+ first B2) landed, [1] main MMA retired, [2] distance MMA retired, [3] B2 of the second class landed
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&sm.bars[i]), 1);
+    for (int i = 0; i < 4; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
+  if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   cta_copy_f4(sm.beta, a.w.beta, H);
   if (VPASS && !VPOS) cta_copy_f4(sm.b2, a.w.b2, H);
   if (VPOS && tid < NH) sm.b2[tid] = a.w.b2[tid];
-  pdl_wait();      // everything above is set-up on static data; below this line the previous kernels' results are visible
+  if (first) pdl_wait();      // everything above is set-up on static data; below this line the previous kernels' results are visible
   const int n_dst = a.n_dst_dev ? min(__ldg(a.n_dst_dev), a.n_dst) : a.n_dst;      // device-side count: receptive-field pruning
   const int n_tiles = (n_dst + 3) / 4;
   __syncthreads();
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
   if (warp >= 16) {
     // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
 #ifndef DDB_NO_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");      // a no-op in the second phase of a paired launch (already at 32)
 #endif
     if (warp == 16) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
           float cpos = 0.f;
           if (prev_ok) {
 #pragma unroll
-            for (int h = 0; h < NH; ++h) cpos = fmaf(__ldg(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + h), __uint_as_float(v16[h]) + sm.b2[h], cpos);
+            for (int h = 0; h < NH; ++h) cpos = fmaf(a.wbuf[((size_t)prev_node * KNN + lane) * NH + h], __uint_as_float(v16[h]) + sm.b2[h], cpos);
           }
           const float ax = warp_sum(cpos * prev_rel.x), ay = warp_sum(cpos * prev_rel.y), az = warp_sum(cpos * prev_rel.z);
           if (lane == 0 && prev_node >= 0) st4(a.out_dx + (size_t)prev_slot * 4, make_float4(ax * (1.f / NH), ay * (1.f / NH), az * (1.f / NH), 0.f));
@@ -484,8 +487,31 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  __syncthreads();      // also orders this phase's global writes (attention weights) before the next phase's reads within the CTA
+  if (last && warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_kernel(const KnnAttnArgs a) { knn_tc_body<PASS>(a, true, true); }
+// key pass + value pass of one edge family in one launch (P2 = 1: node update, 2: position update)
+template <int P2>
+__global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_pair_kernel(const KnnAttnArgs ak, const KnnAttnArgs av) {
+  knn_tc_body<0>(ak, true, false);
+  knn_tc_body<P2>(av, false, true);
+}
+
+void launch_knn_tc_pair(const KnnAttnArgs& ak, const KnnAttnArgs& av, bool pos, int num_sms, cudaStream_t stream) {
+  if (ak.n_dst <= 0) return;
+  static DeviceOnce once;
+  const int bytes = KnnTcSmem::bytes();
+  if (!once.done()) {
+    cudaFuncSetAttribute(knn_tc_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(knn_tc_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    once.mark();
+  }
+  const int grid = atc_grid((ak.n_dst + 3) / 4, num_sms);
+  if (pos) launch_pdl(knn_tc_pair_kernel<2>, dim3(grid), dim3(KT_THREADS), bytes, stream, ak, av);
+  else launch_pdl(knn_tc_pair_kernel<1>, dim3(grid), dim3(KT_THREADS), bytes, stream, ak, av);
 }
 
 void launch_knn_tc(const KnnAttnArgs& a, int pass, int num_sms, cudaStream_t stream) {      // pass: 0 key, 1 node value, 2 position value

@@ -58,8 +58,9 @@ __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 constexpr int BAR_A2_READY = 5, BAR_A_READY = 6;  // named barriers: every warp arrives, the issuing warp waits on them
 
+// `first` / `last`: key pass and value pass may run back to back inside one launch (trip_tc_pair_kernel, see attn_tc_knn.cu)
 template <bool VPASS>
-__global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a) {
+__device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first, const bool last) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TripTcSmem sm(smem_raw);
   const TripSide& side = VPASS ? a.v : a.k;
@@ -67,10 +68,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
   // barriers: [0] weights landed, [1] main MMA retired, [2] angular MMA retired
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    mbar_init(smem_u32(&sm.bars[0]), 1); mbar_init(smem_u32(&sm.bars[1]), 1); mbar_init(smem_u32(&sm.bars[2]), 1);
+    for (int i = 0; i < 3; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
+  if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
   cta_copy_f4(sm.b2, side.w.b2, H);
   // rows of A2 are 128 bytes but only 16 features are used: clear both images once (features 13..31 stay zero)
   for (int i = tid * 16; i < TT_A2_BYTES; i += TT_THREADS * 16) *reinterpret_cast<float4*>(sm.A2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
+  if (first) pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
   const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]);
@@ -439,8 +440,26 @@ __global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  __syncthreads();      // also orders this phase's attention weights before the next phase's reads within the CTA
+  if (last && warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool VPASS>
+__global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_kernel(const TripArgs a) { trip_tc_body<VPASS>(a, true, true); }
+__global__ void __launch_bounds__(TT_THREADS, 1) trip_tc_pair_kernel(const TripArgs a) {
+  trip_tc_body<false>(a, true, false);
+  trip_tc_body<true>(a, false, true);
+}
+
+// key + value pass in one launch: every (CTA, quadrant) walks the same groups in both phases (not for chunked groups, whose
+// rescale factors need every CTA's key pass)
+void launch_trip_tc_pair(const TripArgs& a, int num_sms, cudaStream_t stream) {
+  if (a.n_bonds <= 0 || a.n_groups <= 0) return;
+  static DeviceOnce once;
+  const int bytes = TripTcSmem::bytes();
+  if (!once.done()) { cudaFuncSetAttribute(trip_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); once.mark(); }
+  const int grid = atc_grid((a.n_groups + 3) / 4, num_sms);
+  launch_pdl(trip_tc_pair_kernel, dim3(grid), dim3(TT_THREADS), bytes, stream, a);
 }
 
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream) {

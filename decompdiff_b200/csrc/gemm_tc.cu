@@ -264,6 +264,8 @@ void launch_gemm128_tc_batch(const GemmArgs* args, const float* const* Wtc, int 
       const double cost = 1.0 + rows_each * (1.5 + (double)tiles / ns);
       if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
     }
+    static const int force_ns = getenv("DDB_GEMM_NS") ? atoi(getenv("DDB_GEMM_NS")) : 0;      // experiment: fixed column split
+    if (force_ns > 0 && tiles % force_ns == 0) best = force_ns;
     const int per = tiles / best;
     gb.p[np] = a; gb.Wtc[np] = Wtc[i]; gb.per[np] = per;
     gb.gx[np] = std::max(1, std::min(row_tiles, num_sms / best)); gb.gy[np] = (tiles + per - 1) / per;

@@ -185,14 +185,16 @@ void launch_trip_v(const TripArgs& a, int num_sms, cudaStream_t stream);
 
 // ---- tensor-core variants (attn_tc.cu): same arguments, wbuf rows of a group are 32 apart; groups of <= 32 rows only
 void launch_knn_tc(const KnnAttnArgs& a, int pass /* 0 key, 1 node value, 2 position value */, int num_sms, cudaStream_t stream);
+void launch_knn_tc_pair(const KnnAttnArgs& key, const KnnAttnArgs& value, bool pos, int num_sms, cudaStream_t stream);   // key + value phase, one launch
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
+void launch_trip_tc_pair(const TripArgs& a, int num_sms, cudaStream_t stream);      // key + value phase, one launch (no chunked groups)
 void launch_trip2(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);      // attn_trip2.cu (groups of <= 32 rows)
 void pack_wa_sw32(const float* Wa, float* out /* 4096 floats */);
 void pack_w2k_pairs(const float* W2, float* out /* 128*128 floats */);
 void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, const int* nlig, const uint8_t* is_lig, int2* out,
                           cudaStream_t stream);
 void launch_knn_dist(const float* x4, const int* nbr, const int* deg, int n, float* dist, cudaStream_t stream);
-void launch_bond_tc(const BondAttnArgs& a, bool pos, int num_sms, cudaStream_t stream);      // attn_tc_bond.cu (groups of <= 32 edges)
+int launch_bond_tc(const BondAttnArgs& a, bool pos, int num_sms, cudaStream_t stream);      // attn_tc_bond.cu (groups of <= 32 edges)
 void pack_w2_tc(const float* W2, float* out);
 void pack_w2x_tc(const float* W2 /* [16][128] */, float* out /* 2*16*128 floats */);
 void pack_wg_tc(const float* Wg, int type_p, int type_l, float* out /* 2 * 5120 floats */);
