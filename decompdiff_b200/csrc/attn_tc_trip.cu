@@ -25,10 +25,10 @@ struct TripTcSmem {
     qrow = reinterpret_cast<float*>(p); p += 16 * 64 * 4;       // per warp: 2 x 32-float slices of the centred Q row
     xyz = reinterpret_cast<float*>(p); p += 16 * 34 * 16;       // per warp: positions x_k of its 32 rows, x_i, x_j (cp.async staging)
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][row][slice] {sum, sum of squares}
-    bars = reinterpret_cast<uint64_t*>(p); p += 32;
+    bars = reinterpret_cast<uint64_t*>(p); p += 64;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 16 * 34 * 4 + 2 * 2 * 128 * 4) * 4 + 64; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 16 * 34 * 4 + 2 * 2 * 128 * 4) * 4 + 96; }
 };
 static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -68,7 +68,9 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
   // barriers: [0] weights landed, [1] main MMA retired, [2] angular MMA retired
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    for (int i = 0; i < 3; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), 1); }
+    // [0] weights landed, [1] main MMA retired, [2] angular MMA retired, [3] angular features of a tile written (3 producer warps),
+    // [4] D2 of a tile read by every worker warp
+    for (int i = 0; i < 5; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), i == 3 ? 3 : i == 4 ? 16 : 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
@@ -91,7 +93,7 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
   if (first) pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
-  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]);
+  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]), bar_a2f = smem_u32(&sm.bars[3]), bar_d2c = smem_u32(&sm.bars[4]);
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
   // Work distribution: the groups (bond edges j->i) are visited in SOURCE-major order (a.grp_order) and every (CTA, quadrant)
   // pair walks one contiguous chunk of that order.  All groups with the same source j read the same rows P'[k->j], so a thread
@@ -99,16 +101,17 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
   const int per = (a.n_groups + 4 * (int)gridDim.x - 1) / (4 * (int)gridDim.x);      // iterations of every CTA
 
   if (warp >= 16) {
-    // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
+    // ---------------------------------------------------------------- warp 16 issues the MMAs, warps 17..19 produce the angular features
 #ifndef DDB_NO_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
 #endif
     if (warp == TT_ISSUER) {
       // tensor-pipe order: ang(t0), [ang(t1), main(t0)], [ang(t2), main(t1)], ...  - the angular MMA runs one tile ahead
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      auto issue_ang = [&]() {
-        named_sync(BAR_A2_READY, TT_SYNC);          // every worker has written its A2 features and is done with D2
+      auto issue_ang = [&](int t) {
         if (lane == 0) {
+          mbar_wait(bar_a2f, t & 1);                   // the producers have written the features of tile t
+          if (t > 0) mbar_wait(bar_d2c, (t - 1) & 1);   // every worker warp has read D2 of tile t-1
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {             // K = 16 features: two k-steps of 8 inside the first 64 bytes of the rows
@@ -120,74 +123,77 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
         }
         __syncwarp();
       };
-      if (per > 0) issue_ang();
+      if (per > 0) issue_ang(0);
       for (int it = 0; it < per; ++it) {
-        if (it + 1 < per) issue_ang();
+        if (it + 1 < per) issue_ang(it + 1);
         named_sync(BAR_A_READY, TT_SYNC);           // hidden activations are in TMEM, D of the previous tile is in registers
         if (lane == 0) { tc_fence_after(); atc_issue_mma(tmem_base, w2_smem, bar_mma); }
         __syncwarp();
       }
-    }
-  } else {
-#ifndef DDB_NO_SETMAXNREG
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-#endif
-    auto hand_over_a2 = [&]() { named_arrive(BAR_A2_READY, TT_SYNC); };
-    auto hand_over_a = [&]() { named_arrive(BAR_A_READY, TT_SYNC); };
-    // ---------------------------------------------------------------- 16 warps: thread = (row r, channel slice s)
-    // geometry of a row -> angular features -> A2 (the 13 features are split over the 4 slice-warps), then hand A2 over
-    // positions for the features of a tile: requested one phase early with cp.async (gathers through L2 that hold no registers
-    // while in flight) into this warp's staging rows, consumed in features()
-    float* const wxyz = sm.xyz + warp * (34 * 4);
-    auto cp16 = [](float* dst, const float* src) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-    };
-    auto request_xyz = [&](int2 gm, int2 rm) {
-      cp16(wxyz + lane * 4, a.x4 + (size_t)(rm.y >= 0 ? rm.y : gm.y) * 4);      // excluded rows: k := j, theta = 0
-      if (lane < 2) cp16(wxyz + (32 + lane) * 4, a.x4 + (size_t)(lane == 0 ? gm.x : gm.y) * 4);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto fetch_xyz = [&](float4& xi, float4& xj, float4& xk) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      xk = ld4(wxyz + lane * 4); xi = ld4(wxyz + 32 * 4); xj = ld4(wxyz + 33 * 4);
-      __syncwarp();
-    };
-    auto features = [&](int2 rm, float4 xi, float4 xj, float4 xk) {
-      const bool rowok = rm.y >= 0;
-      const float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
-      const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
-      float cn = sqrtf(cx * cx + cy * cy + cz * cz);             // |(j-i) x (k-i)|          (:134-137)
-      float dot = ax * bx + ay * by + az * bz;
-      if (!rowok) { cn = 0.f; dot = 1.f; }
-      // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3] (common.py:46-54).  sin / cos of theta
-      // follow from (cn, dot) directly (cn^2 + dot^2 = |a|^2 |b|^2), multiples and the half angle from the usual identities;
-      // only theta itself and theta/3 need atan2f / sincosf
-      if (s == 0) {
-        a2_put(sm.A2, r, 0, atan2f(cn, dot));
-      } else if (s == 3) {
-        float sv, cv;
-        sincosf(atan2f(cn, dot) * (float)(1.0 / 3.0), &sv, &cv);
-        a2_put(sm.A2, r, 6, sv); a2_put(sm.A2, r, 12, cv);
-      } else {
+    } else {
+      // ---------------------------------------------------------------- producers: geometry of a row -> its 13 angular features -> A2.
+      // Thread = row; warp 17 serves quadrants 0 and 3, warps 18 / 19 quadrants 1 / 2.  Everything here used to sit on the worker
+      // warps' critical path (~125 instructions per thread and tile, the slice with atan2f + sincosf the slowest of its quadrant).
+      const int pw = warp - 17;
+      auto row_meta_of = [&](int qq, int t, int2& gm, int2& rm) {
+        gm = make_int2(0, 0); rm = make_int2(-1, -1);
+        const int gb = ((int)blockIdx.x * 4 + qq) * per, pos = gb + t;
+        if (t < per && pos < min(a.n_groups, gb + per)) { gm = __ldg(a.grp_meta + pos); rm = __ldg(a.row_meta + (size_t)pos * 32 + lane); }
+      };
+      auto put_features = [&](int qq, int2 rm, float4 xi, float4 xj, float4 xk) {
+        const int rr = qq * 32 + lane;
+        const bool rowok = rm.y >= 0;
+        const float ax = xj.x - xi.x, ay = xj.y - xi.y, az = xj.z - xi.z, bx = xk.x - xi.x, by = xk.y - xi.y, bz = xk.z - xi.z;
+        const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+        float cn = sqrtf(cx * cx + cy * cy + cz * cz);             // |(j-i) x (k-i)|          (:134-137)
+        float dot = ax * bx + ay * by + az * bz;
+        if (!rowok) { cn = 0.f; dot = 1.f; }
+        // AngularEncoding [theta, sin(f theta), cos(f theta)], f = [1,2,3,1,1/2,1/3] (common.py:46-54): sin / cos of theta follow
+        // from (cn, dot), multiples and the half angle from the usual identities; only theta and theta / 3 need atan2f / sincosf
+        const float theta = atan2f(cn, dot);
         const float n2 = cn * cn + dot * dot;
         const float inv = n2 > 0.f ? rsqrtf(n2) : 0.f;
         const float sn = cn * inv, cs = n2 > 0.f ? dot * inv : 1.f;
-        if (s == 1) {
-          a2_put(sm.A2, r, 1, sn); a2_put(sm.A2, r, 4, sn); a2_put(sm.A2, r, 7, cs); a2_put(sm.A2, r, 10, cs);
-          a2_put(sm.A2, r, 2, 2.f * sn * cs); a2_put(sm.A2, r, 8, cs * cs - sn * sn);
-          a2_put(sm.A2, r, 3, sn * (3.f - 4.f * sn * sn)); a2_put(sm.A2, r, 9, cs * (4.f * cs * cs - 3.f));
-        } else {    // half angle, theta/2 in [0, pi/2]: take the root that does not cancel, derive the other from sin(theta)
-          float sh, ch;
-          if (cs >= 0.f) { ch = sqrtf(0.5f * (1.f + cs)); sh = sn / (2.f * ch); }
-          else { sh = sqrtf(0.5f * (1.f - cs)); ch = sn / (2.f * sh); }
-          a2_put(sm.A2, r, 5, sh); a2_put(sm.A2, r, 11, ch);
+        float sh, ch, s3, c3;
+        if (cs >= 0.f) { ch = sqrtf(0.5f * (1.f + cs)); sh = sn / (2.f * ch); }
+        else { sh = sqrtf(0.5f * (1.f - cs)); ch = sn / (2.f * sh); }
+        sincosf(theta * (float)(1.0 / 3.0), &s3, &c3);
+        a2_put(sm.A2, rr, 0, theta);
+        a2_put(sm.A2, rr, 1, sn); a2_put(sm.A2, rr, 2, 2.f * sn * cs); a2_put(sm.A2, rr, 3, sn * (3.f - 4.f * sn * sn));
+        a2_put(sm.A2, rr, 4, sn); a2_put(sm.A2, rr, 5, sh); a2_put(sm.A2, rr, 6, s3);
+        a2_put(sm.A2, rr, 7, cs); a2_put(sm.A2, rr, 8, cs * cs - sn * sn); a2_put(sm.A2, rr, 9, cs * (4.f * cs * cs - 3.f));
+        a2_put(sm.A2, rr, 10, cs); a2_put(sm.A2, rr, 11, ch); a2_put(sm.A2, rr, 12, c3);
+      };
+      const int q0 = pw == 0 ? 0 : pw, q1 = 3;          // warp 17 also serves quadrant 3
+      int2 gm0, rm0, gm1, rm1;
+      row_meta_of(q0, 0, gm0, rm0);
+      if (pw == 0) row_meta_of(q1, 0, gm1, rm1);
+      for (int t = 0; t < per; ++t) {
+        // positions of this tile's rows (requested first), metadata of the next tile
+        const float4 xi0 = ldg4(a.x4 + (size_t)gm0.x * 4), xj0 = ldg4(a.x4 + (size_t)gm0.y * 4),
+                     xk0 = ldg4(a.x4 + (size_t)(rm0.y >= 0 ? rm0.y : gm0.y) * 4);
+        float4 xi1 = xi0, xj1 = xj0, xk1 = xk0;
+        if (pw == 0) {
+          xi1 = ldg4(a.x4 + (size_t)gm1.x * 4); xj1 = ldg4(a.x4 + (size_t)gm1.y * 4);
+          xk1 = ldg4(a.x4 + (size_t)(rm1.y >= 0 ? rm1.y : gm1.y) * 4);
         }
+        const int2 rm0c = rm0, rm1c = rm1;
+        row_meta_of(q0, t + 1, gm0, rm0);
+        if (pw == 0) row_meta_of(q1, t + 1, gm1, rm1);
+        if (t > 0) mbar_wait(bar_ang, (t - 1) & 1);      // the angular MMA of the previous tile has read A2
+        put_features(q0, rm0c, xi0, xj0, xk0);
+        if (pw == 0) put_features(q1, rm1c, xi1, xj1, xk1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a2f) : "memory");
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
-      tc_fence_before();
-      hand_over_a2();
-    };
+    }
+  } else {
+#ifndef DDB_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+#endif
+    auto hand_over_a = [&]() { named_arrive(BAR_A_READY, TT_SYNC); };
+    // ---------------------------------------------------------------- 16 warps: thread = (row r, channel slice s)
     // metadata of a tile: clamped so that every load below is unconditional (padding rows read edge 0 / node 0; their
     // results are never stored and they get zero attention weight)
     const int g_begin = ((int)blockIdx.x * 4 + q) * per, g_end = min(a.n_groups, g_begin + per);
@@ -227,10 +233,6 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
     load_meta(1, e_n, gm_n, rm_n);
     float4 pv[8];
     if (per > 0) {
-      float4 xi, xj, xk;
-      request_xyz(gm, rm);
-      fetch_xyz(xi, xj, xk);
-      features(rm, xi, xj, xk);          // prologue: the angular MMA of the first tile
       const float* prow = Pc + (size_t)max(rm.x, 0) * H + s * 32;
 #pragma unroll
       for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
@@ -247,7 +249,6 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
       int2 gm_nn, rm_nn;
       int e_nn;
       load_meta(it + 2, e_nn, gm_nn, rm_nn);
-      request_xyz(gm_n, rm_n);
       const int tb = (g_begin + it) * 32;      // wbuf rows of a (group, chunk) are its 32 slots in visiting order
       const int pair = e >= 0 ? __ldg(a.vg_pair + g_begin + it) : -1;
       // ---- first Linear: z = P'[kj] (in registers) + Q'[ji] (staged) + D2 (angular MMA, issued one iteration ago)
@@ -269,6 +270,9 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], u2f(v[2 * i], v[2 * i + 1]));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_d2c) : "memory");      // D2 may be overwritten
       }
       // ---- prefetch the P' rows of the next tile (consumed one iteration from now), stage its Q slice and this tile's query
       // ---- the next group reads other rows only when its source atom differs: gather them now, consumed one iteration later
@@ -282,12 +286,6 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
         if (!VPASS) wqry[(it & 3) * 32 + lane] = qry_v;
       }
       TL_MARK(2);
-      // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
-      if (it + 1 < per) {
-        float4 nxi, nxj, nxk;
-        fetch_xyz(nxi, nxj, nxk);
-        features(rm_n, nxi, nxj, nxk);
-      }
       TL_MARK(3);
       // ---- LayerNorm with ONE exchange (single-pass statistics: the rows are centred up to the small angular term), ReLU
       {
