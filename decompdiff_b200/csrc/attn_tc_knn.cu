@@ -24,7 +24,7 @@ constexpr int KT_SYNC = ATC_THREADS + 32;         // participants of the hand-ov
 constexpr int KT_KB = 5;                          // 40 feature columns = 5 k-steps of 8
 constexpr int KT_IMG = KT_KB * 128 * 32;          // one TF32 image of a [128 rows][40 cols] SWIZZLE_32B operand: 20480 bytes
 constexpr int KT_COL_D2 = 384;
-constexpr int KBAR_A2_READY = 5, KBAR_A_READY = 6;
+constexpr int KBAR_A_READY = 6;
 
 struct KnnTcSmem {
   uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *hit, *qry; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
@@ -39,10 +39,10 @@ struct KnnTcSmem {
     hit = reinterpret_cast<float*>(p); p += 16 * 64 * 4;        // per warp: dst-side row slice + Wt[type], for protein | ligand sources
     qry = reinterpret_cast<float*>(p); p += 16 * 64 * 4;        // per warp: 2-deep ring of 32-float query slices
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;  // [parity][row][slice] {sum, sum of squares}
-    bars = reinterpret_cast<uint64_t*>(p); p += 32;
+    bars = reinterpret_cast<uint64_t*>(p); p += 64;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 4 * KT_IMG + (3 * H + 16 * 64 * 2 + 2 * 128 * 4 * 2) * 4 + 64; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 4 * KT_IMG + (3 * H + 16 * 64 * 2 + 2 * 128 * 4 * 2) * 4 + 96; }
 };
 static_assert(KnnTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -104,10 +104,11 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   KnnTcSmem sm(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
-  // barriers: [0] W2 (+ first B2) landed, [1] main MMA retired, [2] distance MMA retired, [3] B2 of the second class landed
+  // barriers: [0] W2 (+ first B2) landed, [1] main MMA retired, [2] distance MMA retired, [3] B2 of the second class landed,
+  // [4] Gaussian features of a tile written (3 producer warps), [5] D2 of a tile read by every worker warp
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), 1); }
+    for (int i = 0; i < 6; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), i == 4 ? 3 : i == 5 ? 16 : 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
@@ -133,20 +134,21 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
   const int n_tiles = (n_dst + 3) / 4;
   __syncthreads();
   mbar_wait(smem_u32(&sm.bars[0]), 0);
-  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_d2 = smem_u32(&sm.bars[2]);
+  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_d2 = smem_u32(&sm.bars[2]), bar_a2f = smem_u32(&sm.bars[4]), bar_d2c = smem_u32(&sm.bars[5]);
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
 
   if (warp >= 16) {
-    // ---------------------------------------------------------------- MMA issuer warpgroup (warp 16 issues, 17..19 idle)
+    // ---------------------------------------------------------------- warp 16 issues the MMAs, warps 17..19 produce the distance features
 #ifndef DDB_NO_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");      // a no-op in the second phase of a paired launch (already at 32)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // a no-op in the second phase of a paired launch (already there)
 #endif
     if (warp == 16) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int cur_class = class_of(blockIdx.x);
-      auto issue_d2 = [&](int tile) {
-        knamed_sync(KBAR_A2_READY, KT_SYNC);          // every worker has written its A2 features and has read D2 of the tile before
+      auto issue_d2 = [&](int tile, int t) {
         if (lane == 0) {
+          mbar_wait(bar_a2f, t & 1);                     // the producers have written the features of this tile
+          if (t > 0) mbar_wait(bar_d2c, (t - 1) & 1);     // every worker warp has read D2 of the tile before
           tc_fence_after();
           const int cls = class_of(tile);
           if (cls != cur_class) {                     // class boundary: every distance MMA issued so far has retired (workers
@@ -177,17 +179,59 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
         }
         __syncwarp();
       };
-      if ((int)blockIdx.x < n_tiles) issue_d2(blockIdx.x);
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (tile + (int)gridDim.x < n_tiles) issue_d2(tile + gridDim.x);
+      if ((int)blockIdx.x < n_tiles) issue_d2(blockIdx.x, 0);
+      int t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        if (tile + (int)gridDim.x < n_tiles) issue_d2(tile + gridDim.x, t + 1);
         knamed_sync(KBAR_A_READY, KT_SYNC);           // hidden activations are in TMEM, D of the previous tile is in registers
         if (lane == 0) { tc_fence_after(); if (VPOS) atc_issue_mma_n<NH>(tmem_base, w2_smem, bar_mma); else atc_issue_mma(tmem_base, w2_smem, bar_mma); }
         __syncwarp();
       }
+    } else {
+      // ---------------------------------------------------------------- producers: distance of a row -> its 20 Gaussians -> A2.
+      // Thread = row.  Warp 17 + p writes quadrant p; quadrant 3 is shared by 4-column chunk ({0,1} | {2,3} | {4}).  A chunk goes to
+      // the column block of the row's source class, the other block gets zeros.  (On the worker warps this was ~70 instructions per
+      // thread and tile, twice that on the slice-0 warps the rest of the quadrant then waited for.)
+      const int pw = warp - 17, step = gridDim.x;
+      auto meta_of = [&](int tile, int qq) {
+        const int slot = tile * 4 + qq;
+        return tile < n_tiles && slot < n_dst ? __ldg(a.slot_meta + slot) : make_int2(-1, 0);
+      };
+      auto put_chunk = [&](int rr, int c, float d, bool src_lig) {
+        float g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float u = d - c_gauss_offset[c * 4 + i]; g[i] = expf(-0.5f * u * u); }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tf32_split(g[i], hi[i], lo[i]);
+        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]), z4 = make_uint4(0u, 0u, 0u, 0u);
+        const int off_p = kt_chunk_off(rr, c), off_l = kt_chunk_off(rr, 5 + c);
+        *reinterpret_cast<uint4*>(sm.A2 + off_p) = src_lig ? z4 : vh;
+        *reinterpret_cast<uint4*>(sm.A2 + KT_IMG + off_p) = src_lig ? z4 : vl;
+        *reinterpret_cast<uint4*>(sm.A2 + off_l) = src_lig ? vh : z4;
+        *reinterpret_cast<uint4*>(sm.A2 + KT_IMG + off_l) = src_lig ? vl : z4;
+      };
+      const int c3_lo = pw * 2, c3_hi = pw == 2 ? 5 : pw * 2 + 2;
+      int2 m0 = meta_of(blockIdx.x, pw), m3 = meta_of(blockIdx.x, 3);
+      int t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += step, ++t) {
+        const float d0 = m0.x >= 0 ? __ldg(a.dist + (size_t)m0.x * KNN + lane) : 0.f;
+        const float d3 = m3.x >= 0 ? __ldg(a.dist + (size_t)m3.x * KNN + lane) : 0.f;
+        const bool l0 = lane < ((m0.y >> 8) & 0xff), l3 = lane < ((m3.y >> 8) & 0xff);
+        m0 = meta_of(tile + step, pw); m3 = meta_of(tile + step, 3);
+        if (t > 0) mbar_wait(bar_d2, (t - 1) & 1);      // the distance MMA of the tile before has read A2
+#pragma unroll
+        for (int c = 0; c < 5; ++c) put_chunk(pw * 32 + lane, c, d0, l0);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) if (c >= c3_lo && c < c3_hi) put_chunk(96 + lane, c, d3, l3);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a2f) : "memory");
+      }
     }
   } else {
 #ifndef DDB_NO_SETMAXNREG
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
 #endif
     // ---------------------------------------------------------------- 16 worker warps: thread = (row r, channel slice s)
     struct Grp {            // one destination group, 2 registers: node id (-1: padding) and deg | nlig << 8 | is_ligand << 16
@@ -202,30 +246,6 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
       const int slot = tile * 4 + q;
       if (tile < n_tiles && slot < n_dst) { const int2 m = __ldg(a.slot_meta + slot); g.node = m.x; g.pk = m.y; }
       return g;
-    };
-    // Gaussian features of this thread's row -> A2.  Slice-warp s owns the 4-column chunks {s} (and {4} for s == 0); a chunk goes
-    // to the column block of the row's source class, the other block gets zeros.
-    auto features = [&](float d, bool src_lig) {
-#pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-        if (rep == 1 && s != 0) break;
-        const int c = rep == 0 ? s : 4;
-        float g[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const float t = d - c_gauss_offset[c * 4 + i]; g[i] = expf(-0.5f * t * t); }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) tf32_split(g[i], hi[i], lo[i]);
-        const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]), z4 = make_uint4(0u, 0u, 0u, 0u);
-        const int off_p = kt_chunk_off(r, c), off_l = kt_chunk_off(r, 5 + c);
-        *reinterpret_cast<uint4*>(sm.A2 + off_p) = src_lig ? z4 : vh;
-        *reinterpret_cast<uint4*>(sm.A2 + KT_IMG + off_p) = src_lig ? z4 : vl;
-        *reinterpret_cast<uint4*>(sm.A2 + off_l) = src_lig ? vh : z4;
-        *reinterpret_cast<uint4*>(sm.A2 + KT_IMG + off_l) = src_lig ? vl : z4;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
-      tc_fence_before();
-      knamed_arrive(KBAR_A2_READY, KT_SYNC);
     };
     float* const whit = sm.hit + warp * 64;         // [2 source classes][32]
     float* const wqry = sm.qry + warp * 64;         // [2-deep ring][32]
@@ -243,8 +263,6 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
     float hi_cur = g.valid() ? __ldg(a.Hi + (size_t)hidx(g, blockIdx.x) * a.ldhi + s * 32 + lane) : 0.f;
     float4 pv[8];
     if ((int)blockIdx.x < n_tiles) {
-      const float d0 = g.valid() ? __ldg(a.dist + (size_t)g.node * KNN + lane) : 0.f;
-      features(d0, lane < g.nlig());                // prologue: the distance MMA of the first tile
       const float* prow = a.Hj + (size_t)j * a.ldhj + s * 32;
 #pragma unroll
       for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
@@ -257,7 +275,6 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
       const bool rowok = lane < g.deg();            // deg is 0 for padding groups
       // ---- requests for later: rows of the next tile, group metadata two tiles ahead, this tile's query / edge weight
       const int j_n = lane < g_n.deg() ? __ldg(a.nbr + (size_t)g_n.node * KNN + lane) : 0;
-      const float d_n = g_n.valid() ? __ldg(a.dist + (size_t)g_n.node * KNN + lane) : 0.f;
       const float hi_n = g_n.valid() ? __ldg(a.Hi + (size_t)hidx(g_n, tile + step) * a.ldhi + s * 32 + lane) : 0.f;
       const Grp g_nn = load_group(tile + 2 * step);
       float4 rel = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -297,10 +314,11 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], ku2f(v[2 * i], v[2 * i + 1]));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_d2c) : "memory");      // D2 may be overwritten
       }
-      // ---- features of the NEXT tile -> A2 (D2 and A2 are free again: every worker got here through the wait above)
       TL_MARK(3);
-      if (tile + step < n_tiles) features(d_n, lane < g_n.nlig());
       TL_MARK(4);
       // ---- LayerNorm with one exchange between the 4 slice-warps of the quadrant, ReLU
       {

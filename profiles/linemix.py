@@ -33,24 +33,33 @@ def main(src_csv, sass, want_csv, want, units=None):
         i += 1
     hdr = rows[i + 1]
     st, ei = hdr.index('# Samples'), hdr.index('Instructions Executed')
-    data = []
+    stall_cols = [(k, c) for k, c in enumerate(hdr) if c.startswith('stall_') and 'Not Issued' not in c]
+    data, reasons = [], []
     j = i + 2
     while j < len(rows) and not (rows[j] and rows[j][0] == 'Kernel Name'):
         try:
             data.append((int(rows[j][st] or 0), int(rows[j][ei] or 0)))
+            reasons.append({c[6:]: int(rows[j][k] or 0) for k, c in stall_cols})
         except Exception:
             pass
         j += 1
     sl = sass_lines(sass, want)
     print(len(data), 'profiled instructions,', len(sl), 'disassembled')
     n = min(len(data), len(sl))
-    ex, sm = defaultdict(int), defaultdict(int)
-    for (s_, e_), (line, _) in zip(data[:n], sl[:n]):
+    ex, sm, why, total_why = defaultdict(int), defaultdict(int), defaultdict(lambda: defaultdict(int)), defaultdict(int)
+    for (s_, e_), (line, _), rs in zip(data[:n], sl[:n], reasons[:n]):
         ex[line] += e_
         sm[line] += s_
+        for k, v in rs.items():
+            why[line][k] += v
+            total_why[k] += v
     te, ts = sum(ex.values()), sum(sm.values()) or 1
     for line in sorted(ex, key=lambda l: -sm[l])[:45]:
-        print(f'{str(line):38s} exec {ex[line] / te:6.3f}' + (f' {ex[line] / units:7.1f}/unit' if units else '') + f'  samples {sm[line] / ts:6.3f}')
+        top = sorted(why[line].items(), key=lambda kv: -kv[1])[:2]
+        print(f'{str(line):38s} exec {ex[line] / te:6.3f}' + (f' {ex[line] / units:7.1f}/unit' if units else '') + f'  samples {sm[line] / ts:6.3f}  '
+              + ' '.join(f'{k}={v / max(sm[line], 1):.2f}' for k, v in top if v))
+    tw = sum(total_why.values()) or 1
+    print('stall reasons overall: ' + ' '.join(f'{k}={v / tw:.3f}' for k, v in sorted(total_why.items(), key=lambda kv: -kv[1])[:10]))
 
 
 if __name__ == '__main__':
