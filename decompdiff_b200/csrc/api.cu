@@ -354,7 +354,7 @@ struct ddb_batch {
   int *node_ptr = nullptr, *graph_of = nullptr, *lig_idx = nullptr, *lig_ptr = nullptr;
   uint8_t *is_lig = nullptr, *upd_mask = nullptr;
   int *bsrc = nullptr, *bdst = nullptr, *in_ptr = nullptr, *in_eid = nullptr, *in_src = nullptr, *trip_base = nullptr;
-  int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr, *trip_grp_we = nullptr; int *trip_grp_order = nullptr, *trip_row_src = nullptr;
+  int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr; int* trip_grp_order = nullptr;
   int4* bond_vg = nullptr; int n_bvg = 0, n_tvg = 0; float2 *bond_stats = nullptr, *trip_stats = nullptr;
   float *bond_factor = nullptr, *bond_part_h = nullptr, *bond_part_dx = nullptr, *trip_factor = nullptr, *trip_part = nullptr; int* trip_vg_pair = nullptr;
   int4* trip_grp4 = nullptr; int *trip_grp_pk = nullptr, *csr_slot = nullptr; float *PcsrK = nullptr, *PcsrV = nullptr, *xcsr = nullptr;
@@ -616,13 +616,6 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
     }
     DDB_TRY(b->upload(&b->trip_row_meta, row_meta)); DDB_TRY(b->upload(&b->trip_grp_meta, grp_meta));
     DDB_TRY(b->upload(&b->trip_grp_order, grp_order)); DDB_TRY(b->upload(&b->trip_vg_pair, vg_pair));
-    // the worker warps' view of the same metadata (one 4-byte word per row, one 8-byte word per group: staged with cp.async)
-    std::vector<int> row_src((size_t)nvg * 32);
-    std::vector<int2> grp_we(nvg);
-    for (size_t r = 0; r < row_src.size(); ++r)
-      row_src[r] = row_meta[r].x < 0 ? -1 : (row_meta[r].x | (row_meta[r].y < 0 ? TRIP_ROW_EXCLUDED : 0));
-    for (int pos = 0; pos < nvg; ++pos) grp_we[pos] = make_int2(grp_order[pos], vg_pair[pos]);
-    DDB_TRY(b->upload(&b->trip_row_src, row_src)); DDB_TRY(b->upload(&b->trip_grp_we, grp_we));
     DDB_TRY(b->dalloc(&b->trip_stats, (size_t)nvg * NH)); DDB_TRY(b->dalloc(&b->trip_factor, (size_t)nvg * NH));
     DDB_TRY(b->dalloc(&b->trip_part, (size_t)(nvg > Eb ? nvg : 1) * H));
   }
@@ -1032,7 +1025,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     // --- bond update over triplets -> hb_out
     TripArgs ta;
     ta.n_bonds = Eb; ta.bsrc = b->bsrc; ta.bdst = b->bdst; ta.lig_idx = b->lig_idx; ta.in_ptr = b->in_ptr;
-    ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.row_meta = b->trip_row_meta; ta.grp_meta = b->trip_grp_meta; ta.grp_order = b->trip_grp_order; ta.row_src = b->trip_row_src; ta.grp_we = b->trip_grp_we; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
+    ta.in_eid = b->in_eid; ta.in_src = b->in_src; ta.trip_base = b->trip_base; ta.row_meta = b->trip_row_meta; ta.grp_meta = b->trip_grp_meta; ta.grp_order = b->trip_grp_order; ta.x4 = x_in; ta.ldh = 10 * H; ta.ldpe = 5 * H;
     ta.k.Pe = b->PB + 2 * H; ta.k.Hk = b->PL + 5 * H; ta.k.Hj = b->PL + 6 * H; ta.k.Wd = m->p(L.bl_k.Wd);
     ta.k.Wc = m->p(L.bl_k.Wc); ta.k.Wa = m->p(L.bl_k.Wa); ta.k.P = b->Pk; ta.k.w = bond_w(m, L.bl_k.m); ta.k.W2tc = m->p(L.bl_k.m.W2tc); ta.k.Watc = m->p(L.bl_k.Watc);
     const bool trip2 = (b->tc_attn & 35) == 35 && b->max_indeg <= 32;      // commuted-W2 kernels for both passes

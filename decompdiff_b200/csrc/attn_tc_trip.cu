@@ -12,7 +12,7 @@ constexpr int TT_A2_BYTES = 2 * 128 * 128;        // hi | lo, [128 rows][128 B] 
 constexpr int TT_COL_D2 = 384;
 
 struct TripTcSmem {
-  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *qry, *qrow; int* mrow; int2* mgrp; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
+  uint8_t *W2, *B2, *A2; float *gamma, *beta, *b2, *qry, *qrow, *xyz; float2* stat; uint64_t* bars; uint32_t* tmem_slot;
   __device__ explicit TripTcSmem(uint8_t* raw) {
     uint8_t* p = raw;      // purely additive carving keeps everything in the shared address space (LDS / STS)
     W2 = p; p += ATC_W2_BYTES;
@@ -21,15 +21,14 @@ struct TripTcSmem {
     gamma = reinterpret_cast<float*>(p); p += H * 4;
     beta = reinterpret_cast<float*>(p); p += H * 4;
     b2 = reinterpret_cast<float*>(p); p += H * 4;
-    qry = reinterpret_cast<float*>(p); p += 16 * 128 * 4;       // per warp: 4-deep ring of 32-float query slices (value pass: residual slices)
+    qry = reinterpret_cast<float*>(p); p += 16 * 128 * 4;       // per warp: 4-deep ring of 32-float query slices
     qrow = reinterpret_cast<float*>(p); p += 16 * 64 * 4;       // per warp: 2 x 32-float slices of the centred Q row
-    mrow = reinterpret_cast<int*>(p); p += 16 * 128 * 4;        // per warp: 4-deep ring of the 32 row words (row_src) of a tile
-    mgrp = reinterpret_cast<int2*>(p); p += 16 * 4 * 8;         // per warp: 4-deep ring of {edge id, partner chunk}
+    xyz = reinterpret_cast<float*>(p); p += 16 * 34 * 16;       // per warp: positions x_k of its 32 rows, x_i, x_j (cp.async staging)
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][row][slice] {sum, sum of squares}
     bars = reinterpret_cast<uint64_t*>(p); p += 64;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 16 * 128 + 16 * 8 + 2 * 2 * 128 * 4) * 4 + 96; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 16 * 34 * 4 + 2 * 2 * 128 * 4) * 4 + 96; }
 };
 static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -195,38 +194,18 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
 #endif
     auto hand_over_a = [&]() { named_arrive(BAR_A_READY, TT_SYNC); };
     // ---------------------------------------------------------------- 16 warps: thread = (row r, channel slice s)
-    // Everything a tile needs besides the P' rows is staged with cp.async into rings private to the warp - metadata two tiles ahead,
-    // the Q' / query (value pass: residual) slices one tile ahead.  Staging through registers made ptxas spill the prefetched
-    // values, and a spill store waits for its load: the prefetch then stalled the warp for the full L2 latency.
+    // metadata of a tile: clamped so that every load below is unconditional (padding rows read edge 0 / node 0; their
+    // results are never stored and they get zero attention weight)
     const int g_begin = ((int)blockIdx.x * 4 + q) * per, g_end = min(a.n_groups, g_begin + per);
-    int* const mrow = sm.mrow + warp * 128;
-    int2* const mgrp = sm.mgrp + warp * 4;
-    auto cp4 = [](const void* dst, const void* src) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-    };
-    auto cp_commit = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
-    auto cp_wait_all = [&]() { asm volatile("cp.async.wait_group 0;" ::: "memory"); __syncwarp(); };
-    auto stage_meta = [&](int i) {      // padding tiles: edge -1, no rows
-      const int pos = g_begin + i, slot = i & 3;
-      if (pos < g_end) {
-        cp4(mrow + slot * 32 + lane, a.row_src + (size_t)pos * 32 + lane);
-        if (lane < 2) cp4(reinterpret_cast<int*>(mgrp + slot) + lane, reinterpret_cast<const int*>(a.grp_we + pos) + lane);
-      } else {
-        mrow[slot * 32 + lane] = -1;
-        if (lane == 0) mgrp[slot] = make_int2(-1, -1);
-      }
+    auto load_meta = [&](int i, int& e, int2& gm, int2& rm) {      // metadata is stored in visiting order: three independent loads
+      e = -1; gm = make_int2(0, 0); rm = make_int2(-1, -1);
+      const int pos = g_begin + i;
+      if (pos < g_end) { e = __ldg(a.grp_order + pos); gm = __ldg(a.grp_meta + pos); rm = __ldg(a.row_meta + (size_t)pos * 32 + lane); }
     };
     float* const wq = sm.qrow + warp * 64;          // this warp's private staging: [parity][32] slice of the Q row
     float* const wqry = sm.qry + warp * 128;        // k pass: [4-deep ring][32] slice of the query row
     const float* __restrict__ Pc = side.P;          // centred rows (trip_prep): LayerNorm is shift invariant
     const float* __restrict__ Qc = side.Q;
-    auto stage_rows = [&](int i, int e_i) {      // slices of the rows of edge e_i that tile i adds to every one of its rows
-      const size_t ee = (size_t)max(e_i, 0);
-      cp4(wq + (i & 1) * 32 + lane, Qc + ee * H + s * 32 + lane);
-      if (!VPASS) cp4(wqry + (i & 3) * 32 + lane, a.q + ee * a.ldq + s * 32 + lane);
-      else cp4(wqry + (i & 3) * 32 + lane, a.h_bond_in + ee * H + s * 32 + lane);
-    };
-    auto row_of = [](int v) { return v < 0 ? 0 : v & (TRIP_ROW_EXCLUDED - 1); };
 
     // softmax over the 32 rows of the previous group for heads 4s..4s+3 -> wbuf; chunked groups also record {max, sum of exp}
     auto finish_k = [&](const float (&lg)[4], bool ok, int pe, int tb, int pair) {
@@ -248,30 +227,30 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
     };
     int it = 0;
     int prev_e = -1, prev_tb = 0, prev_pair = -1; bool prev_ok = false; int prev_nvalid = 0;
-    int e = -1, pair = -1, rv = -1;      // current tile: edge id, partner chunk, this thread's row word
+    int2 gm, rm, gm_n, rm_n;
+    int e, e_n;
+    load_meta(0, e, gm, rm);
+    load_meta(1, e_n, gm_n, rm_n);
     float4 pv[8];
     if (per > 0) {
-      stage_meta(0); stage_meta(1);
-      cp_commit(); cp_wait_all();
-      e = mgrp[0].x; pair = mgrp[0].y; rv = mrow[lane];
-      stage_rows(0, e);
-      cp_commit();
-      const float* prow = Pc + (size_t)row_of(rv) * H + s * 32;
+      const float* prow = Pc + (size_t)max(rm.x, 0) * H + s * 32;
 #pragma unroll
       for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+      wq[lane] = __ldg(Qc + (size_t)max(e, 0) * H + s * 32 + lane);
     }
     TL_DECL
     for (; it < per; ++it) {
       TL_MARK(0);
-      const bool rowok = (unsigned)rv < (unsigned)TRIP_ROW_EXCLUDED;          // valid and k != i (:117-118)
-      // what the previous iteration staged has landed: rows of this tile, metadata of the next.  Stage one step further.
-      cp_wait_all();
-      const int2 ge_n = mgrp[(it + 1) & 3];
-      const int rv_n = mrow[((it + 1) & 3) * 32 + lane];
-      stage_rows(it + 1, ge_n.x);
-      stage_meta(it + 2);
-      cp_commit();
+      const bool rowok = rm.y >= 0;          // valid and k != i (:117-118)
+      // requests for later: the Q slice of the next group, the query slice of this one, metadata two groups ahead
+      const float q_next = __ldg(Qc + (size_t)max(e_n, 0) * H + s * 32 + lane);
+      float qry_v = 0.f;
+      if (!VPASS) qry_v = __ldg(a.q + (size_t)max(e, 0) * a.ldq + s * 32 + lane);
+      int2 gm_nn, rm_nn;
+      int e_nn;
+      load_meta(it + 2, e_nn, gm_nn, rm_nn);
       const int tb = (g_begin + it) * 32;      // wbuf rows of a (group, chunk) are its 32 slots in visiting order
+      const int pair = e >= 0 ? __ldg(a.vg_pair + g_begin + it) : -1;
       // ---- first Linear: z = P'[kj] (in registers) + Q'[ji] (staged) + D2 (angular MMA, issued one iteration ago)
       float2 z[16];
       {
@@ -297,10 +276,14 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
       }
       // ---- prefetch the P' rows of the next tile (consumed one iteration from now), stage its Q slice and this tile's query
       // ---- the next group reads other rows only when its source atom differs: gather them now, consumed one iteration later
-      if (__any_sync(FULL, ((rv_n ^ rv) & ~TRIP_ROW_EXCLUDED) != 0)) {
-        const float* prow_next = Pc + (size_t)row_of(rv_n) * H + s * 32;
+      if (__any_sync(FULL, rm_n.x != rm.x)) {
+        const float* prow_next = Pc + (size_t)max(rm_n.x, 0) * H + s * 32;
 #pragma unroll
         for (int i8 = 0; i8 < 4; ++i8) ldg8(prow_next + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
+      }
+      {
+        wq[((it + 1) & 1) * 32 + lane] = q_next;
+        if (!VPASS) wqry[(it & 3) * 32 + lane] = qry_v;
       }
       TL_MARK(2);
       TL_MARK(3);
@@ -333,11 +316,13 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
       float lg[4] = {0.f, 0.f, 0.f, 0.f};
       float val[32];
       float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (VPASS && it > 0) {      // requested before the wait on the tensor core: attention weights of this thread's row
+      float hb_in = 0.f;
+      if (VPASS && it > 0) {      // requested before the wait on the tensor core: attention weights of this thread's row, residual input
         if (prev_ok) {
           w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
           if (prev_pair >= 0) w4 = mul4(w4, ld4(a.factor + (size_t)(prev_tb >> 5) * NH + s * 4));      // chunk -> whole-group softmax
         }
+        if (prev_e >= 0) hb_in = __ldg(a.h_bond_in + (size_t)prev_e * H + s * 32 + lane);
       }
       TL_MARK(6);
       if (it > 0) {
@@ -405,13 +390,13 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
               a.part[(size_t)(prev_tb >> 5) * H + c] = val[0];      // chunked group: launch_trip_combine finishes the edge
             } else {
               const float upd = prev_nvalid > 0 ? val[0] + sm.b2[c] : 0.f;
-              a.h_bond_out[(size_t)prev_e * H + c] = wqry[((it - 1) & 3) * 32 + lane] + upd;      // :274 (residual slice staged with the rows)
+              a.h_bond_out[(size_t)prev_e * H + c] = hb_in + upd;      // :274
             }
           }
         }
       }
       prev_e = e; prev_ok = rowok; prev_nvalid = __popc(__ballot_sync(FULL, rowok)); prev_tb = tb; prev_pair = pair;
-      e = ge_n.x; pair = ge_n.y; rv = rv_n;
+      e = e_n; gm = gm_n; rm = rm_n; e_n = e_nn; gm_n = gm_nn; rm_n = rm_nn;
       TL_MARK(10);
     }
     TL_FLUSH(VPASS ? 1 : 0);
@@ -446,7 +431,7 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
             a.part[(size_t)(prev_tb >> 5) * H + c] = tot;
           } else {
             float upd = prev_nvalid > 0 ? tot + sm.b2[c] : 0.f;
-            a.h_bond_out[(size_t)prev_e * H + c] = wqry[((it - 1) & 3) * 32 + lane] + upd;
+            a.h_bond_out[(size_t)prev_e * H + c] = a.h_bond_in[(size_t)prev_e * H + c] + upd;
           }
         }
       }

@@ -153,7 +153,6 @@ struct TripSide {
   const float* W2c = nullptr;         // k: W2 in the pair layout of pack_w2k_pairs; v: W2 natural [out][in]
   const float* Wa32 = nullptr;        // hi | lo SWIZZLE_32B image of Wa^T (pack_wa_sw32)
 };
-constexpr int TRIP_ROW_EXCLUDED = 0x40000000;
 struct TripArgs {
   int n_bonds = 0;
   const int* bsrc = nullptr; const int* bdst = nullptr;   // ligand-atom endpoints of each edge id
@@ -164,8 +163,6 @@ struct TripArgs {
   // grp_order, e = grp_order[pos]): row_meta[pos*32+p] = {edge id k->j or -1, merged node id of k or -1 when k == i};
   // grp_meta[pos] = {merged node id of i, of j}
   const int2* row_meta = nullptr; const int2* grp_meta = nullptr;
-  // the same for the worker warps: row_src[pos*32+p] = edge id k->j (| TRIP_ROW_EXCLUDED when k == i) or -1; grp_we[pos] = {e, vg_pair[pos]}
-  const int* row_src = nullptr; const int2* grp_we = nullptr;
   const int* grp_order = nullptr;     // (Eb) edge ids sorted by (source atom, destination atom): the visiting order of the tensor-core kernels
   const float* x4 = nullptr;
   int ldh = 0, ldpe = 0;
