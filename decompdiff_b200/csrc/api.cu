@@ -59,6 +59,7 @@ struct ddb_model {
   bool finalized = false;
   bool refine_only = false;      // only the refine_net.* tensors are required (stand-alone refine-net seam)
   float r_max = 0.f;             // > 0: cutoff_mode 'radius' (ddb_model_set_cutoff)
+  bool hybrid = false;           // cutoff_mode 'hybrid': ligand-ligand fully connected + k nearest protein atoms per ligand atom
   Blob blob;
   float* dev = nullptr;
   std::vector<LayerOff> layers;
@@ -228,8 +229,9 @@ extern "C" int ddb_model_set_refine_only(ddb_model* m, int32_t on) {
 
 extern "C" int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max) {
   if (!m) return fail(DDB_ERR_INVALID, "null model");
-  if (mode == 0) { m->r_max = 0.f; return DDB_OK; }
-  if (mode == 1 && r_max > 0.f) { m->r_max = r_max; return DDB_OK; }
+  if (mode == 0) { m->r_max = 0.f; m->hybrid = false; return DDB_OK; }
+  if (mode == 1 && r_max > 0.f) { m->r_max = r_max; m->hybrid = false; return DDB_OK; }
+  if (mode == 2) { m->r_max = 0.f; m->hybrid = true; return DDB_OK; }      // batch_hybrid_edge_connection, common.py:250-277
   return fail(DDB_ERR_INVALID, "Not supported cutoff mode");      // uni_transformer_edge.py:358
 }
 
@@ -394,6 +396,7 @@ struct ddb_batch {
   float *tap_h = nullptr, *tap_x = nullptr, *tap_hb = nullptr;      // optional per-layer copies of h / x / h_bond (ddb_batch_set_layer_tap)
   float* v_logits0 = nullptr;   // return_all: v_inference of the input embedding (decompdiff.py:345-346)
   bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
+  int ldn = KNN;             // row stride of nbr / e_w / wb_knn (wider for 'hybrid' graphs)
   int tc_attn = 31;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels; bit 5 (off by default, measured
                              // slower - DESIGN.md section 4.1): commuted-W2 fp32 triplet kernels of attn_trip2.cu (DDB_TC_ATTN=<mask>)
   int max_indeg = 0;
@@ -485,6 +488,19 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
     lig_ptr[g + 1] = lig_ptr[g] + cnt_l[g];
     prot_ptr[g + 1] = prot_ptr[g] + cnt_p[g];
     b->max_graph_nodes = std::max(b->max_graph_nodes, cnt_p[g] + cnt_l[g]);
+  }
+  if (m->hybrid) {
+    // 'hybrid' graphs: a ligand destination has n_lig - 1 + k incoming edges, so the neighbour rows get a wider stride and the kNN
+    // edge family runs on the fp32 FMA kernels (the tensor-core kernels, the receptive-field pruning and the caches are built on
+    // <= 32 edges per destination)
+    int max_lig = 0;
+    for (int g = 0; g < B; ++g) {
+      max_lig = std::max(max_lig, cnt_l[g]);
+      if (cnt_l[g] > 0 && cnt_p[g] < m->cfg.knn) { ddb_batch_destroy(b); return fail(DDB_ERR_INVALID, "hybrid graph: selected index k out of range (fewer protein atoms than k)"); }      // torch.topk, common.py:242
+    }
+    b->ldn = (std::max(max_lig - 1, 0) + m->cfg.knn + 3) & ~3;
+    if (b->ldn < KNN) b->ldn = KNN;
+    b->tc_attn &= ~12;
   }
   std::vector<int> graph_of(N), lig_idx(NL), prot_idx(NP);
   std::vector<uint8_t> is_lig(N, 0);
@@ -697,20 +713,20 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
   DDB_TRY(b->dalloc(&b->PBx, eb * 2 * H));
   DDB_TRY(b->dalloc(&b->Qk, eb * H)); DDB_TRY(b->dalloc(&b->Qv, eb * H));
   DDB_TRY(b->dalloc(&b->Pmk, eb)); DDB_TRY(b->dalloc(&b->Pmv, eb)); DDB_TRY(b->dalloc(&b->Qmk, eb)); DDB_TRY(b->dalloc(&b->Qmv, eb));
-  DDB_TRY(b->dalloc(&b->wb_knn, n * KNN * NH)); DDB_TRY(b->dalloc(&b->wb_bond, eb * NH));
+  DDB_TRY(b->dalloc(&b->wb_knn, n * b->ldn * NH)); DDB_TRY(b->dalloc(&b->wb_bond, eb * NH));
   DDB_TRY(b->dalloc(&b->wb_trip, (size_t)slots * NH));
-  DDB_TRY(b->dalloc(&b->e_w, n * KNN)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4)); DDB_TRY(b->dalloc(&b->dist, n * KNN));
-  DDB_TRY(b->dalloc(&b->nbr, n * KNN)); DDB_TRY(b->dalloc(&b->deg, n)); DDB_TRY(b->dalloc(&b->nlig, n));
+  DDB_TRY(b->dalloc(&b->e_w, n * b->ldn)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4)); DDB_TRY(b->dalloc(&b->dist, n * KNN));
+  DDB_TRY(b->dalloc(&b->nbr, n * b->ldn)); DDB_TRY(b->dalloc(&b->deg, n)); DDB_TRY(b->dalloc(&b->nlig, n));
   {
     int max_lig = 0;
     for (int g = 0; g < B; ++g) max_lig = std::max(max_lig, cnt_l[g]);
-    b->knn_cache = !refine && max_lig <= 64 && NP > 0 && !getenv("DDB_NO_KNN_CACHE");
+    b->knn_cache = !refine && !m->hybrid && max_lig <= 64 && NP > 0 && !getenv("DDB_NO_KNN_CACHE");
     if (b->knn_cache) { DDB_TRY(b->dalloc(&b->skeys, n * KNN)); DDB_TRY(b->dalloc(&b->sdeg, n)); }
   }
   DDB_TRY(b->dalloc(&b->hid_v, nl * H)); DDB_TRY(b->dalloc(&b->v_logits, nl * c.num_classes));
   DDB_TRY(b->dalloc(&b->b_logits, eb * c.num_bond_classes)); DDB_TRY(b->dalloc(&b->x0, nl * 3));
   DDB_TRY(b->dalloc(&b->grad, nl * 3)); DDB_TRY(b->dalloc(&b->v_logits0, nl * c.num_classes));
-  cudaMemset(b->nbr, 0, n * KNN * sizeof(int));
+  cudaMemset(b->nbr, 0, n * b->ldn * sizeof(int));
   cudaMemset(b->deg, 0, n * sizeof(int)); cudaMemset(b->nlig, 0, n * sizeof(int));
   // padding slots of the destination lists keep {-1, 0} for good (launch_graph_lists rewrites the live entries every step)
   launch_knn_slot_meta(b->dst_lvl, b->lig_block + NP, b->deg, b->nlig, b->is_lig, b->slot_meta_lvl, 0);
@@ -912,13 +928,14 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     b->launches += 2;
   } else {
     ProfScope ps(b, s, PC_KNN_GRAPH);
-    launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s, m->r_max);
+    launch_knn(b->x4_0, b->node_ptr, b->graph_of, b->is_lig, N, c.knn, b->max_graph_nodes, b->nbr, b->deg, b->nlig, s, m->r_max, nullptr,
+               b->n_protein_of, nullptr, b->ldn, m->hybrid);
     b->launches++;
   }
   EdgeWeightCache ewc;
   ewc.table = b->ew_table; ewc.table_base = b->ew_table_base; ewc.n_protein = b->n_protein_of; ewc.node_ptr = b->node_ptr; ewc.graph_of = b->graph_of;
   { ProfScope ps(b, s, PC_EDGE_WEIGHT); launch_edge_weight(b->x4_0, b->nbr, b->deg, N, m->p(m->ew_W1t), m->p(m->ew_b1), m->p(m->ew_gamma), m->p(m->ew_beta),
-                     m->p(m->ew_w2), m->ew_b2, b->e_w, ewc, s); }
+                     m->p(m->ew_w2), m->ew_b2, b->e_w, ewc, s, b->ldn); }
   b->launches++;
   if (b->tc_attn & 12) {
     ProfScope ps(b, s, PC_KNN_GRAPH);
@@ -986,7 +1003,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     // --- node update over kNN edges  -> h1
     KnnAttnArgs ka;
     ka.n_dst = N; ka.Hi = PNl; ka.ldhi = 5 * H; ka.Hj = PNl + H; ka.ldhj = 5 * H; ka.q = b->qN; ka.ldq = H;
-    ka.x4 = x_in; ka.nbr = b->nbr; ka.deg = b->deg; ka.nlig = b->nlig; ka.is_lig = b->is_lig; ka.e_w = b->e_w;
+    ka.x4 = x_in; ka.nbr = b->nbr; ka.deg = b->deg; ka.nlig = b->nlig; ka.is_lig = b->is_lig; ka.e_w = b->e_w; ka.ldn = b->ldn;
     ka.wbuf = b->wb_knn; ka.w = knn_w(m, L.ne_k); ka.W2tc = m->p(L.ne_k.m.W2tc);
     if (b->tc_attn & 12) { ProfScope ps(b, s, PC_KNN_GRAPH); launch_knn_dist(x_in, b->nbr, b->deg, N, b->dist, s); b->launches += 1; }
     auto tc_dsts = [&](KnnAttnArgs& k, const KnnMlpOff& o, bool on) {      // the tensor-core kernels walk destinations by class
@@ -1066,7 +1083,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     KnnAttnArgs kp;
     kp.n_dst = NL; kp.dst_list = b->lig_idx; kp.Hi = b->PLx; kp.ldhi = 8 * H; kp.hi_by_slot = 1;
     kp.Hj = b->PNx; kp.ldhj = 2 * H; kp.q = b->qXe; kp.ldq = H; kp.q_by_slot = 1;
-    kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w;
+    kp.x4 = x_in; kp.nbr = b->nbr; kp.deg = b->deg; kp.nlig = b->nlig; kp.is_lig = b->is_lig; kp.e_w = b->e_w; kp.ldn = b->ldn;
     kp.wbuf = b->wb_knn; kp.w = knn_w(m, L.pe_k); kp.W2tc = m->p(L.pe_k.m.W2tc);
     kp.dist = b->dist; kp.B2tc[0] = m->p(L.pe_k.B2tc[0]); kp.B2tc[1] = m->p(L.pe_k.B2tc[1]); kp.n_slots_first = 0; kp.first_class = 0; kp.slot_meta = b->slot_meta_lig;      // ligand destinations only
     const KnnAttnArgs kp_key = kp;
@@ -1330,10 +1347,10 @@ extern "C" int ddb_batch_debug_buffer(const ddb_batch* b, const char* name, cons
   if (n == "h") { *ptr = b->h_fin; *rows = b->N; *cols = H; }
   else if (n == "x") { *ptr = b->x_fin; *rows = b->N; *cols = 4; }
   else if (n == "h_bond") { *ptr = b->hb_fin; *rows = b->Eb; *cols = H; }
-  else if (n == "nbr") { *ptr = b->nbr; *rows = b->N; *cols = KNN; }
+  else if (n == "nbr") { *ptr = b->nbr; *rows = b->N; *cols = b->ldn; }
   else if (n == "deg") { *ptr = b->deg; *rows = b->N; *cols = 1; }
   else if (n == "nlig") { *ptr = b->nlig; *rows = b->N; *cols = 1; }
-  else if (n == "e_w") { *ptr = b->e_w; *rows = b->N; *cols = KNN; }
+  else if (n == "e_w") { *ptr = b->e_w; *rows = b->N; *cols = b->ldn; }
   else if (n == "grad") { *ptr = b->grad; *rows = b->NL; *cols = 3; }
   else return fail(DDB_ERR_INVALID, "unknown buffer " + n);
   if (*ptr == nullptr) return fail(DDB_ERR_STATE, "no forward has run yet");

@@ -39,7 +39,7 @@ __device__ __forceinline__ void knn_hidden4(const KnnAttnArgs& a, const KnnSmem&
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     int e = min(e0 + s, seg_end - 1);
-    js[s] = __ldg(a.nbr + (size_t)node * KNN + e);
+    js[s] = __ldg(a.nbr + (size_t)node * a.ldn + e);
     float4 xj = ldg4(a.x4 + (size_t)js[s] * 4);
     rel[s][0] = xi.x - xj.x; rel[s][1] = xi.y - xj.y; rel[s][2] = xi.z - xj.z;
     d[s] = sqrtf(rel[s][0] * rel[s][0] + rel[s][1] * rel[s][1] + rel[s][2] * rel[s][2]);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) knn_attn_k_kernel(const KnnAtt
     }
     const float4 xi = ldg4(a.x4 + (size_t)node * 4);
     const float4 hi = ldg4(a.Hi + (size_t)(a.hi_by_slot ? slot : node) * a.ldhi + lane * 4);
-    float* wrow = a.wbuf + (size_t)node * KNN * NH;
+    float* wrow = a.wbuf + (size_t)node * a.ldn * NH;
 #pragma unroll 1
     for (int seg = 0; seg < 2; ++seg) {
       const int seg_start = seg ? nlig : 0, seg_end = seg ? deg : nlig;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) knn_attn_k_kernel(const KnnAtt
     ssum += __shfl_xor_sync(FULL, ssum, 16);
     for (int e = half; e < deg; e += 2) {
       float w = expf(__ldcg(wrow + e * NH + h) - m) / ssum;
-      wrow[e * NH + h] = w * __ldg(a.e_w + (size_t)node * KNN + e);
+      wrow[e * NH + h] = w * __ldg(a.e_w + (size_t)node * a.ldn + e);
     }
   }
 }
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) knn_attn_v_node_kernel(const K
     for (int h = 0; h < NH; ++h) { S[h] = make_float4(0.f, 0.f, 0.f, 0.f); wsum[h] = 0.f; }
     const float4 xi = ldg4(a.x4 + (size_t)node * 4);
     const float4 hi = ldg4(a.Hi + (size_t)(a.hi_by_slot ? slot : node) * a.ldhi + lane * 4);
-    const float* wrow = a.wbuf + (size_t)node * KNN * NH;
+    const float* wrow = a.wbuf + (size_t)node * a.ldn * NH;
 #pragma unroll 1
     for (int seg = 0; seg < 2; ++seg) {
       const int seg_start = seg ? nlig : 0, seg_end = seg ? deg : nlig;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) knn_attn_v_pos_kernel(const Kn
     float acc[3] = {0.f, 0.f, 0.f};
     const float4 xi = ldg4(a.x4 + (size_t)node * 4);
     const float4 hi = ldg4(a.Hi + (size_t)(a.hi_by_slot ? slot : node) * a.ldhi + lane * 4);
-    const float* wrow = a.wbuf + (size_t)node * KNN * NH;
+    const float* wrow = a.wbuf + (size_t)node * a.ldn * NH;
 #pragma unroll 1
     for (int seg = 0; seg < 2; ++seg) {
       const int seg_start = seg ? nlig : 0, seg_end = seg ? deg : nlig;

@@ -28,9 +28,13 @@ namespace ddb {
 // phase of the tile loop to g_timeline[pass][warp slot][phase]; read with ddb_debug_timeline_{trip,knn}() (profiles/timeline.py).
 #ifdef DDB_TIMELINE
 static __device__ unsigned long long g_timeline[2][2][16];      // one copy per translation unit: [pass][warp slot][phase]
-#define TL_DECL unsigned long long tl_t = clock64(), tl_acc[12] = {0}; const bool tl_on = blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 13);
+#ifndef TL_WA
+#define TL_WA 0
+#define TL_WB 13
+#endif
+#define TL_DECL unsigned long long tl_t = clock64(), tl_acc[12] = {0}; const bool tl_on = blockIdx.x == 0 && lane == 0 && (warp == TL_WA || warp == TL_WB);
 #define TL_MARK(i) do { if (tl_on) { unsigned long long n_ = clock64(); tl_acc[i] += n_ - tl_t; tl_t = n_; } } while (0)
-#define TL_FLUSH(kid) do { if (tl_on) { for (int i_ = 0; i_ < 12; ++i_) g_timeline[kid][warp == 0 ? 0 : 1][i_] = tl_acc[i_]; g_timeline[kid][warp == 0 ? 0 : 1][12] = it; } } while (0)
+#define TL_FLUSH(kid) do { if (tl_on) { for (int i_ = 0; i_ < 12; ++i_) g_timeline[kid][warp == TL_WA ? 0 : 1][i_] = tl_acc[i_]; g_timeline[kid][warp == TL_WA ? 0 : 1][12] = it; } } while (0)
 #else
 #define TL_DECL
 #define TL_MARK(i)
@@ -61,8 +65,10 @@ __device__ __forceinline__ void atc_issue_mma(uint32_t tmem_base, uint32_t w2_sm
   for (int kk = 0; kk < 16; ++kk) {
     const uint64_t bo = (uint64_t)(((kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4);      // start-address field is in 16-byte units
     umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, b_hi0 + bo, idesc, kk ? 1u : 0u);
+#ifndef DDB_EXP_MMA1      // timing experiment only (wrong results): one pass instead of the 3xTF32 split
     umma_tf32_ts(d, tmem_base + ATC_COL_ALO + kk * 8, b_hi0 + bo, idesc, 1u);
     umma_tf32_ts(d, tmem_base + ATC_COL_AHI + kk * 8, b_lo0 + bo, idesc, 1u);
+#endif
   }
   umma_commit(bar);
 }

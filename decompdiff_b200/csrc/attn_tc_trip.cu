@@ -24,7 +24,7 @@ struct TripTcSmem {
     qry = reinterpret_cast<float*>(p); p += 16 * 128 * 4;       // per warp: 4-deep ring of 32-float query slices
     qrow = reinterpret_cast<float*>(p); p += 16 * 64 * 4;       // per warp: 2 x 32-float slices of the centred Q row
     xyz = reinterpret_cast<float*>(p); p += 16 * 34 * 16;       // per warp: positions x_k of its 32 rows, x_i, x_j (cp.async staging)
-    stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][row][slice] {sum, sum of squares}
+    stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][slice][row] {sum, sum of squares}
     bars = reinterpret_cast<uint64_t*>(p); p += 64;
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
@@ -35,12 +35,16 @@ static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 // byte offset of feature k (< 32) of row r inside a [128 rows][128 B] K-major SWIZZLE_128B tile
 __device__ __forceinline__ int a2_off(int r, int k) { return r * 128 + ((((k >> 2) ^ (r & 7))) << 4) + (k & 3) * 4; }
 
-__device__ __forceinline__ void a2_put(uint8_t* A2, int r, int k, float v) {
-  uint32_t hi, lo;
-  tf32_split(v, hi, lo);
-  *reinterpret_cast<uint32_t*>(A2 + a2_off(r, k)) = hi;
-  *reinterpret_cast<uint32_t*>(A2 + TT_A2_BYTES / 2 + a2_off(r, k)) = lo;
+// four consecutive features (chunk c = k / 4) of row r -> both images with one 16-byte store each (conflict-free: the swizzle
+// spreads 8 consecutive rows over the 8 chunks of a 128-byte line; single 4-byte stores were 4-way bank conflicts)
+__device__ __forceinline__ void a2_put4(uint8_t* A2, int r, int c, float v0, float v1, float v2, float v3) {
+  uint4 hi, lo;
+  tf32_split(v0, hi.x, lo.x); tf32_split(v1, hi.y, lo.y); tf32_split(v2, hi.z, lo.z); tf32_split(v3, hi.w, lo.w);
+  const int off = r * 128 + ((c ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(A2 + off) = hi;
+  *reinterpret_cast<uint4*>(A2 + TT_A2_BYTES / 2 + off) = lo;
 }
+
 
 // ---- packed fp32 (FADD2 / FMUL2 / FFMA2 on sm_100): the element-wise phases work on channel pairs
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
@@ -158,11 +162,10 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
         if (cs >= 0.f) { ch = sqrtf(0.5f * (1.f + cs)); sh = sn / (2.f * ch); }
         else { sh = sqrtf(0.5f * (1.f - cs)); ch = sn / (2.f * sh); }
         sincosf(theta * (float)(1.0 / 3.0), &s3, &c3);
-        a2_put(sm.A2, rr, 0, theta);
-        a2_put(sm.A2, rr, 1, sn); a2_put(sm.A2, rr, 2, 2.f * sn * cs); a2_put(sm.A2, rr, 3, sn * (3.f - 4.f * sn * sn));
-        a2_put(sm.A2, rr, 4, sn); a2_put(sm.A2, rr, 5, sh); a2_put(sm.A2, rr, 6, s3);
-        a2_put(sm.A2, rr, 7, cs); a2_put(sm.A2, rr, 8, cs * cs - sn * sn); a2_put(sm.A2, rr, 9, cs * (4.f * cs * cs - 3.f));
-        a2_put(sm.A2, rr, 10, cs); a2_put(sm.A2, rr, 11, ch); a2_put(sm.A2, rr, 12, c3);
+        a2_put4(sm.A2, rr, 0, theta, sn, 2.f * sn * cs, sn * (3.f - 4.f * sn * sn));
+        a2_put4(sm.A2, rr, 1, sn, sh, s3, cs);
+        a2_put4(sm.A2, rr, 2, cs * cs - sn * sn, cs * (4.f * cs * cs - 3.f), cs, ch);
+        a2_put4(sm.A2, rr, 3, c3, 0.f, 0.f, 0.f);
       };
       const int q0 = pw == 0 ? 0 : pw, q1 = 3;          // warp 17 also serves quadrant 3
       int2 gm0, rm0, gm1, rm1;
@@ -181,8 +184,10 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
         row_meta_of(q0, t + 1, gm0, rm0);
         if (pw == 0) row_meta_of(q1, t + 1, gm1, rm1);
         if (t > 0) mbar_wait(bar_ang, (t - 1) & 1);      // the angular MMA of the previous tile has read A2
+#ifndef DDB_EXP_NOFEAT      // timing experiment only
         put_features(q0, rm0c, xi0, xj0, xk0);
         if (pw == 0) put_features(q1, rm1c, xi1, xj1, xk1);
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A2 was written through the generic proxy
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a2f) : "memory");
@@ -259,17 +264,15 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
         tc_fence_after();
         __syncwarp();
         const float* qs = wq + (it & 1) * 32;
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 qv = ld4(qs + i4 * 4);
-          z[i4 * 2] = __fadd2_rn(f2(pv[i4].x, pv[i4].y), f2(qv.x, qv.y));
-          z[i4 * 2 + 1] = __fadd2_rn(f2(pv[i4].z, pv[i4].w), f2(qv.z, qv.w));
-        }
-        uint32_t v[32];
+        uint32_t v[32];      // D2 first: z[i] is born as v[i] dies (z = P' + Q' before the load kept 96 registers live)
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TT_COL_D2 + s * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 16; ++i) z[i] = __fadd2_rn(z[i], u2f(v[2 * i], v[2 * i + 1]));
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 qv = ld4(qs + i4 * 4);
+          z[i4 * 2] = __fadd2_rn(__fadd2_rn(f2(pv[i4].x, pv[i4].y), f2(qv.x, qv.y)), u2f(v[4 * i4], v[4 * i4 + 1]));
+          z[i4 * 2 + 1] = __fadd2_rn(__fadd2_rn(f2(pv[i4].z, pv[i4].w), f2(qv.z, qv.w)), u2f(v[4 * i4 + 2], v[4 * i4 + 3]));
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_d2c) : "memory");      // D2 may be overwritten
@@ -292,16 +295,19 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
         float2 s1 = f2(0.f, 0.f), s2 = f2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i) { s1 = __fadd2_rn(s1, z[i]); s2 = __ffma2_rn(z[i], z[i], s2); }
-        float2* st = sm.stat + ((it & 1) * 128 + r) * 4;
-        st[s] = make_float2(s1.x + s1.y, s2.x + s2.y);
+        float2* st = sm.stat + (it & 1) * 512 + r;      // [parity][slice][row]: every access below is a contiguous 256 bytes per warp
+        st[s * 128] = make_float2(s1.x + s1.y, s2.x + s2.y);
         TL_MARK(4);
         quad_barrier(q);
         TL_MARK(5);
-        const float4 t01 = *reinterpret_cast<const float4*>(st), t23 = *reinterpret_cast<const float4*>(st + 2);
-        const float mu = ((t01.x + t01.z) + (t23.x + t23.z)) * (1.0f / H);
-        const float var = fmaxf(((t01.y + t01.w) + (t23.y + t23.w)) * (1.0f / H) - mu * mu, 0.f);
+        const float2 t0 = st[0], t1 = st[128], t2 = st[256], t3 = st[384];
+        const float mu = ((t0.x + t1.x) + (t2.x + t3.x)) * (1.0f / H);
+        const float var = fmaxf(((t0.y + t1.y) + (t2.y + t3.y)) * (1.0f / H) - mu * mu, 0.f);
         const float rstd = rsqrtf(var + LN_EPS);
         const float2 rs2 = f2(rstd, rstd), nm2 = f2(-mu * rstd, -mu * rstd);
+#ifdef DDB_EXP_NONORM      // timing experiment only: rstd is never negative
+        if (rstd < 0.f)
+#endif
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 g = ld4(sm.gamma + s * 32 + i4 * 4), b = ld4(sm.beta + s * 32 + i4 * 4);
@@ -315,12 +321,12 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
       // ---- drain D of the previous tile into registers (its main MMA had this tile's first Linear / LayerNorm to finish)
       float lg[4] = {0.f, 0.f, 0.f, 0.f};
       float val[32];
-      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), f4 = make_float4(1.f, 1.f, 1.f, 1.f);
       float hb_in = 0.f;
       if (VPASS && it > 0) {      // requested before the wait on the tensor core: attention weights of this thread's row, residual input
-        if (prev_ok) {
+        if (prev_ok) {           // (the chunk -> whole-group factor is applied after the wait: a multiply here would stall on the loads)
           w4 = ld4(a.wbuf + ((size_t)prev_tb + lane) * NH + s * 4);
-          if (prev_pair >= 0) w4 = mul4(w4, ld4(a.factor + (size_t)(prev_tb >> 5) * NH + s * 4));      // chunk -> whole-group softmax
+          if (prev_pair >= 0) f4 = ld4(a.factor + (size_t)(prev_tb >> 5) * NH + s * 4);
         }
         if (prev_e >= 0) hb_in = __ldg(a.h_bond_in + (size_t)prev_e * H + s * 32 + lane);
       }
@@ -344,6 +350,7 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
             lg[hh] = prev_ok ? acc.x + acc.y : -INFINITY;
           }
         } else {
+          w4 = mul4(w4, f4);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, 
                                                   const int* __restrict__ graph_of, const uint8_t* __restrict__ is_lig,
                                                   int n, int k, float r2max, int* __restrict__ nbr, int* __restrict__ deg_out,
                                                   int* __restrict__ nlig_out, const int* __restrict__ node_list,
-                                                  const int* __restrict__ n_protein, unsigned long long* __restrict__ skeys) {
+                                                  const int* __restrict__ n_protein, unsigned long long* __restrict__ skeys,
+                                                  int ld, bool hybrid) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= n) return;
@@ -45,10 +46,13 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, 
   const int g = graph_of[i];
   const int s = node_ptr[g];
   // static mode (skeys != null): candidates are the graph's PROTEIN atoms only, the sorted keys are the output
-  const int e = skeys ? s + n_protein[g] : node_ptr[g + 1];
+  // 'hybrid' graphs (common.py:230-277): a ligand destination gets every other ligand atom of its complex plus its k nearest
+  // PROTEIN atoms; protein destinations keep the plain kNN list over all atoms
+  const bool hyb_lig = hybrid && is_lig[i];
+  const int e = (skeys || hyb_lig) ? s + n_protein[g] : node_ptr[g + 1];
   if (skeys && i >= e) return;                     // ligand node: no static list
   const float4 xi = ldg4(x4 + (size_t)i * 4);
-  int deg = min(k, e - s - 1);
+  int deg = hyb_lig ? min(k, e - s) : min(k, e - s - 1);
 
   unsigned long long keys[MAXT > 0 ? MAXT : 1];
   if (MAXT > 0) {
@@ -85,6 +89,14 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, 
     if (skeys && lane == r) skeys[(size_t)i * KNN + r] = best;
   }
   if (skeys) { if (lane == 0) deg_out[i] = deg; return; }
+  if (hyb_lig) {      // ligand sources first (index order, self skipped), then the protein sources nearest first
+    const int l0 = e, l1 = node_ptr[g + 1], nl = l1 - l0 - 1;
+    for (int c = l0 + lane; c < l1; c += 32)
+      if (c != i) nbr[(size_t)i * ld + (c - l0) - (c > i ? 1 : 0)] = c;
+    if (lane < deg) nbr[(size_t)i * ld + nl + lane] = mine;
+    if (lane == 0) { deg_out[i] = nl + deg; nlig_out[i] = nl; }
+    return;
+  }
   // stable partition: ligand sources first (so the attention kernels see type-uniform runs)
   const bool has = lane < deg;
   const bool lig = has && is_lig[mine];
@@ -93,22 +105,22 @@ __global__ void __launch_bounds__(256) knn_kernel(const float* __restrict__ x4, 
   const unsigned below = (1u << lane) - 1u;
   if (has) {
     int pos = lig ? __popc(mlig & below) : nlig + __popc(mhas & ~mlig & below);
-    nbr[(size_t)i * KNN + pos] = mine;
+    nbr[(size_t)i * ld + pos] = mine;
   }
   if (lane == 0) { deg_out[i] = deg; nlig_out[i] = nlig; }
 }
 
 void launch_knn(const float* x4, const int* node_ptr, const int* graph_of, const uint8_t* is_lig, int n, int k,
                 int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream, float r_max, const int* node_list,
-                const int* n_protein, unsigned long long* skeys) {
+                const int* n_protein, unsigned long long* skeys, int ld, bool hybrid) {
   const float r2max = r_max > 0.f ? r_max * r_max : INFINITY;
   if (n <= 0) return;
   const int wpb = 8;
   dim3 grid((n + wpb - 1) / wpb), block(wpb * 32);
-  if (max_graph_nodes <= 32 * 16) knn_kernel<16><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
-  else if (max_graph_nodes <= 32 * 32) knn_kernel<32><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
-  else if (max_graph_nodes <= 32 * 64) knn_kernel<64><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
-  else knn_kernel<0><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys);
+  if (max_graph_nodes <= 32 * 16) knn_kernel<16><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys, ld, hybrid);
+  else if (max_graph_nodes <= 32 * 32) knn_kernel<32><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys, ld, hybrid);
+  else if (max_graph_nodes <= 32 * 64) knn_kernel<64><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys, ld, hybrid);
+  else knn_kernel<0><<<grid, block, 0, stream>>>(x4, node_ptr, graph_of, is_lig, n, k, r2max, nbr, deg, nlig, node_list, n_protein, skeys, ld, hybrid);
 }
 
 // Protein destinations with the cached static part (launch_knn with skeys, once per run: protein atoms never move): the k nearest
@@ -180,54 +192,57 @@ __global__ void __launch_bounds__(256) edge_weight_kernel(const float* __restric
                                                           const float* __restrict__ W1t /*[20][128]*/,
                                                           const float* __restrict__ b1, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ w2,
-                                                          float b2, float* __restrict__ e_w, EdgeWeightCache c) {
+                                                          float b2, float* __restrict__ e_w, EdgeWeightCache c, int ld) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
   const float4 xi = ldg4(x4 + (size_t)i * 4);
-  const int d_i = deg[i];
-  // ---- lookup phase: lane = edge
-  const int j = lane < d_i ? nbr[(size_t)i * KNN + lane] : i;
-  const float4 xj = ldg4(x4 + (size_t)j * 4);
-  float val = __int_as_float(0x7fc00000);
-  long long slot = -1;
-  if (c.table != nullptr && lane < d_i) {
-    const int g = c.graph_of[i], base = c.node_ptr[g], np = c.n_protein[g];
-    const int il = i - base, jl = j - base;
-    if (il < np && jl < np) { slot = c.table_base[g] + (long long)il * np + jl; val = __ldcg(c.table + slot); }
-  }
-  unsigned todo = __ballot_sync(FULL, lane < d_i && val != val);
-  if (todo) {
-    // ---- evaluation phase: the warp computes the missing edges one at a time
-    float4 w[NG];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) w[g] = ldg4(W1t + g * H + lane * 4);
-    const float4 bb = ldg4(b1 + lane * 4), gm = ldg4(gamma + lane * 4), bt = ldg4(beta + lane * 4), w2v = ldg4(w2 + lane * 4);
-    while (todo) {
-      const int e = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const float xjx = __shfl_sync(FULL, xj.x, e), xjy = __shfl_sync(FULL, xj.y, e), xjz = __shfl_sync(FULL, xj.z, e);
-      const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
-      const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-      const float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
-      float4 z[1] = {bb};
-#pragma unroll
-      for (int g = 0; g < NG; ++g) z[0] = fma4(__shfl_sync(FULL, gl, g), w[g], z[0]);
-      ln_relu_rows<1>(z, gm, bt, lane);
-      const float logit = warp_sum(dot4(z[0], w2v)) + b2;
-      const float r = 1.0f / (1.0f + expf(-logit));
-      if (lane == e) { val = r; if (slot >= 0) c.table[slot] = r; }
+  const int d_all = deg[i];
+  for (int e0 = 0; e0 < d_all; e0 += 32) {      // 32 edges at a time ('hybrid' graphs have longer lists)
+    const int d_i = min(d_all - e0, 32);
+    // ---- lookup phase: lane = edge
+    const int j = lane < d_i ? nbr[(size_t)i * ld + e0 + lane] : i;
+    const float4 xj = ldg4(x4 + (size_t)j * 4);
+    float val = __int_as_float(0x7fc00000);
+    long long slot = -1;
+    if (c.table != nullptr && lane < d_i) {
+      const int g = c.graph_of[i], base = c.node_ptr[g], np = c.n_protein[g];
+      const int il = i - base, jl = j - base;
+      if (il < np && jl < np) { slot = c.table_base[g] + (long long)il * np + jl; val = __ldcg(c.table + slot); }
     }
+    unsigned todo = __ballot_sync(FULL, lane < d_i && val != val);
+    if (todo) {
+      // ---- evaluation phase: the warp computes the missing edges one at a time
+      float4 w[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) w[g] = ldg4(W1t + g * H + lane * 4);
+      const float4 bb = ldg4(b1 + lane * 4), gm = ldg4(gamma + lane * 4), bt = ldg4(beta + lane * 4), w2v = ldg4(w2 + lane * 4);
+      while (todo) {
+        const int e = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float xjx = __shfl_sync(FULL, xj.x, e), xjy = __shfl_sync(FULL, xj.y, e), xjz = __shfl_sync(FULL, xj.z, e);
+        const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
+        const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
+        float4 z[1] = {bb};
+#pragma unroll
+        for (int g = 0; g < NG; ++g) z[0] = fma4(__shfl_sync(FULL, gl, g), w[g], z[0]);
+        ln_relu_rows<1>(z, gm, bt, lane);
+        const float logit = warp_sum(dot4(z[0], w2v)) + b2;
+        const float r = 1.0f / (1.0f + expf(-logit));
+        if (lane == e) { val = r; if (slot >= 0) c.table[slot] = r; }
+      }
+    }
+    if (lane < d_i) e_w[(size_t)i * ld + e0 + lane] = val;
   }
-  if (lane < d_i) e_w[(size_t)i * KNN + lane] = val;
 }
 
 void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, const float* W1t, const float* b1,
                         const float* gamma, const float* beta, const float* w2, float b2, float* e_w,
-                        const EdgeWeightCache& cache, cudaStream_t stream) {
+                        const EdgeWeightCache& cache, cudaStream_t stream, int ld) {
   if (n <= 0) return;
   const int wpb = 8;
-  edge_weight_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, stream>>>(x4, nbr, deg, n, W1t, b1, gamma, beta, w2, b2, e_w, cache);
+  edge_weight_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, stream>>>(x4, nbr, deg, n, W1t, b1, gamma, beta, w2, b2, e_w, cache, ld);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

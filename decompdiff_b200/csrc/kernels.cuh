@@ -9,7 +9,8 @@ namespace ddb {
 // r_max > 0: 'radius' cut-off - the k nearest neighbours within r_max (|x_i - x_j| <= r_max) only
 void launch_knn(const float* x4, const int* node_ptr, const int* graph_of, const uint8_t* is_lig, int n, int k,
                 int max_graph_nodes, int* nbr, int* deg, int* nlig, cudaStream_t stream, float r_max = 0.f,
-                const int* node_list = nullptr, const int* n_protein = nullptr, unsigned long long* skeys = nullptr);
+                const int* node_list = nullptr, const int* n_protein = nullptr, unsigned long long* skeys = nullptr, int ld = KNN,
+                bool hybrid = false);      // hybrid: ligand rows = every other ligand atom + k nearest protein atoms (row stride ld)
 // static protein neighbour cache: launch_knn(..., n_protein, skeys) once per run writes every protein node's sorted keys of its k
 // nearest PROTEIN atoms (and their number into `deg`); per step launch_knn over the ligand nodes (node_list) + launch_knn_merge
 // over the protein nodes reproduce launch_knn over all nodes bit for bit
@@ -25,7 +26,7 @@ struct EdgeWeightCache {
 };
 void launch_edge_weight(const float* x4, const int* nbr, const int* deg, int n, const float* W1t, const float* b1,
                         const float* gamma, const float* beta, const float* w2, float b2, float* e_w,
-                        const EdgeWeightCache& cache, cudaStream_t stream);
+                        const EdgeWeightCache& cache, cudaStream_t stream, int ld = KNN);
 
 // exact receptive field of the outputs: hop level per node, protein destinations listed by level behind the ligand block of
 // `dst_list`, per-layer prefix lengths in `counts` (graph.cu)
@@ -65,6 +66,7 @@ struct KnnAttnArgs {
   const float* q = nullptr; int ldq = 0; int q_by_slot = 0;      // query rows (k pass)
   const float* x4 = nullptr;          // positions at layer entry (N,4)
   const int* nbr = nullptr; const int* deg = nullptr; const int* nlig = nullptr;
+  int ldn = KNN;                      // row stride of nbr / e_w / wbuf (> 32 only for 'hybrid' graphs, which run on the SIMT kernels)
   const uint8_t* is_lig = nullptr;
   const float* e_w = nullptr;         // (N,32) global edge weight
   float* wbuf = nullptr;              // (N*32,16) logits -> alpha * e_w

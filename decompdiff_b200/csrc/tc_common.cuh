@@ -85,6 +85,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+
 // ---- UMMA ----------------------------------------------------------------------------------------
 // K-major, SWIZZLE_128B shared-memory matrix descriptor: start>>4 | LBO(1)<<16 | SBO(1024 B >> 4)<<32 | version 1 << 46 |
 // layout SWIZZLE_128B (2) << 61.  The tile is rows of 128 bytes (32 tf32 along K), 8-row groups 1024 bytes apart.

@@ -104,8 +104,9 @@ class UniTransformerO2TwoUpdateGeneralBond(nn.Module):
                  act_fn='relu', norm=True, cutoff_mode='radius', r_max=10., x2h_out_fc=True, sync_twoup=False,
                  h_node_in_bond_net=False):
         super().__init__()
-        if cutoff_mode not in ('knn', 'radius'):      # 'hybrid' (common.py:250-277): not implemented
-            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')
+        if cutoff_mode not in ('knn', 'radius', 'hybrid'):
+            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')      # uni_transformer_edge.py:358
+        # 'hybrid' (common.py:250-277): ligand atoms fully connected + their k nearest protein atoms; kNN for protein destinations
         # 'radius' raises upstream (`self.r` is never set, :351); here it is radius_graph(r = r_max, max_num_neighbors = k) with
         # nearest-first truncation (include/decompdiff_b200.h: ddb_model_set_cutoff)
         self.cutoff_mode, self.r_max = cutoff_mode, float(r_max)

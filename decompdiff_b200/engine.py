@@ -61,9 +61,9 @@ class EngineModel:
         L = _lib.lib()
         self.device = _device_of(default=device)
         self.refine_only = refine_only
-        if cutoff_mode not in ('knn', 'radius'):
-            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')
-        self.cutoff = (1 if cutoff_mode == 'radius' else 0, float(r_max))
+        if cutoff_mode not in ('knn', 'radius', 'hybrid'):
+            raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')      # uni_transformer_edge.py:358
+        self.cutoff = ({'knn': 0, 'radius': 1, 'hybrid': 2}[cutoff_mode], float(r_max))
         with torch.cuda.device(self.device):
             self._init(L, cfg, state_dict)
 

@@ -74,7 +74,12 @@ void ddb_model_destroy(ddb_model* m);
 /* Graph construction of the refine net (uni_transformer_edge.py:349-359): mode 0 = 'knn' (k nearest neighbours per node within
  * its graph, the shipped configuration), mode 1 = 'radius': the k nearest neighbours within r_max.  Upstream 'radius' raises
  * (it reads an attribute `self.r` that is never set, :351), so mode 1 is DEFINED here as radius_graph(r = r_max,
- * max_num_neighbors = k) with nearest-first truncation; 'hybrid' is not implemented.  Call before any batch is created. */
+ * max_num_neighbors = k) with nearest-first truncation.  Mode 2 = 'hybrid' (batch_hybrid_edge_connection with add_p_index,
+ * models/common.py:230-277): the ligand atoms of a complex are fully connected, every ligand atom also receives its k nearest
+ * PROTEIN atoms (a complex with ligand atoms but fewer than k protein atoms is rejected with DDB_ERR_INVALID, as torch.topk raises
+ * upstream), protein destinations keep their k nearest atoms of the whole complex.  A ligand destination then has n_lig - 1 + k
+ * incoming edges, so this mode runs the kNN edge family on the fp32 FMA kernels with wide neighbour rows (no receptive-field
+ * pruning, no neighbour cache).  Call before any batch is created. */
 int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max);
 /* Stand-alone refine net (get_refine_net('uni_o2_bond', config), models/encoders/__init__.py:27-43): call before
  * ddb_model_finalize; only the "refine_net.*" tensors are then required and the model serves ddb_refine_batch_create /

@@ -238,15 +238,40 @@ def attention_layer(sd, p, h, x, edge_type_1h, src, dst, h_bond, bsrc, bdst, mas
     return new_h, new_h_bond, x
 
 
+def hybrid_edges(x, k, mask_ligand, batch):
+    """batch_hybrid_edge_connection(add_p_index=True) (models/common.py:230-277): per complex, ligand atoms fully connected; every
+    ligand atom receives its k nearest PROTEIN atoms (torch.topk, :241-242); protein destinations receive their k nearest atoms
+    of the whole complex (knn_graph over [protein; ligand], edges into ligand atoms dropped, :262-268)."""
+    out = []
+    for g in range(int(batch.max()) + 1):
+        lig = ((batch == g) & mask_ligand).nonzero()[:, 0]
+        pro = ((batch == g) & ~mask_ligand).nonzero()[:, 0]
+        dst = torch.repeat_interleave(lig, len(lig))
+        src = lig.repeat(len(lig))
+        keep = dst != src
+        ll = torch.stack([src[keep], dst[keep]])
+        d = torch.norm(x[lig].unsqueeze(1) - x[pro].unsqueeze(0), p=2, dim=-1)
+        near = torch.topk(d, k=k, largest=False, dim=1).indices          # raises when the complex has fewer than k protein atoms
+        pl = torch.stack([pro[near], lig.unsqueeze(1).repeat(1, k)]).view(2, -1)
+        all_idx = torch.cat([pro, lig])
+        pe = knn_graph(x[all_idx], k=k)
+        pe = pe[:, pe[1] < len(pro)]
+        out.append(torch.cat([ll, pl, torch.stack([all_idx[pe[0]], all_idx[pe[1]]])], -1))
+    return torch.cat(out, -1)
+
+
 def refine_net(sd, cfg, h, x, bond_index, h_bond, mask_ligand, mask_ligand_atom, batch,
                return_all=False, knn_edge_index=None):
-    """UniTransformerO2TwoUpdateGeneralBond.forward, cutoff_mode='knn' (:394-443)."""
+    """UniTransformerO2TwoUpdateGeneralBond.forward (:394-443); cutoff_mode 'knn' (shipped), 'hybrid', and the product's 'radius'."""
     p = 'refine_net'
     n_heads = cfg['n_heads']
     all_x, all_h, all_hb = [x], [h], [h_bond]
     edge_index = None
     for _ in range(cfg['num_blocks']):
-        edge_index = knn_graph(x, k=cfg['knn'], batch=batch) if knn_edge_index is None else knn_edge_index
+        if cfg.get('cutoff_mode', 'knn') == 'hybrid':
+            edge_index = hybrid_edges(x, cfg['knn'], mask_ligand.bool(), batch)
+        else:
+            edge_index = knn_graph(x, k=cfg['knn'], batch=batch) if knn_edge_index is None else knn_edge_index
         if cfg.get('cutoff_mode', 'knn') == 'radius':
             # upstream raises here (`self.r` undefined, :351); the product DEFINES the mode as the k nearest neighbours within r_max
             # (include/decompdiff_b200.h: ddb_model_set_cutoff) and this restates that definition

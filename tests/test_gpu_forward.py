@@ -5,7 +5,7 @@ import torch
 
 from conftest import load_golden, tol_ratio
 from decompdiff_b200 import synthetic as syn
-from oracle import make_golden, restate
+from oracle import make_golden, make_golden_hybrid, restate
 
 pytestmark = pytest.mark.gpu
 
@@ -89,5 +89,42 @@ def test_radius_cutoff_mode_matches_its_restatement(weights, oracle_cfg):
         assert tol_ratio(out[k], ref[k]) <= 1.0, k
     assert float((ref['pred_ligand_v'] - knn['pred_ligand_v']).abs().max()) > 1e-3      # the cut-off changes the graph
     with pytest.raises(ValueError):
-        ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='hybrid'), syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM,
+        ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='ball'), syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM,
                                 syn.NUM_CLASSES)
+
+
+@pytest.mark.parametrize('case', list(make_golden_hybrid.HYBRID_CASES))
+def test_hybrid_cutoff_mode_matches_reference_golden(case, weights, oracle_cfg):
+    """cutoff_mode='hybrid' (batch_hybrid_edge_connection, models/common.py:250-277): ligand atoms fully connected + their k nearest
+    protein atoms, kNN for protein destinations.  A ligand destination has n_lig - 1 + 32 incoming edges (71 in the large case), so
+    the kNN edge family runs with wide neighbour rows.  Against the unmodified reference's outputs and the oracle."""
+    import decompdiff_b200 as ddb
+    m = ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='hybrid'), syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM,
+                                syn.NUM_CLASSES)
+    m.load_state_dict(weights)
+    kw = syn.make_batch(**make_golden_hybrid.HYBRID_CASES[case])
+    gold = load_golden(case)
+    fk = syn.forward_kwargs(kw, None)
+    out = m.eval()(**fk)
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
+        r = tol_ratio(out[k], gold[k])
+        print(case, k, 'max err / tol =', r)
+        assert r <= 1.0, f'{case}:{k} ({r:.3f} x tol)'
+    # the sampling loop on the same graph mode: three reverse steps against the oracle with shared noise
+    noise = syn.step_noise(kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel(), 3, seed=5)
+    got = m.sample_diffusion(**kw, num_steps=3, center_pos_mode='protein', noise=noise)
+    with torch.no_grad():
+        want = restate.sample_diffusion(weights, dict(oracle_cfg, cutoff_mode='hybrid'), **kw, num_steps=3, center_pos_mode='protein', noise=noise)
+    assert tol_ratio(got['pos'].cpu(), want['pos']) <= 1.0
+    assert torch.equal(got['v'].cpu(), want['v']) and torch.equal(got['bond'].cpu(), want['bond'])
+
+
+def test_hybrid_needs_k_protein_atoms(weights):
+    """torch.topk(k) over the protein atoms of a complex raises upstream when there are fewer than k of them (common.py:241-242)."""
+    import decompdiff_b200 as ddb
+    m = ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='hybrid'), syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM,
+                                syn.NUM_CLASSES)
+    m.load_state_dict(weights)
+    kw = syn.make_batch(n_pockets=2, n_protein=[60, 20], arm_sizes=(3,), n_scaffold=3, seed=94)
+    with pytest.raises((ValueError, RuntimeError), match='out of range'):
+        m.eval()(**syn.forward_kwargs(kw, None))

@@ -29,8 +29,8 @@ def test_state_dict_matches_reference_keys(model_cpu):
 
 
 def test_unsupported_configurations_raise():
-    cfg = dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='hybrid')
-    with pytest.raises(ValueError):                # uni_transformer_edge.py:358 ('radius' is defined here, see test_gpu_forward.py)
+    cfg = dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='ball')
+    with pytest.raises(ValueError):                # uni_transformer_edge.py:358 ('knn', 'hybrid' and the product's 'radius' exist)
         ddb.DecompScorePosNet3D(cfg, 29, 10, 8)
     for key, val in (('add_prior_node', True), ('time_emb_dim', 8), ('model_type', 'uni_o2')):
         with pytest.raises((NotImplementedError, ValueError)):

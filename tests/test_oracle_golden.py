@@ -5,7 +5,7 @@ import torch
 
 from conftest import load_golden, tol_ratio
 from decompdiff_b200 import synthetic as syn
-from oracle import fused_algebra, make_golden, restate
+from oracle import fused_algebra, make_golden, make_golden_hybrid, restate
 
 
 @pytest.mark.parametrize('case', list(make_golden.FORWARD_CASES))
@@ -17,6 +17,19 @@ def test_oracle_forward_matches_reference(case, weights, oracle_cfg):
     for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
         assert out[k].shape == gold[k].shape
         # bit-identical in the build container; other hosts / BLAS kernels may re-associate fp32 sums
+        assert tol_ratio(out[k], gold[k]) <= 0.2, (case, k, tol_ratio(out[k], gold[k]))
+
+
+@pytest.mark.parametrize('case', list(make_golden_hybrid.HYBRID_CASES))
+def test_oracle_hybrid_mode_matches_reference(case, weights, oracle_cfg):
+    """cutoff_mode='hybrid': the oracle's edge list is the reference's batch_hybrid_edge_connection edge for edge (same order), and
+    its forward reproduces the reference model's outputs."""
+    kw = syn.make_batch(**make_golden_hybrid.HYBRID_CASES[case])
+    gold = load_golden(case)
+    with torch.no_grad():
+        out = restate.forward(weights, dict(oracle_cfg, cutoff_mode='hybrid'), **syn.forward_kwargs(kw, None), return_all=True)
+    assert torch.equal(out['edge_index'].to(torch.int32), gold['edge_index'])
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
         assert tol_ratio(out[k], gold[k]) <= 0.2, (case, k, tol_ratio(out[k], gold[k]))
 
 
