@@ -13,6 +13,7 @@ Out of scope (raises NotImplementedError): training loss, `add_prior_node`, time
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -182,6 +183,11 @@ def as_config(cfg):
 
 
 # ---------------------------------------------------------------------------------------------------
+def _ddb_env():
+    """The DDB_* diagnostic switches (kernel selection, pruning, caches) are read when a batch is created."""
+    return tuple(sorted((k, v) for k, v in os.environ.items() if k.startswith('DDB_')))
+
+
 class DecompScorePosNet3D(nn.Module):
 
     def __init__(self, config, protein_atom_feature_dim, ligand_atom_feature_dim, num_classes,
@@ -273,8 +279,8 @@ class DecompScorePosNet3D(nn.Module):
         ddb_batch_create.  Inputs are compared by value (cheap next to a rebuild); `clear_forward_cache()` drops the batch."""
         cached = getattr(self, '_fwd_cache', None)
         if cached is not None:
-            keys, eb = cached
-            same = len(keys) == len(static) and eb.model is self._engine
+            keys, eb, env = cached
+            same = len(keys) == len(static) and eb.model is self._engine and env == _ddb_env()
             for a, b in zip(keys, static):
                 if not same:
                     break
@@ -285,7 +291,7 @@ class DecompScorePosNet3D(nn.Module):
             if same:
                 return eb
         eb = self._new_batch(*static, center_mode=0)
-        self._fwd_cache = (tuple(None if t is None else t.detach().clone() for t in static), eb)
+        self._fwd_cache = (tuple(None if t is None else t.detach().clone() for t in static), eb, _ddb_env())
         return eb
 
     def clear_forward_cache(self):

@@ -40,10 +40,15 @@ def test_receptive_field_pruning_is_exact(model_cpu, monkeypatch):
     DDB_NO_PRUNE / DDB_NO_EW_CACHE are read when a batch is created."""
     kw = syn.make_batch(n_pockets=3, n_protein=370, arm_sizes=(8, 8), n_scaffold=14, seed=91)     # deep enough for 6 hops to matter
     fk = syn.forward_kwargs(kw, None)
-    pruned, again = model_cpu(**fk), model_cpu(**fk)
+    model_cpu.clear_forward_cache()
+    pruned = model_cpu(**fk)
+    model_cpu.clear_forward_cache()      # forward() keeps its collated batch: bit reproducibility is a statement about fresh batches
+    again = model_cpu(**fk)
     monkeypatch.setenv('DDB_NO_PRUNE', '1')
     monkeypatch.setenv('DDB_NO_EW_CACHE', '1')
+    model_cpu.clear_forward_cache()      # the switches are read when a batch is created
     full = model_cpu(**fk)
+    model_cpu.clear_forward_cache()
     for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
         assert torch.equal(pruned[k], again[k]), k
         assert float((pruned[k] - full[k]).abs().max()) <= 5e-6, k
