@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libdecompdiff_b200.so')
 BUILD_DIR = os.path.join(HERE, 'build')
-SOURCES = ['gemm.cu', 'gemm_tc.cu', 'graph.cu', 'attn_knn.cu', 'attn_bond.cu', 'attn_tc_knn.cu', 'attn_tc_trip.cu', 'attn_trip2.cu', 'attn_tc_bond.cu', 'attn_chunks.cu', 'step.cu', 'api.cu']
+SOURCES = ['gemm.cu', 'gemm_tc.cu', 'graph.cu', 'attn_knn.cu', 'attn_bond.cu', 'attn_tc_knn.cu', 'attn_tc_trip.cu', 'attn_tc_trip3.cu', 'attn_trip2.cu', 'attn_tc_bond.cu', 'attn_chunks.cu', 'step.cu', 'api.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + (['-DDDB_TIMELINE'] if os.environ.get('DDB_TIMELINE') else []) + \
              [f for f in os.environ.get('DDB_EXTRA_NVCC', '').split() if f]

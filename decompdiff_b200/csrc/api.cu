@@ -39,7 +39,7 @@ struct Blob {
 
 struct Mlp2 { size_t gamma, beta, W2, b2, W2tc; };   // offsets: LayerNorm affine + second Linear (natural layout) + tensor-core image
 struct KnnMlpOff { size_t Wg, Wt, B2tc[2]; Mlp2 m; };
-struct TripOff { size_t Wd, Wc, Wa, Watc, Wa32, W2c; Mlp2 m; };
+struct TripOff { size_t Wd, Wc, Wa, Watc, Wa32, Wa64, W2c; Mlp2 m; };
 struct GemmW { size_t Wt, bias, Wtc; int N; };     // K-major weight (128 x N) + bias (N) + tensor-core image (2*128*N)
 
 struct LayerOff {
@@ -170,6 +170,11 @@ struct Packer {
     {
       std::vector<float> wa(m.blob.data.begin() + r.Wa, m.blob.data.begin() + r.Wa + (size_t)NANG * H);
       pack_wa_sw32(wa.data(), m.blob.data.data() + r.Wa32);
+    }
+    r.Wa64 = m.blob.alloc(4096);
+    {
+      std::vector<float> wa(m.blob.data.begin() + r.Wa, m.blob.data.begin() + r.Wa + (size_t)NANG * H);
+      pack_wa_sw64(wa.data(), m.blob.data.data() + r.Wa64);
     }
     if (key) {
       r.W2c = m.blob.alloc((size_t)H * H);
@@ -359,6 +364,7 @@ struct ddb_batch {
   int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr; int* trip_grp_order = nullptr;
   int4* bond_vg = nullptr; int n_bvg = 0, n_tvg = 0; float2 *bond_stats = nullptr, *trip_stats = nullptr;
   float *bond_factor = nullptr, *bond_part_h = nullptr, *bond_part_dx = nullptr, *trip_factor = nullptr, *trip_part = nullptr; int* trip_vg_pair = nullptr;
+  int4* trip_tile_rec = nullptr; bool trip_chunked = false;
   int4* trip_grp4 = nullptr; int *trip_grp_pk = nullptr, *csr_slot = nullptr; float *PcsrK = nullptr, *PcsrV = nullptr, *xcsr = nullptr;
   float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
   // evolving state
@@ -397,8 +403,9 @@ struct ddb_batch {
   float* v_logits0 = nullptr;   // return_all: v_inference of the input embedding (decompdiff.py:345-346)
   bool use_tc = true;        // tcgen05 3xTF32 projection GEMMs (DDB_GEMM=simt selects the fp32 FMA kernel)
   int ldn = KNN;             // row stride of nbr / e_w / wb_knn (wider for 'hybrid' graphs)
-  int tc_attn = 31;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels; bit 5 (off by default, measured
-                             // slower - DESIGN.md section 4.1): commuted-W2 fp32 triplet kernels of attn_trip2.cu (DDB_TC_ATTN=<mask>)
+  int tc_attn = 95;          // bit 0 trip k, 1 trip v, 2 knn k, 3 knn v, 4 bond edges: tensor-core attention kernels; bit 5 (off by default, measured
+                             // slower - DESIGN.md section 4.1): commuted-W2 fp32 triplet kernels of attn_trip2.cu; bit 6: the triplet passes
+                             // run attn_tc_trip3.cu (P' rows staged in shared memory) instead of attn_tc_trip.cu (DDB_TC_ATTN=<mask>)
   int max_indeg = 0;
   // the bond / triplet branch of a layer runs on a side stream (fork / join by events; becomes parallel branches of the step
   // graph under capture); DDB_NO_FORK=1 keeps everything on the caller's stream
@@ -616,13 +623,43 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
       if (x.c != y.c) return x.c < y.c;
       return bdst[x.e] < bdst[y.e];
     });
+    // attn_tc_trip3.cu stages the rows P'[k->j] of one unit = (source atom, chunk) in shared memory, two units at a time: the
+    // visiting order is padded (e = -1 entries, never stored) so that no aligned block of 4 positions (= one tile) touches more
+    // than two units.  Ligands of >= 4 atoms need no padding except to close the last tile.
+    {
+      std::vector<VG> padded;
+      int units_in_block = 0, last_src = -1, last_ch = -1;
+      for (const VG& g : order) {
+        if (padded.size() % 4 == 0) { units_in_block = 0; last_src = -1; last_ch = -1; }
+        const bool new_unit = bsrc[g.e] != last_src || g.c != last_ch;
+        if (new_unit && units_in_block == 2) {
+          while (padded.size() % 4 != 0) padded.push_back({-1, -1});
+          units_in_block = 0;
+        }
+        if (new_unit) { ++units_in_block; last_src = bsrc[g.e]; last_ch = g.c; }
+        padded.push_back(g);
+      }
+      while (padded.size() % 4 != 0) padded.push_back({-1, -1});
+      order.swap(padded);
+    }
     const int nvg = (int)order.size();
     b->n_tvg = nvg;
+    b->trip_chunked = b->max_indeg > 32;
+    std::vector<int4> tile_rec((size_t)nvg * 2, make_int4(-1, -1, 0, 0));
     std::vector<int2> row_meta((size_t)nvg * 32, make_int2(-1, -1)), grp_meta(nvg);
     std::vector<int> grp_order(nvg), vg_pair(nvg, -1), first_pos(Eb, -1);
+    int unit_ord = -1, unit_src = -1, unit_ch = -1, unit_row0 = 0;
     for (int pos = 0; pos < nvg; ++pos) {
+      if (order[pos].e < 0) {      // padding: belongs to the unit before it (its rows are computed on whatever is staged and dropped)
+        grp_order[pos] = -1; grp_meta[pos] = make_int2(0, 0);
+        tile_rec[(size_t)pos * 2] = make_int4(-1, -1, 0, std::max(unit_ord, 0));
+        tile_rec[(size_t)pos * 2 + 1] = make_int4(unit_row0, 0, 0, 0);
+        continue;
+      }
       const int e = order[pos].e, ch = order[pos].c, j = bsrc[e], i = bdst[e];
+      if (j != unit_src || ch != unit_ch) { ++unit_ord; unit_src = j; unit_ch = ch; unit_row0 = in_ptr[j] + 32 * ch; }
       grp_order[pos] = e;
+      tile_rec[(size_t)pos * 2].w = unit_ord; tile_rec[(size_t)pos * 2 + 1] = make_int4(unit_row0, 0, 0, 0);
       grp_meta[pos] = make_int2(lig_idx[i], lig_idx[j]);
       for (int p = in_ptr[j] + 32 * ch; p < std::min(in_ptr[j + 1], in_ptr[j] + 32 * (ch + 1)); ++p) {
         const int k = in_src[p];
@@ -630,13 +667,20 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
       }
       if (first_pos[e] < 0) first_pos[e] = pos; else { vg_pair[pos] = first_pos[e]; vg_pair[first_pos[e]] = pos; }
     }
+    for (int pos = 0; pos < nvg; ++pos) {
+      if (order[pos].e < 0) continue;
+      unsigned mask = 0;
+      for (int p = 0; p < 32; ++p) if (row_meta[(size_t)pos * 32 + p].y >= 0) mask |= 1u << p;
+      tile_rec[(size_t)pos * 2].x = order[pos].e; tile_rec[(size_t)pos * 2].y = vg_pair[pos]; tile_rec[(size_t)pos * 2].z = (int)mask;
+    }
+    DDB_TRY(b->upload(&b->trip_tile_rec, tile_rec));
     DDB_TRY(b->upload(&b->trip_row_meta, row_meta)); DDB_TRY(b->upload(&b->trip_grp_meta, grp_meta));
     DDB_TRY(b->upload(&b->trip_grp_order, grp_order)); DDB_TRY(b->upload(&b->trip_vg_pair, vg_pair));
     DDB_TRY(b->dalloc(&b->trip_stats, (size_t)nvg * NH)); DDB_TRY(b->dalloc(&b->trip_factor, (size_t)nvg * NH));
-    DDB_TRY(b->dalloc(&b->trip_part, (size_t)(nvg > Eb ? nvg : 1) * H));
+    DDB_TRY(b->dalloc(&b->trip_part, (size_t)(b->trip_chunked ? nvg : 1) * H));
   }
-  if (b->max_indeg <= 32) {
-    std::vector<int> order(Eb);      // the visiting order above (one chunk per group)
+  if (tc_groups) {
+    std::vector<int> order(Eb);      // source-major order of the edges (commuted-W2 kernels; groups of <= 32 rows only)
     for (int e = 0; e < Eb; ++e) order[e] = e;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return bsrc[x] != bsrc[y] ? bsrc[x] < bsrc[y] : bdst[x] < bdst[y]; });
     // commuted-W2 kernels: per group {edge id, node of i, node of j, first CSR row of j}, deg(j) | excluded slot << 8; CSR row per edge
@@ -714,7 +758,7 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
   DDB_TRY(b->dalloc(&b->Qk, eb * H)); DDB_TRY(b->dalloc(&b->Qv, eb * H));
   DDB_TRY(b->dalloc(&b->Pmk, eb)); DDB_TRY(b->dalloc(&b->Pmv, eb)); DDB_TRY(b->dalloc(&b->Qmk, eb)); DDB_TRY(b->dalloc(&b->Qmv, eb));
   DDB_TRY(b->dalloc(&b->wb_knn, n * b->ldn * NH)); DDB_TRY(b->dalloc(&b->wb_bond, eb * NH));
-  DDB_TRY(b->dalloc(&b->wb_trip, (size_t)slots * NH));
+  DDB_TRY(b->dalloc(&b->wb_trip, (size_t)std::max<long long>(slots, (long long)b->n_tvg * 32) * NH));
   DDB_TRY(b->dalloc(&b->e_w, n * b->ldn)); DDB_TRY(b->dalloc(&b->dx_edge, nl * 4)); DDB_TRY(b->dalloc(&b->dist, n * KNN));
   DDB_TRY(b->dalloc(&b->nbr, n * b->ldn)); DDB_TRY(b->dalloc(&b->deg, n)); DDB_TRY(b->dalloc(&b->nlig, n));
   {
@@ -1052,18 +1096,24 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     if (b->tc_attn & 2) { ta.v.Q = b->Qv; ta.v.Pm = b->Pmv; ta.v.Qm = b->Qmv; }
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
     ta.n_groups = b->n_tvg; ta.vg_pair = b->trip_vg_pair; ta.stats = b->trip_stats; ta.factor = b->trip_factor; ta.part = b->trip_part;
-    const bool trip_chunked = b->n_tvg > Eb;
+    const bool trip_chunked = b->trip_chunked;
     if (trip2) {
       ta.k.Pcsr = b->PcsrK; ta.v.Pcsr = b->PcsrV; ta.k.W2c = m->p(L.bl_k.W2c); ta.v.W2c = m->p(L.bl_v.W2c);
       ta.k.Wa32 = m->p(L.bl_k.Wa32); ta.v.Wa32 = m->p(L.bl_v.Wa32);
       ta.grp4 = b->trip_grp4; ta.grp_pk = b->trip_grp_pk; ta.csr_slot = b->csr_slot; ta.xcsr = b->xcsr;
     }
+    const bool trip3 = !trip2 && (b->tc_attn & 67) == 67;      // shared-memory staged P' rows (CSR order), both passes
+    if (trip3) {
+      ta.k.Pcsr = b->PcsrK; ta.v.Pcsr = b->PcsrV; ta.csr_slot = b->csr_slot;
+      ta.k.Wa64 = m->p(L.bl_k.Wa64); ta.v.Wa64 = m->p(L.bl_v.Wa64);
+      ta.tile_rec = b->trip_tile_rec; ta.n_tiles3 = b->n_tvg / 4;
+    }
     { ProfScope ps(b, sb, PC_TRIP_PREP); launch_trip_prep(ta, sb); }
     const bool trip_pair = !trip2 && (b->tc_attn & 3) == 3 && !trip_chunked && !b->profiling && want_pair((b->n_tvg + 3) / 4);
-    if (trip_pair) { launch_trip_tc_pair(ta, sms, sb); b->launches -= 1; }
-    if (!trip_pair) { ProfScope ps(b, sb, PC_TRIP_K); if (trip2) launch_trip2(ta, false, sms, sb); else if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
+    if (trip_pair) { if (trip3) launch_trip3_pair(ta, sms, sb); else launch_trip_tc_pair(ta, sms, sb); b->launches -= 1; }
+    if (!trip_pair) { ProfScope ps(b, sb, PC_TRIP_K); if (trip2) launch_trip2(ta, false, sms, sb); else if (trip3) launch_trip3(ta, false, sms, sb); else if (b->tc_attn & 1) launch_trip_tc(ta, false, sms, sb); else launch_trip_k(ta, sms, sb); }
     if (trip_chunked && (b->tc_attn & 3) == 3) { launch_chunk_factors(ta.stats, ta.vg_pair, 1, ta.n_groups, b->trip_factor, sb); b->launches++; }
-    if (!trip_pair) { ProfScope ps(b, sb, PC_TRIP_V); if (trip2) launch_trip2(ta, true, sms, sb); else if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
+    if (!trip_pair) { ProfScope ps(b, sb, PC_TRIP_V); if (trip2) launch_trip2(ta, true, sms, sb); else if (trip3) launch_trip3(ta, true, sms, sb); else if (b->tc_attn & 2) launch_trip_tc(ta, true, sms, sb); else launch_trip_v(ta, sms, sb); }
     if (trip_chunked && (b->tc_attn & 3) == 3) { launch_trip_combine(ta, m->p(L.bl_v.m.b2), sb); b->launches++; }
     gemm(b, sb, PC_GEMM_BOND, hb_out, H, nullptr, Eb, L.b2, b->PBx, 2 * H);      // projection of the new h_bond for the position update
     if (fork) cudaEventRecord(b->ev_trip, sb);

@@ -154,6 +154,7 @@ struct TripSide {
   float* Pcsr = nullptr;              // (Eb + 32, 128) centred P rows in CSR order (rows of the edges entering one atom contiguous)
   const float* W2c = nullptr;         // k: W2 in the pair layout of pack_w2k_pairs; v: W2 natural [out][in]
   const float* Wa32 = nullptr;        // hi | lo SWIZZLE_32B image of Wa^T (pack_wa_sw32)
+  const float* Wa64 = nullptr;        // hi | lo SWIZZLE_64B image of Wa^T (pack_wa_sw64, attn_tc_trip3.cu)
 };
 struct TripArgs {
   int n_bonds = 0;
@@ -179,6 +180,10 @@ struct TripArgs {
   // chunked groups (see BondAttnArgs): n_groups = number of (edge, chunk) pairs in visiting order (= n_bonds when every atom has
   // <= 32 incoming edges); vg_pair[pos] = position of the partner chunk or -1
   int n_groups = 0; const int* vg_pair = nullptr; float2* stats = nullptr; const float* factor = nullptr; float* part = nullptr;
+  // attn_tc_trip3.cu: a tile = 4 consecutive positions of the (padded) visiting order; 8 int4 per tile, position p at [2p] =
+  // {edge id or -1, partner chunk position or -1, mask of valid rows, ordinal of the position's unit (source atom, chunk)} and
+  // [2p + 1] = {first CSR row of that unit, 0, 0, 0}; a tile touches at most two consecutive units (ddb_batch_create pads)
+  const int4* tile_rec = nullptr; int n_tiles3 = 0;
 };
 void launch_trip_combine(const TripArgs& a, const float* b2, cudaStream_t stream);
 void launch_trip_prep(const TripArgs& a, cudaStream_t stream);
@@ -191,6 +196,9 @@ void launch_knn_tc_pair(const KnnAttnArgs& key, const KnnAttnArgs& value, bool p
 void launch_trip_tc(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);
 void launch_trip_tc_pair(const TripArgs& a, int num_sms, cudaStream_t stream);      // key + value phase, one launch (no chunked groups)
 void launch_trip2(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);      // attn_trip2.cu (groups of <= 32 rows)
+void launch_trip3(const TripArgs& a, bool vpass, int num_sms, cudaStream_t stream);      // attn_tc_trip3.cu (P' rows staged in shared memory)
+void launch_trip3_pair(const TripArgs& a, int num_sms, cudaStream_t stream);
+void pack_wa_sw64(const float* Wa, float* out /* 4096 floats */);
 void pack_wa_sw32(const float* Wa, float* out /* 4096 floats */);
 void pack_w2k_pairs(const float* W2, float* out /* 128*128 floats */);
 void launch_knn_slot_meta(const int* dst_list, int n_slots, const int* deg, const int* nlig, const uint8_t* is_lig, int2* out,
