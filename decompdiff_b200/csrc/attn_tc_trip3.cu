@@ -346,27 +346,40 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
           z[i4 * 2 + 1] = t3f2(fmaxf(w1.x, 0.f), fmaxf(w1.y, 0.f));
         }
       }
-      // ---- drain D of the previous tile into registers (its main MMA had this tile's first Linear / LayerNorm to finish)
-      float lg[4] = {0.f, 0.f, 0.f, 0.f};
-      float val[32];
+      // ---- TF32 split of the hidden activations BEFORE the wait on the tensor core: hi = z truncated to TF32, lo = z - hi (exact)
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        hi[2 * i] = __float_as_uint(z[i].x) & 0xffffe000u;
+        hi[2 * i + 1] = __float_as_uint(z[i].y) & 0xffffe000u;
+        const float2 l = __fadd2_rn(z[i], t3f2(-__uint_as_float(hi[2 * i]), -__uint_as_float(hi[2 * i + 1])));
+        lo[2 * i] = __float_as_uint(l.x); lo[2 * i + 1] = __float_as_uint(l.y);
+      }
+      int4 rp = make_int4(-1, -1, 0, 0);
+      bool prev_ok = false;
       if (it > 0) {
-        const int4 rp = rec0(it - 1, q);
-        const bool prev_ok = (rp.z >> lane) & 1;
-        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (VPASS) {
-          cpa_wait_all();      // weights / factor / residual requested at the top of this iteration
-          __syncwarp();
-          if (prev_ok) {
-            w4 = ld4(reinterpret_cast<const float*>(ring + T3_RING_X) + lane * 4);
-            if (rp.y >= 0) w4 = mul4(w4, ld4(reinterpret_cast<const float*>(ring + T3_RING_X + 512)));
-          }
-        }
-        mbar_wait(bar_mma, (it - 1) & 1);
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        rp = rec0(it - 1, q);
+        prev_ok = (rp.z >> lane) & 1;
+      }
+      // ---- the only work between "main MMA of the previous tile retired" and "main MMA of this tile may start": store the new A
+      // operand, pull the previous D into registers.  Everything else (logits / weighted sums, softmax) runs under the next MMA.
+      uint32_t v[32];
+      {
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (it > 0) { mbar_wait(bar_mma, (it - 1) & 1); tc_fence_after(); }
+        tmem_st32(lane_addr + ATC_COL_AHI + s * 32, hi);
+        tmem_st32(lane_addr + ATC_COL_ALO + s * 32, lo);
+        if (it > 0) tmem_ld32(lane_addr + ATC_COL_D + s * 32, v);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (it > 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        t3_arrive(T3_BAR_A_READY, T3_SYNC);
+      }
+      // ---- epilogue of the previous tile from registers while the tensor core works
+      if (it > 0) {
+        const int ptb = tb - 4 * 32;      // same quadrant, previous tile
         if (!VPASS) {
+          float lg[4];
           const float* qr = reinterpret_cast<const float*>(ring + T3_RING_X + ((it - 1) & 1) * 128);
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) {
@@ -377,50 +390,31 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
             acc = __ffma2_rn(t3f2(q1.z, q1.w), t3u2f(v[hh * 8 + 6], v[hh * 8 + 7]), acc);
             lg[hh] = prev_ok ? acc.x + acc.y : -INFINITY;
           }
+          finish_k(lg, prev_ok, rp.x, ptb, rp.y);
         } else {
+          float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          cpa_wait_all();      // weights / factor / residual row requested at the top of this iteration
+          __syncwarp();
+          if (prev_ok) {
+            w4 = ld4(reinterpret_cast<const float*>(ring + T3_RING_X) + lane * 4);
+            if (rp.y >= 0) w4 = mul4(w4, ld4(reinterpret_cast<const float*>(ring + T3_RING_X + 512)));
+          }
+          float val[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;
             val[i] = wh * __uint_as_float(v[i]);
           }
-          warp_reduce_scatter<32>(val, lane);      // 32 live values become one before the TF32 split needs its registers
-        }
-      }
-      // ---- hidden activations -> TMEM (D is in registers, so the issuer may start the main MMA right away)
-      {
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float2 zz = z[half * 8 + i];
-            hi[2 * i] = __float_as_uint(zz.x) & 0xffffe000u;
-            hi[2 * i + 1] = __float_as_uint(zz.y) & 0xffffe000u;
-            const float2 l = __fadd2_rn(zz, t3f2(-__uint_as_float(hi[2 * i]), -__uint_as_float(hi[2 * i + 1])));
-            lo[2 * i] = __float_as_uint(l.x); lo[2 * i + 1] = __float_as_uint(l.y);
-          }
-          tmem_st16(lane_addr + ATC_COL_AHI + s * 32 + half * 16, hi);
-          tmem_st16(lane_addr + ATC_COL_ALO + s * 32 + half * 16, lo);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        t3_arrive(T3_BAR_A_READY, T3_SYNC);
-      }
-      // ---- finish the epilogue of the previous tile from registers while the tensor core works
-      if (it > 0) {
-        const int4 rp = rec0(it - 1, q);
-        const int ptb = tb - 4 * 32;
-        if (!VPASS) {
-          finish_k(lg, (rp.z >> lane) & 1, rp.x, ptb, rp.y);
-        } else if (rp.x >= 0) {
-          const int c = s * 32 + lane;
-          if (rp.y >= 0) {
-            a.part[(size_t)(ptb >> 5) * H + c] = val[0];      // chunked group: launch_trip_combine finishes the edge
-          } else {
-            const float hb_in = *reinterpret_cast<const float*>(ring + T3_RING_X + 576 + lane * 4);
-            const float upd = rp.z != 0 ? val[0] + sm.b2[c] : 0.f;
-            a.h_bond_out[(size_t)rp.x * H + c] = hb_in + upd;      // :274
+          warp_reduce_scatter<32>(val, lane);
+          if (rp.x >= 0) {
+            const int c = s * 32 + lane;
+            if (rp.y >= 0) {
+              a.part[(size_t)(ptb >> 5) * H + c] = val[0];      // chunked group: launch_trip_combine finishes the edge
+            } else {
+              const float hb_in = *reinterpret_cast<const float*>(ring + T3_RING_X + 576 + lane * 4);
+              const float upd = rp.z != 0 ? val[0] + sm.b2[c] : 0.f;
+              a.h_bond_out[(size_t)rp.x * H + c] = hb_in + upd;      // :274
+            }
           }
         }
       }
