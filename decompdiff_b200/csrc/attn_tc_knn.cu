@@ -274,8 +274,8 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
       TL_MARK(0);
       const bool rowok = lane < g.deg();            // deg is 0 for padding groups
       // ---- requests for later: rows of the next tile, group metadata two tiles ahead, this tile's query / edge weight
-      const int j_n = lane < g_n.deg() ? __ldg(a.nbr + (size_t)g_n.node * KNN + lane) : 0;
-      const float hi_n = g_n.valid() ? __ldg(a.Hi + (size_t)hidx(g_n, tile + step) * a.ldhi + s * 32 + lane) : 0.f;
+      const int j_n = lane < g_n.deg() ? ldna_i(a.nbr + (size_t)g_n.node * KNN + lane) : 0;
+      const float hi_n = g_n.valid() ? ldna_f(a.Hi + (size_t)hidx(g_n, tile + step) * a.ldhi + s * 32 + lane) : 0.f;
       const Grp g_nn = load_group(tile + 2 * step);
       float4 rel = make_float4(0.f, 0.f, 0.f, 0.f);
       if (VPOS && s == 0 && rowok) {          // x_i - x_j of this thread's edge (rel_x, :198-199)
@@ -284,8 +284,8 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
       }
       float qry_v = 0.f, ew = 0.f;
       if (!VPASS) {
-        if (g.valid()) qry_v = __ldg(a.q + (size_t)(a.q_by_slot ? tile * 4 + q : g.node) * a.ldq + s * 32 + lane);
-        if (rowok) ew = __ldg(a.e_w + (size_t)g.node * KNN + lane);
+        if (g.valid()) qry_v = ldna_f(a.q + (size_t)(a.q_by_slot ? tile * 4 + q : g.node) * a.ldq + s * 32 + lane);
+        if (rowok) ew = ldna_f(a.e_w + (size_t)g.node * KNN + lane);
       }
       // dst-side term of the first Linear + type bias, for protein and for ligand sources (uni_transformer_edge.py:371-377)
       {
@@ -353,42 +353,39 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
           z[i4 * 2 + 1] = kf2(fmaxf(u1.x, 0.f), fmaxf(u1.y, 0.f));
         }
       }
-      // ---- drain D of the previous tile into registers
+      uint32_t v[32];
       float lg[4] = {0.f, 0.f, 0.f, 0.f};
-      float val[32];
-      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (VPASS && !VPOS && it > 0 && prev_ok) w4 = ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
-      float4 wpos[4];
-      float cpos = 0.f;
-      if (VPOS && it > 0 && s == 0) {
+      if (VPASS) {
+        // ---- value passes: TF32 split BEFORE the wait on the tensor core (hi = z truncated to TF32, lo = z - hi, exact); between
+        // "main MMA of the previous tile retired" and "main MMA of this tile may start" only the A store and the D load remain
+        uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int h4 = 0; h4 < 4; ++h4) wpos[h4] = prev_ok ? ld4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + h4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      TL_MARK(7);
-      if (it > 0) {
-        mbar_wait(bar_mma, (it - 1) & 1);
-        TL_MARK(8);
-        tc_fence_after();
-        uint32_t v[32];
-        if (VPOS) {
-          if (s == 0) {           // 16 head outputs of this row; c = sum_h (alpha e_w)[h] (D[h] + b2[h])   (:199-208)
-            uint32_t v16[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D, v16);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int h4 = 0; h4 < 4; ++h4) {
-              cpos = fmaf(wpos[h4].x, __uint_as_float(v16[h4 * 4 + 0]) + sm.b2[h4 * 4 + 0], cpos);
-              cpos = fmaf(wpos[h4].y, __uint_as_float(v16[h4 * 4 + 1]) + sm.b2[h4 * 4 + 1], cpos);
-              cpos = fmaf(wpos[h4].z, __uint_as_float(v16[h4 * 4 + 2]) + sm.b2[h4 * 4 + 2], cpos);
-              cpos = fmaf(wpos[h4].w, __uint_as_float(v16[h4 * 4 + 3]) + sm.b2[h4 * 4 + 3], cpos);
-            }
-          }
-        } else {
+        for (int i = 0; i < 16; ++i) {
+          hi[2 * i] = __float_as_uint(z[i].x) & 0xffffe000u;
+          hi[2 * i + 1] = __float_as_uint(z[i].y) & 0xffffe000u;
+          const float2 l = __fadd2_rn(z[i], kf2(-__uint_as_float(hi[2 * i]), -__uint_as_float(hi[2 * i + 1])));
+          lo[2 * i] = __float_as_uint(l.x); lo[2 * i + 1] = __float_as_uint(l.y);
+        }
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (it > 0) { mbar_wait(bar_mma, (it - 1) & 1); tc_fence_after(); }
+        tmem_st32(lane_addr + ATC_COL_AHI + s * 32, hi);
+        tmem_st32(lane_addr + ATC_COL_ALO + s * 32, lo);
+        if (it > 0) {
+          if (VPOS) { if (s == 0) tmem_ld16(lane_addr + ATC_COL_D, reinterpret_cast<uint32_t (&)[16]>(v)); }
+          else tmem_ld32(lane_addr + ATC_COL_D + s * 32, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (it > 0) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        knamed_arrive(KBAR_A_READY, KT_SYNC);
+      } else {
+        // ---- key pass (measured: holding hi | lo across the wait costs more in spills than it saves): drain D into the 4 head
+        // logits, then split and store 16 columns at a time
+        if (it > 0) {
+          mbar_wait(bar_mma, (it - 1) & 1);
+          tc_fence_after();
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ATC_COL_D + s * 32, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
-        if (VPOS) {
-        } else if (!VPASS) {
           const float* qr = wqry + ((it - 1) & 1) * 32;
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) {
@@ -399,17 +396,7 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
             acc = __ffma2_rn(kf2(q1.z, q1.w), ku2f(v[hh * 8 + 6], v[hh * 8 + 7]), acc);
             lg[hh] = prev_ok ? acc.x + acc.y : -INFINITY;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;
-            val[i] = wh * __uint_as_float(v[i]);
-          }
-          warp_reduce_scatter<32>(val, lane);      // 32 live values -> 1 before the TF32 split needs the registers
         }
-      }
-      // ---- hidden activations -> TMEM, 16 columns at a time (hi = z truncated to TF32, lo = z - hi, exact)
-      {
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -428,7 +415,6 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         knamed_arrive(KBAR_A_READY, KT_SYNC);
-        TL_MARK(9);
       }
       // ---- row gather of the next tile (consumed one iteration from now)
       {
@@ -436,7 +422,7 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
 #pragma unroll
         for (int i8 = 0; i8 < 4; ++i8) ldg8(prow + i8 * 8, pv[2 * i8], pv[2 * i8 + 1]);
       }
-      // ---- finish the epilogue of the previous tile from registers while the tensor core works
+      // ---- epilogue of the previous tile from registers while the tensor core works
       if (it > 0) {
         if (!VPASS) {
           float ex[4];
@@ -453,11 +439,29 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
           for (int hh = 0; hh < 4; ++hh) w[hh] = sum[hh] > 0.f ? __fdividef(ex[hh], sum[hh]) * prev_ew : 0.f;
           if (prev_ok) st4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4, make_float4(w[0], w[1], w[2], w[3]));
         } else if (VPOS) {
-          if (s == 0) {
+          if (s == 0) {           // 16 head outputs of this row; c = sum_h (alpha e_w)[h] (D[h] + b2[h])   (:199-208)
+            float cpos = 0.f;
+#pragma unroll
+            for (int h4 = 0; h4 < 4; ++h4) {
+              const float4 wp = prev_ok ? ldna_c4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + h4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              cpos = fmaf(wp.x, __uint_as_float(v[h4 * 4 + 0]) + sm.b2[h4 * 4 + 0], cpos);
+              cpos = fmaf(wp.y, __uint_as_float(v[h4 * 4 + 1]) + sm.b2[h4 * 4 + 1], cpos);
+              cpos = fmaf(wp.z, __uint_as_float(v[h4 * 4 + 2]) + sm.b2[h4 * 4 + 2], cpos);
+              cpos = fmaf(wp.w, __uint_as_float(v[h4 * 4 + 3]) + sm.b2[h4 * 4 + 3], cpos);
+            }
             const float ax = warp_sum(cpos * prev_rel.x), ay = warp_sum(cpos * prev_rel.y), az = warp_sum(cpos * prev_rel.z);
             if (lane == 0 && prev_node >= 0) st4(a.out_dx + (size_t)prev_slot * 4, make_float4(ax * (1.f / NH), ay * (1.f / NH), az * (1.f / NH), 0.f));
           }
         } else {
+          float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (prev_ok) w4 = ldna_c4(a.wbuf + ((size_t)prev_node * KNN + lane) * NH + s * 4);
+          float val[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float wh = (i < 8) ? w4.x : (i < 16) ? w4.y : (i < 24) ? w4.z : w4.w;
+            val[i] = wh * __uint_as_float(v[i]);
+          }
+          warp_reduce_scatter<32>(val, lane);
           float ws[4] = {w4.x, w4.y, w4.z, w4.w};
           warp_allreduce4(ws, lane);
           if (prev_node >= 0) {
