@@ -47,11 +47,14 @@ __device__ __forceinline__ float ssp(float x) { return (x > 20.f ? x : log1pf(ex
 __device__ __forceinline__ void tc_quad_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(128) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-// One launch serves up to GEMM_MAX_BATCH independent problems (blockIdx.z selects one): the projections of a layer phase share a
+// One launch serves up to GEMM_MAX_BATCH independent problems (a flat grid, problem after problem): the projections of a layer phase share a
 // launch, so the 15-CTA ligand problems run next to the wide ones instead of paying a launch of their own.
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBatch gb) {
-  const int pz = blockIdx.z;
-  if ((int)blockIdx.x >= gb.gx[pz] || (int)blockIdx.y >= gb.gy[pz]) { pdl_wait(); return; }
+  // flat grid: the CTAs of problem 0 come first, then those of problem 1, ... (no empty CTAs; the launcher gives every problem a
+  // share of the SMs in proportion to its work, so the whole batch is one wave of persistent CTAs)
+  int pz = 0, bid = blockIdx.x;
+  while (pz + 1 < GEMM_MAX_BATCH && bid >= gb.gx[pz] * gb.gy[pz]) { bid -= gb.gx[pz] * gb.gy[pz]; ++pz; }
+  const int bx = bid % gb.gx[pz], by = bid / gb.gx[pz];
   const GemmArgs& a = gb.p[pz];
   const float* __restrict__ Wtc = gb.Wtc[pz];
   const int tiles_per_cta = gb.per[pz], grid_x = gb.gx[pz];
@@ -66,11 +69,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
   pdl_wait();      // the row count below may be a device-side counter of the previous kernels
   const int M = a.M_dev ? min(__ldg(a.M_dev), a.M) : a.M;      // device-side row count: exact receptive-field pruning
   const int row_tiles = (M + TC_BM - 1) / TC_BM;
-  if ((int)blockIdx.x >= row_tiles) return;
-  // persistent over row tiles: blockIdx.x, blockIdx.x + gridDim.x, ...  (one TMEM allocation / barrier set-up per CTA; with a
+  if (bx >= row_tiles) return;
+  // persistent over row tiles: bx, bx + grid_x, ...  (one TMEM allocation / barrier set-up per CTA; with a
   // single output tile the whole weight stays resident in the ring and is streamed once).
-  const int my_rows = (row_tiles - (int)blockIdx.x + grid_x - 1) / grid_x;
-  const int tile0 = blockIdx.y * tiles_per_cta;
+  const int my_rows = (row_tiles - bx + grid_x - 1) / grid_x;
+  const int tile0 = by * tiles_per_cta;
   const int n_tiles = min(tiles_per_cta, a.N / TC_BN - tile0);
   auto bar_full = [&](int i) { return smem_u32(&bars[i]); };                        // K-block landed in stage i
   auto bar_empty = [&](int i) { return smem_u32(&bars[TC_STAGES + i]); };           // MMAs reading stage i retired
@@ -145,13 +148,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
     const int q = warp & 3, s = warp >> 2;                  // TMEM lane quadrant, channel slice
     float* tile = sEpi + warp * 32 * TC_EPI_LD;
     int tg = 0;
-    for (int rt = 0; rt < my_rows; ++rt) {
-    const int row0 = ((int)blockIdx.x + rt * grid_x) * TC_BM;
-    {
-      // ---- stage A into TMEM: this thread owns channels [32s, 32s+32) of row 32q + lane.  Every MMA that read the previous
-      // A tile has retired: this warp waited on the last accumulator's "full" barrier in its epilogue below
-      const int r = q * 32 + lane, m = row0 + r;
-      float z[32];
+    // rows of a row tile -> registers: this thread owns channels [32s, 32s+32) of row 32q + lane.  The loads of row tile rt + 1 are
+    // issued BEFORE the epilogues of row tile rt, so the gather latency (two dependent L2 round trips with a row map) is off the
+    // path between the last MMA of one row tile and the first MMA of the next.
+    float z[32];
+    auto load_rows = [&](int rt) {
+      const int m = (bx + rt * grid_x) * TC_BM + q * 32 + lane;
 #pragma unroll
       for (int i = 0; i < 32; ++i) z[i] = 0.f;
       const int ar = m < M ? (a.a_rows ? a.a_rows[m] : m) : -1;
@@ -168,6 +170,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
           }
         }
       }
+    };
+    load_rows(0);
+    for (int rt = 0; rt < my_rows; ++rt) {
+    const int row0 = (bx + rt * grid_x) * TC_BM;
+    {
+      // ---- stage A into TMEM.  Every MMA that read the previous A tile has retired: this warp waited on the last accumulator's
+      // "full" barrier in its epilogue below
+      const int r = q * 32 + lane;
       if (a.ln_gamma != nullptr) {       // LayerNorm + ReLU over the full row: two-pass statistics via smem
         float p = 0.f;
 #pragma unroll
@@ -192,15 +202,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
           z[i4 * 4 + 3] = fmaxf(fmaf(z[i4 * 4 + 3] * rstd, g.w, b.w), 0.f);
         }
       }
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) { float h = tf32_rna(z[i]); hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(tf32_rna(z[i] - h)); }
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-      tmem_st32(lane_addr + TC_COL_AHI + s * 32, hi);
-      tmem_st32(lane_addr + TC_COL_ALO + s * 32, lo);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {      // 16 columns at a time: the next row tile's rows are about to occupy z again
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { float h = tf32_rna(z[half * 16 + i]); hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(tf32_rna(z[half * 16 + i] - h)); }
+        tmem_st16(lane_addr + TC_COL_AHI + s * 32 + half * 16, hi);
+        tmem_st16(lane_addr + TC_COL_ALO + s * 32 + half * 16, lo);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       asm volatile("bar.arrive %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_WORKERS + 32) : "memory");
+      if (rt + 1 < my_rows) load_rows(rt + 1);      // in flight during the epilogues below
     }
     // ---- epilogue: warp (s, q) drains rows 32q.., columns 32s.. of every output tile
     for (int t = 0; t < n_tiles; ++t, ++tg) {
@@ -248,18 +262,24 @@ void launch_gemm128_tc_batch(const GemmArgs* args, const float* const* Wtc, int 
     attr_set.mark();
   }
   GemmBatch gb;
-  int np = 0, gx = 1, gy = 1;
+  int np = 0;
+  // every problem gets SMs in proportion to its work (row tiles x (A staging + output tiles), in units of one output tile of MMAs)
+  double total_work = 0.0;
+  for (int i = 0; i < n; ++i)
+    if (args[i].M > 0 && args[i].N > 0) total_work += (double)((args[i].M + TC_BM - 1) / TC_BM) * (1.5 + args[i].N / TC_BN);
+  int cta_total = 0;
   for (int i = 0; i < n && np < GEMM_MAX_BATCH; ++i) {
     const GemmArgs& a = args[i];
     if (a.M <= 0 || a.N <= 0) continue;
     const int row_tiles = (a.M + TC_BM - 1) / TC_BM, tiles = a.N / TC_BN;
+    const int share = std::max(1, (int)(num_sms * ((double)row_tiles * (1.5 + tiles)) / total_work));
     // Split the output tiles over `nsplit` CTAs per row tile.  Cost model in units of one output tile of MMA work: every CTA
-    // pays ~1.5 units to stage its A tile, then tiles/nsplit units; CTAs run in waves of num_sms (1 CTA per SM).
+    // pays ~1.5 units to stage its A tile, then tiles/nsplit units; the problem owns `share` SMs (1 CTA per SM).
     int best = 1; double best_cost = 1e30;
     for (int ns = 1; ns <= tiles; ++ns) {
       if (tiles % ns) continue;
-      // CTAs are persistent over row tiles: num_sms / ns of them per column range, each walking ceil(row_tiles / that) row tiles
-      const int per_col = std::max(1, std::min(row_tiles, num_sms / ns));
+      // CTAs are persistent over row tiles: share / ns of them per column range, each walking ceil(row_tiles / that) row tiles
+      const int per_col = std::max(1, std::min(row_tiles, share / ns));
       const double rows_each = (double)((row_tiles + per_col - 1) / per_col);
       const double cost = 1.0 + rows_each * (1.5 + (double)tiles / ns);
       if (cost < best_cost - 1e-9) { best_cost = cost; best = ns; }
@@ -268,13 +288,13 @@ void launch_gemm128_tc_batch(const GemmArgs* args, const float* const* Wtc, int 
     if (force_ns > 0 && tiles % force_ns == 0) best = force_ns;
     const int per = tiles / best;
     gb.p[np] = a; gb.Wtc[np] = Wtc[i]; gb.per[np] = per;
-    gb.gx[np] = std::max(1, std::min(row_tiles, num_sms / best)); gb.gy[np] = (tiles + per - 1) / per;
-    gx = std::max(gx, gb.gx[np]); gy = std::max(gy, gb.gy[np]);
+    gb.gx[np] = std::max(1, std::min(row_tiles, share / best)); gb.gy[np] = (tiles + per - 1) / per;
+    cta_total += gb.gx[np] * gb.gy[np];
     ++np;
   }
   if (np == 0) return;
   for (int i = np; i < GEMM_MAX_BATCH; ++i) { gb.gx[i] = 0; gb.gy[i] = 0; gb.per[i] = 0; gb.Wtc[i] = nullptr; }
-  launch_pdl(gemm128_tc_kernel, dim3(gx, gy, np), dim3(TC_THREADS), TC_SMEM, stream, gb);
+  launch_pdl(gemm128_tc_kernel, dim3(cta_total), dim3(TC_THREADS), TC_SMEM, stream, gb);
 }
 
 void launch_gemm128_tc(const GemmArgs& a, const float* Wtc, int num_sms, cudaStream_t stream) {
