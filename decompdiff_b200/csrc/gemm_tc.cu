@@ -171,40 +171,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
         }
       }
     };
-    load_rows(0);
-    for (int rt = 0; rt < my_rows; ++rt) {
-    const int row0 = (bx + rt * grid_x) * TC_BM;
-    {
-      // ---- stage A into TMEM.  Every MMA that read the previous A tile has retired: this warp waited on the last accumulator's
-      // "full" barrier in its epilogue below
-      const int r = q * 32 + lane;
-      if (a.ln_gamma != nullptr) {       // LayerNorm + ReLU over the full row: two-pass statistics via smem
-        float p = 0.f;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    auto ln_relu = [&]() {       // LayerNorm + ReLU over the full row: two-pass statistics via smem
+      if (a.ln_gamma == nullptr) return;
+      float p = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) p += z[i];
-        sStatA[r * 4 + s] = p;
-        tc_quad_barrier(q);
-        float4 t = ld4(sStatA + r * 4);
-        const float mu = ((t.x + t.y) + (t.z + t.w)) * (1.0f / H);
-        p = 0.f;
+      for (int i = 0; i < 32; ++i) p += z[i];
+      sStatA[r * 4 + s] = p;
+      tc_quad_barrier(q);
+      float4 t = ld4(sStatA + r * 4);
+      const float mu = ((t.x + t.y) + (t.z + t.w)) * (1.0f / H);
+      p = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { z[i] -= mu; p = fmaf(z[i], z[i], p); }
-        sStatB[r * 4 + s] = p;
-        tc_quad_barrier(q);
-        t = ld4(sStatB + r * 4);
-        const float rstd = 1.0f / sqrtf(((t.x + t.y) + (t.z + t.w)) * (1.0f / H) + LN_EPS);
+      for (int i = 0; i < 32; ++i) { z[i] -= mu; p = fmaf(z[i], z[i], p); }
+      sStatB[r * 4 + s] = p;
+      tc_quad_barrier(q);
+      t = ld4(sStatB + r * 4);
+      const float rstd = 1.0f / sqrtf(((t.x + t.y) + (t.z + t.w)) * (1.0f / H) + LN_EPS);
 #pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 g = ldg4(a.ln_gamma + s * 32 + i4 * 4), b = ldg4(a.ln_beta + s * 32 + i4 * 4);
-          z[i4 * 4 + 0] = fmaxf(fmaf(z[i4 * 4 + 0] * rstd, g.x, b.x), 0.f);
-          z[i4 * 4 + 1] = fmaxf(fmaf(z[i4 * 4 + 1] * rstd, g.y, b.y), 0.f);
-          z[i4 * 4 + 2] = fmaxf(fmaf(z[i4 * 4 + 2] * rstd, g.z, b.z), 0.f);
-          z[i4 * 4 + 3] = fmaxf(fmaf(z[i4 * 4 + 3] * rstd, g.w, b.w), 0.f);
-        }
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 g = ldg4(a.ln_gamma + s * 32 + i4 * 4), b = ldg4(a.ln_beta + s * 32 + i4 * 4);
+        z[i4 * 4 + 0] = fmaxf(fmaf(z[i4 * 4 + 0] * rstd, g.x, b.x), 0.f);
+        z[i4 * 4 + 1] = fmaxf(fmaf(z[i4 * 4 + 1] * rstd, g.y, b.y), 0.f);
+        z[i4 * 4 + 2] = fmaxf(fmaf(z[i4 * 4 + 2] * rstd, g.z, b.z), 0.f);
+        z[i4 * 4 + 3] = fmaxf(fmaf(z[i4 * 4 + 3] * rstd, g.w, b.w), 0.f);
       }
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    };
+    auto store_a = [&]() {       // hi / lo split -> TMEM, 16 columns at a time, then the hand-over to the issuing warp
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {      // 16 columns at a time: the next row tile's rows are about to occupy z again
+      for (int half = 0; half < 2; ++half) {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { float h = tf32_rna(z[half * 16 + i]); hi[i] = __float_as_uint(h); lo[i] = __float_as_uint(tf32_rna(z[half * 16 + i] - h)); }
@@ -214,40 +210,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       asm volatile("bar.arrive %0, %1;" ::"r"(TC_BAR_A_READY), "r"(TC_WORKERS + 32) : "memory");
-      if (rt + 1 < my_rows) load_rows(rt + 1);      // in flight during the epilogues below
-    }
-    // ---- epilogue: warp (s, q) drains rows 32q.., columns 32s.. of every output tile
-    for (int t = 0; t < n_tiles; ++t, ++tg) {
-      const int db = tg & 1;
-      mbar_wait(bar_dfull(db), (tg >> 1) & 1);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + TC_COL_D + db * TC_BN + s * 32, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_dempty(db));           // this warp's part of the accumulator may be overwritten
-      // thread = row -> transpose through smem so that 8 lanes write one 128-byte segment of a row
+    };
+    load_rows(0);
+    ln_relu();
+    store_a();
+    for (int rt = 0; rt < my_rows; ++rt) {
+      const int row0 = (bx + rt * grid_x) * TC_BM;
+      const bool more = rt + 1 < my_rows;
+      if (more) load_rows(rt + 1);      // in flight during the epilogues below
+      // ---- epilogue: warp (s, q) drains rows 32q.., columns 32s.. of every output tile.  With the LAST output tile of a row tile
+      // the A operand is free as well (its commit covers every MMA of the row tile): the next row tile's A is stored and handed
+      // over between the accumulator load and the global stores, so the tensor core restarts under this epilogue.
+      for (int t = 0; t < n_tiles; ++t, ++tg) {
+        const int db = tg & 1;
+        const bool last_tile = t + 1 == n_tiles;
+        if (last_tile && more) ln_relu();      // needs the prefetched rows; runs under the MMAs of the last output tile
+        mbar_wait(bar_dfull(db), (tg >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(lane_addr + TC_COL_D + db * TC_BN + s * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dempty(db));           // this warp's part of the accumulator may be overwritten
+        if (last_tile && more) { tc_fence_after(); store_a(); }
+        // thread = row -> transpose through smem so that 8 lanes write one 128-byte segment of a row
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        st4(tile + lane * TC_EPI_LD + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-      __syncwarp();
-      const int n0 = (tile0 + t) * TC_BN + s * 32 + (lane & 7) * 4;
-      const float4 bias4 = a.bias ? ldg4(a.bias + n0) : make_float4(0, 0, 0, 0);
+        for (int j = 0; j < 32; j += 4)
+          st4(tile + lane * TC_EPI_LD + j, make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+        __syncwarp();
+        const int n0 = (tile0 + t) * TC_BN + s * 32 + (lane & 7) * 4;
+        const float4 bias4 = a.bias ? ldg4(a.bias + n0) : make_float4(0, 0, 0, 0);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rl = it * 4 + (lane >> 3);
-        const int m = row0 + q * 32 + rl;
-        const int cr = m < M ? (a.c_rows ? a.c_rows[m] : m) : -1;
-        if (cr >= 0) {
-          float4 o = add4(ld4(tile + rl * TC_EPI_LD + (lane & 7) * 4), bias4);
-          if (a.R) o = add4(o, ld4(a.R + (size_t)cr * a.ldr + n0));
-          if (a.act == 1) { o.x = ssp(o.x); o.y = ssp(o.y); o.z = ssp(o.z); o.w = ssp(o.w); }
-          st4(a.C + (size_t)cr * a.ldc + n0, o);
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + (lane >> 3);
+          const int m = row0 + q * 32 + rl;
+          const int cr = m < M ? (a.c_rows ? a.c_rows[m] : m) : -1;
+          if (cr >= 0) {
+            float4 o = add4(ld4(tile + rl * TC_EPI_LD + (lane & 7) * 4), bias4);
+            if (a.R) o = add4(o, ld4(a.R + (size_t)cr * a.ldr + n0));
+            if (a.act == 1) { o.x = ssp(o.x); o.y = ssp(o.y); o.z = ssp(o.z); o.w = ssp(o.w); }
+            st4(a.C + (size_t)cr * a.ldc + n0, o);
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
-    }
     }
   }
   tc_fence_before();
