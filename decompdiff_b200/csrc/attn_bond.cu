@@ -243,6 +243,12 @@ void launch_bond_attn_pos(const BondAttnArgs& a, int num_sms, cudaStream_t strea
 // a time (lane = 4 channels) so that every weight row fetched from L1 feeds several edges - the kernel is bound by the L1
 // wavefronts of the Wd / Wc reads otherwise.
 constexpr int PREP_EDGES = 2;      // 2 edges x 64 registers -> 32 warps per SM: the kernel is latency / HBM bound, occupancy matters more than weight reuse
+__device__ __forceinline__ float4 fma4p(float s, float4 w, float4 acc) {      // acc + s * w as two packed FFMA2
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __ffma2_rn(make_float2(w.x, w.y), ss, make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(make_float2(w.z, w.w), ss, make_float2(acc.z, acc.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 __global__ void __launch_bounds__(256, 4) trip_prep_kernel(const TripArgs a) {
   const int lane = threadIdx.x & 31;
   const int e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PREP_EDGES;
@@ -259,46 +265,59 @@ __global__ void __launch_bounds__(256, 4) trip_prep_kernel(const TripArgs a) {
     gl[u] = lane < NG ? gauss_feat(d, lane) : 0.f;
     if (a.xcsr && lane == 0 && e0 + u < a.n_bonds) st4(a.xcsr + (size_t)a.csr_slot[es[u]] * 4, xk);
   }
+  // both MLPs in one sweep over the 20 Gaussians: one broadcast per (edge, Gaussian) serves the four weight rows, and the
+  // accumulations run as packed FFMA2 (same per-element fma as before, bit-identical results)
+  float4 z[2][PREP_EDGES], qv[2][PREP_EDGES];
 #pragma unroll
   for (int side = 0; side < 2; ++side) {
     const TripSide& t = side ? a.v : a.k;
-    float4 z[PREP_EDGES], qv[PREP_EDGES];
 #pragma unroll
     for (int u = 0; u < PREP_EDGES; ++u) {
-      z[u] = add4(add4(ldg4(t.Pe + (size_t)es[u] * a.ldpe + lane * 4), ldg4(t.Hk + (size_t)ks[u] * a.ldh + lane * 4)),
-                  ldg4(t.Hj + (size_t)js[u] * a.ldh + lane * 4));
-      qv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      z[side][u] = add4(add4(ldg4(t.Pe + (size_t)es[u] * a.ldpe + lane * 4), ldg4(t.Hk + (size_t)ks[u] * a.ldh + lane * 4)),
+                        ldg4(t.Hj + (size_t)js[u] * a.ldh + lane * 4));
+      qv[side][u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+  const bool tc = a.k.Q != nullptr;      // the tensor-core kernels take both sides or none (ddb_batch_create)
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
+  for (int g = 0; g < NG; ++g) {
+    float gg[PREP_EDGES];
+#pragma unroll
+    for (int u = 0; u < PREP_EDGES; ++u) gg[u] = __shfl_sync(FULL, gl[u], g);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const TripSide& t = side ? a.v : a.k;
       const float4 wd = ldg4(t.Wd + g * H + lane * 4);
       float4 wc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t.Q) wc = ldg4(t.Wc + g * H + lane * 4);
+      if (tc) wc = ldg4(t.Wc + g * H + lane * 4);
 #pragma unroll
       for (int u = 0; u < PREP_EDGES; ++u) {
-        const float gg = __shfl_sync(FULL, gl[u], g);
-        z[u] = fma4(gg, wd, z[u]);
-        if (t.Q) qv[u] = fma4(gg, wc, qv[u]);
+        z[side][u] = fma4p(gg[u], wd, z[side][u]);
+        if (tc) qv[side][u] = fma4p(gg[u], wc, qv[side][u]);
       }
     }
+  }
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const TripSide& t = side ? a.v : a.k;
 #pragma unroll
     for (int u = 0; u < PREP_EDGES; ++u) {
       if (t.Q) {      // tensor-core kernels: rows are stored CENTRED (LayerNorm is invariant to a per-row shift, and centred rows
         // keep its single-pass statistics well conditioned); Q = Wc . gauss(d) is the same edge seen as j->i
-        const float pm = warp_sum((z[u].x + z[u].y) + (z[u].z + z[u].w)) * (1.0f / H);
-        const float qm = warp_sum((qv[u].x + qv[u].y) + (qv[u].z + qv[u].w)) * (1.0f / H);
+        const float4 zz = z[side][u], qq = qv[side][u];
+        const float pm = warp_sum((zz.x + zz.y) + (zz.z + zz.w)) * (1.0f / H);
+        const float qm = warp_sum((qq.x + qq.y) + (qq.z + qq.w)) * (1.0f / H);
         if (e0 + u < a.n_bonds) {
           float* prow = t.Pcsr ? t.Pcsr + (size_t)a.csr_slot[es[u]] * H : t.P + (size_t)es[u] * H;
-          st4(prow + lane * 4, make_float4(z[u].x - pm, z[u].y - pm, z[u].z - pm, z[u].w - pm));
-          st4(t.Q + (size_t)es[u] * H + lane * 4, make_float4(qv[u].x - qm, qv[u].y - qm, qv[u].z - qm, qv[u].w - qm));
+          st4(prow + lane * 4, make_float4(zz.x - pm, zz.y - pm, zz.z - pm, zz.w - pm));
+          st4(t.Q + (size_t)es[u] * H + lane * 4, make_float4(qq.x - qm, qq.y - qm, qq.z - qm, qq.w - qm));
         }
       } else if (e0 + u < a.n_bonds) {
-        st4(t.P + (size_t)es[u] * H + lane * 4, z[u]);
+        st4(t.P + (size_t)es[u] * H + lane * 4, z[side][u]);
       }
     }
   }
 }
-
 void launch_trip_prep(const TripArgs& a, cudaStream_t stream) {
   if (a.n_bonds <= 0) return;
   const int per_block = 8 * PREP_EDGES;
