@@ -182,17 +182,22 @@ void launch_knn_merge(const float* x4, const int* node_ptr, const int* graph_of,
 }
 
 // e_w = sigmoid(MLP_{20->128->1}(gauss(d)))  (uni_transformer_edge.py:422-427), one warp per destination node,
-// lane = 4 hidden channels, first-layer weights (20 x 128) held in registers.
+// lane = 4 hidden channels, first-layer weights (20 x 128) in shared memory.
 //
 // e_w depends on the distance only, and protein atoms never move during a sampling run: the value of every protein-protein
 // pair is memoised in a per-graph table (NaN = not yet computed), filled on first use by the same arithmetic, so later steps
 // only evaluate the MLP for edges that touch a ligand atom (a cache hit returns the bits a recomputation would produce).
-__global__ void __launch_bounds__(256) edge_weight_kernel(const float* __restrict__ x4, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(256, 4) edge_weight_kernel(const float* __restrict__ x4, const int* __restrict__ nbr,
                                                           const int* __restrict__ deg, int n,
                                                           const float* __restrict__ W1t /*[20][128]*/,
                                                           const float* __restrict__ b1, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ w2,
                                                           float b2, float* __restrict__ e_w, EdgeWeightCache c, int ld) {
+  // first-layer weights in shared memory (10 KB per CTA): in registers (80 per thread) they capped the kernel at one CTA per SM,
+  // and the kernel is a chain of dependent L2 reads (neighbour row -> positions -> memo table) that only occupancy hides
+  __shared__ float4 sW[NG * H / 4];
+  for (int t = threadIdx.x; t < NG * H / 4; t += blockDim.x) sW[t] = ldg4(W1t + t * 4);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
@@ -213,24 +218,54 @@ __global__ void __launch_bounds__(256) edge_weight_kernel(const float* __restric
     unsigned todo = __ballot_sync(FULL, lane < d_i && val != val);
     if (todo) {
       // ---- evaluation phase: the warp computes the missing edges one at a time
-      float4 w[NG];
-#pragma unroll
-      for (int g = 0; g < NG; ++g) w[g] = ldg4(W1t + g * H + lane * 4);
       const float4 bb = ldg4(b1 + lane * 4), gm = ldg4(gamma + lane * 4), bt = ldg4(beta + lane * 4), w2v = ldg4(w2 + lane * 4);
+      // four missing edges per pass: the same per-edge arithmetic as one at a time (every reduction is a plain warp_sum of that
+      // edge's values, so the bits do not depend on which edges share a pass), with four independent dependency chains in flight
       while (todo) {
-        const int e = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const float xjx = __shfl_sync(FULL, xj.x, e), xjy = __shfl_sync(FULL, xj.y, e), xjz = __shfl_sync(FULL, xj.z, e);
-        const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
-        const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-        const float gl = lane < NG ? gauss_feat(d, lane) : 0.f;
-        float4 z[1] = {bb};
+        int e[4];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) z[0] = fma4(__shfl_sync(FULL, gl, g), w[g], z[0]);
-        ln_relu_rows<1>(z, gm, bt, lane);
-        const float logit = warp_sum(dot4(z[0], w2v)) + b2;
-        const float r = 1.0f / (1.0f + expf(-logit));
-        if (lane == e) { val = r; if (slot >= 0) c.table[slot] = r; }
+        for (int u = 0; u < 4; ++u) { e[u] = todo ? __ffs(todo) - 1 : -1; todo &= todo - 1; }
+        float gl[4];
+        float4 z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int eu = max(e[u], 0);
+          const float xjx = __shfl_sync(FULL, xj.x, eu), xjy = __shfl_sync(FULL, xj.y, eu), xjz = __shfl_sync(FULL, xj.z, eu);
+          const float dx = xi.x - xjx, dy = xi.y - xjy, dz = xi.z - xjz;
+          const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+          gl[u] = lane < NG ? gauss_feat(d, lane) : 0.f;
+          z[u] = bb;
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float4 wg = sW[g * (H / 4) + lane];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) z[u] = fma4(__shfl_sync(FULL, gl[u], g), wg, z[u]);
+        }
+        float sm[4], sq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sm[u] = warp_sum((z[u].x + z[u].y) + (z[u].z + z[u].w));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float mu = sm[u] * (1.0f / H);
+          z[u].x -= mu; z[u].y -= mu; z[u].z -= mu; z[u].w -= mu;
+          sq[u] = warp_sum((z[u].x * z[u].x + z[u].y * z[u].y) + (z[u].z * z[u].z + z[u].w * z[u].w));
+        }
+        float lg[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float rstd = 1.0f / sqrtf(sq[u] * (1.0f / H) + LN_EPS);
+          z[u].x = fmaxf(fmaf(z[u].x * rstd, gm.x, bt.x), 0.f);
+          z[u].y = fmaxf(fmaf(z[u].y * rstd, gm.y, bt.y), 0.f);
+          z[u].z = fmaxf(fmaf(z[u].z * rstd, gm.z, bt.z), 0.f);
+          z[u].w = fmaxf(fmaf(z[u].w * rstd, gm.w, bt.w), 0.f);
+          lg[u] = warp_sum(dot4(z[u], w2v)) + b2;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float r = 1.0f / (1.0f + expf(-lg[u]));
+          if (e[u] >= 0 && lane == e[u]) { val = r; if (slot >= 0) c.table[slot] = r; }
+        }
       }
     }
     if (lane < d_i) e_w[(size_t)i * ld + e0 + lane] = val;
