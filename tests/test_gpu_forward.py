@@ -63,6 +63,10 @@ def test_receptive_field_pruning_is_exact(model_cpu, monkeypatch):
     ('n1100', dict(n_pockets=1, n_protein=1070, arm_sizes=(8, 8), n_scaffold=14, seed=503)),
     # a batch whose graphs differ a lot in size, one without ligand arms' scaffold and a 2-atom ligand
     ('mixed', dict(n_pockets=4, n_protein=[40, 300, 90, 500], arm_sizes=(1,), n_scaffold=1, seed=504)),
+    # 3- and 5-atom ligands: a source atom owns 2 / 4 triplet groups, so the visiting order of attn_tc_trip3.cu needs padding
+    # positions to keep every 4-position tile within two shared-memory units
+    ('lig3', dict(n_pockets=5, n_protein=70, arm_sizes=(1,), n_scaffold=2, seed=505)),
+    ('lig5', dict(n_pockets=3, n_protein=90, arm_sizes=(2, 1), n_scaffold=2, seed=506)),
 ])
 def test_forward_edge_shapes_match_oracle(name, kwargs, model_cpu, weights, oracle_cfg):
     kw = syn.make_batch(**kwargs)
