@@ -1065,7 +1065,8 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     // 11.22 -> 11.43 ms/step - one long kernel per branch shares the SMs worse than two), so full grids keep two launches.
     // DDB_PAIR=0 / 1 forces never / always.
     static const int pair_mode = getenv("DDB_PAIR") ? atoi(getenv("DDB_PAIR")) : -1;
-    auto want_pair = [&](int tiles) { return pair_mode >= 0 ? pair_mode != 0 : tiles < sms; };
+    static const int pair_waves = getenv("DDB_PAIR_WAVES") ? atoi(getenv("DDB_PAIR_WAVES")) : 4;      // key + value phases share a launch below this many tiles per SM (cfg 2: bond-edge and position passes; 123 -> 105 launches per step, time unchanged within noise)
+    auto want_pair = [&](int tiles) { return pair_mode >= 0 ? pair_mode != 0 : tiles < pair_waves * sms; };
     const bool knn_pair = (b->tc_attn & 12) == 12 && !b->profiling && want_pair((n_node_rows + 3) / 4);      // key + value phase in one launch (timed passes stay apart)
     const KnnAttnArgs ka_key = ka;
     if (!knn_pair) { ProfScope ps(b, s, PC_KNN_ATTN_K); if (b->tc_attn & 4) launch_knn_tc(ka, 0, sms, s); else launch_knn_attn_k(ka, sms, s); }

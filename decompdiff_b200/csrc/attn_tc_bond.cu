@@ -434,7 +434,8 @@ int launch_bond_tc(const BondAttnArgs& a, bool pos, int num_sms, cudaStream_t st
   if (a.n_lig <= 0 || a.n_vg <= 0) return 0;
   const bool chunked = a.n_vg > a.n_lig;      // some atom has more than 32 incoming edges
   static const int pair_mode = getenv("DDB_PAIR") ? atoi(getenv("DDB_PAIR")) : -1;      // see api.cu: pairs pay on small grids only
-  const bool pair = pair_mode >= 0 ? pair_mode != 0 : (a.n_vg + 3) / 4 < num_sms;
+  static const int pair_waves = getenv("DDB_PAIR_WAVES") ? atoi(getenv("DDB_PAIR_WAVES")) : 4;
+  const bool pair = pair_mode >= 0 ? pair_mode != 0 : (a.n_vg + 3) / 4 < pair_waves * num_sms;
   if (!chunked && pair) {      // key + value phase in one launch (a chunked group needs the factors of all CTAs in between)
     if (pos) launch_bond_tc_pair<BT_V_POS>(a, num_sms, stream); else launch_bond_tc_pair<BT_V_NODE>(a, num_sms, stream);
     return 1;

@@ -24,6 +24,11 @@ constexpr int T3_THREADS = ATC_THREADS + 128;
 constexpr int T3_ISSUER = 16;
 constexpr int T3_SYNC = ATC_THREADS + 32;
 constexpr int T3_BAR_A_READY = 6, T3_BAR_WORKERS = 7;
+#ifdef T3_SPIN
+#define T3_WAIT mbar_wait_spin
+#else
+#define T3_WAIT mbar_wait
+#endif
 // per-warp ring (bytes): scalars 4 stages x 128 | Q' slice 2 x 128 | k: query slice 2 x 128 / v: weights 512 + factor 64 + residual 128
 constexpr int T3_RING_SCAL = 0, T3_RING_Q = 512, T3_RING_X = 768;
 constexpr int T3_RING_K = 1024, T3_RING_V = 1472;
@@ -296,7 +301,7 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
       // ---- first Linear: z = P'[kj] (unit buffer) + Q'[ji] (ring) + D2 (angular MMA, issued one iteration ago)
       float2 z[16];
       {
-        mbar_wait(bar_ang, it & 1);
+        T3_WAIT(bar_ang, it & 1);
         tc_fence_after();
         __syncwarp();
         const float* qs = reinterpret_cast<const float*>(ring + T3_RING_Q + (it & 1) * 128);
@@ -366,7 +371,7 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
       uint32_t v[32];
       {
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (it > 0) { mbar_wait(bar_mma, (it - 1) & 1); tc_fence_after(); }
+        if (it > 0) { T3_WAIT(bar_mma, (it - 1) & 1); tc_fence_after(); }
         tmem_st32(lane_addr + ATC_COL_AHI + s * 32, hi);
         tmem_st32(lane_addr + ATC_COL_ALO + s * 32, lo);
         if (it > 0) tmem_ld32(lane_addr + ATC_COL_D + s * 32, v);
