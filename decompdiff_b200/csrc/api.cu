@@ -67,7 +67,8 @@ struct ddb_model {
   size_t lig_Wv = 0, bond_table = 0;
   GemmW v_head0{}, b_head0{};
   size_t v_W2 = 0, v_b2 = 0, b_W2 = 0, b_b2 = 0;
-  size_t tab_c0 = 0, tab_ct = 0, tab_logvar = 0, tab_score = 0;
+  size_t tab_c0 = 0, tab_ct = 0, tab_logvar = 0, tab_score = 0, tab_recip = 0, tab_recipm1 = 0;
+  bool mean_noise = false;     // model_mean_type 'noise'
   size_t tab_a[5] = {0, 0, 0, 0, 0}, tab_b[5] = {0, 0, 0, 0, 0};   // log_alpha, log_1m_alpha, log_cumprod, log_1m_cumprod, prior
   const float* p(size_t off) const { return dev + off; }
 };
@@ -240,6 +241,13 @@ extern "C" int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max) {
   return fail(DDB_ERR_INVALID, "Not supported cutoff mode");      // uni_transformer_edge.py:358
 }
 
+extern "C" int ddb_model_set_mean_type(ddb_model* m, int32_t noise) {
+  if (!m) return fail(DDB_ERR_INVALID, "null model");
+  if (noise != 0 && noise != 1) return fail(DDB_ERR_INVALID, "model_mean_type: 0 = C0, 1 = noise");      // decompdiff.py:610 raises ValueError
+  m->mean_noise = noise != 0;
+  return DDB_OK;
+}
+
 extern "C" void ddb_model_destroy(ddb_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
@@ -335,6 +343,7 @@ extern "C" int ddb_model_finalize(ddb_model* m) {
   m->tab_ct = P.vec("posterior_mean_ct_coef", T);
   m->tab_logvar = P.vec("posterior_logvar", T);
   m->tab_score = P.vec("pos_score_coef", T);
+  if (m->mean_noise) { m->tab_recip = P.vec("sqrt_recip_alphas_cumprod", T); m->tab_recipm1 = P.vec("sqrt_recipm1_alphas_cumprod", T); }
   const char* tn[4] = {"log_alphas_v", "log_one_minus_alphas_v", "log_alphas_cumprod_v", "log_one_minus_alphas_cumprod_v"};
   for (int i = 0; i < 4; ++i) {
     m->tab_a[i] = P.vec(std::string("atom_type_trans.") + tn[i], T);
@@ -1319,6 +1328,7 @@ extern "C" int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* strea
   a.n_lig = b->NL; a.n_bonds = b->Eb; a.C = c.num_classes; a.Cb = c.num_bond_classes; a.num_timesteps = c.num_timesteps;
   a.t_dev = b->t_dev; a.t_start_dev = b->t_start_dev;
   a.c0 = m->p(m->tab_c0); a.ct = m->p(m->tab_ct); a.logvar = m->p(m->tab_logvar);
+  if (m->mean_noise) { a.recip = m->p(m->tab_recip); a.recipm1 = m->p(m->tab_recipm1); }
   a.a_log_alpha = m->p(m->tab_a[0]); a.a_log_1m_alpha = m->p(m->tab_a[1]); a.a_log_cumprod = m->p(m->tab_a[2]);
   a.a_log_1m_cumprod = m->p(m->tab_a[3]); a.a_prior = m->p(m->tab_a[4]);
   a.b_log_alpha = m->p(m->tab_b[0]); a.b_log_1m_alpha = m->p(m->tab_b[1]); a.b_log_cumprod = m->p(m->tab_b[2]);

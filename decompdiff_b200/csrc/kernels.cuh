@@ -228,6 +228,7 @@ struct StepArgs {
   const int* graph_of_lig = nullptr;   // unused by the math (t is uniform over graphs) - kept for clarity
   // schedule tables (num_timesteps each)
   const float* c0 = nullptr; const float* ct = nullptr; const float* logvar = nullptr;
+  const float* recip = nullptr; const float* recipm1 = nullptr;   // model_mean_type 'noise' only (null: the network predicts x_0)
   const float* a_log_alpha = nullptr; const float* a_log_1m_alpha = nullptr;
   const float* a_log_cumprod = nullptr; const float* a_log_1m_cumprod = nullptr; const float* a_prior = nullptr;
   const float* b_log_alpha = nullptr; const float* b_log_1m_alpha = nullptr;

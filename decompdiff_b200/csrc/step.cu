@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(256) reverse_step_kernel(const StepArgs a) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       float xt = a.x[r * 3 + d];
-      float mean = c0 * a.x0[r * 3 + d] + ct * xt;
+      float x0 = a.x0[r * 3 + d];
+      // model_mean_type 'noise' (:602-605): eps = pred - x_t, x_0 = sqrt(1/acp) x_t - sqrt(1/acp - 1) eps  (two products, one
+      // difference, as torch evaluates it - no contraction)
+      if (a.recip) x0 = __fsub_rn(__fmul_rn(a.recip[t], xt), __fmul_rn(a.recipm1[t], __fsub_rn(x0, xt)));
+      float mean = c0 * x0 + ct * xt;
       if (a.grad) mean -= a.grad[r * 3 + d];
       float v = mean + sig * a.eps[r * 3 + d] * a.prior_std[r * 3 + d];
       nx[d] = frozen ? xt : v;

@@ -7,8 +7,8 @@ Mirrors /root/reference/models/decompdiff.py:75-703 for the sampling path:
   * `sample_diffusion(...)`   -> {'pos','v','bond', '*_traj'}                             (:552-703)
 All arithmetic runs in the CUDA library (`decompdiff_b200/csrc`); there is no torch / CPU fallback.
 
-Out of scope (raises NotImplementedError): training loss, `add_prior_node`, time embedding,
-`model_mean_type='noise'`, other refine nets / cutoff modes.
+Out of scope (raises NotImplementedError): training loss, `add_prior_node`, time embedding, other refine nets
+(SURVEY.md section 8f).  `model_mean_type='noise'` selects the x_0-from-noise branch of the posterior step.
 """
 from __future__ import annotations
 
@@ -250,7 +250,7 @@ class DecompScorePosNet3D(nn.Module):
         device = torch.device(device)
         if self._engine is None or self._engine.device != device:
             self._engine = EngineModel(self.engine_config(), self.state_dict(), device, cutoff_mode=self.refine_net.cutoff_mode,
-                                       r_max=self.refine_net.r_max)
+                                       r_max=self.refine_net.r_max, mean_type=self.model_mean_type)
         return self._engine
 
     def refresh_engine(self):
@@ -345,8 +345,8 @@ class DecompScorePosNet3D(nn.Module):
         """Set a reverse-diffusion run up (everything of `sample_diffusion` before its loop) and return the
         handle that advances it; `sample_diffusion` = `begin_sampling(...).advance(num_steps)` + `.finish()`."""
         require_cuda()
-        if self.model_mean_type != 'C0':
-            raise NotImplementedError("model_mean_type 'noise' (N4)") if self.model_mean_type == 'noise' else ValueError
+        if self.model_mean_type not in ('C0', 'noise'):
+            raise ValueError      # models/decompdiff.py:610
         if ligand_fc_bond_index is None or init_ligand_fc_bond_type is None:
             raise NotImplementedError('uni_o2_bond needs the ligand bond graph')
         if center_pos_mode == 'protein':

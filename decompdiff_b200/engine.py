@@ -56,7 +56,7 @@ def _device_of(*tensors, default=None) -> torch.device:
 
 class EngineModel:
     def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor], device=None, refine_only: bool = False,
-                 cutoff_mode: str = 'knn', r_max: float = 0.0):
+                 cutoff_mode: str = 'knn', r_max: float = 0.0, mean_type: str = 'C0'):
         require_cuda()
         L = _lib.lib()
         self.device = _device_of(default=device)
@@ -64,6 +64,9 @@ class EngineModel:
         if cutoff_mode not in ('knn', 'radius', 'hybrid'):
             raise ValueError(f'Not supported cutoff mode: {cutoff_mode}')      # uni_transformer_edge.py:358
         self.cutoff = ({'knn': 0, 'radius': 1, 'hybrid': 2}[cutoff_mode], float(r_max))
+        if mean_type not in ('C0', 'noise'):
+            raise ValueError(mean_type)      # models/decompdiff.py:610
+        self.mean_noise = mean_type == 'noise'
         with torch.cuda.device(self.device):
             self._init(L, cfg, state_dict)
 
@@ -80,6 +83,7 @@ class EngineModel:
         if self.refine_only:
             _lib.check(L.ddb_model_set_refine_only(self._h, 1))
         _lib.check(L.ddb_model_set_cutoff(self._h, self.cutoff[0], self.cutoff[1]))
+        _lib.check(L.ddb_model_set_mean_type(self._h, 1 if self.mean_noise else 0))
         _lib.check(L.ddb_model_finalize(self._h))
 
     def __del__(self):

@@ -81,6 +81,11 @@ void ddb_model_destroy(ddb_model* m);
  * incoming edges, so this mode runs the kNN edge family on the fp32 FMA kernels with wide neighbour rows (no receptive-field
  * pruning, no neighbour cache).  Call before any batch is created. */
 int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max);
+/* model_mean_type (models/decompdiff.py:84, :602-611): 0 = 'C0' (the network output is x_0; the shipped configuration),
+ * 1 = 'noise' (the network output minus x_t is the predicted noise, x_0 = sqrt(1/acp_t) x_t - sqrt(1/acp_t - 1) eps,
+ * _predict_x0_from_eps :353-356).  Selects the branch of the posterior step in ddb_reverse_step; call before ddb_model_finalize
+ * (the two extra schedule tables "sqrt_recip_alphas_cumprod" / "sqrt_recipm1_alphas_cumprod" are then required). */
+int ddb_model_set_mean_type(ddb_model* m, int32_t noise);
 /* Stand-alone refine net (get_refine_net('uni_o2_bond', config), models/encoders/__init__.py:27-43): call before
  * ddb_model_finalize; only the "refine_net.*" tensors are then required and the model serves ddb_refine_batch_create /
  * ddb_refine_forward only. */

@@ -419,6 +419,12 @@ def reverse_step(tab, cfg, preds, ligand_pos, ligand_v, ligand_bond, t, batch_li
     (u_atom (n,8) uniform, u_bond (Eb,5) uniform, eps_pos (n,3) normal) - decompdiff.py:601-685."""
     nc, nb = cfg['num_classes'], cfg['num_bond_classes']
     x0 = preds['pred_ligand_pos']
+    if cfg.get('model_mean_type', 'C0') == 'noise':      # decompdiff.py:602-605, _predict_x0_from_eps :353-356
+        eps_pred = x0 - ligand_pos
+        x0 = tab['sqrt_recip_alphas_cumprod'][t][batch_ligand].unsqueeze(-1) * ligand_pos - \
+            tab['sqrt_recipm1_alphas_cumprod'][t][batch_ligand].unsqueeze(-1) * eps_pred
+    elif cfg.get('model_mean_type', 'C0') != 'C0':
+        raise ValueError
     c0 = tab['posterior_mean_c0_coef'][t][batch_ligand].unsqueeze(-1)
     ct = tab['posterior_mean_ct_coef'][t][batch_ligand].unsqueeze(-1)
     mean = c0 * x0 + ct * ligand_pos

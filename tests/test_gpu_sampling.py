@@ -240,3 +240,31 @@ def test_scaled_drift_matches_oracle_and_center_prox_fails_like_the_reference(mo
     assert float((want['pos'] - plain['pos']).abs().max()) > 1e-4          # the option changes the result
     with pytest.raises(RuntimeError, match='scalar outputs'):
         model_cpu.sample_diffusion(**kw, num_steps=1, center_pos_mode='protein', energy_drift_opt=[{'type': 'center_prox'}])
+
+
+@pytest.mark.parametrize('case', ['traj_noise_T12', 'traj_noise_T6_guided'])
+def test_noise_mean_type_matches_reference(case, weights):
+    """model_mean_type='noise' (models/decompdiff.py:602-605; ddb_model_set_mean_type): the network output minus x_t is the
+    predicted noise and x_0 comes from _predict_x0_from_eps.  Free-running sample_diffusion with the reference's noise stream
+    against the UNMODIFIED reference's trajectory (with and without the drift guidance)."""
+    import decompdiff_b200 as ddb
+    from oracle import make_golden_noise
+    spec = make_golden_noise.NOISE_CASES[case]
+    m = ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, model_mean_type='noise'), syn.PROTEIN_FEATURE_DIM,
+                                syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
+    m.load_state_dict(weights)
+    kw = syn.make_batch(**spec['batch'])
+    gold = load_golden(case)
+    n, Eb, S = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel(), spec['num_steps']
+    noise = syn.step_noise(n, Eb, S, spec['noise_seed'])
+    r = m.eval().sample_diffusion(**kw, num_steps=S, center_pos_mode='protein', energy_drift_opt=spec['drift'], noise=noise)
+    v_traj, b_traj = torch.stack([t.cpu() for t in r['v_traj']]), torch.stack([t.cpu() for t in r['bond_traj']])
+    pos_traj = torch.stack([t.cpu() for t in r['pos_traj']])
+    flips = (v_traj != gold['v_traj'].long()).flatten(1).any(1) | (b_traj != gold['bond_traj'].long()).flatten(1).any(1)
+    first_flip = int(flips.float().argmax()) if bool(flips.any()) else S
+    print(case, 'first discrete flip at step', first_flip, 'of', S)
+    assert first_flip >= min(S, 4)                       # a Gumbel near-tie may flip a sample late in a free-running trajectory
+    assert tol_ratio(pos_traj[:first_flip], gold['pos_traj'][:first_flip]) <= 1.0
+    with pytest.raises(ValueError):
+        ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, model_mean_type='x0'), syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM,
+                                syn.NUM_CLASSES).sample_diffusion(**kw, num_steps=1, center_pos_mode='protein')

@@ -5,7 +5,7 @@ import torch
 
 from conftest import load_golden, tol_ratio
 from decompdiff_b200 import synthetic as syn
-from oracle import fused_algebra, make_golden, make_golden_hybrid, restate
+from oracle import fused_algebra, make_golden, make_golden_hybrid, make_golden_noise, restate
 
 
 @pytest.mark.parametrize('case', list(make_golden.FORWARD_CASES))
@@ -45,6 +45,24 @@ def test_oracle_guided_trajectory_matches_reference(weights, oracle_cfg):
     assert torch.equal(torch.stack(r['bond_traj']), gold['bond_traj'].long())
     assert tol_ratio(torch.stack(r['pos_traj']), gold['pos_traj']) <= 1.0
     assert tol_ratio(r['vt_traj'][-1], gold['vt_last']) <= 1.0
+
+
+@pytest.mark.parametrize('case', list(make_golden_noise.NOISE_CASES))
+def test_oracle_noise_mean_type_matches_reference(case, weights, oracle_cfg):
+    """model_mean_type='noise' (models/decompdiff.py:602-605): the restatement's branch against the unmodified reference's run."""
+    spec = make_golden_noise.NOISE_CASES[case]
+    kw = syn.make_batch(**spec['batch'])
+    gold = load_golden(case)
+    n, Eb = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel()
+    noise = syn.step_noise(n, Eb, spec['num_steps'], spec['noise_seed'])
+    cfg = dict(oracle_cfg, model_mean_type='noise')
+    r = restate.sample_diffusion(weights, cfg, **kw, num_steps=spec['num_steps'], center_pos_mode='protein',
+                                 energy_drift_opt=spec['drift'], noise=noise)
+    assert torch.equal(torch.stack(r['v_traj']), gold['v_traj'].long())
+    assert torch.equal(torch.stack(r['bond_traj']), gold['bond_traj'].long())
+    assert tol_ratio(torch.stack(r['pos_traj']), gold['pos_traj']) <= 1.0
+    c0 = restate.sample_diffusion(weights, oracle_cfg, **kw, num_steps=2, center_pos_mode='protein', energy_drift_opt=spec['drift'], noise=noise)
+    assert float((c0['pos_traj'][1] - gold['pos_traj'][1]).abs().max()) > 1e-3      # the branch changes the trajectory
 
 
 def test_oracle_cfg1_first_steps_match_reference(weights, oracle_cfg):
