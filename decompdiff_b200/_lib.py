@@ -19,7 +19,7 @@ SYMBOLS = [
     'ddb_forward', 'ddb_batch_set_time', 'ddb_reverse_step', 'ddb_batch_set_guidance',
     'ddb_knn_graph', 'ddb_gemm128', 'ddb_batch_debug_buffer', 'ddb_copy_device', 'ddb_batch_last_launch_count', 'ddb_batch_h2d_bytes',
     'ddb_batch_profile', 'ddb_profile_num_categories', 'ddb_profile_category_name', 'ddb_batch_profile_read',
-    'ddb_batch_executed_rows', 'ddb_model_set_refine_only', 'ddb_forward_ex', 'ddb_refine_batch_create', 'ddb_refine_forward', 'ddb_batch_set_layer_tap', 'ddb_batch_set_guidance_scale', 'ddb_model_set_cutoff', 'ddb_model_set_mean_type',
+    'ddb_batch_executed_rows', 'ddb_model_set_refine_only', 'ddb_forward_ex', 'ddb_refine_batch_create', 'ddb_refine_forward', 'ddb_batch_set_layer_tap', 'ddb_batch_set_guidance_scale', 'ddb_model_set_cutoff', 'ddb_model_set_mean_type', 'ddb_model_set_time_emb', 'ddb_batch_set_time_steps',
 ]
 
 
@@ -82,6 +82,8 @@ def lib():
     L.ddb_refine_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.ddb_model_set_cutoff.argtypes = [vp, i32, f32]
     L.ddb_model_set_mean_type.argtypes = [vp, i32]
+    L.ddb_model_set_time_emb.argtypes = [vp, i32]
+    L.ddb_batch_set_time_steps.argtypes = [vp, vp, vp]
     L.ddb_batch_set_guidance_scale.argtypes = [vp, i32, i32]
     L.ddb_batch_set_layer_tap.argtypes = [vp, vp, vp, vp]
     L.ddb_batch_executed_rows.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]

@@ -64,7 +64,8 @@ struct ddb_model {
   float* dev = nullptr;
   std::vector<LayerOff> layers;
   size_t ew_W1t = 0, ew_b1 = 0, ew_gamma = 0, ew_beta = 0, ew_w2 = 0; float ew_b2 = 0.f;
-  size_t lig_Wv = 0, bond_table = 0;
+  size_t lig_Wv = 0, bond_table = 0, lig_Wt = 0;
+  bool time_simple = false;    // 'simple' time embedding: the last input column of ligand_atom_emb multiplies t / T
   GemmW v_head0{}, b_head0{};
   size_t v_W2 = 0, v_b2 = 0, b_W2 = 0, b_b2 = 0;
   size_t tab_c0 = 0, tab_ct = 0, tab_logvar = 0, tab_score = 0, tab_recip = 0, tab_recipm1 = 0;
@@ -241,6 +242,13 @@ extern "C" int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max) {
   return fail(DDB_ERR_INVALID, "Not supported cutoff mode");      // uni_transformer_edge.py:358
 }
 
+extern "C" int ddb_model_set_time_emb(ddb_model* m, int32_t mode) {
+  if (!m) return fail(DDB_ERR_INVALID, "null model");
+  if (mode != 0 && mode != 1) return fail(DDB_ERR_INVALID, "time embedding: 0 = none, 1 = simple");      // decompdiff.py:182 raises NotImplementedError
+  m->time_simple = mode == 1;
+  return DDB_OK;
+}
+
 extern "C" int ddb_model_set_mean_type(ddb_model* m, int32_t noise) {
   if (!m) return fail(DDB_ERR_INVALID, "null model");
   if (noise != 0 && noise != 1) return fail(DDB_ERR_INVALID, "model_mean_type: 0 = C0, 1 = noise");      // decompdiff.py:610 raises ValueError
@@ -321,6 +329,11 @@ extern "C" int ddb_model_finalize(ddb_model* m) {
   if (auto* w = P.get("ligand_atom_emb.weight", (size_t)(H - 1) * c.ligand_feature_dim))
     for (int v = 0; v < C; ++v)
       for (int ch = 0; ch < H - 1; ++ch) m->blob.data[m->lig_Wv + (size_t)v * H + ch] = (*w)[(size_t)ch * c.ligand_feature_dim + v];
+  if (m->time_simple) {
+    m->lig_Wt = m->blob.alloc(H);
+    if (auto* w = P.get("ligand_atom_emb.weight", (size_t)(H - 1) * c.ligand_feature_dim))
+      for (int ch = 0; ch < H - 1; ++ch) m->blob.data[m->lig_Wt + ch] = (*w)[(size_t)ch * c.ligand_feature_dim + c.ligand_feature_dim - 1];
+  }
   P.get("ligand_atom_emb.bias", H - 1);
   P.get("protein_atom_emb.weight", (size_t)(H - 1) * c.protein_feature_dim);
   P.get("protein_atom_emb.bias", H - 1);
@@ -374,6 +387,7 @@ struct ddb_batch {
   int4* bond_vg = nullptr; int n_bvg = 0, n_tvg = 0; float2 *bond_stats = nullptr, *trip_stats = nullptr;
   float *bond_factor = nullptr, *bond_part_h = nullptr, *bond_part_dx = nullptr, *trip_factor = nullptr, *trip_part = nullptr; int* trip_vg_pair = nullptr;
   int4* trip_tile_rec = nullptr; bool trip_chunked = false;
+  int* t_graph = nullptr; bool t_per_graph = false;      // forward() with explicit per-graph time steps ('simple' time embedding)
   int4* trip_grp4 = nullptr; int *trip_grp_pk = nullptr, *csr_slot = nullptr; float *PcsrK = nullptr, *PcsrV = nullptr, *xcsr = nullptr;
   float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
   // evolving state
@@ -568,7 +582,7 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
   if (!refine) {
     const auto& W = m->host.at("ligand_atom_emb.weight");
     const auto& bias = m->host.at("ligand_atom_emb.bias");
-    const int F = c.ligand_feature_dim, C = c.num_classes, A = F - C;
+    const int F = c.ligand_feature_dim, C = c.num_classes, A = F - C - (m->time_simple ? 1 : 0);      // aux columns (the time column is applied per step)
     for (int i = 0; i < NL; ++i) {
       float* row = &lig_base[(size_t)i * H];
       for (int ch = 0; ch < H - 1; ++ch) {
@@ -958,7 +972,9 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
   b->launches = 0;
   if (!b->refine) {      // refine seam: x4_0 / h0 / hbA were filled from the caller's tensors
     { ProfScope ps(b, s, PC_SETUP); launch_set_ligand_x(b->x_lig, NL, b->lig_idx, b->x4_0, s); }
-    { ProfScope ps(b, s, PC_SETUP); launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s); }
+    { ProfScope ps(b, s, PC_SETUP); launch_embed_ligand(b->lig_base, m->p(m->lig_Wv), b->v, NL, b->lig_idx, b->h0, s,
+                                                        m->time_simple ? m->p(m->lig_Wt) : nullptr, b->t_dev,
+                                                        b->t_per_graph ? b->t_graph : nullptr, b->graph_of, c.num_timesteps); }
     { ProfScope ps(b, s, PC_SETUP); launch_embed_bond(m->p(m->bond_table), b->bond, Eb, b->hbA, s); }
   }
   // fork: the bond / triplet branch of a layer needs only the layer input, so it runs on the side stream next to the kNN branch
@@ -1256,6 +1272,23 @@ extern "C" int ddb_batch_set_time(ddb_batch* b, int32_t t_start, void* stream) {
   set_int_kernel<<<1, 1, 0, s>>>(b->t_dev, t_start);
   set_int_kernel<<<1, 1, 0, s>>>(b->t_start_dev, t_start);
   DDB_CUDA(cudaGetLastError());
+  b->t_per_graph = false;
+  return DDB_OK;
+}
+
+extern "C" int ddb_batch_set_time_steps(ddb_batch* b, const int64_t* time_step, void* stream) {
+  if (!b || !time_step) return fail(DDB_ERR_INVALID, "null argument");
+  const int B = b->B, T = b->m->cfg.num_timesteps;
+  std::vector<int> t(B);
+  for (int g = 0; g < B; ++g) {
+    if (time_step[g] < 0 || time_step[g] >= T) return fail(DDB_ERR_INVALID, "time_step out of range");
+    t[g] = (int)time_step[g];
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!b->t_graph) { const int r = b->dalloc(&b->t_graph, (size_t)B); if (r) return r; }
+  DDB_CUDA(cudaMemcpyAsync(b->t_graph, t.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  DDB_CUDA(cudaStreamSynchronize(s));      // the staging vector goes out of scope
+  b->t_per_graph = true;
   return DDB_OK;
 }
 

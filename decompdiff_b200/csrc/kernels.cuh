@@ -212,7 +212,10 @@ void pack_wa_tc(const float* Wa, float* out);
 
 // ---- embeddings, heads, reverse step, guidance (step.cu) -----------------------------------------
 void launch_embed_ligand(const float* base /*(n,128) W[:,8:10] aux + b, col 127 = 1*/, const float* Wv /*[8][128]*/,
-                         const int64_t* v, int n, const int* lig_idx, float* h /*(N,128)*/, cudaStream_t stream);
+                         const int64_t* v, int n, const int* lig_idx, float* h /*(N,128)*/, cudaStream_t stream,
+                         const float* Wt = nullptr /*[128] time column of ligand_atom_emb ('simple' time embedding) or null*/,
+                         const int* t_dev = nullptr, const int* t_graph = nullptr /*per-graph time steps (forward) or null*/,
+                         const int* graph_of_lig = nullptr, int num_timesteps = 1);
 void launch_embed_bond(const float* table /*[Cb][128] incl. bias*/, const int64_t* btype, int n_bonds, float* h_bond,
                        cudaStream_t stream);
 void launch_set_ligand_x(const float* x_lig /*(n,3) centred*/, int n, const int* lig_idx, float* x4, cudaStream_t stream);

@@ -5,22 +5,32 @@
 
 namespace ddb {
 
-// h[lig_idx[a]] = base[a] + Wv[v[a]]   (ligand_atom_emb on [onehot(v) | aux] with the node indicator column)
+// h[lig_idx[a]] = base[a] + Wv[v[a]] (+ Wt * t / T)   (ligand_atom_emb on [onehot(v) | aux (| t / T)] with the node indicator column;
+// the time column is the 'simple' time embedding, models/decompdiff.py:224-230: t is the run's device-side time index, or one
+// entry per graph when forward() was given explicit time steps)
 __global__ void embed_ligand_kernel(const float* __restrict__ base, const float* __restrict__ Wv,
                                     const int64_t* __restrict__ v, int n, const int* __restrict__ lig_idx,
-                                    float* __restrict__ h) {
+                                    float* __restrict__ h, const float* __restrict__ Wt, const int* __restrict__ t_dev,
+                                    const int* __restrict__ t_graph, const int* __restrict__ graph_of_lig, float num_timesteps) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;     // one float4 per thread
   if (idx >= n * (H / 4)) return;
   int a = idx / (H / 4), c4 = idx - a * (H / 4);
   int vt = (int)v[a];
   float4 o = add4(ldg4(base + (size_t)a * H + c4 * 4), ldg4(Wv + (size_t)vt * H + c4 * 4));
+  if (Wt != nullptr) {
+    const int t = t_graph != nullptr ? t_graph[graph_of_lig[lig_idx[a]]] : *t_dev;      // graph_of_lig: graph of a merged node
+    const float tf = __fdiv_rn((float)t, num_timesteps);      // time_step / self.num_timesteps
+    o = fma4(tf, ldg4(Wt + c4 * 4), o);
+  }
   st4(h + (size_t)lig_idx[a] * H + c4 * 4, o);
 }
 void launch_embed_ligand(const float* base, const float* Wv, const int64_t* v, int n, const int* lig_idx, float* h,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const float* Wt, const int* t_dev, const int* t_graph, const int* graph_of_lig,
+                         int num_timesteps) {
   if (n <= 0) return;
   int total = n * (H / 4);
-  embed_ligand_kernel<<<(total + 255) / 256, 256, 0, stream>>>(base, Wv, v, n, lig_idx, h);
+  embed_ligand_kernel<<<(total + 255) / 256, 256, 0, stream>>>(base, Wv, v, n, lig_idx, h, Wt, t_dev, t_graph, graph_of_lig,
+                                                               (float)num_timesteps);
 }
 
 __global__ void embed_bond_kernel(const float* __restrict__ table, const int64_t* __restrict__ btype, int n_bonds,

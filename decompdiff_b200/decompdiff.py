@@ -7,8 +7,8 @@ Mirrors /root/reference/models/decompdiff.py:75-703 for the sampling path:
   * `sample_diffusion(...)`   -> {'pos','v','bond', '*_traj'}                             (:552-703)
 All arithmetic runs in the CUDA library (`decompdiff_b200/csrc`); there is no torch / CPU fallback.
 
-Out of scope (raises NotImplementedError): training loss, `add_prior_node`, time embedding, other refine nets
-(SURVEY.md section 8f).  `model_mean_type='noise'` selects the x_0-from-noise branch of the posterior step.
+Out of scope (raises NotImplementedError): training loss, `add_prior_node`, the 'sin' time embedding (broken upstream),
+other refine nets.  time_emb_dim > 0 with time_emb_mode='simple' adds the t / T input column.  `model_mean_type='noise'` selects the x_0-from-noise branch of the posterior step.
 """
 from __future__ import annotations
 
@@ -200,8 +200,13 @@ class DecompScorePosNet3D(nn.Module):
         self.bond_diffusion = getattr(config, 'bond_diffusion', False)
         self.bond_net_type = getattr(config, 'bond_net_type', 'mlp')
         if self.add_prior_node or not self.bond_diffusion or self.bond_net_type != 'lin' \
-                or config.time_emb_dim != 0 or not config.node_indicator or config.model_type != 'uni_o2_bond':
+                or not config.node_indicator or config.model_type != 'uni_o2_bond':
             raise NotImplementedError('only the shipped configuration (configs/training.yml:16-57) is implemented')
+        self.time_emb_mode = getattr(config, 'time_emb_mode', 'simple')
+        if config.time_emb_dim > 0 and self.time_emb_mode != 'simple':
+            # 'sin' builds upstream but its forward concatenates a per-GRAPH embedding to per-ATOM features (decompdiff.py:231-232),
+            # which only runs when every graph has exactly one ligand atom; anything else raises NotImplementedError upstream (:182)
+            raise NotImplementedError(f"time_emb_mode '{self.time_emb_mode}'")
         for k, v in schedules.position_tables(config).items():
             setattr(self, k, _const(v))
         self.num_timesteps = self.betas.size(0)
@@ -219,7 +224,8 @@ class DecompScorePosNet3D(nn.Module):
         self.protein_atom_emb = nn.Linear(protein_atom_feature_dim, emb_dim)
         self.center_pos_mode = config.center_pos_mode
         self.time_emb_dim = config.time_emb_dim
-        self.ligand_atom_emb = nn.Linear(ligand_atom_feature_dim, emb_dim)
+        # 'simple' time embedding: one more input column, time_step / num_timesteps (decompdiff.py:171-173, 225-229)
+        self.ligand_atom_emb = nn.Linear(ligand_atom_feature_dim + (1 if self.time_emb_dim > 0 else 0), emb_dim)
         self.refine_net_type = config.model_type
         self.refine_net = get_refine_net(self.refine_net_type, config)
         self.ligand_bond_emb = nn.Linear(self.num_bond_classes, self.hidden_dim)
@@ -240,7 +246,8 @@ class DecompScorePosNet3D(nn.Module):
         c = self.config
         return dict(hidden_dim=c.hidden_dim, n_heads=c.n_heads, knn=c.knn, num_layers=c.num_layers,
                     num_blocks=c.num_blocks, num_classes=self.num_classes, num_bond_classes=self.num_bond_classes,
-                    protein_feature_dim=self.protein_atom_feature_dim, ligand_feature_dim=self.ligand_atom_feature_dim,
+                    protein_feature_dim=self.protein_atom_feature_dim,
+                    ligand_feature_dim=self.ligand_atom_feature_dim + (1 if self.time_emb_dim > 0 else 0),
                     num_timesteps=self.num_timesteps)
 
     def engine(self, device=None) -> EngineModel:
@@ -250,7 +257,8 @@ class DecompScorePosNet3D(nn.Module):
         device = torch.device(device)
         if self._engine is None or self._engine.device != device:
             self._engine = EngineModel(self.engine_config(), self.state_dict(), device, cutoff_mode=self.refine_net.cutoff_mode,
-                                       r_max=self.refine_net.r_max, mean_type=self.model_mean_type)
+                                       r_max=self.refine_net.r_max, mean_type=self.model_mean_type,
+                                       time_emb='simple' if self.time_emb_dim > 0 else None)
         return self._engine
 
     def refresh_engine(self):
@@ -311,6 +319,10 @@ class DecompScorePosNet3D(nn.Module):
         eb = self._forward_batch(protein_pos, protein_v, batch_protein, batch_ligand, init_ligand_v_aux,
                                  ligand_fc_bond_index, ligand_atom_mask)
         eb.set_state(init_ligand_pos, init_ligand_v, init_ligand_fc_bond_type)
+        if self.time_emb_dim > 0:
+            if time_step is None:
+                raise TypeError('time_step is required with a time embedding')      # upstream: None / int (:227)
+            eb.set_time_steps(time_step)
         v0 = None
         if return_all:
             pos, v_logits, b_logits, v0 = eb.forward_all()

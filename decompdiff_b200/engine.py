@@ -56,7 +56,7 @@ def _device_of(*tensors, default=None) -> torch.device:
 
 class EngineModel:
     def __init__(self, cfg: Dict[str, int], state_dict: Dict[str, torch.Tensor], device=None, refine_only: bool = False,
-                 cutoff_mode: str = 'knn', r_max: float = 0.0, mean_type: str = 'C0'):
+                 cutoff_mode: str = 'knn', r_max: float = 0.0, mean_type: str = 'C0', time_emb=None):
         require_cuda()
         L = _lib.lib()
         self.device = _device_of(default=device)
@@ -67,6 +67,9 @@ class EngineModel:
         if mean_type not in ('C0', 'noise'):
             raise ValueError(mean_type)      # models/decompdiff.py:610
         self.mean_noise = mean_type == 'noise'
+        if time_emb not in (None, 'simple'):
+            raise NotImplementedError(time_emb)      # models/decompdiff.py:182
+        self.time_emb = time_emb
         with torch.cuda.device(self.device):
             self._init(L, cfg, state_dict)
 
@@ -84,6 +87,7 @@ class EngineModel:
             _lib.check(L.ddb_model_set_refine_only(self._h, 1))
         _lib.check(L.ddb_model_set_cutoff(self._h, self.cutoff[0], self.cutoff[1]))
         _lib.check(L.ddb_model_set_mean_type(self._h, 1 if self.mean_noise else 0))
+        _lib.check(L.ddb_model_set_time_emb(self._h, 1 if self.time_emb == 'simple' else 0))
         _lib.check(L.ddb_model_finalize(self._h))
 
     def __del__(self):
@@ -114,7 +118,7 @@ class EngineBatch:
         mask = None if ligand_atom_mask is None else _host(ligand_atom_mask, torch.uint8)
         if pv.dim() != 2 or pv.size(1) != model.cfg['protein_feature_dim']:
             raise ValueError(f'protein_v must be (n, {model.cfg["protein_feature_dim"]})')
-        if aux.numel() != bl.numel() * (model.cfg['ligand_feature_dim'] - model.cfg['num_classes']):
+        if aux.numel() != bl.numel() * (model.cfg['ligand_feature_dim'] - model.cfg['num_classes'] - (1 if model.time_emb else 0)):
             raise ValueError('ligand_v_aux has the wrong width')
         self.n_protein, self.n_ligand, self.n_bonds = pp.size(0), bl.numel(), bi.size(1)
         self.num_graphs = num_graphs
@@ -186,6 +190,14 @@ class EngineBatch:
         bl = torch.empty(self.n_bonds, self.Cb, device=dev, dtype=torch.float32)
         _lib.check(_lib.lib().ddb_forward_ex(self._h, _ptr(pos), _ptr(vl), _ptr(bl), _ptr(v0), _stream_ptr(self.device)))
         return pos, vl, bl, v0
+
+    @_on_device
+    def set_time_steps(self, time_step):
+        """Per-graph time steps of a forward() call (only the 'simple' time embedding reads them)."""
+        ts = _host(torch.as_tensor(time_step).reshape(-1), torch.int64)
+        if ts.numel() != self.num_graphs:
+            raise ValueError('time_step needs one entry per graph')
+        _lib.check(_lib.lib().ddb_batch_set_time_steps(self._h, C.c_void_p(ts.data_ptr()), _stream_ptr(self.device)))
 
     def set_time(self, t_start: int):
         _lib.check(_lib.lib().ddb_batch_set_time(self._h, int(t_start), _stream_ptr(self.device)))

@@ -86,6 +86,12 @@ int ddb_model_set_cutoff(ddb_model* m, int32_t mode, float r_max);
  * _predict_x0_from_eps :353-356).  Selects the branch of the posterior step in ddb_reverse_step; call before ddb_model_finalize
  * (the two extra schedule tables "sqrt_recip_alphas_cumprod" / "sqrt_recipm1_alphas_cumprod" are then required). */
 int ddb_model_set_mean_type(ddb_model* m, int32_t noise);
+/* Time embedding (models/decompdiff.py:168-183, 224-236): 0 = none (time_emb_dim = 0, the shipped configuration), 1 = 'simple'
+ * (the ligand feature vector gets one more column, time_step / num_timesteps; "ligand_atom_emb.weight" then has
+ * ligand_feature_dim = classes + aux + 1 input columns and ddb_config.ligand_feature_dim must say so).  The 'sin' mode cannot run
+ * upstream for real batches (it concatenates a per-GRAPH embedding to per-ATOM features, :231-232) and is not offered.  Call
+ * before ddb_model_finalize. */
+int ddb_model_set_time_emb(ddb_model* m, int32_t mode);
 /* Stand-alone refine net (get_refine_net('uni_o2_bond', config), models/encoders/__init__.py:27-43): call before
  * ddb_model_finalize; only the "refine_net.*" tensors are then required and the model serves ddb_refine_batch_create /
  * ddb_refine_forward only. */
@@ -165,6 +171,9 @@ typedef struct ddb_step_io {
   int64_t* bond_traj; float* bt_traj;
 } ddb_step_io;
 int ddb_batch_set_time(ddb_batch* b, int32_t t_start, void* stream);
+/* forward() with explicit time steps (DecompScorePosNet3D.forward(..., time_step), one int64 per graph, host memory): only the
+ * 'simple' time embedding reads them.  ddb_batch_set_time returns the batch to the run's single device-side time index. */
+int ddb_batch_set_time_steps(ddb_batch* b, const int64_t* time_step, void* stream);
 int ddb_reverse_step(ddb_batch* b, const ddb_step_io* io, void* stream);
 
 /* Drift guidance (decompdiff.py:638-677, utils/guidance_funcs.py:24-78); host pointers, copied.

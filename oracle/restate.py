@@ -300,9 +300,13 @@ def refine_net(sd, cfg, h, x, bond_index, h_bond, mask_ligand, mask_ligand_atom,
 # ----------------------------------------------------------------------------
 def forward(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand_pos, init_ligand_v,
             init_ligand_v_aux, batch_ligand, ligand_fc_bond_index, init_ligand_fc_bond_type,
-            ligand_atom_mask=None, return_all=False, knn_edge_index=None, **_unused):
+            ligand_atom_mask=None, return_all=False, knn_edge_index=None, time_step=None, **_unused):
     nc, nb = cfg['num_classes'], cfg['num_bond_classes']
     lig_feat = torch.cat([F.one_hot(init_ligand_v, nc).float(), init_ligand_v_aux], -1)
+    if cfg.get('time_emb_dim', 0) > 0:      # 'simple' time embedding (decompdiff.py:224-229)
+        if cfg.get('time_emb_mode', 'simple') != 'simple':
+            raise NotImplementedError
+        lig_feat = torch.cat([lig_feat, (time_step / cfg['num_diffusion_timesteps'])[batch_ligand].unsqueeze(-1)], -1)
     h_p = F.linear(protein_v, sd['protein_atom_emb.weight'], sd['protein_atom_emb.bias'])
     h_l = F.linear(lig_feat, sd['ligand_atom_emb.weight'], sd['ligand_atom_emb.bias'])
     h_p = torch.cat([h_p, torch.zeros(h_p.size(0), 1)], -1)   # node indicator 0 / 1 (:252-256)
@@ -479,7 +483,7 @@ def sample_diffusion(sd, cfg, protein_pos, protein_v, batch_protein, init_ligand
     for s, i in enumerate(reversed(range(t_hi - num_steps, t_hi))):
         t = torch.full((B,), i, dtype=torch.long)
         preds = forward(sd, cfg, protein_pos, protein_v, batch_protein, ligand_pos, ligand_v, ligand_v_aux,
-                        batch_ligand, ligand_fc_bond_index, ligand_bond, ligand_atom_mask=ligand_atom_mask)
+                        batch_ligand, ligand_fc_bond_index, ligand_bond, ligand_atom_mask=ligand_atom_mask, time_step=t)
         if noise is not None:
             u_a, u_b, eps = noise[s]['u_atom'], noise[s]['u_bond'], noise[s]['eps_pos']
         else:

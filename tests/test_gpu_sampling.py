@@ -268,3 +268,39 @@ def test_noise_mean_type_matches_reference(case, weights):
     with pytest.raises(ValueError):
         ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, model_mean_type='x0'), syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM,
                                 syn.NUM_CLASSES).sample_diffusion(**kw, num_steps=1, center_pos_mode='protein')
+
+
+def test_simple_time_embedding_matches_reference():
+    """time_emb_dim > 0 with time_emb_mode='simple' (models/decompdiff.py:168-173, 224-229; ddb_model_set_time_emb,
+    ddb_batch_set_time_steps): forward with one time step per graph and a free-running 8-step sample_diffusion against the
+    UNMODIFIED reference; the 'sin' mode (broken upstream for real batches) is refused at construction."""
+    import decompdiff_b200 as ddb
+    from oracle import make_golden_time
+    cfg = dict(syn.DEFAULT_MODEL_CONFIG, time_emb_dim=1, time_emb_mode='simple')
+    m = ddb.DecompScorePosNet3D(cfg, syn.PROTEIN_FEATURE_DIM, syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
+    m.load_state_dict(syn.synthetic_state_dict(m, seed=0))
+    m.eval()
+    kw = syn.make_batch(**make_golden_time.TIME_FWD['batch'])
+    gold = load_golden('fwd_time_simple')
+    out = m(**syn.forward_kwargs(kw, torch.tensor(make_golden_time.TIME_FWD['time_step'])))
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
+        assert tol_ratio(out[k], gold[k]) <= 1.0, (k, tol_ratio(out[k], gold[k]))
+    other = m(**syn.forward_kwargs(kw, torch.full((4,), 500)))      # same collated batch, other time steps
+    assert tol_ratio(other['pred_ligand_v'], gold['pred_ligand_v_t500']) <= 1.0
+    with pytest.raises(TypeError):
+        m(**syn.forward_kwargs(kw, None))
+    spec = make_golden_time.TIME_TRAJ
+    kw = syn.make_batch(**spec['batch'])
+    gold = load_golden('traj_time_simple')
+    n, Eb, S = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel(), spec['num_steps']
+    noise = syn.step_noise(n, Eb, S, spec['noise_seed'])
+    r = m.sample_diffusion(**kw, num_steps=S, center_pos_mode='protein', noise=noise)
+    v_traj, b_traj = torch.stack([t.cpu() for t in r['v_traj']]), torch.stack([t.cpu() for t in r['bond_traj']])
+    pos_traj = torch.stack([t.cpu() for t in r['pos_traj']])
+    flips = (v_traj != gold['v_traj'].long()).flatten(1).any(1) | (b_traj != gold['bond_traj'].long()).flatten(1).any(1)
+    first_flip = int(flips.float().argmax()) if bool(flips.any()) else S
+    assert first_flip >= min(S, 4)
+    assert tol_ratio(pos_traj[:first_flip], gold['pos_traj'][:first_flip]) <= 1.0
+    with pytest.raises(NotImplementedError):
+        ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, time_emb_dim=4, time_emb_mode='sin'), syn.PROTEIN_FEATURE_DIM,
+                                syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)

@@ -32,9 +32,11 @@ def test_unsupported_configurations_raise():
     cfg = dict(syn.DEFAULT_MODEL_CONFIG, cutoff_mode='ball')
     with pytest.raises(ValueError):                # uni_transformer_edge.py:358 ('knn', 'hybrid' and the product's 'radius' exist)
         ddb.DecompScorePosNet3D(cfg, 29, 10, 8)
-    for key, val in (('add_prior_node', True), ('time_emb_dim', 8), ('model_type', 'uni_o2')):
+    for extra in (dict(add_prior_node=True), dict(time_emb_dim=8, time_emb_mode='sin'), dict(model_type='uni_o2')):
         with pytest.raises((NotImplementedError, ValueError)):
-            ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, **{key: val}), 29, 10, 8)
+            ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, **extra), 29, 10, 8)
+    m = ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, time_emb_dim=1, time_emb_mode='simple'), 29, 10, 8)
+    assert m.ligand_atom_emb.in_features == 11      # 'simple' time embedding: one more input column (decompdiff.py:173)
     with pytest.raises(ValueError):
         ddb.get_refine_net('uni_o2', ddb.AttrDict(syn.DEFAULT_MODEL_CONFIG))
 

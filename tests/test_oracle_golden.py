@@ -5,7 +5,7 @@ import torch
 
 from conftest import load_golden, tol_ratio
 from decompdiff_b200 import synthetic as syn
-from oracle import fused_algebra, make_golden, make_golden_hybrid, make_golden_noise, restate
+from oracle import fused_algebra, make_golden, make_golden_hybrid, make_golden_noise, make_golden_time, restate
 
 
 @pytest.mark.parametrize('case', list(make_golden.FORWARD_CASES))
@@ -63,6 +63,38 @@ def test_oracle_noise_mean_type_matches_reference(case, weights, oracle_cfg):
     assert tol_ratio(torch.stack(r['pos_traj']), gold['pos_traj']) <= 1.0
     c0 = restate.sample_diffusion(weights, oracle_cfg, **kw, num_steps=2, center_pos_mode='protein', energy_drift_opt=spec['drift'], noise=noise)
     assert float((c0['pos_traj'][1] - gold['pos_traj'][1]).abs().max()) > 1e-3      # the branch changes the trajectory
+
+
+def _time_weights():
+    """Name-keyed synthetic weights of the model WITH the 'simple' time embedding (ligand_atom_emb has one more input column)."""
+    import decompdiff_b200 as ddb
+    m = ddb.DecompScorePosNet3D(dict(syn.DEFAULT_MODEL_CONFIG, time_emb_dim=1, time_emb_mode='simple'), syn.PROTEIN_FEATURE_DIM,
+                                syn.LIGAND_FEATURE_DIM, syn.NUM_CLASSES)
+    m.load_state_dict(syn.synthetic_state_dict(m, seed=0))
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def test_oracle_simple_time_embedding_matches_reference(oracle_cfg):
+    """time_emb_dim > 0, time_emb_mode='simple' (models/decompdiff.py:224-229): forward with one time step per graph and a short
+    sampling run against the unmodified reference."""
+    _, w = _time_weights()
+    assert w['ligand_atom_emb.weight'].shape[1] == syn.LIGAND_FEATURE_DIM + 1
+    cfg = dict(oracle_cfg, time_emb_dim=1, time_emb_mode='simple')
+    kw = syn.make_batch(**make_golden_time.TIME_FWD['batch'])
+    gold = load_golden('fwd_time_simple')
+    with torch.no_grad():
+        out = restate.forward(w, cfg, **syn.forward_kwargs(kw, torch.tensor(make_golden_time.TIME_FWD['time_step'])))
+    for k in ('pred_ligand_pos', 'pred_ligand_v', 'pred_bond'):
+        assert tol_ratio(out[k], gold[k]) <= 0.2, (k, tol_ratio(out[k], gold[k]))
+    assert float((gold['pred_ligand_v'] - gold['pred_ligand_v_t500']).abs().max()) > 1e-2      # the time step matters
+    spec = make_golden_time.TIME_TRAJ
+    kw = syn.make_batch(**spec['batch'])
+    gold = load_golden('traj_time_simple')
+    n, Eb = kw['init_ligand_pos'].size(0), kw['init_ligand_fc_bond_type'].numel()
+    noise = syn.step_noise(n, Eb, spec['num_steps'], spec['noise_seed'])
+    r = restate.sample_diffusion(w, cfg, **kw, num_steps=spec['num_steps'], center_pos_mode='protein', noise=noise)
+    assert torch.equal(torch.stack(r['v_traj']), gold['v_traj'].long()) and torch.equal(torch.stack(r['bond_traj']), gold['bond_traj'].long())
+    assert tol_ratio(torch.stack(r['pos_traj']), gold['pos_traj']) <= 1.0
 
 
 def test_oracle_cfg1_first_steps_match_reference(weights, oracle_cfg):
