@@ -386,7 +386,7 @@ struct ddb_batch {
   int2 *trip_row_meta = nullptr, *trip_grp_meta = nullptr; int* trip_grp_order = nullptr;
   int4* bond_vg = nullptr; int n_bvg = 0, n_tvg = 0; float2 *bond_stats = nullptr, *trip_stats = nullptr;
   float *bond_factor = nullptr, *bond_part_h = nullptr, *bond_part_dx = nullptr, *trip_factor = nullptr, *trip_part = nullptr; int* trip_vg_pair = nullptr;
-  int4* trip_tile_rec = nullptr; bool trip_chunked = false;
+  int4* trip_tile_rec = nullptr; bool trip_chunked = false; int4* trip_edge_meta = nullptr;
   int* t_graph = nullptr; bool t_per_graph = false;      // forward() with explicit per-graph time steps ('simple' time embedding)
   int4* trip_grp4 = nullptr; int *trip_grp_pk = nullptr, *csr_slot = nullptr; float *PcsrK = nullptr, *PcsrV = nullptr, *xcsr = nullptr;
   float *x4_0 = nullptr, *x4_a = nullptr, *x4_b = nullptr, *h0 = nullptr, *lig_base = nullptr, *offset_lig = nullptr;
@@ -764,6 +764,11 @@ static int batch_create_impl(ddb_batch** out, const ddb_model* m, int32_t num_gr
   DDB_TRY(b->upload(&b->lig_idx, lig_idx)); DDB_TRY(b->upload(&b->lig_ptr, lig_ptr));
   DDB_TRY(b->upload(&b->is_lig, is_lig)); DDB_TRY(b->upload(&b->upd_mask, upd));
   DDB_TRY(b->upload(&b->bsrc, bsrc)); DDB_TRY(b->upload(&b->bdst, bdst));
+  {
+    std::vector<int4> em(Eb);
+    for (int e = 0; e < Eb; ++e) em[e] = make_int4(bsrc[e], bdst[e], lig_idx[bsrc[e]], lig_idx[bdst[e]]);
+    DDB_TRY(b->upload(&b->trip_edge_meta, em));
+  }
   DDB_TRY(b->upload(&b->in_ptr, in_ptr)); DDB_TRY(b->upload(&b->in_eid, in_eid)); DDB_TRY(b->upload(&b->in_src, in_src));
   DDB_TRY(b->upload(&b->trip_base, trip_base));
   DDB_TRY(b->upload(&b->x4_0, x4)); DDB_TRY(b->upload(&b->x4_a, x4)); DDB_TRY(b->upload(&b->x4_b, x4));
@@ -1121,6 +1126,7 @@ int run_forward(ddb_batch* b, cudaStream_t s) {
     ta.v.Wc = m->p(L.bl_v.Wc); ta.v.Wa = m->p(L.bl_v.Wa); ta.v.P = b->Pv; ta.v.w = bond_w(m, L.bl_v.m); ta.v.W2tc = m->p(L.bl_v.m.W2tc); ta.v.Watc = m->p(L.bl_v.Watc);
     if (b->tc_attn & 2) { ta.v.Q = b->Qv; ta.v.Pm = b->Pmv; ta.v.Qm = b->Qmv; }
     ta.q = b->qE; ta.ldq = H; ta.wbuf = b->wb_trip; ta.h_bond_in = hb_in; ta.h_bond_out = hb_out;
+    ta.edge_meta = b->trip_edge_meta;
     ta.n_groups = b->n_tvg; ta.vg_pair = b->trip_vg_pair; ta.stats = b->trip_stats; ta.factor = b->trip_factor; ta.part = b->trip_part;
     const bool trip_chunked = b->trip_chunked;
     if (trip2) {

@@ -258,8 +258,10 @@ __global__ void __launch_bounds__(256, 4) trip_prep_kernel(const TripArgs a) {
 #pragma unroll
   for (int u = 0; u < PREP_EDGES; ++u) {
     es[u] = min(e0 + u, a.n_bonds - 1);
-    ks[u] = a.bsrc[es[u]]; js[u] = a.bdst[es[u]];
-    float4 xk = ldg4(a.x4 + (size_t)a.lig_idx[ks[u]] * 4), xj = ldg4(a.x4 + (size_t)a.lig_idx[js[u]] * 4);
+    int nk, nj;
+    if (a.edge_meta) { const int4 em = __ldg(a.edge_meta + es[u]); ks[u] = em.x; js[u] = em.y; nk = em.z; nj = em.w; }
+    else { ks[u] = a.bsrc[es[u]]; js[u] = a.bdst[es[u]]; nk = a.lig_idx[ks[u]]; nj = a.lig_idx[js[u]]; }
+    float4 xk = ldg4(a.x4 + (size_t)nk * 4), xj = ldg4(a.x4 + (size_t)nj * 4);
     float dx = xj.x - xk.x, dy = xj.y - xk.y, dz = xj.z - xk.z;
     float d = sqrtf(dx * dx + dy * dy + dz * dz);       // (pos[i]-pos[j]).pow(2).sum(-1).sqrt()  (:130)
     gl[u] = lane < NG ? gauss_feat(d, lane) : 0.f;

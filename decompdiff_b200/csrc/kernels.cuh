@@ -184,6 +184,7 @@ struct TripArgs {
   // {edge id or -1, partner chunk position or -1, mask of valid rows, ordinal of the position's unit (source atom, chunk)} and
   // [2p + 1] = {first CSR row of that unit, 0, 0, 0}; a tile touches at most two consecutive units (ddb_batch_create pads)
   const int4* tile_rec = nullptr; int n_tiles3 = 0;
+  const int4* edge_meta = nullptr;    // (Eb) {src atom k, dst atom j, merged node of k, merged node of j}: one load instead of a 3-deep chain in trip_prep
 };
 void launch_trip_combine(const TripArgs& a, const float* b2, cudaStream_t stream);
 void launch_trip_prep(const TripArgs& a, cudaStream_t stream);
