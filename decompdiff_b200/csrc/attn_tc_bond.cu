@@ -31,10 +31,10 @@ struct BondTcSmem {
     hit = reinterpret_cast<float*>(p); p += 16 * 32 * 4;        // per warp: dst-side row slice
     qry = reinterpret_cast<float*>(p); p += 16 * 64 * 4;        // per warp: 2-deep ring of 32-float query slices
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;  // [parity][row][slice] {sum, centred sum of squares}
-    bars = reinterpret_cast<uint64_t*>(p); p += 32;
+    bars = reinterpret_cast<uint64_t*>(p); p += 64;        // two sets of 4: the second phase of a paired launch uses its own
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + (3 * H + 16 * 32 + 16 * 64 + 2 * 128 * 4 * 2) * 4 + 64; }
+  static constexpr int bytes() { return ATC_W2_BYTES + (3 * H + 16 * 32 + 16 * 64 + 2 * 128 * 4 * 2) * 4 + 96; }
 };
 
 __device__ __forceinline__ float2 bf2(float a, float b) { return make_float2(a, b); }
@@ -64,12 +64,12 @@ __device__ __forceinline__ void bond_tc_body(const BondAttnArgs& a, const bool f
   constexpr int W2_BYTES = 2 * NOUT * 128 * 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   BondTcSmem sm(smem_raw);
+  uint64_t* const bars = sm.bars + (first ? 0 : 4);      // a fresh barrier set per phase (no re-initialisation of used barriers)
   const BondSide& side = PASS == BT_K ? a.k : a.v;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    if (!first) { mbar_inval(smem_u32(&sm.bars[0])); mbar_inval(smem_u32(&sm.bars[1])); }
-    mbar_init(smem_u32(&sm.bars[0]), 1); mbar_init(smem_u32(&sm.bars[1]), 1);
+    mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
@@ -77,7 +77,7 @@ __device__ __forceinline__ void bond_tc_body(const BondAttnArgs& a, const bool f
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    const uint32_t bar = smem_u32(&sm.bars[0]);
+    const uint32_t bar = smem_u32(&bars[0]);
     mbar_expect_tx(bar, W2_BYTES);
     bulk_g2s(smem_u32(sm.W2), side.W2tc, W2_BYTES / 2, bar);
     bulk_g2s(smem_u32(sm.W2) + W2_BYTES / 2, side.W2tc + W2_BYTES / 8, W2_BYTES / 2, bar);
@@ -89,8 +89,8 @@ __device__ __forceinline__ void bond_tc_body(const BondAttnArgs& a, const bool f
   if (PASS == BT_V_POS && tid < 16) sm.b2[tid] = side.w.b2[tid];
   if (first) pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
-  mbar_wait(smem_u32(&sm.bars[0]), 0);
-  const uint32_t bar_mma = smem_u32(&sm.bars[1]), w2_smem = smem_u32(sm.W2);
+  mbar_wait(smem_u32(&bars[0]), 0);
+  const uint32_t bar_mma = smem_u32(&bars[1]), w2_smem = smem_u32(sm.W2);
   const int n_tiles = (a.n_vg + 3) / 4;
 
   if (warp >= 16) {

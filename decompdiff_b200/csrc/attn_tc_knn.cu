@@ -39,10 +39,10 @@ struct KnnTcSmem {
     hit = reinterpret_cast<float*>(p); p += 16 * 64 * 4;        // per warp: dst-side row slice + Wt[type], for protein | ligand sources
     qry = reinterpret_cast<float*>(p); p += 16 * 64 * 4;        // per warp: 2-deep ring of 32-float query slices
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;  // [parity][row][slice] {sum, sum of squares}
-    bars = reinterpret_cast<uint64_t*>(p); p += 64;
+    bars = reinterpret_cast<uint64_t*>(p); p += 128;       // two sets of 8: the second phase of a paired launch uses its own
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 4 * KT_IMG + (3 * H + 16 * 64 * 2 + 2 * 128 * 4 * 2) * 4 + 96; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 4 * KT_IMG + (3 * H + 16 * 64 * 2 + 2 * 128 * 4 * 2) * 4 + 160; }
 };
 static_assert(KnnTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -103,12 +103,13 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
   constexpr int W2_BYTES = VPOS ? 2 * NH * 128 * 4 : ATC_W2_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   KnnTcSmem sm(smem_raw);
+  uint64_t* const bars = sm.bars + (first ? 0 : 8);      // a fresh barrier set per phase (no re-initialisation of used barriers)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
   // barriers: [0] W2 (+ first B2) landed, [1] main MMA retired, [2] distance MMA retired, [3] B2 of the second class landed,
   // [4] Gaussian features of a tile written (3 producer warps), [5] D2 of a tile read by every worker warp
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), i == 4 ? 3 : i == 5 ? 16 : 1); }
+    for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&bars[i]), i == 4 ? 3 : i == 5 ? 16 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
@@ -118,7 +119,7 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
   const int tile_first = a.n_slots_first / 4;          // tiles below this hold destinations of class a.first_class
   auto class_of = [&](int tile) { return tile < tile_first ? a.first_class : 1 - a.first_class; };
   if (tid == 0) {
-    const uint32_t bar = smem_u32(&sm.bars[0]);
+    const uint32_t bar = smem_u32(&bars[0]);
     mbar_expect_tx(bar, W2_BYTES + 2 * KT_IMG);
     bulk_g2s(smem_u32(sm.W2), a.W2tc, W2_BYTES / 2, bar);
     bulk_g2s(smem_u32(sm.W2) + W2_BYTES / 2, a.W2tc + W2_BYTES / 8, W2_BYTES / 2, bar);
@@ -133,8 +134,8 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
   const int n_dst = a.n_dst_dev ? min(__ldg(a.n_dst_dev), a.n_dst) : a.n_dst;      // device-side count: receptive-field pruning
   const int n_tiles = (n_dst + 3) / 4;
   __syncthreads();
-  mbar_wait(smem_u32(&sm.bars[0]), 0);
-  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_d2 = smem_u32(&sm.bars[2]), bar_a2f = smem_u32(&sm.bars[4]), bar_d2c = smem_u32(&sm.bars[5]);
+  mbar_wait(smem_u32(&bars[0]), 0);
+  const uint32_t bar_mma = smem_u32(&bars[1]), bar_d2 = smem_u32(&bars[2]), bar_a2f = smem_u32(&bars[4]), bar_d2c = smem_u32(&bars[5]);
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
 
   if (warp >= 16) {
@@ -153,7 +154,7 @@ __device__ __forceinline__ void knn_tc_body(const KnnAttnArgs& a, const bool fir
           const int cls = class_of(tile);
           if (cls != cur_class) {                     // class boundary: every distance MMA issued so far has retired (workers
             cur_class = cls;                          // waited on it), so B2 can be replaced
-            const uint32_t bar = smem_u32(&sm.bars[3]);
+            const uint32_t bar = smem_u32(&bars[3]);
             mbar_expect_tx(bar, 2 * KT_IMG);
             bulk_g2s(b2_smem, a.B2tc[cls], 2 * KT_IMG, bar);
             mbar_wait(bar, 0);

@@ -25,10 +25,10 @@ struct TripTcSmem {
     qrow = reinterpret_cast<float*>(p); p += 16 * 64 * 4;       // per warp: 2 x 32-float slices of the centred Q row
     xyz = reinterpret_cast<float*>(p); p += 16 * 34 * 16;       // per warp: positions x_k of its 32 rows, x_i, x_j (cp.async staging)
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][slice][row] {sum, sum of squares}
-    bars = reinterpret_cast<uint64_t*>(p); p += 64;
+    bars = reinterpret_cast<uint64_t*>(p); p += 128;       // two sets of 8: the second phase of a paired launch uses its own
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 16 * 34 * 4 + 2 * 2 * 128 * 4) * 4 + 96; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 2 * TT_A2_BYTES + (3 * H + 16 * H + 16 * 64 + 16 * 34 * 4 + 2 * 2 * 128 * 4) * 4 + 160; }
 };
 static_assert(TripTcSmem::bytes() <= 232448, "shared memory budget");
 
@@ -67,6 +67,7 @@ template <bool VPASS>
 __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first, const bool last) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TripTcSmem sm(smem_raw);
+  uint64_t* const bars = sm.bars + (first ? 0 : 8);      // a fresh barrier set per phase (no re-initialisation of used barriers)
   const TripSide& side = VPASS ? a.v : a.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
   // barriers: [0] weights landed, [1] main MMA retired, [2] angular MMA retired
@@ -74,7 +75,7 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
   if (tid == 0) {
     // [0] weights landed, [1] main MMA retired, [2] angular MMA retired, [3] angular features of a tile written (3 producer warps),
     // [4] D2 of a tile read by every worker warp
-    for (int i = 0; i < 5; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), i == 3 ? 3 : i == 4 ? 16 : 1); }
+    for (int i = 0; i < 5; ++i) mbar_init(smem_u32(&bars[i]), i == 3 ? 3 : i == 4 ? 16 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
@@ -82,7 +83,7 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    const uint32_t bar = smem_u32(&sm.bars[0]);
+    const uint32_t bar = smem_u32(&bars[0]);
     mbar_expect_tx(bar, ATC_W2_BYTES + TT_A2_BYTES);
     bulk_g2s(smem_u32(sm.W2), side.W2tc, ATC_W2_BYTES / 2, bar);
     bulk_g2s(smem_u32(sm.W2) + ATC_W2_BYTES / 2, side.W2tc + ATC_W2_BYTES / 8, ATC_W2_BYTES / 2, bar);
@@ -96,8 +97,8 @@ __device__ __forceinline__ void trip_tc_body(const TripArgs& a, const bool first
   for (int i = tid * 16; i < TT_A2_BYTES; i += TT_THREADS * 16) *reinterpret_cast<float4*>(sm.A2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (first) pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
-  mbar_wait(smem_u32(&sm.bars[0]), 0);
-  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]), bar_a2f = smem_u32(&sm.bars[3]), bar_d2c = smem_u32(&sm.bars[4]);
+  mbar_wait(smem_u32(&bars[0]), 0);
+  const uint32_t bar_mma = smem_u32(&bars[1]), bar_ang = smem_u32(&bars[2]), bar_a2f = smem_u32(&bars[3]), bar_d2c = smem_u32(&bars[4]);
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
   // Work distribution: the groups (bond edges j->i) are visited in SOURCE-major order (a.grp_order) and every (CTA, quadrant)
   // pair walks one contiguous chunk of that order.  All groups with the same source j read the same rows P'[k->j], so a thread

@@ -48,10 +48,10 @@ struct Trip3Smem {
     b2 = reinterpret_cast<float*>(p); p += H * 4;
     stat = reinterpret_cast<float2*>(p); p += 2 * 128 * 4 * 8;      // [parity][slice][row] {sum, sum of squares}
     ring = p; p += 16 * T3_RING_V;                                  // both passes carve the larger ring (one layout for the pair kernel)
-    bars = reinterpret_cast<uint64_t*>(p); p += 64;
+    bars = reinterpret_cast<uint64_t*>(p); p += 128;       // two sets of 8: the second phase of a paired launch uses its own
     tmem_slot = reinterpret_cast<uint32_t*>(p);
   }
-  static constexpr int bytes() { return ATC_W2_BYTES + 4 * T3_IMG + 2 * T3_PBUF * 4 + 3 * H * 4 + 2 * 128 * 4 * 8 + 16 * T3_RING_V + 64 + 32; }
+  static constexpr int bytes() { return ATC_W2_BYTES + 4 * T3_IMG + 2 * T3_PBUF * 4 + 3 * H * 4 + 2 * 128 * 4 * 8 + 16 * T3_RING_V + 128 + 32; }
 };
 static_assert(Trip3Smem<true>::bytes() <= 232448, "shared memory budget");
 
@@ -85,13 +85,14 @@ template <bool VPASS>
 __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, const bool last) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Trip3Smem<VPASS> sm(smem_raw);
+  uint64_t* const bars = sm.bars + (first ? 0 : 8);      // a fresh barrier set per phase (no re-initialisation of used barriers)
   const TripSide& side = VPASS ? a.v : a.k;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, s = (warp >> 2) & 3, r = q * 32 + lane;
   if ((smem_u32(sm.W2) & 1023u) != 0u) __trap();
   if (tid == 0) {
     // [0] weights landed, [1] main MMA retired, [2] angular MMA retired, [3] angular features of a tile written (3 producer warps),
     // [4] D2 of a tile read by every worker warp, [5] / [6] unit buffer 0 / 1 landed
-    for (int i = 0; i < 7; ++i) { if (!first) mbar_inval(smem_u32(&sm.bars[i])); mbar_init(smem_u32(&sm.bars[i]), i == 3 ? 3 : i == 4 ? 16 : 1); }
+    for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&bars[i]), i == 3 ? 3 : i == 4 ? 16 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (first && warp == 0) { __syncwarp(); tmem_alloc(smem_u32(sm.tmem_slot), 512); }
@@ -99,7 +100,7 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    const uint32_t bar = smem_u32(&sm.bars[0]);
+    const uint32_t bar = smem_u32(&bars[0]);
     mbar_expect_tx(bar, ATC_W2_BYTES + 2 * T3_IMG);
     bulk_g2s(smem_u32(sm.W2), side.W2tc, ATC_W2_BYTES / 2, bar);
     bulk_g2s(smem_u32(sm.W2) + ATC_W2_BYTES / 2, side.W2tc + ATC_W2_BYTES / 8, ATC_W2_BYTES / 2, bar);
@@ -117,8 +118,8 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the unit buffers are written by the bulk-copy engine later
   if (first) pdl_wait();      // set-up on static data above; the previous kernels' results are visible below
   __syncthreads();
-  mbar_wait(smem_u32(&sm.bars[0]), 0);
-  const uint32_t bar_mma = smem_u32(&sm.bars[1]), bar_ang = smem_u32(&sm.bars[2]), bar_a2f = smem_u32(&sm.bars[3]), bar_d2c = smem_u32(&sm.bars[4]);
+  mbar_wait(smem_u32(&bars[0]), 0);
+  const uint32_t bar_mma = smem_u32(&bars[1]), bar_ang = smem_u32(&bars[2]), bar_a2f = smem_u32(&bars[3]), bar_d2c = smem_u32(&bars[4]);
   const uint32_t w2_smem = smem_u32(sm.W2), a2_smem = smem_u32(sm.A2), b2_smem = smem_u32(sm.B2);
   // a CTA walks the contiguous tile range [t0, t0 + cnt); every role derives the same count
   const int per = (a.n_tiles3 + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -230,7 +231,7 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
       const int uf = rec0(it, 0).w, ul = rec0(it, 3).w;
       for (int u = max(uf, ul_before + 1); u <= ul; ++u) {
         const int row0 = u == uf ? rec1x(it, 0) : rec1x(it, 3);
-        const uint32_t bar = smem_u32(&sm.bars[5 + (u & 1)]);
+        const uint32_t bar = smem_u32(&bars[5 + (u & 1)]);
         if (lane == 0) mbar_expect_tx(bar, 32 * H * 4);
         __syncwarp();
         bulk_g2s(smem_u32(sm.P + (u & 1) * T3_PBUF + lane * T3_PROW), Pcsr + ((size_t)row0 + lane) * H, H * 4, bar);
@@ -295,7 +296,7 @@ __device__ __forceinline__ void trip3_body(const TripArgs& a, const bool first, 
       cpa_commit();
       // ---- units first used by this tile were requested one tile ago (prologue for the first tile): wait for them
       for (int u = max(uf, ul_prev + 1); u <= ul; ++u) {
-        mbar_wait(smem_u32(&sm.bars[5 + (u & 1)]), (unit_phase >> (u & 1)) & 1u);
+        mbar_wait(smem_u32(&bars[5 + (u & 1)]), (unit_phase >> (u & 1)) & 1u);
         unit_phase ^= 1u << (u & 1);
       }
       // ---- first Linear: z = P'[kj] (unit buffer) + Q'[ji] (ring) + D2 (angular MMA, issued one iteration ago)
