@@ -347,8 +347,8 @@ def main():
             if t and args.workload == 'cfg2':
                 traffic, traffic_src = t['dram_bytes_per_layer'], t['source']
                 tensor_pct, tensor_src = t.get('tensor_pipe_pct'), t.get('tensor_pipe_source', t['source'])
-        roof = {'kernel': 'knn_edge_attention: the fused EGNN layer over kNN edges = 4 launches per layer (tcgen05 key / node-value / '
-                          'position-key / position-value passes); one "launch" below = one layer',
+        roof = {'kernel': 'knn_edge_attention: the fused EGNN layer over kNN edges = 3 launches per layer (tcgen05 key pass, node-value pass, '
+                          'position key + value passes in one launch; 4 when the position grid fills the GPU); one "launch" below = one layer',
                 'bound': 'hbm', 'achieved': egnn['achieved_gbs'], 'peak': peak_gbs, 'unit': 'GB/s', 'frac': egnn['hbm_frac'],
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'time_share_of_step': egnn['share'],
                 'alg_bytes_per_launch': egnn['alg_bytes_per_step'] / layers, 'ms_per_launch': egnn['ms_per_step'] / layers,

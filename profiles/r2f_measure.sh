@@ -11,7 +11,7 @@ python profiles/sweep_cfg5.py --steps 100 > gpurun_out/r2f_sweep_cfg5.jsonl 2> g
 # every launch of 2 steps with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 260 -c 260 --csv --log-file gpurun_out/r2f_launches.csv \
     python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-profile > gpurun_out/r2f_launches.log 2>&1
-for spec in "knn:knn_tc_kernel:0:4" "trip:trip3_kernel:0:2" "bond:bond_tc:0:2" "gemm:gemm128_tc_kernel:1:7" "graph:knn_merge_kernel|knn_kernel|graph_levels_kernel|graph_lists_kernel|edge_weight_kernel|trip_prep_kernel:2:6"; do
+for spec in "knn:knn_tc:0:3" "trip:trip3_kernel:0:2" "bond:bond_tc:0:2" "gemm:gemm128_tc_kernel:1:7" "graph:knn_merge_kernel|knn_kernel|graph_levels_kernel|graph_lists_kernel|edge_weight_kernel|trip_prep_kernel:2:6"; do
   IFS=: read tag re skip cnt <<< "$spec"
   ncu --set full --clock-control none --import-source on -k regex:"$re" -s $skip -c $cnt -o gpurun_out/prof_r2f_$tag -f \
       python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-profile > gpurun_out/prof_r2f_$tag.log 2>&1
