@@ -397,6 +397,7 @@ def main():
         e2e = {'value': wl['n_pockets'] * world / (el * T_FULL / e2e_steps), 'unit': 'molecules/s', 'step_ms_by_t': by_t,
                'h2d_bytes_per_step': h2d / e2e_steps, 'd2h_bytes_per_step': d2h / e2e_steps,
                'h2d_bytes_per_call': h2d, 'd2h_bytes_per_call': d2h, 'steps_run': e2e_steps, 'seconds': el,
+               'host_phases': {k: round(v, 4) for k, v in getattr(model, 'last_call_timing', {}).items()},
                'call': 'DecompScorePosNet3D.sample_diffusion(pinned host tensors) -> molecules + 6 trajectories on the host'}
     clocks = sampler.stop()
 

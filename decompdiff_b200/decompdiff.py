@@ -416,6 +416,8 @@ class DecompScorePosNet3D(nn.Module):
         `noise` injects the per-step draws ({'u_atom','u_bond','eps_pos'}, first step first) instead of the
         torch generator; `keep_traj=False` skips the six per-step trajectories; `traj_on_device=True`
         returns them as stacked device tensors instead of lists of CPU tensors."""
+        import time as _time
+        _t0 = _time.perf_counter()
         run = self.begin_sampling(
             protein_pos, protein_v, batch_protein, protein_group_idx, init_ligand_pos, init_ligand_v, ligand_v_aux,
             batch_ligand, ligand_group_idx, prior_centers, prior_stds, prior_num_atoms, batch_prior, prior_group_idx,
@@ -424,8 +426,15 @@ class DecompScorePosNet3D(nn.Module):
             keep_traj)
         if keep_traj and not traj_on_device:      # the reference's trajectories are CPU tensors whatever the input device
             run.enable_host_streaming()
+        _t1 = _time.perf_counter()
         run.advance(run.num_steps, noise=noise)
-        return run.finish(traj_on_device=traj_on_device)
+        _t2 = _time.perf_counter()
+        out = run.finish(traj_on_device=traj_on_device)
+        # host-side wall time of the call's phases (the loop only ENQUEUES: the device finishes inside `finish`); profiling aid
+        self.last_call_timing = {'begin_sampling_s': _t1 - _t0, 'enqueue_loop_s': _t2 - _t1, 'finish_s': _time.perf_counter() - _t2,
+                                 'stream_out_host_s': run.stream_out_host_s, 'stream_out_max_s': run.stream_out_max_s,
+                                 'stream_chunk_steps': getattr(run, 'stream_chunk', 0)}
+        return out
 
 
 class SamplingRun:
@@ -463,6 +472,7 @@ class SamplingRun:
         # trajectories stream to pinned host memory while later steps run (side stream, every STREAM_CHUNK steps), so the end
         # of a run only waits for the last chunk instead of a 1.7 GB device->host copy (cfg 2)
         self.host_traj, self.copied, self.copy_stream = None, 0, None
+        self.stream_out_host_s, self.stream_out_max_s = 0.0, 0.0
 
     STREAM_CHUNK = 64
 
@@ -470,23 +480,42 @@ class SamplingRun:
         if self.keep_traj and self.host_traj is None and self.num_steps > 0:
             self.host_traj = {k: [] for k in self.traj}          # per key: list of pinned chunks, allocated when they are needed
             self.copy_stream = torch.cuda.Stream(device=self.eb.device)
+            # One pinned arena per stream-out, carved into the six arrays.  torch's pinned allocator rounds every request up to a
+            # power of two, so the chunk length is chosen to make the arena just fit one (cfg 2: 78 steps = 134 MB, nothing wasted;
+            # six separate 64-step buffers pinned 170 MB for 110 MB of data) - page-locking is the host-side cost of this path.
+            self._step_bytes = sum(v[0].numel() * v.element_size() for v in self.traj.values())
+            if self._step_bytes > 0:
+                pow2 = 1 << max((128 * self._step_bytes).bit_length() - 1, 4)
+                self.stream_chunk = int(min(max(pow2 // self._step_bytes, 16), 256))
+            else:
+                self.stream_chunk = self.STREAM_CHUNK
         return self
 
     def _stream_out(self, force: bool = False):
-        if self.host_traj is None or self.done == self.copied or (not force and self.done - self.copied < self.STREAM_CHUNK):
+        if self.host_traj is None or self.done == self.copied or (not force and self.done - self.copied < self.stream_chunk):
             return
+        import time as _time
+        _t0 = _time.perf_counter()
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.copy_stream.wait_event(ev)
         # page-locking 1.7 GB up front costs ~1.1 s; chunk by chunk it happens while the GPU works through the steps that are
         # already queued (the host runs far ahead of the device once the step is a CUDA graph)
         with torch.cuda.stream(self.copy_stream):
-            for k, v in self.traj.items():
+            steps = self.done - self.copied
+            arena = torch.empty(steps * self._step_bytes, dtype=torch.uint8, pin_memory=True)
+            off = 0
+            for k, v in sorted(self.traj.items(), key=lambda kv: -kv[1].element_size()):      # int64 arrays first: 8-byte aligned views
                 part = v[self.copied:self.done]
-                chunk = torch.empty(part.shape, dtype=part.dtype, pin_memory=True)
+                nbytes = part.numel() * part.element_size()
+                chunk = arena[off:off + nbytes].view(part.dtype).view(part.shape)
                 chunk.copy_(part, non_blocking=True)
                 self.host_traj[k].append(chunk)
+                off += nbytes
         self.copied = self.done
+        _dt = _time.perf_counter() - _t0
+        self.stream_out_host_s += _dt
+        self.stream_out_max_s = max(self.stream_out_max_s, _dt)
 
     def _draw(self):
         # the three draws of the reference: same order, shapes and generator
