@@ -160,13 +160,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm128_tc_kernel(const GemmBat
       if (ar >= 0) {
         const float* src = a.A + (size_t)ar * a.lda + s * 32;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { float4 v = ld4(src + i * 4); z[4 * i] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w; }
+        for (int i = 0; i < 4; ++i) {      // LDG.256: a thread walks its 128-byte row slice in 4 instead of 8 L1 tag look-ups per line
+          float4 v, w;
+          ldg8(src + i * 8, v, w);
+          z[8 * i] = v.x; z[8 * i + 1] = v.y; z[8 * i + 2] = v.z; z[8 * i + 3] = v.w;
+          z[8 * i + 4] = w.x; z[8 * i + 5] = w.y; z[8 * i + 6] = w.z; z[8 * i + 7] = w.w;
+        }
         if (a.A2) {
           int r2 = a.a2_rows[m];
           if (r2 >= 0) {
             const float* s2 = a.A2 + (size_t)r2 * a.lda2 + s * 32;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { float4 v = ld4(s2 + i * 4); z[4 * i] += v.x; z[4 * i + 1] += v.y; z[4 * i + 2] += v.z; z[4 * i + 3] += v.w; }
+            for (int i = 0; i < 4; ++i) {
+              float4 v, w;
+              ldg8(s2 + i * 8, v, w);
+              z[8 * i] += v.x; z[8 * i + 1] += v.y; z[8 * i + 2] += v.z; z[8 * i + 3] += v.w;
+              z[8 * i + 4] += w.x; z[8 * i + 5] += w.y; z[8 * i + 6] += w.z; z[8 * i + 7] += w.w;
+            }
           }
         }
       }
